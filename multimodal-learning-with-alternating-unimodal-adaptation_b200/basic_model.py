@@ -1,0 +1,39 @@
+"""AVClassifier (reference models/basic_model.py:14-77), gs_flag path.
+
+forward(audio [B,1,H,W], visual [B,3,T,H,W]) -> (a, v), each [B,512]; features require grad
+in training. Sub-module names (`fusion_module.fc_out`, `audio_net`, `visual_net`) and their
+creation order follow the reference so state dicts and seeded initialisation are identical.
+Only the concat head under --gs_flag is in scope (QMF / film / gated / sum are
+out of scope and raise).
+"""
+import torch.nn as nn
+
+from .backbone import resnet18
+from .fusion_modules import ConcatFusion
+
+_N_CLASSES = {"CREMAD": 6}
+
+
+class AVClassifier(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        if args.dataset not in _N_CLASSES:
+            raise NotImplementedError("Incorrect dataset name {}".format(args.dataset))
+        n_classes = _N_CLASSES[args.dataset]
+        if args.fusion_method != "concat":
+            raise NotImplementedError("mla_b200 implements the concat head of the --gs_flag path only "
+                                      "(got fusion_method={})".format(args.fusion_method))
+        if getattr(args, "modulation", "Normal") == "QMF":
+            raise NotImplementedError("QMF is outside the MLA --gs_flag path (SURVEY.md §2)")
+        # basic_model.py:31-34: 512-wide shared head under gs_flag, 1024 (concat) otherwise
+        self.fusion_module = ConcatFusion(input_dim=512 if args.gs_flag else 1024, output_dim=n_classes)
+        self.audio_net = resnet18(modality="audio")
+        self.visual_net = resnet18(modality="visual")
+        self.args = args
+
+    def forward(self, audio, visual):
+        a = self.audio_net.pooled(audio)        # backbone + adaptive_avg_pool2d + flatten
+        v = self.visual_net.pooled(visual)      # backbone + adaptive_avg_pool3d over (T,H,W) + flatten
+        if not self.args.gs_flag:
+            return self.fusion_module(a, v)
+        return a, v

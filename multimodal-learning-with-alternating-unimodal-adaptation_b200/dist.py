@@ -1,0 +1,93 @@
+"""Data-parallel runtime: one process per GPU, NCCL over NVLink.
+
+Replaces the reference's single-process nn.DataParallel (main.py:730-734), which re-broadcasts
+all parameters and gathers features to GPU 0 every step. Here parameters are never
+re-broadcast after initialisation; per modality turn there are exactly two collectives:
+  1. all-reduce(avg) of the ACTIVE encoder's gradients, as one flat bucket (views of one
+     contiguous buffer: no pack/unpack copies), and
+  2. one small all-reduce(sum) of the packed head buffer [dW | db | sum_b feat] so that every
+     rank forms the same averaged head gradient and the same global-batch r; the GS kernel is
+     deterministic, hence P stays bit-identical on all ranks without a broadcast.
+With world_size == 1 (or torch.distributed not initialised) everything is a no-op.
+The same code runs on CPU with the gloo backend (tests, world_size 2).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def world_size():
+    return dist.get_world_size() if is_dist() else 1
+
+
+def rank():
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment (RANK/WORLD_SIZE/LOCAL_RANK/MASTER_*)."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1 or (dist.is_available() and dist.is_initialized()):
+        return rank(), world_size()
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend=backend)
+    return rank(), world_size()
+
+
+class FlatGrads:
+    """One contiguous gradient buffer per parameter group (an encoder); `.views[i]` aliases it.
+
+    Backward kernels write (or autograd accumulates) straight into the views, the all-reduce
+    runs on the flat buffer, and the optimizer reads the same memory through p.grad."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def attach(self, zero=True):
+        """Point p.grad at the views (zeroed: autograd accumulates into them)."""
+        if zero:
+            self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def allreduce_avg(self):
+        if is_dist():
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / world_size())
+
+
+def allreduce_sum_(t):
+    if is_dist():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def all_gather_rows(t):
+    """Concatenate equally sized [B_local, ...] tensors from all ranks in rank order."""
+    if not is_dist():
+        return t
+    out = [torch.empty_like(t) for _ in range(world_size())]
+    dist.all_gather(out, t.contiguous())
+    return torch.cat(out, dim=0)
+
+
+def params_checksum(t):
+    """Order-independent integer checksum of a tensor's bits (cross-rank bit-identity checks)."""
+    return int(t.detach().contiguous().view(torch.int32).to(torch.int64).sum().item())

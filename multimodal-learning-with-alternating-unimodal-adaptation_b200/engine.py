@@ -1,0 +1,173 @@
+"""train_epoch / valid — the reference's L4 drivers for the --gs_flag path (main.py:127-484,
+486-679), same signatures and return values, B200-native underneath:
+
+  * per modality turn the head forward+loss+backward is ONE fused call (head kernel), the GS
+    hook is one fused kernel, the encoder backward gets dfeat directly;
+  * no per-step `.item()` syncs: epoch losses accumulate on the device and are read once;
+  * evaluation does fusion, argmax and per-class counters in one kernel per batch — the
+    reference's per-sample numpy loop (~8 D2H syncs per sample, main.py:659-676) is gone;
+  * multi-GPU is one process per GPU with two NCCL all-reduces per turn (dist.py).
+Out of scope (raises): the joint-training branch without --gs_flag (main.py:165-418).
+"""
+import torch
+import torch.nn as nn
+
+from . import dist as mdist
+from . import ops
+from .fusion_modules import head_turn
+
+N_CLASSES = {"MVSA": 3, "CREMAD": 6, "Food101": 101, "IEMOCAP": 4}
+
+
+class ModuleHolder(nn.Module):
+    """Stand-in for nn.DataParallel's `.module` indirection (main.py:732): keeps
+    `model.module.fusion_module.fc_out` and the `module.`-prefixed state-dict keys of the
+    reference's checkpoints, without DataParallel's per-step replicate/scatter/gather."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+def _unpack(args, data_packet, device):
+    """Batch tuple layouts of the reference's datasets (main.py:143-162)."""
+    nb = dict(non_blocking=True)
+    if args.lorb == "m3ae":
+        if args.modal3:
+            token, padding_mask, image, spec, label, idx = data_packet
+            return (token.to(device, **nb), padding_mask.to(device, **nb), image.to(device, **nb),
+                    spec.to(device, **nb)), label.to(device, **nb)
+        token, padding_mask, image, label, idx = data_packet
+        return (token.to(device, **nb), padding_mask.to(device, **nb), image.to(device, **nb)), label.to(device, **nb)
+    spec, image, label = data_packet[0], data_packet[1], data_packet[2]
+    spec, image = spec.to(device, **nb), image.to(device, **nb)
+    if getattr(args, "clip", False):
+        return (spec, image), label.to(device, **nb)
+    return (spec.unsqueeze(1).float(), image.float()), label.to(device, **nb)
+
+
+class _TurnState:
+    """Per-model buffers reused across steps: packed head buffer and flat encoder grads."""
+
+    def __init__(self, net):
+        fc = net.fusion_module.fc_out
+        C, D = fc.weight.shape
+        dev = fc.weight.device
+        self.packed = torch.empty(C * D + C + D, dtype=torch.float32, device=dev)
+        self.head_out = {"dW": self.packed[:C * D].view(C, D), "db": self.packed[C * D:C * D + C],
+                         "feat_sum": self.packed[C * D + C:]}
+        self.encoders = encoder_param_groups(net)
+        self.flat = [mdist.FlatGrads(g) for g in self.encoders]
+
+
+def encoder_param_groups(net):
+    """Parameters of each modality's encoder, in the fixed turn order a -> v -> t (main.py:432-466)."""
+    names = []
+    for cand in (("audio_net", "visual_net"), ("mae_a", "mae_v", "mae_t")):
+        if all(hasattr(net, n) for n in cand[:2]):
+            names = [n for n in cand if hasattr(net, n)]
+            break
+    if not names:
+        raise RuntimeError("model has no known encoders (audio_net/visual_net or mae_a/mae_v[/mae_t])")
+    return [[p for p in getattr(net, n).parameters()] for n in names]
+
+
+def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
+                gs_plugin=None, writer=None, gs_flag=False, av_alpha=0.5,
+                txt_history=None, img_history=None, audio_history=None):
+    """main.py:127-484. Returns (loss, loss_a, loss_v[, loss_t]) as Python floats."""
+    if not gs_flag:
+        raise NotImplementedError("mla_b200 implements MLA's alternating step (--gs_flag) only; the joint-training "
+                                  "branch (main.py:165-418) is out of scope")
+    net = _unwrap(model)
+    model.train()
+    print("Start training ... ")
+    fc = net.fusion_module.fc_out
+    st = getattr(net, "_mla_turn_state", None)
+    if st is None:
+        st = _TurnState(net)
+        net._mla_turn_state = st
+    world = mdist.world_size()
+    len_dataloader = len(dataloader)
+    n_mod = len(st.encoders)
+    acc = torch.zeros(1 + n_mod, dtype=torch.float64, device=device)      # _loss, _loss_a, _loss_v[, _loss_t]
+
+    for batch_step, data_packet in enumerate(dataloader):
+        inputs, label = _unpack(args, data_packet, device)
+        optimizer.zero_grad()                                              # main.py:164
+        feats = model(*inputs)                                             # main.py:421-431
+        if len(feats) != n_mod:
+            raise RuntimeError("model returned %d features for %d encoders" % (len(feats), n_mod))
+        B = feats[0].shape[0]
+        inv_global = 1.0 / (B * world)
+        losses = []
+        for m, feat in enumerate(feats):                                   # a -> v -> (t)
+            fdet = feat.detach()
+            o = head_turn(fc, fdet, label, grad_scale=inv_global, out=st.head_out)   # main.py:432-435 (head part)
+            st.flat[m].attach(zero=True)
+            feat.backward(o["dfeat"])                                      # main.py:435 (encoder part)
+            if world > 1:                                                  # two collectives per turn
+                mdist.allreduce_sum_(st.flat[m].flat)
+                mdist.allreduce_sum_(st.packed)
+            gs_plugin.before_update(fc, fdet, batch_step, len_dataloader, gs_plugin.exp_count,
+                                    feat_sum=o["feat_sum"], inv_batch=inv_global)     # main.py:437-438
+            optimizer.step()                                               # main.py:439
+            optimizer.zero_grad()                                          # main.py:440
+            gs_plugin.exp_count += 1                                       # main.py:442
+            losses.append(o["loss"].clone())
+        if n_mod == 2:                                                     # main.py:472 (fp32, like the reference)
+            mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
+        else:
+            mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
+        acc[0:1] += mix.double()
+        for m in range(n_mod):
+            acc[1 + m:2 + m] += losses[m].double()
+    scheduler.step()                                                       # main.py:481
+    if world > 1:
+        mdist.allreduce_sum_(acc)
+        acc /= world
+    vals = (acc / len_dataloader).tolist()                                 # the only device->host sync of the epoch
+    return tuple(vals)
+
+
+@torch.no_grad()
+def valid(args, model, device, dataloader, gs_flag=False, av_alpha=0.5,
+          a_alpha=0.35, v_alpha=0.25, t_alpha=0.4):
+    """main.py:486-679 (gs branch). Returns (acc, acc_a, acc_v[, acc_t]) micro-accuracies."""
+    if args.dataset not in N_CLASSES:
+        raise NotImplementedError("Incorrect dataset name {}".format(args.dataset))
+    if not gs_flag:
+        raise NotImplementedError("mla_b200 implements the --gs_flag evaluation branch only (main.py:622-679)")
+    n_classes = N_CLASSES[args.dataset]
+    net = _unwrap(model)
+    model.eval()
+    fc = net.fusion_module.fc_out
+    n_mod = 3 if getattr(args, "modal3", False) else 2
+    num = torch.zeros(n_classes, dtype=torch.int64, device=device)
+    hits = torch.zeros(n_mod + 1, n_classes, dtype=torch.int64, device=device)
+    if args.dynamic:
+        fixed = None
+    elif n_mod == 3:
+        fixed = (a_alpha, v_alpha, t_alpha)                                # main.py:649
+    else:
+        fixed = (av_alpha, 1 - av_alpha)                                   # main.py:651
+    for data_packet in dataloader:
+        inputs, label = _unpack(args, data_packet, device)
+        feats = model(*inputs)                                             # main.py:624-634
+        logits = [fc(f.contiguous()) for f in feats]                       # main.py:636-639
+        if mdist.is_dist():
+            # the entropy weights are a GLOBAL-batch quantity: gather the tiny logits
+            logits = [mdist.all_gather_rows(x) for x in logits]
+            label = mdist.all_gather_rows(label)
+        ops.fuse_eval(logits, label, dynamic=bool(args.dynamic), fixed_w=fixed, hits=hits, num=num,
+                      want_fused=False, want_argmax=False)                 # main.py:640-676
+    h = hits.sum(dim=1).tolist()
+    n = float(num.sum().item())
+    return tuple(x / n for x in h)

@@ -1,0 +1,151 @@
+"""Command-line driver with the reference's flag surface (main.py:18-63, 697-964) for the
+MLA --gs_flag path, on synthetic data of the BASELINE.json shapes.
+
+    python -m mla_b200.main --train --lorb base --gs_flag --dynamic --dataset CREMAD --ckpt_path ckpt \
+        --synthetic --steps 8 --epochs 1
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m mla_b200.main ... (one process per GPU)
+
+Every reference flag is accepted with the reference's default. Real datasets are out of scope
+(they need private files under /data1/...), so data is always synthetic here.
+"""
+import argparse
+import os
+
+import torch
+import torch.optim as optim
+
+from . import dist as mdist
+from .basic_model import AVClassifier
+from .engine import ModuleHolder, train_epoch, valid
+from .gs_plugin import GSPlugin
+from .utils import setup_seed, weight_init
+
+
+def get_arguments(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--dataset", default="CREMA-D", type=str)
+    p.add_argument("--modulation", default="Normal", type=str, choices=["Normal", "OGM", "OGM_GE", "QMF"])
+    p.add_argument("--fusion_method", default="concat", type=str, choices=["sum", "concat", "gated", "film"])
+    p.add_argument("--fps", default=1, type=int)
+    p.add_argument("--use_video_frames", default=3, type=int)
+    p.add_argument("--batch_size", default=64, type=int)
+    p.add_argument("--epochs", default=100, type=int)
+    p.add_argument("--optimizer", default="sgd", type=str, choices=["sgd", "adam"])
+    p.add_argument("--learning_rate", default=0.001, type=float)
+    p.add_argument("--lr_decay_step", default=70, type=int)
+    p.add_argument("--lr_decay_ratio", default=0.1, type=float)
+    p.add_argument("--modulation_starts", default=0, type=int)
+    p.add_argument("--modulation_ends", default=50, type=int)
+    p.add_argument("--alpha", default=0.3, type=float)
+    p.add_argument("--ckpt_path", required=True, type=str)
+    p.add_argument("--train", action="store_true")
+    p.add_argument("--use_tensorboard", default=True, type=bool)
+    p.add_argument("--tensorboard_path", default="ckpt/", type=str)
+    p.add_argument("--random_seed", default=0, type=int)
+    p.add_argument("--gpu_ids", default="0, 1, 2", type=str)
+    p.add_argument("--lorb", default="m3ae", type=str)
+    p.add_argument("--gs_flag", action="store_true")
+    p.add_argument("--av_alpha", default=0.5, type=float)
+    p.add_argument("--cav_opti", action="store_true")
+    p.add_argument("--cav_lrs", action="store_true")
+    p.add_argument("--cav_augnois", action="store_true")
+    p.add_argument("--modal3", action="store_true")
+    p.add_argument("--dynamic", action="store_true")
+    p.add_argument("--a_alpha", default=0.35, type=float)
+    p.add_argument("--v_alpha", default=0.25, type=float)
+    p.add_argument("--t_alpha", default=0.4, type=float)
+    p.add_argument("--clip", action="store_true")
+    p.add_argument("--ckpt_load_path_train", default=None, type=str)
+    # additions (not in the reference)
+    p.add_argument("--synthetic", action="store_true", help="synthetic batches of the BASELINE.json shapes")
+    p.add_argument("--steps", default=8, type=int, help="synthetic batches per epoch")
+    p.add_argument("--force_projection", action="store_true",
+                   help="fire the GS projection on the bare Linear (the published hook is a no-op, SURVEY F1)")
+    return p.parse_args(argv)
+
+
+class SyntheticAVLoader:
+    """len()-able iterable of CREMA-D-shaped batches (spec [B,257,188], image [B,3,T,224,224],
+    label, idx), pinned host memory, seeded per rank."""
+
+    def __init__(self, batch_size, steps, seed, frames=2, spec_hw=(257, 188), image_hw=(224, 224), n_classes=6,
+                 distinct=2):
+        g = torch.Generator().manual_seed(seed)
+        self.batches = []
+        for _ in range(min(distinct, steps)):
+            spec = torch.randn(batch_size, *spec_hw, generator=g)
+            image = torch.randn(batch_size, 3, frames, *image_hw, generator=g)
+            label = torch.randint(0, n_classes, (batch_size,), generator=g)
+            idx = torch.zeros(batch_size, 1, dtype=torch.long)
+            if torch.cuda.is_available():
+                spec, image, label = spec.pin_memory(), image.pin_memory(), label.pin_memory()
+            self.batches.append((spec, image, label, idx))
+        self.steps = steps
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self):
+        for i in range(self.steps):
+            yield self.batches[i % len(self.batches)]
+
+
+def build_model(args, device):
+    """main.py:707-734 for the paths in scope."""
+    if args.lorb in ("large", "m3ae") or args.clip:
+        raise NotImplementedError("round 1 implements --lorb base (AVClassifier); m3ae / modal3 encoders are the "
+                                  "next rows of SURVEY.md §8")
+    model = AVClassifier(args)
+    model.apply(weight_init)
+    if args.ckpt_load_path_train:
+        loaded = torch.load(args.ckpt_load_path_train, map_location="cpu")["model"]
+        state = {k[7:]: v for k, v in loaded.items()}            # strip 'module.' (main.py:723)
+        state.pop("fusion_module.fc_out.weight", None)
+        state.pop("fusion_module.fc_out.bias", None)
+        model.load_state_dict(state, strict=False)
+        print("Trained model loaded!")
+    return ModuleHolder(model.to(device))
+
+
+def main(av_alpha=0.5):
+    args = get_arguments()
+    if args.dataset == "CREMA-D":
+        args.dataset = "CREMAD"
+    rank, world = mdist.init_from_env()
+    setup_seed(args.random_seed)
+    device = torch.device("cuda", torch.cuda.current_device())
+    model = build_model(args, device)
+    optimizer = optim.SGD(model.parameters(), lr=args.learning_rate, momentum=0.9, weight_decay=1e-4)   # main.py:749
+    scheduler = optim.lr_scheduler.StepLR(optimizer, args.lr_decay_step, args.lr_decay_ratio)           # main.py:760
+    train_loader = SyntheticAVLoader(args.batch_size, args.steps, seed=1 + rank)
+    test_loader = SyntheticAVLoader(args.batch_size, max(1, args.steps // 2), seed=1001 + rank)
+    gs = GSPlugin(force_projection=args.force_projection) if args.gs_flag else None                     # main.py:819
+    if args.train:
+        best_acc = 0.0
+        for epoch in range(args.epochs):
+            if rank == 0:
+                print("Epoch: {}: ".format(epoch))
+            losses = train_epoch(args, epoch, model, device, train_loader, optimizer, scheduler, gs_plugin=gs,
+                                 gs_flag=args.gs_flag, av_alpha=av_alpha)
+            accs = valid(args, model, device, test_loader, gs_flag=args.gs_flag, av_alpha=av_alpha,
+                         a_alpha=args.a_alpha, v_alpha=args.v_alpha, t_alpha=args.t_alpha)
+            if rank == 0:
+                print("Loss: {:.4f}, Acc: {:.4f}, Acc_a: {:.4f}, Acc_v: {:.4f}".format(losses[0], accs[0], accs[1],
+                                                                                       accs[2]))
+                if accs[0] > best_acc:
+                    best_acc = float(accs[0])
+                    os.makedirs(args.ckpt_path, exist_ok=True)
+                    torch.save({"saved_epoch": epoch, "modulation": args.modulation, "alpha": args.alpha,
+                                "fusion": args.fusion_method, "acc": accs[0], "model": model.state_dict(),
+                                "optimizer": optimizer.state_dict(), "scheduler": scheduler.state_dict(),
+                                "gs_plugin": gs.state_dict() if gs is not None else None},
+                               os.path.join(args.ckpt_path, "best_model_of_dataset_{}_gs_epoch_{}.pth".format(
+                                   args.dataset, epoch)))
+    else:
+        accs = valid(args, model, device, test_loader, gs_flag=args.gs_flag, av_alpha=av_alpha)
+        if rank == 0:
+            print("Acc: {:.4f}, Acc_a: {:.4f}, Acc_v: {:.4f}".format(*accs[:3]))
+
+
+if __name__ == "__main__":
+    main(av_alpha=0.55)        # main.py:968

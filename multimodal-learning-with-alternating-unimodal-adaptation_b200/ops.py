@@ -1,0 +1,140 @@
+"""Tensor-level wrappers over the C ABI (one Python function per entry point).
+
+These are thin: argument checking, workspace sizing, pointer extraction, error mapping.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_ws = {}
+
+
+def _workspace(key, nbytes, device):
+    ws = _ws.setdefault((key, device), _lib.Workspace())
+    return ws.get(nbytes, device)
+
+
+def _f32(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+    return t
+
+
+def gs_project(P, grad_w, alpha, feat=None, feat_sum=None, inv_batch=None, mode=0):
+    """In-place P update + gradient projection (utils/utils.py:34-41). See mla_gs_project."""
+    L = _lib.lib()
+    if (feat is None) == (feat_sum is None):
+        raise RuntimeError("gs_project: pass exactly one of feat / feat_sum")
+    D = P.shape[0]
+    if P.dim() != 2 or P.shape[1] != D:
+        raise RuntimeError("gs_project: P must be (D, D)")
+    if feat is not None:
+        B = feat.shape[0]
+        if feat.shape[1] != D:
+            raise RuntimeError("gs_project: feature width %d does not match P (%d)" % (feat.shape[1], D))
+    else:
+        if inv_batch is None:
+            raise RuntimeError("gs_project: feat_sum needs inv_batch")
+        B = 1
+        if feat_sum.numel() != D:
+            raise RuntimeError("gs_project: feat_sum must have D elements")
+    if inv_batch is None:
+        inv_batch = 1.0 / B
+    C = 0 if grad_w is None else grad_w.shape[0]
+    if grad_w is not None and grad_w.shape[1] != D:
+        raise RuntimeError("gs_project: grad width %d does not match P (%d)" % (grad_w.shape[1], D))
+    nbytes = L.mla_gs_project_workspace_bytes(B, D, C)
+    if nbytes == 0:
+        raise RuntimeError("gs_project: unsupported shape B=%d D=%d C=%d" % (B, D, C))
+    ws = _workspace("gs", nbytes, P.device)
+    rc = L.mla_gs_project(_lib.ptr(_f32(P, "P")), _lib.ptr(_f32(feat, "feat")), _lib.ptr(_f32(feat_sum, "feat_sum")),
+                          float(inv_batch), float(alpha), _lib.ptr(_f32(grad_w, "grad_w")), B, D, C, int(mode),
+                          ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "mla_gs_project")
+
+
+def head_ce(feat, weight, bias, label, grad_scale=None, need_grad=True, need_logits=True, need_dfeat=True,
+            out=None):
+    """One head turn. Returns dict(logits, loss, dW, db, dfeat, feat_sum); loss is a 1-element tensor."""
+    L = _lib.lib()
+    B, D = feat.shape
+    C = weight.shape[0]
+    if weight.shape[1] != D:
+        raise RuntimeError("head_ce: weight is %s, features are %d wide" % (tuple(weight.shape), D))
+    if label.dtype != torch.int64:
+        raise RuntimeError("head_ce: label must be int64")
+    dev = feat.device
+    o = out if out is not None else {}
+
+    def buf(name, shape, want=True):
+        if not want:
+            o[name] = None
+            return None
+        t = o.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float32, device=dev)
+            o[name] = t
+        return t
+
+    logits = buf("logits", (B, C), need_logits)
+    loss = buf("loss", (1,))
+    dW = buf("dW", (C, D), need_grad)
+    db = buf("db", (C,), need_grad)
+    dfeat = buf("dfeat", (B, D), need_grad and need_dfeat)
+    feat_sum = buf("feat_sum", (D,))
+    if grad_scale is None:
+        grad_scale = 1.0 / B
+    nbytes = L.mla_head_ce_workspace_bytes(B, D, C)
+    ws = _workspace("head", nbytes, dev)
+    rc = L.mla_head_ce(_lib.ptr(_f32(feat, "feat")), _lib.ptr(_f32(weight, "weight")), _lib.ptr(_f32(bias, "bias")),
+                       _lib.ptr(label), B, D, C, _lib.ptr(logits), _lib.ptr(loss), _lib.ptr(dW), _lib.ptr(db),
+                       _lib.ptr(dfeat), _lib.ptr(feat_sum), float(grad_scale), ws.data_ptr(), ws.numel(),
+                       _lib.stream_ptr())
+    _lib.check(rc, "mla_head_ce")
+    return o
+
+
+def fuse_eval(logits, label=None, dynamic=True, fixed_w=None, hits=None, num=None, want_fused=True,
+              want_argmax=True, want_entropy=False):
+    """Fusion + accuracy counters (main.py:65-106, 640-676). Returns (fused, w, argmax[, entropy])."""
+    L = _lib.lib()
+    M = len(logits)
+    B, C = logits[0].shape
+    dev = logits[0].device
+    for t in logits:
+        if tuple(t.shape) != (B, C):
+            raise RuntimeError("fuse_eval: all logit matrices must have the same shape")
+        _f32(t, "logits")
+    fused = torch.empty((B, C), dtype=torch.float32, device=dev) if want_fused else None
+    w = torch.empty((M,), dtype=torch.float32, device=dev)
+    ent = torch.empty((M,), dtype=torch.float32, device=dev) if (dynamic and want_entropy) else None
+    argmax = torch.empty((M + 1, B), dtype=torch.int32, device=dev) if want_argmax else None
+    if (hits is None) != (num is None):
+        raise RuntimeError("fuse_eval: hits and num come together")
+    if hits is not None:
+        if label is None or label.dtype != torch.int64:
+            raise RuntimeError("fuse_eval: counting needs int64 labels")
+        if hits.dtype != torch.int64 or num.dtype != torch.int64 or tuple(hits.shape) != (M + 1, C) \
+                or num.numel() != C:
+            raise RuntimeError("fuse_eval: hits must be int64 (M+1, C) and num int64 (C)")
+    ptrs = (ctypes.c_void_p * M)(*[_lib.ptr(t) for t in logits])
+    fw = None
+    if not dynamic:
+        if fixed_w is None or len(fixed_w) != M:
+            raise RuntimeError("fuse_eval: fixed fusion needs M weights")
+        fw = (ctypes.c_float * M)(*[float(x) for x in fixed_w])
+    nbytes = L.mla_fuse_eval_workspace_bytes(M, B, C)
+    if nbytes == 0:
+        raise RuntimeError("fuse_eval: unsupported shape M=%d B=%d C=%d" % (M, B, C))
+    ws = _workspace("fuse", nbytes, dev)
+    rc = L.mla_fuse_eval(ptrs, M, B, C, 1 if dynamic else 0, fw, _lib.ptr(label) if hits is not None else None,
+                         _lib.ptr(fused), _lib.ptr(w), _lib.ptr(ent), _lib.ptr(argmax), _lib.ptr(hits), _lib.ptr(num),
+                         ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "mla_fuse_eval")
+    if want_entropy:
+        return fused, w, argmax, ent
+    return fused, w, argmax

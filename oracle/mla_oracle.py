@@ -1,0 +1,339 @@
+"""CPU ORACLE for the MLA hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+import this module, and only as the checker / the timed CPU baseline. Nothing under the
+product package imports it; the product path has no CPU fallback.
+
+It restates, on the CPU, what the reference computes on the path named by BASELINE.json:
+  * GSPlugin.before_update            utils/utils.py:24-41          (numpy, fp32 or fp64)
+  * calculate_entropy / gating        main.py:65-106                (numpy)
+  * eval fusion + accuracy counters   main.py:636-679               (numpy)
+  * shared head + CrossEntropyLoss    fusion_modules.py:19, main.py:130,432-435 (numpy)
+  * ResNet-18 encoders / AVClassifier models/backbone.py:142-160, basic_model.py:52-77 (torch CPU fp32)
+  * the alternating gs train step     main.py:419-476               (torch CPU fp32 + autograd + SGD)
+  * valid() gs branch                 main.py:622-679
+
+Pinning: the reference ships no tests or golden vectors, so this oracle is
+pinned against OUTPUTS OF THE REFERENCE ITSELF, executed in the build container under torch
+2.11: tests/golden/make_golden.py imports /root/reference, runs its functions on
+seeded inputs and commits the results as fixtures under tests/golden/; tests/test_oracle_golden.py
+checks every function here against them. The floating-point encoder/step restatement uses
+torch CPU fp32 ops (the task allows a torch fp32 reference for floating-point kernels).
+"""
+import math
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------------
+# GSPlugin.before_update — utils/utils.py:24-41
+# --------------------------------------------------------------------------------------------
+
+
+def gs_alpha(batch_index, len_dataloader):
+    """utils.py:26-27 — Python double arithmetic."""
+    lamda = batch_index / len_dataloader + 1
+    return 1.0 * 0.1 ** lamda
+
+
+def gs_before_update(P, feat, grad_w, batch_index, len_dataloader, counter, dtype=np.float32, mode=0):
+    """utils.py:24-41 with the parameter already selected (the 'module.weight' name gate is
+    host logic). Returns (P_out, grad_out) as new arrays of `dtype`.
+    mode 0 = the reference's elementwise denominator; mode 1 = scalar OWM."""
+    P = np.asarray(P, dtype=dtype)
+    g = None if grad_w is None else np.asarray(grad_w, dtype=dtype)
+    if counter == 0:                                             # utils.py:29
+        return P.copy(), (None if g is None else g.copy())
+    alpha = dtype(gs_alpha(batch_index, len_dataloader))
+    feat = np.asarray(feat, dtype=dtype)
+    r = feat.mean(axis=0, keepdims=True, dtype=dtype)            # utils.py:34  [1, D]
+    k = P @ r.T                                                  # utils.py:35  [D, 1]
+    if mode == 0:
+        den = alpha + k @ r                                      # [D, D] outer product: elementwise
+    else:
+        den = alpha + (r @ k)[0, 0]
+    P1 = P - (k @ k.T) / den                                     # utils.py:36
+    P1 = (P1 / np.sqrt((P1.astype(dtype) ** 2).sum(dtype=dtype))).astype(dtype)   # utils.py:38-40
+    g1 = None if g is None else (g @ P1.T).astype(dtype)         # utils.py:41
+    return P1, g1
+
+
+def gs_before_update_sum(P, feat_sum, inv_batch, grad_w, alpha, dtype=np.float32, mode=0):
+    """Same update driven by an already reduced sum_b feat (data-parallel form)."""
+    P = np.asarray(P, dtype=dtype)
+    r = (np.asarray(feat_sum, dtype=dtype) * dtype(inv_batch)).reshape(1, -1)
+    k = P @ r.T
+    den = dtype(alpha) + (k @ r if mode == 0 else (r @ k)[0, 0])
+    P1 = P - (k @ k.T) / den
+    P1 = (P1 / np.sqrt((P1 ** 2).sum(dtype=dtype))).astype(dtype)
+    g1 = None if grad_w is None else (np.asarray(grad_w, dtype=dtype) @ P1.T).astype(dtype)
+    return P1, g1
+
+
+# --------------------------------------------------------------------------------------------
+# Test-time fusion — main.py:65-106, 636-679
+# --------------------------------------------------------------------------------------------
+
+
+def calculate_entropy(output, dtype=np.float32):
+    """main.py:65-70 — softmax over dim 0 (the batch axis), summed over everything."""
+    x = np.asarray(output, dtype=dtype)
+    e = np.exp(x - x.max(axis=0, keepdims=True))
+    p = (e / e.sum(axis=0, keepdims=True, dtype=dtype)).astype(dtype)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return dtype(-(p * np.log(p)).sum(dtype=dtype))
+
+
+def calculate_gating_weights(*outputs, dtype=np.float32):
+    """main.py:72-87 (2 modalities) / 89-106 (3): w = softmax(-H) with Python max()."""
+    ents = [calculate_entropy(o, dtype) for o in outputs]
+    mx = ents[0]
+    for e in ents[1:]:           # Python max(): first argument wins unless a later one is greater
+        if e > mx:
+            mx = e
+    with np.errstate(invalid="ignore"):
+        g = [np.exp(dtype(mx - e)) for e in ents]
+        s = dtype(0)
+        for x in g:
+            s = dtype(s + x)
+        return tuple(dtype(x / s) for x in g)
+
+
+def fuse_eval(outputs, label, n_classes, dynamic=True, fixed_w=None, dtype=np.float32):
+    """main.py:636-676. Returns dict(fused, w, argmax[(M+1),B], num[C], hits[(M+1),C])."""
+    outs = [np.asarray(o, dtype=dtype) for o in outputs]
+    M = len(outs)
+    if dynamic:
+        w = calculate_gating_weights(*outs, dtype=dtype)                       # main.py:640-646
+    else:
+        w = tuple(dtype(x) for x in fixed_w)                                   # main.py:648-651
+    with np.errstate(invalid="ignore"):
+        fused = outs[0] * w[0]
+        for m in range(1, M):
+            fused = (fused + outs[m] * w[m]).astype(dtype)
+
+    def row_argmax(x):
+        # np.argmax(softmax(x)) (main.py:653-664): NaN anywhere -> NaN row -> index 0
+        out = np.argmax(x, axis=1).astype(np.int32)
+        out[np.isnan(x).any(axis=1)] = 0
+        return out
+
+    argmax = np.stack([row_argmax(fused)] + [row_argmax(o) for o in outs])
+    num = np.zeros(n_classes, np.int64)
+    hits = np.zeros((M + 1, n_classes), np.int64)
+    if label is not None:
+        lab = np.asarray(label)
+        for i in range(lab.shape[0]):                                          # main.py:659-676
+            num[lab[i]] += 1
+            for j in range(M + 1):
+                if argmax[j, i] == lab[i]:
+                    hits[j, lab[i]] += 1
+    return dict(fused=fused, w=np.array(w, dtype=dtype), argmax=argmax, num=num, hits=hits)
+
+
+# --------------------------------------------------------------------------------------------
+# Shared head + CrossEntropyLoss — fusion_modules.py:19, main.py:130, 432-435
+# --------------------------------------------------------------------------------------------
+
+
+def head_ce(feat, W, b, label, grad_scale=None, dtype=np.float64):
+    feat = np.asarray(feat, dtype=dtype)
+    W = np.asarray(W, dtype=dtype)
+    b = np.asarray(b, dtype=dtype)
+    lab = np.asarray(label)
+    B = feat.shape[0]
+    logits = feat @ W.T + b
+    m = logits.max(axis=1, keepdims=True)
+    lse = np.log(np.exp(logits - m).sum(axis=1, keepdims=True)) + m
+    logp = logits - lse
+    loss = -logp[np.arange(B), lab].mean()
+    gs = (1.0 / B) if grad_scale is None else grad_scale
+    dl = np.exp(logp)
+    dl[np.arange(B), lab] -= 1.0
+    dl *= gs
+    return dict(logits=logits, loss=loss, dW=dl.T @ feat, db=dl.sum(0), dfeat=dl @ W, feat_sum=feat.sum(0))
+
+
+# --------------------------------------------------------------------------------------------
+# ResNet-18 encoders, AVClassifier, the alternating step — torch CPU fp32 restatement
+# --------------------------------------------------------------------------------------------
+
+_LAYERS = ((64, 1), (128, 2), (256, 2), (512, 2))   # resnet18: BasicBlock x [2,2,2,2], backbone.py:211-213
+
+
+def _bn(x, sd, prefix, training, momentum=0.1, eps=1e-5):
+    import torch.nn.functional as F
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                        sd[prefix + ".bias"], training, momentum, eps)
+
+
+def resnet18_forward(sd, prefix, x, modality, training):
+    """models/backbone.py:142-160 (ResNet.forward) + :36-52 (BasicBlock.forward), functional.
+    `sd` maps the reference's state-dict names to tensors (parameters may require grad;
+    BN running statistics are updated in place when training)."""
+    import torch.nn.functional as F
+    if modality == "visual":
+        B, C, T, H, W = x.shape
+        x = x.permute(0, 2, 1, 3, 4).contiguous().view(B * T, C, H, W)        # backbone.py:144-147
+    x = F.conv2d(x, sd[prefix + "conv1.weight"], None, stride=2, padding=3)    # backbone.py:149
+    x = F.relu(_bn(x, sd, prefix + "bn1", training))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)                    # backbone.py:152
+    inplanes = 64
+    for li, (planes, stride) in enumerate(_LAYERS, start=1):
+        for bi in range(2):
+            s = stride if bi == 0 else 1
+            p = "%slayer%d.%d." % (prefix, li, bi)
+            identity = x
+            out = F.conv2d(x, sd[p + "conv1.weight"], None, stride=s, padding=1)
+            out = F.relu(_bn(out, sd, p + "bn1", training))
+            out = F.conv2d(out, sd[p + "conv2.weight"], None, stride=1, padding=1)
+            out = _bn(out, sd, p + "bn2", training)
+            if bi == 0 and (s != 1 or inplanes != planes):
+                identity = F.conv2d(x, sd[p + "downsample.0.weight"], None, stride=s)
+                identity = _bn(identity, sd, p + "downsample.1", training)
+            x = F.relu(out + identity)
+            inplanes = planes
+    return x
+
+
+def av_forward(sd, audio, visual, training):
+    """models/basic_model.py:52-77, gs_flag branch: returns (a, v) in [B, 512]."""
+    import torch
+    import torch.nn.functional as F
+    a = resnet18_forward(sd, "audio_net.", audio, "audio", training)
+    v = resnet18_forward(sd, "visual_net.", visual, "visual", training)
+    _, C, H, W = v.shape
+    B = a.shape[0]
+    v = v.view(B, -1, C, H, W).permute(0, 2, 1, 3, 4)
+    a = torch.flatten(F.adaptive_avg_pool2d(a, 1), 1)
+    v = torch.flatten(F.adaptive_avg_pool3d(v, 1), 1)
+    return a, v
+
+
+def _bump_num_batches(sd, prefix):
+    for k in sd:
+        if k.startswith(prefix) and k.endswith("num_batches_tracked"):
+            sd[k] += 1
+
+
+class SGD:
+    """torch.optim.SGD(lr, momentum=0.9, weight_decay=1e-4) restated (main.py:749): parameters
+    whose grad is None are skipped, as under torch >= 2.0 zero_grad(set_to_none=True)."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=1e-4):
+        self.params, self.lr, self.momentum, self.wd = list(params), lr, momentum, weight_decay
+        self.buf = {}
+
+    def step(self):
+        import torch
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                if p.grad is None:
+                    continue
+                g = p.grad.add(p, alpha=self.wd)
+                if i not in self.buf:
+                    self.buf[i] = g.clone()
+                else:
+                    self.buf[i].mul_(self.momentum).add_(g)
+                p.add_(self.buf[i], alpha=-self.lr)
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+
+class AVOracle:
+    """State + step functions of the CREMA-D AVClassifier path (configs 1/2 of BASELINE.json).
+
+    `state` is a dict with the reference's state-dict names WITHOUT the 'module.' prefix
+    (audio_net.*, visual_net.*, fusion_module.fc_out.{weight,bias}); tensors are torch CPU."""
+
+    def __init__(self, state, lr=1e-3, force_projection=False, gs_mode=0):
+        import torch
+        self.sd = {k: v.detach().clone() for k, v in state.items()}
+        self.param_names = [k for k in self.sd if self.sd[k].dtype.is_floating_point
+                            and not k.endswith(("running_mean", "running_var"))]
+        for k in self.param_names:
+            self.sd[k].requires_grad_(True)
+        self.opt = SGD([self.sd[k] for k in self.param_names], lr=lr)
+        D = self.sd["fusion_module.fc_out.weight"].shape[1]
+        self.Pl = np.eye(D, dtype=np.float32)         # utils.py:19-20 (sized from the head)
+        self.exp_count = 0
+        self.force_projection = force_projection      # False = as published: the hook never fires
+        self.gs_mode = gs_mode
+        self.torch = torch
+
+    def _turn(self, feat, label, batch_step, len_dl, encoder_prefix):
+        torch = self.torch
+        import torch.nn.functional as F
+        W, b = self.sd["fusion_module.fc_out.weight"], self.sd["fusion_module.fc_out.bias"]
+        out = F.linear(feat, W, b)                                     # main.py:432
+        loss = F.cross_entropy(out, label)                             # main.py:434
+        loss.backward(retain_graph=True)                               # main.py:435
+        if self.force_projection:                                      # main.py:437-438 -> utils.py:24-41
+            P1, g1 = gs_before_update(self.Pl, feat.detach().numpy(), W.grad.numpy(), batch_step, len_dl,
+                                      self.exp_count, mode=self.gs_mode)
+            self.Pl = P1
+            W.grad = torch.from_numpy(np.ascontiguousarray(g1))
+        self.opt.step()                                                # main.py:439
+        self.opt.zero_grad()                                           # main.py:440
+        self.exp_count += 1                                            # main.py:442
+        return float(loss.detach())
+
+    def train_step(self, spec, image, label, batch_step=0, len_dl=1):
+        """One iteration of the loop body main.py:143-476 (gs branch). Returns (loss_a, loss_v)."""
+        self.opt.zero_grad()                                           # main.py:164
+        a, v = av_forward(self.sd, spec.unsqueeze(1).float(), image.float(), training=True)   # main.py:431
+        _bump_num_batches(self.sd, "audio_net.")
+        _bump_num_batches(self.sd, "visual_net.")
+        la = self._turn(a, label, batch_step, len_dl, "audio_net.")
+        lv = self._turn(v, label, batch_step, len_dl, "visual_net.")
+        return la, lv
+
+    def train_epoch(self, batches, av_alpha=0.5):
+        """main.py:127-484 (gs branch) over a list of (spec, image, label). Returns (loss, loss_a, loss_v)."""
+        tot = tot_a = tot_v = 0.0
+        for step, (spec, image, label) in enumerate(batches):
+            la, lv = self.train_step(spec, image, label, step, len(batches))
+            # main.py:472: (loss_a * av_alpha + loss_v * (1 - av_alpha)).item() in fp32
+            tot += float(np.float32(np.float32(la) * np.float32(av_alpha)) +
+                         np.float32(np.float32(lv) * np.float32(1 - av_alpha)))
+            tot_a += la
+            tot_v += lv
+        n = len(batches)
+        return tot / n, tot_a / n, tot_v / n
+
+    def eval_logits(self, spec, image):
+        torch = self.torch
+        import torch.nn.functional as F
+        with torch.no_grad():
+            a, v = av_forward(self.sd, spec.unsqueeze(1).float(), image.float(), training=False)
+            W, b = self.sd["fusion_module.fc_out.weight"], self.sd["fusion_module.fc_out.bias"]
+            return F.linear(a, W, b), F.linear(v, W, b)
+
+    def valid(self, batches, n_classes=6, dynamic=True, av_alpha=0.5):
+        """main.py:486-679 (gs branch, 2 modalities). Returns (acc, acc_a, acc_v)."""
+        num = np.zeros(n_classes, np.int64)
+        hits = np.zeros((3, n_classes), np.int64)
+        for spec, image, label in batches:
+            oa, ov = self.eval_logits(spec, image)
+            r = fuse_eval([oa.numpy(), ov.numpy()], label.numpy(), n_classes, dynamic=dynamic,
+                          fixed_w=(av_alpha, 1 - av_alpha))
+            num += r["num"]
+            hits += r["hits"]
+        tot = float(num.sum())
+        return hits[0].sum() / tot, hits[1].sum() / tot, hits[2].sum() / tot
+
+
+def synthetic_av_batch(batch, seed, spec_hw=(257, 188), frames=2, image_hw=(224, 224), n_classes=6):
+    """Seeded CREMA-D-shaped batch: spec ~ N(0,1) [B,257,188], image ~ N(0,1)
+    [B,3,T,224,224], label ~ U{0..5}. torch CPU generator => identical on every box."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    spec = torch.randn(batch, *spec_hw, generator=g)
+    image = torch.randn(batch, 3, frames, *image_hw, generator=g)
+    label = torch.randint(0, n_classes, (batch,), generator=g)
+    return spec, image, label
+
+
+def math_isclose(a, b, rel):
+    return math.isclose(a, b, rel_tol=rel, abs_tol=rel)

@@ -1,0 +1,309 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE (/root/reference) in the build container.
+
+    python tests/golden/make_golden.py          # needs /root/reference; torch 2.11 CPU
+
+The reference has no tests/fixtures of its own, so these files are the pin for
+oracle/mla_oracle.py and, through it, for the CUDA kernels. Nothing here runs on the GPU box
+(the reference does not travel); only the small .npz outputs are committed.
+
+Shims (no reference source is edited or copied):
+  * stub modules `ml_collections` and `timm` (not installed; not on the CREMA-D path)
+  * GSPlugin built via __new__ + a CPU `Pl` (its __init__ needs torch.cuda.FloatTensor)
+  * nn.DataParallel(model, device_ids=[]) keeps the `.module` indirection on CPU
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = os.environ.get("MLA_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    sys.argv = ["main.py", "--ckpt_path", "x"]
+    sys.path.insert(0, REF)
+    import transformers  # noqa: F401  (must be imported BEFORE the timm stub)
+
+    class ConfigDict(dict):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.__dict__ = self
+
+        def copy_and_resolve_references(self):
+            return ConfigDict(self)
+
+    mlc = types.ModuleType("ml_collections")
+    mlc.ConfigDict = ConfigDict
+    mlc.config_dict = types.ModuleType("ml_collections.config_dict")
+    mlc.config_dict.ConfigDict = ConfigDict
+    mlc.config_dict.config_dict = mlc.config_dict          # models/m3ae.py:6 imports it by this name
+    mlc.config_dict.placeholder = lambda *a, **k: None
+    sys.modules["ml_collections"] = mlc
+    sys.modules["ml_collections.config_dict"] = mlc.config_dict
+
+    import torch.nn as nn
+    timm = types.ModuleType("timm")
+    for name in ("timm.models", "timm.models.layers", "timm.models.vision_transformer", "timm.data"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["timm"] = timm
+    timm.models = sys.modules["timm.models"]
+    timm.data = sys.modules["timm.data"]
+    lay = sys.modules["timm.models.layers"]
+    lay.to_2tuple = lambda x: (x, x)
+    lay.trunc_normal_ = nn.init.trunc_normal_
+    lay.DropPath = nn.Identity
+    vt = sys.modules["timm.models.vision_transformer"]
+    vt.Attention = vt.Mlp = vt.PatchEmbed = vt.Block = nn.Identity
+    sys.modules["timm.data"].create_transform = lambda *a, **k: None
+
+    import main as ref_main
+    from utils import utils as ref_utils
+    return ref_main, ref_utils
+
+
+def make_gs(ref_utils):
+    import torch
+    import torch.nn as nn
+
+    class Wrap(nn.Module):           # makes named_parameters() yield "module.weight" 
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+    def new_plugin(D, dtype=torch.float32):
+        gs = ref_utils.GSPlugin.__new__(ref_utils.GSPlugin)
+        gs.Pl = torch.eye(D, dtype=dtype)
+        gs.exp_count = 0
+        return gs
+
+    out = {}
+    # KAT-1: bare nn.Linear -> the published hook is a no-op for any counter
+    fc = nn.Linear(64, 6)
+    fc.weight.grad = torch.randn(6, 64)
+    g0 = fc.weight.grad.clone()
+    gs = new_plugin(64)
+    gs.before_update(fc, torch.randn(8, 64), 3, 10, 5)
+    out["kat1_noop"] = np.array([bool(torch.equal(gs.Pl, torch.eye(64))), bool(torch.equal(fc.weight.grad, g0))])
+
+    # teacher-forced chains: every step stores the fp32 inputs, the reference's fp32 outputs and
+    # the outputs of the SAME reference code run in fp64 on the same inputs
+    cases = [("signed_d64", 64, 6, 16, False), ("relu_d64", 64, 6, 16, True), ("signed_d128", 128, 11, 32, False),
+             ("relu_d512", 512, 6, 64, True)]
+    for name, D, C, B, relu in cases:
+        g = torch.Generator().manual_seed(sum(map(ord, name)) + D)
+        gs32 = new_plugin(D)
+        steps = 1 if D >= 128 else 3
+        for step in range(steps + 1):
+            feat = torch.randn(B, D, generator=g)
+            if relu:
+                feat = feat.relu()
+            grad = torch.randn(C, D, generator=g)
+            bi, L, counter = step, 7, step            # counter 0 on the first call: skipped (utils.py:29)
+            P_in = gs32.Pl.clone()
+            fc32 = Wrap(nn.Linear(D, C))
+            fc32.module.weight.grad = grad.clone()
+            bias_grad = torch.randn(C, generator=g)
+            fc32.module.bias.grad = bias_grad.clone()
+            gs32.before_update(fc32, feat, bi, L, counter)
+            assert torch.equal(fc32.module.bias.grad, bias_grad)          # bias never touched
+            gs64 = new_plugin(D, torch.float64)
+            gs64.Pl = P_in.double()
+            fc64 = Wrap(nn.Linear(D, C).double())
+            fc64.module.weight.grad = grad.double()
+            gs64.before_update(fc64, feat.double(), bi, L, counter)
+            k = "%s_s%d_" % (name, step)
+            if D >= 512:      # keep the fixture small: inputs regenerate from the seed; store outputs on a row subset
+                rows = np.arange(0, D, 16)
+                out[k + "rows"] = rows
+                out[k + "P_out32"] = gs32.Pl.detach().numpy()[rows]
+                out[k + "P_out64"] = gs64.Pl.detach().numpy()[rows]
+                out[k + "P_fro32"] = np.array(float(gs32.Pl.detach().norm()))
+                out[k + "P_in_is_eye"] = np.array(bool(torch.equal(P_in, torch.eye(D))))
+            else:
+                out[k + "P_in"] = P_in.numpy()
+                out[k + "P_out32"] = gs32.Pl.detach().numpy()
+                out[k + "P_out64"] = gs64.Pl.detach().numpy()
+            out[k + "feat"] = feat.numpy()
+            out[k + "grad_in"] = grad.numpy()
+            out[k + "grad_out32"] = fc32.module.weight.grad.numpy()
+            out[k + "grad_out64"] = fc64.module.weight.grad.numpy()
+            out[k + "meta"] = np.array([bi, L, counter, int(relu)])
+            gs32.Pl = gs32.Pl.detach()
+    np.savez_compressed(os.path.join(OUT, "gs_plugin.npz"), **out)
+
+
+def make_fusion(ref_main):
+    import torch
+    import torch.nn.functional as F
+    out = {}
+    cases = [("b64c6m2", 64, 6, 2), ("b32c101m3", 32, 101, 3), ("b7c4m3", 7, 4, 3), ("b256c6m2", 256, 6, 2)]
+    for name, B, C, M in cases:
+        for scale in (0.3, 1.0, 3.0):
+            g = torch.Generator().manual_seed(B * 131 + C * 7 + M + int(scale * 10))
+            outs = [torch.randn(B, C, generator=g) * scale for _ in range(M)]
+            label = torch.randint(0, C, (B,), generator=g)
+            if M == 2:
+                w = ref_main.calculate_gating_weights(*outs)
+            else:
+                w = ref_main.calculate_gating_weights3(*outs)
+            assert all(x.dim() == 0 for x in w)
+            fused = outs[0] * w[0] + outs[1] * w[1]              # main.py:643 / 646
+            if M == 3:
+                fused = fused + outs[2] * w[2]
+            k = "%s_x%d_" % (name, int(scale * 10))
+            for m in range(M):
+                out[k + "out%d" % m] = outs[m].numpy()
+            out[k + "label"] = label.numpy()
+            out[k + "entropy"] = np.array([float(ref_main.calculate_entropy(o)) for o in outs], np.float32)
+            out[k + "w"] = np.array([float(x) for x in w], np.float32)
+            out[k + "fused"] = fused.numpy()
+            preds = [F.softmax(fused, dim=1)] + [F.softmax(o, dim=1) for o in outs]       # main.py:653-657
+            out[k + "argmax"] = np.stack([np.argmax(p.numpy(), axis=1) for p in preds]).astype(np.int32)
+    # KAT-3: one +200 logit -> 0 * log 0 -> NaN weights
+    g = torch.Generator().manual_seed(5)
+    o1, o2 = torch.randn(64, 6, generator=g), torch.randn(64, 6, generator=g)
+    o1[3, 2] = 200.0
+    w = ref_main.calculate_gating_weights(o1, o2)
+    out["nan_out0"], out["nan_out1"] = o1.numpy(), o2.numpy()
+    out["nan_w"] = np.array([float(x) for x in w], np.float32)
+    np.savez_compressed(os.path.join(OUT, "fusion.npz"), **out)
+
+
+def make_head():
+    """The head is nn.Linear + nn.CrossEntropyLoss + autograd (main.py:130,432-435)."""
+    import torch
+    import torch.nn as nn
+    out = {}
+    for name, B, D, C in [("b16d64c6", 16, 64, 6), ("b8d128c101", 8, 128, 101), ("b32d256c6", 32, 256, 6)]:
+        g = torch.Generator().manual_seed(B + D + C)
+        fc = nn.Linear(D, C).double()
+        with torch.no_grad():
+            fc.weight.copy_(torch.randn(C, D, generator=g).double() * 0.05)
+            fc.bias.copy_(torch.randn(C, generator=g).double() * 0.1)
+        feat = torch.randn(B, D, generator=g).relu().double().requires_grad_(True)
+        label = torch.randint(0, C, (B,), generator=g)
+        logits = fc(feat)
+        loss = nn.CrossEntropyLoss()(logits, label)
+        loss.backward()
+        k = name + "_"
+        out[k + "feat"] = feat.detach().float().numpy()
+        out[k + "W"] = fc.weight.detach().float().numpy()
+        out[k + "b"] = fc.bias.detach().float().numpy()
+        out[k + "label"] = label.numpy()
+        out[k + "logits"] = logits.detach().numpy()
+        out[k + "loss"] = np.array(float(loss))
+        out[k + "dW"] = fc.weight.grad.numpy()
+        out[k + "db"] = fc.bias.grad.numpy()
+        out[k + "dfeat"] = feat.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "head.npz"), **out)
+
+
+def make_av(ref_main, ref_utils):
+    import torch
+    import torch.nn as nn
+    from torch.optim import SGD
+    from torch.optim.lr_scheduler import StepLR
+    out = {}
+    args = ref_main.get_arguments()
+    args.dataset, args.lorb, args.gs_flag, args.dynamic = "CREMAD", "base", True, True
+    args.fusion_method, args.modulation, args.modal3, args.clip = "concat", "Normal", False, False
+
+    def build():
+        ref_utils.setup_seed(0)
+        model = ref_main.AVClassifier(args)
+        model.apply(ref_utils.weight_init)
+        return model
+
+    def batches(n, B, seed, hw, img):
+        g = torch.Generator().manual_seed(seed)
+        res = []
+        for _ in range(n):
+            spec = torch.randn(B, *hw, generator=g)
+            image = torch.randn(B, 3, 2, img, img, generator=g)
+            label = torch.randint(0, 6, (B,), generator=g)
+            res.append((spec, image, label, torch.zeros(B, 1, dtype=torch.long)))
+        return res
+
+    model = build()
+    sd = model.state_dict()
+    out["n_state"] = np.array(len(sd))
+    out["state_names"] = np.array(list(sd.keys()))
+    out["state_sum"] = np.array([float(v.double().sum()) for v in sd.values()])
+    out["state_abs"] = np.array([float(v.double().abs().sum()) for v in sd.values()])
+    out["n_params"] = np.array([sum(p.numel() for p in model.audio_net.parameters()),
+                                sum(p.numel() for p in model.visual_net.parameters()),
+                                sum(p.numel() for p in model.fusion_module.parameters())])
+
+    # forward, train mode (batch statistics) and eval mode (running statistics), small spatial size
+    (spec, image, label, _), = batches(1, 2, 11, (65, 48), 64)
+    model.train()
+    a, v = model(spec.unsqueeze(1).float(), image.float())
+    out["fwd_train_a"], out["fwd_train_v"] = a.detach().numpy(), v.detach().numpy()
+    out["fwd_bn1_running_mean"] = model.audio_net.bn1.running_mean.numpy().copy()
+    out["fwd_bn1_running_var"] = model.audio_net.bn1.running_var.numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        a, v = model(spec.unsqueeze(1).float(), image.float())
+    out["fwd_eval_a"], out["fwd_eval_v"] = a.numpy(), v.numpy()
+    # KAT-4 feature-map shapes at the BASELINE.json input size
+    with torch.no_grad():
+        fa = model.audio_net(torch.zeros(1, 1, 257, 188))
+        fv = model.visual_net(torch.zeros(1, 3, 2, 224, 224))
+    out["kat4_shapes"] = np.array(list(fa.shape) + list(fv.shape))
+
+    def run_epoch(bl, fire):
+        model = build()
+        if fire:   # make the published hook fire: named_parameters() must yield "module.weight" 
+            class Wrap(nn.Module):
+                def __init__(self, m):
+                    super().__init__()
+                    self.module = m
+
+                def forward(self, x):
+                    return self.module(x)
+            model.fusion_module.fc_out = Wrap(model.fusion_module.fc_out)
+        dp = nn.DataParallel(model, device_ids=[])
+        opt = SGD(dp.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+        sch = StepLR(opt, 70, 0.1)
+        gs = ref_utils.GSPlugin.__new__(ref_utils.GSPlugin)
+        gs.Pl = torch.eye(512)
+        gs.exp_count = 0
+        losses = ref_main.train_epoch(args, 0, dp, torch.device("cpu"), bl, opt, sch, gs_plugin=gs, gs_flag=True,
+                                      av_alpha=0.55)
+        accs_dyn = ref_main.valid(args, dp, torch.device("cpu"), bl, gs_flag=True, av_alpha=0.55)
+        args.dynamic = False
+        accs_fix = ref_main.valid(args, dp, torch.device("cpu"), bl, gs_flag=True, av_alpha=0.55)
+        args.dynamic = True
+        fc = model.fusion_module.fc_out.module if fire else model.fusion_module.fc_out
+        return dict(losses=np.array(losses), accs_dyn=np.array(accs_dyn), accs_fix=np.array(accs_fix),
+                    exp_count=np.array(gs.exp_count), Pl_is_eye=np.array(bool(torch.equal(gs.Pl.detach(), torch.eye(512)))),
+                    fc_w=fc.weight.detach().numpy().copy(), fc_b=fc.bias.detach().numpy().copy(),
+                    a_conv1_sum=np.array(float(model.audio_net.conv1.weight.double().sum())),
+                    v_conv1_sum=np.array(float(model.visual_net.conv1.weight.double().sum())),
+                    Pl_fro=np.array(float(gs.Pl.detach().norm())))
+
+    small = batches(3, 4, 1, (65, 48), 64)
+    for tag, fire in (("small_noop", False), ("small_fire", True)):
+        for k, v in run_epoch(small, fire).items():
+            out["%s_%s" % (tag, k)] = v
+    # KAT-6: three B=4 batches at the full BASELINE.json size
+    full = batches(3, 4, 1, (257, 188), 224)
+    for k, v in run_epoch(full, False).items():
+        if k in ("losses", "accs_dyn", "accs_fix", "exp_count", "Pl_is_eye"):
+            out["full_noop_%s" % k] = v
+    np.savez_compressed(os.path.join(OUT, "av_classifier.npz"), **out)
+
+
+if __name__ == "__main__":
+    ref_main, ref_utils = import_reference()
+    import torch
+    torch.set_num_threads(8)
+    make_gs(ref_utils)
+    make_fusion(ref_main)
+    make_head()
+    make_av(ref_main, ref_utils)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))

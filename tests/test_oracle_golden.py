@@ -1,0 +1,182 @@
+"""The CPU oracle (oracle/mla_oracle.py) against fixtures produced by EXECUTING THE REFERENCE
+(tests/golden/make_golden.py). This is what pins the oracle; the GPU tests then compare the
+CUDA kernels with the oracle and with the same fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mla_oracle as orc
+
+
+def relf(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+GS_CASES = [("signed_d64", 3), ("relu_d64", 3), ("signed_d128", 1)]
+
+
+@pytest.mark.parametrize("name,steps", GS_CASES)
+def test_gs_before_update_matches_reference(golden, name, steps):
+    g = golden("gs_plugin")
+    for s in range(steps + 1):
+        k = "%s_s%d_" % (name, s)
+        bi, L, counter, _ = g[k + "meta"]
+        P1, g1 = orc.gs_before_update(g[k + "P_in"], g[k + "feat"], g[k + "grad_in"], int(bi), int(L), int(counter))
+        if counter == 0:   # utils.py:29 — the first call of a run is skipped
+            assert np.array_equal(P1, g[k + "P_in"]) and np.array_equal(g1, g[k + "grad_in"])
+            assert np.array_equal(g[k + "P_out32"], g[k + "P_in"])
+            continue
+        # F10 criterion: error against the fp64 run of the reference code, relative to the
+        # reference's own fp32 error
+        ref_err = relf(g[k + "P_out32"], g[k + "P_out64"])
+        assert relf(P1, g[k + "P_out64"]) <= 4 * ref_err + 1e-6
+        ref_gerr = relf(g[k + "grad_out32"], g[k + "grad_out64"])
+        assert relf(g1, g[k + "grad_out64"]) <= 4 * ref_gerr + 1e-6
+        # fp64 oracle == fp64 reference
+        P64, g64 = orc.gs_before_update(g[k + "P_in"], g[k + "feat"], g[k + "grad_in"], int(bi), int(L), int(counter),
+                                        dtype=np.float64)
+        assert relf(P64, g[k + "P_out64"]) < 1e-12 and relf(g64, g[k + "grad_out64"]) < 1e-12
+        assert abs(np.linalg.norm(P1) - 1) < 2e-6
+
+
+def test_gs_d512_first_update_from_identity(golden):
+    g = golden("gs_plugin")
+    k = "relu_d512_s1_"
+    assert bool(g[k + "P_in_is_eye"])
+    rows = g[k + "rows"]
+    P1, g1 = orc.gs_before_update(np.eye(512, dtype=np.float32), g[k + "feat"], g[k + "grad_in"], 1, 7, 1)
+    assert relf(P1[rows], g[k + "P_out64"]) <= 4 * relf(g[k + "P_out32"], g[k + "P_out64"]) + 1e-6
+    assert np.allclose(P1, P1.T, atol=1e-7)          # KAT-2: symmetric after the first update from I
+    assert relf(g1, g[k + "grad_out64"]) < 1e-5
+    assert bool(g["kat1_noop"].all())                 # KAT-1 is a property of the reference's name gate
+
+
+def test_gs_sum_form_equals_mean_form():
+    rng = np.random.default_rng(0)
+    P = np.eye(64, dtype=np.float32)
+    feat = rng.standard_normal((16, 64)).astype(np.float32)
+    grad = rng.standard_normal((6, 64)).astype(np.float32)
+    a, ga = orc.gs_before_update(P, feat, grad, 2, 5, 1)
+    b, gb = orc.gs_before_update_sum(P, feat.sum(0), 1 / 16, grad, orc.gs_alpha(2, 5))
+    assert relf(a, b) < 1e-6 and relf(ga, gb) < 1e-6
+
+
+FUSION = [(n, x) for n in ("b64c6m2", "b32c101m3", "b7c4m3", "b256c6m2") for x in (3, 10, 30)]
+
+
+@pytest.mark.parametrize("name,x", FUSION)
+def test_fusion_matches_reference(golden, name, x):
+    g = golden("fusion")
+    k = "%s_x%d_" % (name, x)
+    M = 3 if name.endswith("m3") else 2
+    outs = [g[k + "out%d" % m] for m in range(M)]
+    C = outs[0].shape[1]
+    ent = [orc.calculate_entropy(o) for o in outs]
+    assert np.allclose(ent, g[k + "entropy"], rtol=2e-6)
+    r = orc.fuse_eval(outs, g[k + "label"], C)
+    assert np.allclose(r["w"], g[k + "w"], atol=2e-6) and abs(r["w"].sum() - 1) < 1e-6
+    assert np.allclose(r["fused"], g[k + "fused"], atol=1e-5)
+    assert np.array_equal(r["argmax"][1:], g[k + "argmax"][1:])         # per-modality argmax: exact
+    assert np.array_equal(r["argmax"][0], g[k + "argmax"][0])
+    lab = g[k + "label"]
+    assert r["num"].sum() == lab.shape[0]
+    for j in range(M + 1):
+        assert r["hits"][j].sum() == (g[k + "argmax"][j] == lab).sum()
+
+
+def test_fusion_nan_propagates(golden):
+    g = golden("fusion")
+    assert np.isnan(g["nan_w"]).all()                                   # KAT-3 in the reference
+    w = orc.calculate_gating_weights(g["nan_out0"], g["nan_out1"])
+    assert np.isnan(w).all()
+    r = orc.fuse_eval([g["nan_out0"], g["nan_out1"]], None, 6)
+    assert (r["argmax"][0] == 0).all()                                  # NaN row -> np.argmax == 0
+
+
+@pytest.mark.parametrize("name", ["b16d64c6", "b8d128c101", "b32d256c6"])
+def test_head_matches_reference(golden, name):
+    g = golden("head")
+    k = name + "_"
+    r = orc.head_ce(g[k + "feat"], g[k + "W"], g[k + "b"], g[k + "label"])
+    # fixture: fp64 torch on the same (fp32-representable) inputs
+    for key in ("logits", "dW", "db", "dfeat"):
+        assert relf(r[key], g[k + key]) < 1e-6, key
+    assert abs(r["loss"] - float(g[k + "loss"])) < 1e-7
+    assert np.allclose(r["feat_sum"], g[k + "feat"].astype(np.float64).sum(0))
+
+
+def _reference_state(seed=0):
+    """AVClassifier initial state exactly as the reference builds it (setup_seed(0) + weight_init),
+    via the product's parameter container (CPU construction only; no kernels involved)."""
+    import argparse
+    import mla_b200
+    args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modulation="Normal", gs_flag=True,
+                              dynamic=True, lorb="base", modal3=False, clip=False)
+    mla_b200.setup_seed(seed)
+    model = mla_b200.AVClassifier(args)
+    model.apply(mla_b200.weight_init)
+    return model
+
+
+def test_seeded_init_is_bit_identical_to_reference(golden):
+    g = golden("av_classifier")
+    model = _reference_state()
+    sd = model.state_dict()
+    assert len(sd) == int(g["n_state"]) == 242                          # KAT-4
+    assert list(sd.keys()) == list(g["state_names"])
+    assert np.array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["state_sum"])
+    assert np.array_equal(np.array([float(v.double().abs().sum()) for v in sd.values()]), g["state_abs"])
+    n = [sum(p.numel() for p in m.parameters()) for m in (model.audio_net, model.visual_net, model.fusion_module)]
+    assert n == list(g["n_params"]) == [11170240, 11176512, 3078]
+
+
+def _small_batches():
+    gen = torch.Generator().manual_seed(1)
+    res = []
+    for _ in range(3):
+        spec = torch.randn(4, 65, 48, generator=gen)
+        image = torch.randn(4, 3, 2, 64, 64, generator=gen)
+        label = torch.randint(0, 6, (4,), generator=gen)
+        res.append((spec, image, label))
+    return res
+
+
+def test_oracle_forward_matches_reference(golden):
+    g = golden("av_classifier")
+    state = _reference_state().state_dict()
+    gen = torch.Generator().manual_seed(11)
+    spec = torch.randn(2, 65, 48, generator=gen)
+    image = torch.randn(2, 3, 2, 64, 64, generator=gen)
+    o = orc.AVOracle(state)
+    a, v = orc.av_forward(o.sd, spec.unsqueeze(1), image, training=True)
+    assert np.allclose(a.detach().numpy(), g["fwd_train_a"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(v.detach().numpy(), g["fwd_train_v"], rtol=1e-4, atol=1e-5)
+    assert (a.detach().numpy() >= 0).all()
+    assert np.allclose(o.sd["audio_net.bn1.running_mean"].numpy(), g["fwd_bn1_running_mean"], atol=1e-6)
+    assert np.allclose(o.sd["audio_net.bn1.running_var"].numpy(), g["fwd_bn1_running_var"], rtol=1e-5)
+    with torch.no_grad():
+        a, v = orc.av_forward(o.sd, spec.unsqueeze(1), image, training=False)
+    assert np.allclose(a.numpy(), g["fwd_eval_a"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(v.numpy(), g["fwd_eval_v"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("fire", [False, True])
+def test_oracle_train_epoch_and_valid_match_reference(golden, fire):
+    g = golden("av_classifier")
+    tag = "small_fire_" if fire else "small_noop_"
+    o = orc.AVOracle(_reference_state().state_dict(), force_projection=fire)
+    batches = _small_batches()
+    losses = o.train_epoch(batches, av_alpha=0.55)
+    assert np.allclose(losses, g[tag + "losses"], rtol=1e-3), (losses, g[tag + "losses"])
+    assert o.exp_count == int(g[tag + "exp_count"]) == 6
+    assert bool(np.array_equal(o.Pl, np.eye(512, dtype=np.float32))) == bool(g[tag + "Pl_is_eye"])
+    assert np.allclose(o.sd["fusion_module.fc_out.weight"].detach().numpy(), g[tag + "fc_w"], rtol=2e-3, atol=2e-5)
+    assert np.allclose(o.valid(batches, dynamic=True, av_alpha=0.55), g[tag + "accs_dyn"], atol=1e-9)
+    assert np.allclose(o.valid(batches, dynamic=False, av_alpha=0.55), g[tag + "accs_fix"], atol=1e-9)
+
+
+def test_kat6_full_size_losses_are_recorded(golden):
+    g = golden("av_classifier")
+    assert np.allclose(g["full_noop_losses"], [1.5840, 1.5922, 1.5740], atol=1e-4)   # SURVEY KAT-6
+    assert list(g["kat4_shapes"]) == [1, 512, 9, 6, 2, 512, 7, 7]                      # SURVEY KAT-4
