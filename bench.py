@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — MLA train samples/sec (CREMA-D AV, ResNet-18, --gs_flag --dynamic), BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework
+    python bench.py --impl reference ...                           # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+A step = one alternating training step (audio turn + visual turn: forward of both encoders,
+per turn head fwd+bwd, encoder backward, GS projection, SGD) over one synthetic batch of 64
+samples per GPU (spectrogram 1x257x188, 2 frames 3x224x224, 6 classes).
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64
+FLOP_PER_SAMPLE_STEP = 32.47e9          # ResNet-18 pair fwd 10.823 GFLOP x3 (fwd+dgrad+wgrad)
+WORKLOAD = "configs[1]: CREMA-D-shaped MLA (--gs_flag --dynamic) train step, batch 64 per GPU, ResNet-18 x2"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-sweep", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.3 * max(mx)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_args():
+    return argparse.Namespace(dataset="CREMAD", fusion_method="concat", modulation="Normal", gs_flag=True,
+                              dynamic=True, lorb="base", modal3=False, clip=False)
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(a, rank):
+    """The reference's own CPU implementation of the path, as restated by the oracle port (the
+    reference is Python: it cannot travel to the GPU box and may not be copied into the repo).
+    All host threads torch can use; each step is a bounded sample (B_s <= 64 samples)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import mla_oracle as orc
+    import mla_b200
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mla_b200.setup_seed(0)
+    net = mla_b200.AVClassifier(make_args()).apply(mla_b200.weight_init)      # parameter container only (CPU init)
+    o = orc.AVOracle(net.state_dict(), force_projection=True)
+    # calibrate a bounded sample: whole run <= ~150 s
+    spec, image, label = orc.synthetic_av_batch(4, 7)
+    t0 = time.perf_counter(); o.train_step(spec, image, label, 0, 1); per_sample = (time.perf_counter() - t0) / 4
+    budget = 150.0 / max(1, a.steps + a.warmup)
+    bs = int(max(2, min(BATCH, budget / per_sample)))
+    spec, image, label = orc.synthetic_av_batch(bs, 1)
+    for i in range(a.warmup):
+        o.train_step(spec, image, label, i, a.steps + a.warmup)
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        o.train_step(spec, image, label, i, a.steps)
+    dt = time.perf_counter() - t0
+    val = bs * a.steps / dt
+    out = {"impl": "reference", "metric": "MLA train samples/sec (CREMA-D AV, ResNet-18)", "value": val,
+           "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "sample_batch": bs, "device": "host CPU"},
+           "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": "%d timed steps of the oracle's alternating step on %d-sample batches" % (a.steps, bs)},
+           "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline():
+    import torch
+    from oracle import mla_oracle as orc
+    import mla_b200
+    torch.set_num_threads(os.cpu_count() or 1)
+    mla_b200.setup_seed(0)
+    net = mla_b200.AVClassifier(make_args()).apply(mla_b200.weight_init)
+    o = orc.AVOracle(net.state_dict(), force_projection=True)
+    bs = 16
+    spec, image, label = orc.synthetic_av_batch(bs, 1)
+    o.train_step(spec, image, label, 0, 3)
+    t0 = time.perf_counter()
+    n = 0
+    while n < 2 or (time.perf_counter() - t0 < 10 and n < 6):
+        o.train_step(spec, image, label, n + 1, 8)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": bs * n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of the oracle's alternating step on %d-sample batches (1 warm-up)" % (n, bs)}
+
+
+# --------------------------------------------------------------------------------- native arm
+def gs_sweep(torch, ops, pk):
+    """GSPlugin HBM GB/s (second half of BASELINE.json's metric): algorithmic bytes
+    4*(B*D + 2*D*D + 2*C*D) / CUDA-event time, L2 flushed between launches."""
+    from mla_b200.gs_plugin import GSPlugin
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pts = []
+    for (B, D, C) in [(64, 512, 6), (64, 768, 101), (4096, 2048, 6), (4096, 2048, 101)]:
+        feat = torch.randn(B, D, device=dev).relu()
+        grad = torch.randn(C, D, device=dev)
+        P = torch.eye(D, device=dev)
+        alpha = GSPlugin.alpha(1, 10)
+        for _ in range(3):
+            ops.gs_project(P, grad, alpha, feat=feat)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.gs_project(P, grad, alpha, feat=feat); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = statistics.median(ts)
+        nbytes = 4 * (B * D + 2 * D * D + 2 * C * D)
+        pts.append({"B": B, "D": D, "C": C, "us": t * 1e6, "bytes": nbytes, "gbs": nbytes / t / 1e9,
+                    "frac": nbytes / t / 1e9 / pk["hbm"]})
+    return pts
+
+
+def run_native(a, rank, world):
+    import torch
+    import mla_b200
+    from mla_b200 import _lib, dist as mdist, encoder_engine, ops
+    dev = torch.device("cuda", torch.cuda.current_device())
+    args = make_args()
+    mla_b200.setup_seed(0)
+    model = mla_b200.ModuleHolder(mla_b200.AVClassifier(args).apply(mla_b200.weight_init).to(dev))
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    sch = torch.optim.lr_scheduler.StepLR(opt, 70, 0.1)
+    gs = mla_b200.GSPlugin(force_projection=True)      # fire the projection (the published hook is a no-op)
+    from mla_b200.main import SyntheticAVLoader
+    host = SyntheticAVLoader(BATCH, 2, seed=1 + rank).batches                    # pinned host batches
+    resident = [tuple(t.to(dev) for t in b) for b in host]                       # already in HBM
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def epoch(batches, n):
+        return mla_b200.train_epoch(args, 0, model, dev, [batches[i % len(batches)] for i in range(n)], opt, sch,
+                                    gs_plugin=gs, gs_flag=True, av_alpha=0.55)
+
+    import contextlib, io
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    with quiet:
+        epoch(resident, a.warmup)
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    with quiet:
+        t_dev = timed(lambda: epoch(resident, a.steps))
+    launches = _lib.launch_count() - l0
+    # end to end: host (pinned) buffers in, H2D every step, losses read back to the host every step
+    with quiet:
+        for _ in range(min(2, a.warmup)):
+            epoch(host, 1)
+
+        def e2e_loop():
+            for i in range(a.steps):
+                epoch([host[i % len(host)]], 1)
+        t_e2e = timed(e2e_loop)
+        # evaluation with --dynamic (reported, not the headline)
+        t_eval = timed(lambda: mla_b200.valid(args, model, dev, [resident[i % 2] for i in range(a.steps)],
+                                              gs_flag=True, av_alpha=0.55))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    samples = BATCH * world * a.steps
+    value = samples / t_dev
+    h2d = sum(t.numel() * t.element_size() for t in host[0][:3])
+    out = {"metric": "MLA train samples/sec (CREMA-D AV, ResNet-18)", "value": value, "unit": "samples/s",
+           "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "tf32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
+                      "encoder_backend": encoder_engine.BACKEND, "gs_projection": "fires (force_projection)",
+                      "l2": "2 alternating input batches (179 MB) + >1 GB of activations per step exceed the 126 MB L2; no explicit flush"},
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * t_e2e / a.steps},
+           "eval_samples_per_s": samples / t_eval,
+           "encoder_tflops": FLOP_PER_SAMPLE_STEP * samples / t_dev / 1e12}
+    if not a.no_sweep:
+        pts = gs_sweep(torch, ops, pk)
+        top = max(pts, key=lambda p: p["gbs"])
+        out["roofline"] = {"kernel": "gs_project_kernel", "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"],
+                           "unit": "GB/s", "frac": top["frac"], "traffic": None, "peak_source": pk["source"],
+                           "point": {k: top[k] for k in ("B", "D", "C", "us", "bytes")}}
+        out["gs_sweep"] = pts
+    if not a.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    from mla_b200 import dist as mdist
+    if world > 1:
+        mdist.init_from_env("nccl")
+    else:
+        torch.cuda.set_device(0)
+    run_native(a, rank, world)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

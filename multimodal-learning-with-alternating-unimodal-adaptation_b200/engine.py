@@ -60,9 +60,12 @@ class _TurnState:
         fc = net.fusion_module.fc_out
         C, D = fc.weight.shape
         dev = fc.weight.device
-        self.packed = torch.empty(C * D + C + D, dtype=torch.float32, device=dev)
-        self.head_out = {"dW": self.packed[:C * D].view(C, D), "db": self.packed[C * D:C * D + C],
-                         "feat_sum": self.packed[C * D + C:]}
+        # [dW | db | sum_b feat], every section 16-byte aligned (the kernels use float4 accesses)
+        o_db = (C * D + 3) // 4 * 4
+        o_fs = (o_db + C + 3) // 4 * 4
+        self.packed = torch.zeros(o_fs + D, dtype=torch.float32, device=dev)
+        self.head_out = {"dW": self.packed[:C * D].view(C, D), "db": self.packed[o_db:o_db + C],
+                         "feat_sum": self.packed[o_fs:o_fs + D]}
         self.encoders = encoder_param_groups(net)
         self.flat = [mdist.FlatGrads(g) for g in self.encoders]
 

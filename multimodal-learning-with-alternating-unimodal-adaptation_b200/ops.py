@@ -16,6 +16,12 @@ def _workspace(key, nbytes, device):
     return ws.get(nbytes, device)
 
 
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mla_b200 kernels need CUDA tensors; got a %s tensor (no CPU fallback)" % t.device)
+
+
 def _f32(t, name):
     if t is None:
         return None
@@ -27,6 +33,7 @@ def _f32(t, name):
 def gs_project(P, grad_w, alpha, feat=None, feat_sum=None, inv_batch=None, mode=0):
     """In-place P update + gradient projection (utils/utils.py:34-41). See mla_gs_project."""
     L = _lib.lib()
+    _need_cuda(P, grad_w, feat, feat_sum)
     if (feat is None) == (feat_sum is None):
         raise RuntimeError("gs_project: pass exactly one of feat / feat_sum")
     D = P.shape[0]
@@ -61,6 +68,7 @@ def head_ce(feat, weight, bias, label, grad_scale=None, need_grad=True, need_log
             out=None):
     """One head turn. Returns dict(logits, loss, dW, db, dfeat, feat_sum); loss is a 1-element tensor."""
     L = _lib.lib()
+    _need_cuda(feat, weight, bias, label)
     B, D = feat.shape
     C = weight.shape[0]
     if weight.shape[1] != D:
@@ -102,6 +110,7 @@ def fuse_eval(logits, label=None, dynamic=True, fixed_w=None, hits=None, num=Non
               want_argmax=True, want_entropy=False):
     """Fusion + accuracy counters (main.py:65-106, 640-676). Returns (fused, w, argmax[, entropy])."""
     L = _lib.lib()
+    _need_cuda(*logits)
     M = len(logits)
     B, C = logits[0].shape
     dev = logits[0].device

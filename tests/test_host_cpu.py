@@ -1,0 +1,155 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared
+symbol, argument errors are reported (not crashed on), the GSPlugin name/counter gates, the
+fail-loudly rule, and the data-parallel plumbing under gloo with world_size 2."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    names = built_lib.declared_symbols()
+    assert len(names) >= 10 and "mla_gs_project" in names and "mla_fuse_eval" in names
+    raw = ctypes.CDLL(built_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), "libmla_b200.so does not export %s" % n
+    assert built_lib.lib().mla_abi_version() == 1
+    assert b"workspace" in built_lib.lib().mla_error_string(-3)
+
+
+def test_library_is_sm100a_only(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_argument_errors_do_not_need_a_gpu(built_lib):
+    L = built_lib.lib()
+    # both feat and feat_sum NULL -> BADARG before any CUDA call
+    assert L.mla_gs_project(None, None, None, 1.0, 0.1, None, 4, 64, 6, 0, None, 0, None) == -1
+    assert L.mla_head_ce(None, None, None, None, 4, 64, 6, None, None, None, None, None, None, 1.0, None, 0, None) == -1
+    assert L.mla_head_ce_workspace_bytes(0, 64, 6) == 0
+
+
+def test_no_cpu_fallback(built_lib):
+    from mla_b200 import ops
+    P = torch.eye(64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.gs_project(P, torch.zeros(6, 64), 0.1, feat=torch.zeros(4, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.fuse_eval([torch.zeros(4, 6), torch.zeros(4, 6)])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multimodal-learning-with-alternating-unimodal-adaptation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), "%s mentions the oracle" % f
+
+
+def test_gsplugin_gates_match_reference():
+    """KAT-1 / utils.py:29-32: bare Linear -> no-op; counter 0 -> no-op; alpha formula."""
+    import mla_b200
+    gs = mla_b200.GSPlugin(device="cpu")
+    assert gs.exp_count == 0 and torch.equal(gs.Pl, torch.eye(512))
+    fc = torch.nn.Linear(512, 6)
+    fc.weight.grad = torch.randn(6, 512)
+    g0 = fc.weight.grad.clone()
+    gs.before_update(fc, torch.randn(8, 512), 3, 10, 5)                  # bare Linear: names are weight/bias
+    assert torch.equal(fc.weight.grad, g0) and torch.equal(gs.Pl, torch.eye(512))
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    gs.before_update(Wrap(fc), torch.randn(8, 512), 3, 10, 0)           # counter 0: skipped
+    assert torch.equal(fc.weight.grad, g0)
+    with pytest.raises(RuntimeError, match="CUDA"):                      # would fire -> needs the kernel
+        gs.before_update(Wrap(fc), torch.randn(8, 512), 3, 10, 1)
+    assert abs(mla_b200.GSPlugin.alpha(3, 10) - 0.1 ** 1.3) < 1e-15
+    gs2 = mla_b200.GSPlugin(device="cpu", force_projection=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gs2.before_update(fc, torch.randn(8, 512), 3, 10, 1)
+
+
+def test_flag_surface_matches_reference_defaults():
+    import mla_b200
+    a = mla_b200.get_arguments(["--ckpt_path", "x"])
+    assert (a.batch_size, a.learning_rate, a.lr_decay_step, a.lr_decay_ratio, a.random_seed) == (64, 1e-3, 70, 0.1, 0)
+    assert (a.lorb, a.modulation, a.fusion_method, a.av_alpha, a.a_alpha, a.v_alpha, a.t_alpha) == \
+        ("m3ae", "Normal", "concat", 0.5, 0.35, 0.25, 0.4)
+    assert not (a.gs_flag or a.dynamic or a.modal3 or a.train)
+    a = mla_b200.get_arguments(["--ckpt_path", "x", "--lorb", "base", "--gs_flag", "--dynamic", "--modal3",
+                                "--modulation", "OGM_GE"])
+    assert a.gs_flag and a.dynamic and a.modal3 and a.modulation == "OGM_GE"
+
+
+def test_out_of_scope_paths_raise():
+    import argparse
+    import mla_b200
+    args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modulation="Normal", gs_flag=True,
+                              dynamic=True, lorb="base", modal3=False, clip=False)
+    with pytest.raises(NotImplementedError):
+        mla_b200.train_epoch(args, 0, None, "cpu", [], None, None, gs_flag=False)
+    args.fusion_method = "film"
+    with pytest.raises(NotImplementedError):
+        mla_b200.AVClassifier(args)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from mla_b200 import dist as mdist
+from oracle import mla_oracle as orc
+rank, world = mdist.init_from_env("gloo")
+assert world == 2
+rng = np.random.default_rng(0)
+B, D, C = 8, 32, 5
+feat = rng.standard_normal((B, D)); W = rng.standard_normal((C, D)) * 0.1; b = rng.standard_normal(C) * 0.1
+lab = rng.integers(0, C, B)
+full = orc.head_ce(feat, W, b, lab)
+lo, hi = rank * B // 2, (rank + 1) * B // 2
+loc = orc.head_ce(feat[lo:hi], W, b, lab[lo:hi], grad_scale=1.0 / B)       # scaled by 1/B_GLOBAL
+packed = torch.from_numpy(np.concatenate([loc["dW"].ravel(), loc["db"], loc["feat_sum"]]))
+mdist.allreduce_sum_(packed)                                                # the small head all-reduce
+ref = np.concatenate([full["dW"].ravel(), full["db"], full["feat_sum"]])
+assert np.allclose(packed.numpy(), ref, atol=1e-12), "packed head all-reduce != global batch"
+# identical inputs -> identical P on every rank (deterministic update): compare checksums
+P1, _ = orc.gs_before_update_sum(np.eye(D, dtype=np.float32), packed.numpy()[-D:].astype(np.float32), 1.0 / B,
+                                 None, 0.05)
+cs = torch.tensor([mdist.params_checksum(torch.from_numpy(P1))])
+lst = [torch.zeros_like(cs) for _ in range(world)]
+dist.all_gather(lst, cs)
+assert lst[0].item() == lst[1].item(), "P differs across ranks"
+# flat gradient bucket: views alias the flat buffer, all-reduce sums in place
+ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5))]
+fg = mdist.FlatGrads(ps); fg.attach()
+ps[0].grad += rank + 1; ps[1].grad += 10 * (rank + 1)
+mdist.allreduce_sum_(fg.flat)
+assert torch.all(ps[0].grad == 3) and torch.all(ps[1].grad == 30)
+g = mdist.all_gather_rows(torch.full((2, 3), float(rank)))
+assert g.shape == (4, 3) and g[0, 0] == 0 and g[3, 0] == 1
+# loss mean over ranks == global mean
+l = torch.tensor([loc["loss"]], dtype=torch.float64); mdist.allreduce_sum_(l)
+assert abs(l.item() / world - full["loss"]) < 1e-12
+dist.barrier(); print("rank", rank, "ok")
+"""
+
+
+def test_data_parallel_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
