@@ -105,6 +105,27 @@ MLA_API int    mla_fuse_eval(const float* const* logits, int M, int B, int C, in
                      float* entropy_out, int32_t* argmax, int64_t* hits, int64_t* num,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * ResNet-18 encoder convolutions — models/backbone.py:39-50 (BasicBlock 3x3 convs), :126-129
+ * (1x1/2 downsample) and their backward (what loss.backward() runs through cuDNN in the
+ * reference, main.py:435). Implicit GEMM on tcgen05 (TF32 operands, fp32 accumulate in TMEM).
+ * Activations NHWC fp32; weights [Cout][R][S][Cin] fp32 (= torch channels_last memory of the
+ * reference's OIHW parameter). No bias (the reference's convs have none).
+ * Supported: R == S in {1, 3}, stride in {1, 2}, pad <= R/2, Cin and Cout in {64, 128k}.
+ *   fprop : y  [N,OH,OW,Cout] = conv(x [N,H,W,Cin], w)
+ *   dgrad : dx [N,H,W,Cin]    (+)= conv_transpose(dy [N,OH,OW,Cout], w)   (accumulate != 0: +=)
+ *   wgrad : dw [Cout,R,S,Cin] = sum over pixels; split-K partials go to ws and are reduced in
+ *           a fixed order (deterministic).
+ */
+MLA_API int    mla_conv2d_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, void* stream);
+MLA_API int    mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, int accumulate, void* stream);
+MLA_API size_t mla_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S,
+                        int stride, int pad);
+MLA_API int    mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

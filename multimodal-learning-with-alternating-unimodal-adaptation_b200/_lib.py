@@ -32,6 +32,10 @@ _SIGNATURES = {
     "mla_fuse_eval": (_c_int, [ctypes.POINTER(_c_void_p), _c_int, _c_int, _c_int, _c_int,
                                ctypes.POINTER(_c_float), _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "mla_conv2d_fprop": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p]),
+    "mla_conv2d_dgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
+    "mla_conv2d_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 9),
+    "mla_conv2d_wgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),
 }
 
 _lib = None

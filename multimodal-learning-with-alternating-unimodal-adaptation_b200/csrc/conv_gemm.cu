@@ -1,0 +1,440 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma kind::tf32, fp32
+// accumulators in TMEM) for the ResNet-18 encoders — reference models/backbone.py:39-50
+// (BasicBlock convs), :126-129 (1x1 downsample) and their autograd backward.
+//
+// Activations are NHWC fp32, weights are [Cout][R][S][Cin] (= torch channels_last memory of the
+// reference's OIHW parameter, so state dicts stay compatible and no weight transform is needed).
+//
+//   MODE 0  fprop   y[m, co]  = sum_{r,s,ci} x[pix(m,r,s), ci] * w[co, r,s,ci]     M = N*OH*OW
+//   MODE 1  dgrad   dx[m, ci] = sum_{r,s,co} dy[pix'(m,r,s), co] * w[co, r,s,ci]   M = N*H*W
+//   MODE 2  wgrad   dw[co, r,s,ci] = sum_m dy[m, co] * x[pix(m,r,s), ci]           K = N*OH*OW (split)
+//
+// One CTA computes a 128 x BN accumulator tile. Warp roles (192 threads):
+//   warps 0-3  gather producers: one 128-byte channel segment per thread and k-block, copied
+//              with cp.async (zero-fill for padding / stride holes / tails) into the 128B-swizzled
+//              layout the UMMA descriptors expect; afterwards the same warps run the epilogue
+//              (tcgen05.ld 32x32b -> registers -> global).
+//   warp 4     TMA producer for the dense operand (weights, or dy for wgrad): 2-D tiled tensor
+//              map, SWIZZLE_128B, completion on the stage's mbarrier (complete_tx).
+//   warp 5     TMEM allocation + the single MMA-issuing thread: 4 x tcgen05.mma (K = 8 each)
+//              per 32-wide k-block, tcgen05.commit releases the smem stage / publishes TMEM.
+// K-major operands are [rows][32 tf32]; MN-major operands (weights in dgrad, both operands in
+// wgrad) are panels of [k rows][32 elements along M/N] — both are the same physical image, which
+// is why one gather routine serves all three modes.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kGatherThreads = 128;
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 128 B
+
+struct ConvGemmParams {
+  const float* src;  // gathered tensor: x (fprop, wgrad) or dy (dgrad), NHWC
+  int Hs, Ws, Cs;    // its spatial size and channel count
+  int OH, OW;        // the pixel space that indexes GEMM rows (fprop/dgrad) or GEMM K (wgrad)
+  int M;             // number of such pixels = N * OH * OW
+  int R, S;
+  int mul, sgn, off, div;  // source row: (oh*mul + sgn*r + off) / div, must divide and be in range
+  int kcb;           // 32-channel blocks per tap of the gathered tensor (fprop, dgrad)
+  int KB;            // k-blocks this launch iterates (fprop/dgrad: R*S*kcb)
+  int CinW;          // Cin of the weight tensor (column offset of a tap in the 2-D weight view)
+  float* out;
+  long long ldo;     // output row stride in elements
+  int accumulate;    // out += acc instead of out = acc (dgrad into an existing gradient)
+  // wgrad
+  int Cout;
+  int kb_per_split;  // k-blocks (of 32 pixels) per split
+  int KBtot;         // total k-blocks = ceil(M / 32)
+  int splits;
+  long long split_stride;  // elements between split partials
+};
+
+template <bool MN_MAJOR>
+__device__ __forceinline__ void gather_segment(const ConvGemmParams& p, uint32_t dst_row, int row, int m, int r, int s,
+                                               int c0) {
+  // dst_row: smem address of the 128-byte row `row` of its tile/panel
+  const float* src = p.src;
+  uint32_t bytes = 0;
+  if (m < p.M) {
+    const int ow = m % p.OW;
+    const int t = m / p.OW;
+    const int oh = t % p.OH;
+    const int n = t / p.OH;
+    const int hn = oh * p.mul + p.sgn * r + p.off;
+    const int wn = ow * p.mul + p.sgn * s + p.off;
+    if (hn >= 0 && wn >= 0) {
+      int hs = hn, ws = wn;
+      bool ok = true;
+      if (p.div != 1) {
+        hs = hn / p.div;
+        ws = wn / p.div;
+        ok = (hs * p.div == hn) && (ws * p.div == wn);
+      }
+      if (ok && hs < p.Hs && ws < p.Ws) {
+        src = p.src + (((long long)n * p.Hs + hs) * p.Ws + ws) * p.Cs + c0;
+        bytes = 16;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    tc::cp_async16(dst_row + (MN_MAJOR ? tc::swz32(j, row) : tc::swz16(j, row)), src + (bytes ? 4 * j : 0), bytes);
+}
+
+template <int MODE, int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap, ConvGemmParams p) {
+  constexpr uint32_t kBBytes = BN * 128;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr int LAG = STAGES - 1;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), kGatherThreads + 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    tc::mbar_init(tc::smem_u32(&tmem_full_bar), 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap);
+  if (warp == 5) {
+    tc::tmem_alloc(tc::smem_u32(&tmem_slot), BN);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // tile coordinates
+  int m0 = 0, n0 = 0, tap_r = 0, tap_s = 0, kb_begin = 0, KB = p.KB, split = 0;
+  if (MODE == 2) {
+    n0 = blockIdx.x * BN;    // ci tile
+    m0 = blockIdx.y * 128;   // co tile
+    const int tap = blockIdx.z / p.splits;
+    split = blockIdx.z - tap * p.splits;
+    tap_r = tap / p.S;
+    tap_s = tap - tap_r * p.S;
+    kb_begin = split * p.kb_per_split;
+    KB = min(p.kb_per_split, p.KBtot - kb_begin);
+    if (KB < 0) KB = 0;
+  } else {
+    m0 = blockIdx.x * 128;
+    n0 = blockIdx.y * BN;
+  }
+
+  if (warp < 4) {
+    // ===================== gather producers =====================
+    const int t = threadIdx.x;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((kb / STAGES) & 1) ^ 1);
+      const uint32_t stage = tiles + s * kStageBytes;
+      if (MODE == 2) {
+        // B operand: BN/32 panels x 32 pixel rows; segment q = (panel, pixel row)
+        const int pix0 = (kb_begin + kb) * 32;
+        for (int q = t; q < BN; q += kGatherThreads) {
+          const int i = q & 31, pnl = q >> 5;
+          gather_segment<true>(p, stage + kABytes + pnl * 4096 + i * 128, i, pix0 + i, tap_r, tap_s, n0 + pnl * 32);
+        }
+      } else {
+        const int tap = kb / p.kcb;
+        const int cb = kb - tap * p.kcb;
+        const int r = tap / p.S;
+        gather_segment<false>(p, stage + t * 128, t, m0 + t, r, tap - r * p.S, cb * 32);
+      }
+      tc::cp_async_commit();
+      if (kb >= LAG) {
+        tc::cp_async_wait<LAG>();
+        tc::fence_proxy_async();
+        tc::mbar_arrive(tc::smem_u32(&full_bar[(kb - LAG) % STAGES]));
+      }
+    }
+    tc::cp_async_wait<0>();
+    tc::fence_proxy_async();
+    for (int kb = max(KB - LAG, 0); kb < KB; ++kb) tc::mbar_arrive(tc::smem_u32(&full_bar[kb % STAGES]));
+
+    // ===================== epilogue =====================
+    if (KB > 0) {
+      tc::mbar_wait(tc::smem_u32(&tmem_full_bar), 0);
+      tc::tc_fence_after();
+    }
+    const int row = warp * 32 + lane;
+    float* orow = nullptr;
+    if (MODE == 2) {
+      const int co = m0 + row;
+      if (co < p.Cout)
+        orow = p.out + (long long)split * p.split_stride + (long long)co * p.ldo + (tap_r * p.S + tap_s) * p.CinW + n0;
+    } else {
+      const int m = m0 + row;
+      if (m < p.M) orow = p.out + (long long)m * p.ldo + n0;
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      if (KB > 0) {
+        tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (orow != nullptr) {
+        float4* dst = reinterpret_cast<float4*>(orow + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+          if (p.accumulate) {
+            const float4 old = dst[j];
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          dst[j] = o;
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((kb / STAGES) & 1) ^ 1);
+        const uint32_t stage = tiles + s * kStageBytes;
+        const uint32_t bar = tc::smem_u32(&full_bar[s]);
+        if (MODE == 0) {
+          tc::mbar_arrive_expect_tx(bar, kBBytes);
+          tc::tma_load_2d(stage + kABytes, &tmap, bar, kb * 32, n0);  // box {32 k, BN rows}
+        } else if (MODE == 1) {
+          tc::mbar_arrive_expect_tx(bar, kBBytes);
+          const int tap = kb / p.kcb;
+          const int cb = kb - tap * p.kcb;
+#pragma unroll
+          for (int pnl = 0; pnl < BN / 32; ++pnl)  // box {32 ci, 32 co rows}
+            tc::tma_load_2d(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32);
+        } else {
+          tc::mbar_arrive_expect_tx(bar, kABytes);
+#pragma unroll
+          for (int pnl = 0; pnl < 4; ++pnl)  // box {32 co, 32 pixel rows}
+            tc::tma_load_2d(stage + pnl * 4096, &tmap, bar, m0 + pnl * 32, (kb_begin + kb) * 32);
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && KB > 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(128, BN, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0);
+      constexpr bool a_mn = (MODE == 2), b_mn = (MODE != 0);
+      constexpr uint32_t a_lbo = a_mn ? 4096u : 16u, b_lbo = b_mn ? 4096u : 16u;
+      constexpr uint32_t a_sbo = a_mn ? 512u : 1024u, b_sbo = b_mn ? 512u : 1024u;
+      constexpr uint32_t a_lay = a_mn ? tc::kLayoutSw128Base32 : tc::kLayoutSw128;
+      constexpr uint32_t b_lay = b_mn ? tc::kLayoutSw128Base32 : tc::kLayoutSw128;
+      constexpr uint32_t a_kstep = a_mn ? 1024u : 32u, b_kstep = b_mn ? 1024u : 32u;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        tc::mbar_wait(tc::smem_u32(&full_bar[s]), (kb / STAGES) & 1);
+        tc::tc_fence_after();
+        const uint32_t stage = tiles + s * kStageBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = tc::make_smem_desc(stage + k * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t bd = tc::make_smem_desc(stage + kABytes + k * b_kstep, b_lbo, b_sbo, b_lay);
+          tc::umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+      }
+      tc::umma_commit(tc::smem_u32(&tmem_full_bar));
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, BN);
+}
+
+// Fixed-order reduction of split-K partials: dw[i] = sum_s part[s][i].
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4, int splits,
+                                     long long stride4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4* p4 = reinterpret_cast<const float4*>(part);
+  float4 acc = p4[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = p4[i + (long long)s * stride4];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = acc;
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 2-D fp32 row-major [rows][cols] tensor map with a {32 cols (128 B), box_rows} box; 128B swizzle with
+// 16 B chunks (K-major operand tiles) or 32 B chunks (MN-major operand panels).
+int make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols, int box_rows, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return MLA_E_NODEVICE;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
+}
+
+template <int MODE, int BN, int STAGES>
+int launch(const CUtensorMap& map, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (kABytes + BN * 128) + 1024;
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_acquire)) {
+    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    configured.store(1, std::memory_order_release);
+  }
+  conv_gemm_kernel<MODE, BN, STAGES><<<grid, kThreads, smem, st>>>(map, p);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  return 0;
+}
+
+bool conv_shape_ok(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
+  return N > 0 && H > 0 && W > 0 && Cin >= 64 && Cin % 64 == 0 && Cout >= 64 && Cout % 64 == 0 && R == S &&
+         (R == 1 || R == 3) && (stride == 1 || stride == 2) && pad >= 0 && pad <= R / 2 && (Cout == 64 || Cout % 128 == 0) &&
+         (Cin == 64 || Cin % 128 == 0);
+}
+
+int out_size(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / stride + 1; }
+
+}  // namespace
+
+extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int R,
+                                int S, int stride, int pad, void* stream) {
+  if (!x || !w || !y || !mla::aligned16(x) || !mla::aligned16(w) || !mla::aligned16(y)) return MLA_E_BADARG;
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad)) return MLA_E_SHAPE;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
+  if (OH <= 0 || OW <= 0 || (long long)N * OH * OW > 0x7fffffffLL) return MLA_E_SHAPE;
+  ConvGemmParams p{};
+  p.src = x; p.Hs = H; p.Ws = W; p.Cs = Cin; p.OH = OH; p.OW = OW; p.M = N * OH * OW; p.R = R; p.S = S;
+  p.mul = stride; p.sgn = 1; p.off = -pad; p.div = 1; p.kcb = Cin / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
+  p.out = y; p.ldo = Cout; p.accumulate = 0; p.Cout = Cout;
+  const int BN = Cout == 64 ? 64 : 128;
+  CUtensorMap map;
+  int rc = make_map_2d(&map, w, Cout, (long long)R * S * Cin, BN, false);
+  if (rc) return rc;
+  dim3 grid((p.M + 127) / 128, Cout / BN);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return BN == 64 ? launch<0, 64, 4>(map, p, grid, st) : launch<0, 128, 3>(map, p, grid, st);
+}
+
+extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin, int Cout,
+                                int R, int S, int stride, int pad, int accumulate, void* stream) {
+  if (!dy || !w || !dx || !mla::aligned16(dy) || !mla::aligned16(w) || !mla::aligned16(dx)) return MLA_E_BADARG;
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad)) return MLA_E_SHAPE;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
+  if (OH <= 0 || OW <= 0 || (long long)N * H * W > 0x7fffffffLL) return MLA_E_SHAPE;
+  ConvGemmParams p{};
+  p.src = dy; p.Hs = OH; p.Ws = OW; p.Cs = Cout; p.OH = H; p.OW = W; p.M = N * H * W; p.R = R; p.S = S;
+  p.mul = 1; p.sgn = -1; p.off = pad; p.div = stride; p.kcb = Cout / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
+  p.out = dx; p.ldo = Cin; p.accumulate = accumulate ? 1 : 0; p.Cout = Cout;
+  const int BN = Cin == 64 ? 64 : 128;
+  CUtensorMap map;
+  int rc = make_map_2d(&map, w, Cout, (long long)R * S * Cin, 32, true);
+  if (rc) return rc;
+  dim3 grid((p.M + 127) / 128, Cin / BN);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return BN == 64 ? launch<1, 64, 4>(map, p, grid, st) : launch<1, 128, 3>(map, p, grid, st);
+}
+
+namespace {
+struct WgradPlan {
+  int BN, splits, kb_per_split, KBtot, OH, OW;
+  long long M;
+  size_t ws_bytes;
+};
+int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, WgradPlan* pl) {
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad)) return MLA_E_SHAPE;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  pl->OH = out_size(H, R, stride, pad);
+  pl->OW = out_size(W, S, stride, pad);
+  pl->M = (long long)N * pl->OH * pl->OW;
+  if (pl->OH <= 0 || pl->OW <= 0 || pl->M > 0x7fffffffLL) return MLA_E_SHAPE;
+  pl->BN = Cin == 64 ? 64 : 128;
+  pl->KBtot = (int)((pl->M + 31) / 32);
+  const int tiles = R * S * (Cin / pl->BN) * ((Cout + 127) / 128);
+  int splits = (4 * di.sm_count + tiles - 1) / tiles;       // ~4 CTAs per SM in total
+  splits = max(1, min(splits, pl->KBtot / 8 > 0 ? pl->KBtot / 8 : 1));   // >= 8 k-blocks per split
+  pl->kb_per_split = (pl->KBtot + splits - 1) / splits;
+  pl->splits = (pl->KBtot + pl->kb_per_split - 1) / pl->kb_per_split;
+  pl->ws_bytes = pl->splits > 1 ? (size_t)pl->splits * Cout * R * S * Cin * sizeof(float) : 0;
+  return 0;
+}
+}  // namespace
+
+extern "C" size_t mla_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                                                   int pad) {
+  WgradPlan pl;
+  if (wgrad_plan(N, H, W, Cin, Cout, R, S, stride, pad, &pl) != 0) return 0;
+  return pl.ws_bytes + 256;
+}
+
+extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                                int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !dy || !dw || !mla::aligned16(x) || !mla::aligned16(dy) || !mla::aligned16(dw) || !mla::aligned16(ws))
+    return MLA_E_BADARG;
+  WgradPlan pl;
+  int rc = wgrad_plan(N, H, W, Cin, Cout, R, S, stride, pad, &pl);
+  if (rc) return rc;
+  if (pl.splits > 1 && (ws == nullptr || ws_bytes < pl.ws_bytes)) return MLA_E_WORKSPACE;
+  ConvGemmParams p{};
+  p.src = x; p.Hs = H; p.Ws = W; p.Cs = Cin; p.OH = pl.OH; p.OW = pl.OW; p.M = (int)pl.M; p.R = R; p.S = S;
+  p.mul = stride; p.sgn = 1; p.off = -pad; p.div = 1; p.kcb = 0; p.KB = 0; p.CinW = Cin;
+  p.ldo = (long long)R * S * Cin; p.accumulate = 0; p.Cout = Cout;
+  p.kb_per_split = pl.kb_per_split; p.KBtot = pl.KBtot; p.splits = pl.splits;
+  p.split_stride = (long long)Cout * R * S * Cin;
+  p.out = pl.splits > 1 ? static_cast<float*>(ws) : dw;
+  CUtensorMap map;
+  rc = make_map_2d(&map, dy, pl.M, Cout, 32, true);
+  if (rc) return rc;
+  dim3 grid(Cin / pl.BN, (Cout + 127) / 128, R * S * pl.splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = pl.BN == 64 ? launch<2, 64, 4>(map, p, grid, st) : launch<2, 128, 3>(map, p, grid, st);
+  if (rc) return rc;
+  if (pl.splits > 1) {
+    const long long n4 = p.split_stride / 4;
+    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
+    MLA_CUDA_TRY(cudaGetLastError());
+    mla::count_launch();
+  }
+  return 0;
+}

@@ -34,10 +34,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must become an error, never a hung GPU (a hang costs the
-// whole box). ~2^26 polls of a HW-sleeping try_wait is seconds; then trap.
+// whole box). Wall-clock watchdog (%globaltimer, ns): 2 s on one barrier phase, then trap.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 63u) == 0 && globaltimer_ns() - t0 > 2000000000ull) __trap();
   }
 }
 
@@ -112,17 +119,28 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (64 bit):
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset >> 4   [46,48) version = 1 (sm_100)
-//   [49,52) base offset = 0 (tiles are 1024 B aligned)   [61,64) swizzle: 2 = 128 B
-// K-major, 128B swizzle : rows of 128 B (32 tf32 along K), 8-row groups SBO = 1024 B apart; LBO unused (1).
-// MN-major, 128B swizzle: panels of [K rows][128 B along MN]; 8-K-row atoms SBO apart, MN panels LBO apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   [49,52) base offset = 0 (tiles are 1024 B aligned)
+//   [61,64) layout: 2 = SWIZZLE_128B (16 B chunks), 1 = SWIZZLE_128B_BASE32B (32 B chunks)
+// K-major  (layout 2): rows of 128 B (32 tf32 along K), 16 B chunk ^= row & 7; 8-row groups SBO = 1024 B
+//                      apart; LBO unused (16).
+// MN-major (layout 1, the ONLY swizzled layout the hardware accepts for MN-major TF32): panels of
+//                      [K rows][128 B = 32 elements along M/N], 32 B chunk ^= row & 3; 4-K-row atoms SBO =
+//                      512 B apart, M/N panels LBO apart. The matching TMA mode is SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
+}
+// Byte offset of 16-byte chunk j (0..7) of a 128-byte row under the two swizzles.
+__device__ __forceinline__ uint32_t swz16(int j, int row) { return (uint32_t)((j ^ (row & 7)) << 4); }
+__device__ __forceinline__ uint32_t swz32(int j, int row) {
+  return (uint32_t)(((((j >> 1) ^ (row & 3)) << 1) | (j & 1)) << 4);
 }
 // Instruction descriptor (32 bit) for kind::tf32, fp32 accumulate:
 //   [4,6) D format 1 = F32   [7,10) A format 2 = TF32   [10,13) B format 2 = TF32

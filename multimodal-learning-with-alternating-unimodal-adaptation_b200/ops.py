@@ -147,3 +147,54 @@ def fuse_eval(logits, label=None, dynamic=True, fixed_w=None, hits=None, num=Non
     if want_entropy:
         return fused, w, argmax, ent
     return fused, w, argmax
+
+
+# ----------------------------------------------------------------------------------------------
+# Encoder convolutions (NHWC activations, [Cout][R][S][Cin] weights)
+# ----------------------------------------------------------------------------------------------
+def _conv_out(x, k, stride, pad):
+    return (x + 2 * pad - k) // stride + 1
+
+
+def conv2d_fprop(x, w, stride, pad, out=None):
+    """x [N,H,W,Cin] contiguous; w [Cout,R,S,Cin] contiguous -> y [N,OH,OW,Cout]."""
+    L = _lib.lib()
+    _need_cuda(x, w)
+    N, H, W, Cin = x.shape
+    Cout, R, S, _ = w.shape
+    OH, OW = _conv_out(H, R, stride, pad), _conv_out(W, S, stride, pad)
+    y = out if out is not None else torch.empty((N, OH, OW, Cout), dtype=torch.float32, device=x.device)
+    rc = L.mla_conv2d_fprop(_lib.ptr(_f32(x, "x")), _lib.ptr(_f32(w, "w")), _lib.ptr(y), N, H, W, Cin, Cout, R, S,
+                            stride, pad, _lib.stream_ptr())
+    _lib.check(rc, "mla_conv2d_fprop")
+    return y
+
+
+def conv2d_dgrad(dy, w, x_shape, stride, pad, out=None, accumulate=False):
+    """dy [N,OH,OW,Cout], w [Cout,R,S,Cin] -> dx [N,H,W,Cin] (out += if accumulate)."""
+    L = _lib.lib()
+    _need_cuda(dy, w)
+    N, H, W, Cin = x_shape
+    Cout, R, S, _ = w.shape
+    dx = out if out is not None else torch.empty((N, H, W, Cin), dtype=torch.float32, device=dy.device)
+    rc = L.mla_conv2d_dgrad(_lib.ptr(_f32(dy, "dy")), _lib.ptr(_f32(w, "w")), _lib.ptr(dx), N, H, W, Cin, Cout, R, S,
+                            stride, pad, 1 if accumulate else 0, _lib.stream_ptr())
+    _lib.check(rc, "mla_conv2d_dgrad")
+    return dx
+
+
+def conv2d_wgrad(x, dy, w_shape, stride, pad, out=None):
+    """x [N,H,W,Cin], dy [N,OH,OW,Cout] -> dw [Cout,R,S,Cin]."""
+    L = _lib.lib()
+    _need_cuda(x, dy)
+    N, H, W, Cin = x.shape
+    Cout, R, S, _ = w_shape
+    dw = out if out is not None else torch.empty((Cout, R, S, Cin), dtype=torch.float32, device=x.device)
+    nbytes = L.mla_conv2d_wgrad_workspace_bytes(N, H, W, Cin, Cout, R, S, stride, pad)
+    if nbytes == 0:
+        raise RuntimeError("conv2d_wgrad: unsupported shape")
+    ws = _workspace("wgrad", nbytes, x.device)
+    rc = L.mla_conv2d_wgrad(_lib.ptr(_f32(x, "x")), _lib.ptr(_f32(dy, "dy")), _lib.ptr(dw), N, H, W, Cin, Cout, R, S,
+                            stride, pad, ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "mla_conv2d_wgrad")
+    return dw
