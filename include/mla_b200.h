@@ -126,6 +126,55 @@ MLA_API size_t mla_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, in
 MLA_API int    mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin,
                         int Cout, int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Memory-bound encoder pieces (NHWC fp32) — models/backbone.py:142-160 (ResNet.forward),
+ * :36-52 (BasicBlock.forward), nn.BatchNorm2d / nn.MaxPool2d semantics, basic_model.py:56-65
+ * (global average pool), and their backward passes.
+ *
+ * stem_im2col : 7x7/2 stem (backbone.py:78-83,149) as a GEMM: rows m = (n,oh,ow), columns
+ *               k = (r*S+s)*Cin+ci, zero-padded to Kp. Reads the RAW input: element (n,ci,h,w) at
+ *               in[(n/T)*sB + (n%T)*sT + ci*sC + h*W + w]  (frame fold backbone.py:144-147).
+ * pad_rows    : [rows][k] <-> [rows][kp] zero-padded copy (stem weights / weight gradient).
+ * bn_train_stats: batch mean / biased variance per channel over M rows; running stats updated
+ *               in place with momentum and the UNBIASED variance; emits mean, invstd and the
+ *               fused affine scale = gamma*invstd, shift = beta - mean*scale.
+ * bn_eval_coeffs: scale/shift from the running statistics (eval mode).
+ * bn_apply    : out = relu?( y*scale + shift + (res ? res*res_scale + res_shift : 0) );
+ *               res_scale/res_shift NULL = plain identity shortcut.
+ * bn_backward : g = dz * (z > 0) (z NULL: no mask); dgamma = sum g*xhat; dbeta = sum g;
+ *               dy = gamma*invstd*(g - dbeta/M - xhat*dgamma/M); g_out (optional) receives g.
+ * bn_relu_maxpool / maxpool_relu_backward: stem BN+ReLU+MaxPool(3,2,1) fused; idx holds the
+ *               argmax window position (uint8 per element).
+ * avgpool_*   : feat[b] = mean of `rows` consecutive NHWC rows (h*w, or T*h*w for video).
+ * ws for the BN calls: mla_bn_workspace_bytes(M, C).
+ */
+MLA_API int    mla_stem_im2col(const float* in, float* col, int N, int T, long long sB, long long sT,
+                        long long sC, int Cin, int H, int W, int R, int S, int stride, int pad, int Kp,
+                        void* stream);
+/* dst = round-to-nearest-TF32(src), n % 4 == 0 (weights before they feed the tensor cores). */
+MLA_API int    mla_round_tf32(const float* src, float* dst, long long n, void* stream);
+MLA_API int    mla_pad_rows(const float* src, float* dst, int rows, int k, int kp, int unpad, void* stream);
+MLA_API size_t mla_bn_workspace_bytes(long long M, int C);
+MLA_API int    mla_bn_train_stats(const float* y, long long M, int C, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float momentum, float eps,
+                        float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
+                        void* ws, size_t ws_bytes, void* stream);
+MLA_API int    mla_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, int C, float* scale_out, float* shift_out,
+                        void* stream);
+MLA_API int    mla_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
+                        const float* res_scale, const float* res_shift, int relu, float* out,
+                        long long M, int C, void* stream);
+MLA_API int    mla_bn_backward(const float* dz, const float* z, const float* y, const float* mean,
+                        const float* invstd, const float* gamma, long long M, int C, float* dgamma,
+                        float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream);
+MLA_API int    mla_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* out,
+                        unsigned char* idx, int N, int H, int W, int C, void* stream);
+MLA_API int    mla_maxpool_relu_backward(const float* dp, const float* p, const unsigned char* idx, float* g,
+                        int N, int H, int W, int C, void* stream);
+MLA_API int    mla_avgpool_forward(const float* fm, float* feat, int B, int rows, int C, void* stream);
+MLA_API int    mla_avgpool_backward(const float* dfeat, float* dfm, int B, int rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

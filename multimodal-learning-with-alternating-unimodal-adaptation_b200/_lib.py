@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmla_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "mla_b200.h")
 
 _c_int, _c_float, _c_size_t, _c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
+_c_ll = ctypes.c_longlong
 
 _SIGNATURES = {
     "mla_abi_version": (_c_int, []),
@@ -36,6 +37,20 @@ _SIGNATURES = {
     "mla_conv2d_dgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
     "mla_conv2d_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 9),
     "mla_conv2d_wgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),
+    "mla_stem_im2col": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_ll, _c_ll] + [_c_int] * 8 + [_c_void_p]),
+    "mla_round_tf32": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_void_p]),
+    "mla_pad_rows": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "mla_bn_workspace_bytes": (_c_size_t, [_c_ll, _c_int]),
+    "mla_bn_train_stats": (_c_int, [_c_void_p, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float,
+                                    _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_size_t,
+                                    _c_void_p]),
+    "mla_bn_eval_coeffs": (_c_int, [_c_void_p] * 4 + [_c_float, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "mla_bn_apply": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_ll, _c_int, _c_void_p]),
+    "mla_bn_backward": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
+    "mla_bn_relu_maxpool": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
+    "mla_maxpool_relu_backward": (_c_int, [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p]),
+    "mla_avgpool_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "mla_avgpool_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
 }
 
 _lib = None

@@ -325,8 +325,7 @@ int launch(const CUtensorMap& map, const ConvGemmParams& p, dim3 grid, cudaStrea
 
 bool conv_shape_ok(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
   return N > 0 && H > 0 && W > 0 && Cin >= 64 && Cin % 64 == 0 && Cout >= 64 && Cout % 64 == 0 && R == S &&
-         (R == 1 || R == 3) && (stride == 1 || stride == 2) && pad >= 0 && pad <= R / 2 && (Cout == 64 || Cout % 128 == 0) &&
-         (Cin == 64 || Cin % 128 == 0);
+         (R == 1 || R == 3) && (stride == 1 || stride == 2) && pad >= 0 && pad <= R / 2;
 }
 
 int out_size(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / stride + 1; }
@@ -345,7 +344,7 @@ extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N,
   p.src = x; p.Hs = H; p.Ws = W; p.Cs = Cin; p.OH = OH; p.OW = OW; p.M = N * OH * OW; p.R = R; p.S = S;
   p.mul = stride; p.sgn = 1; p.off = -pad; p.div = 1; p.kcb = Cin / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
   p.out = y; p.ldo = Cout; p.accumulate = 0; p.Cout = Cout;
-  const int BN = Cout == 64 ? 64 : 128;
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
   CUtensorMap map;
   int rc = make_map_2d(&map, w, Cout, (long long)R * S * Cin, BN, false);
   if (rc) return rc;
@@ -366,7 +365,7 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
   p.src = dy; p.Hs = OH; p.Ws = OW; p.Cs = Cout; p.OH = H; p.OW = W; p.M = N * H * W; p.R = R; p.S = S;
   p.mul = 1; p.sgn = -1; p.off = pad; p.div = stride; p.kcb = Cout / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
   p.out = dx; p.ldo = Cin; p.accumulate = accumulate ? 1 : 0; p.Cout = Cout;
-  const int BN = Cin == 64 ? 64 : 128;
+  const int BN = (Cin % 128 == 0) ? 128 : 64;
   CUtensorMap map;
   int rc = make_map_2d(&map, w, Cout, (long long)R * S * Cin, 32, true);
   if (rc) return rc;
@@ -389,7 +388,7 @@ int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
   pl->OW = out_size(W, S, stride, pad);
   pl->M = (long long)N * pl->OH * pl->OW;
   if (pl->OH <= 0 || pl->OW <= 0 || pl->M > 0x7fffffffLL) return MLA_E_SHAPE;
-  pl->BN = Cin == 64 ? 64 : 128;
+  pl->BN = (Cin % 128 == 0) ? 128 : 64;
   pl->KBtot = (int)((pl->M + 31) / 32);
   const int tiles = R * S * (Cin / pl->BN) * ((Cout + 127) / 128);
   int splits = (4 * di.sm_count + tiles - 1) / tiles;       // ~4 CTAs per SM in total

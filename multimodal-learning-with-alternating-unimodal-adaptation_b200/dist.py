@@ -57,11 +57,14 @@ class FlatGrads:
         self.views = []
         off = 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            # same shape AND strides as the parameter (conv weights are channels_last): kernels write
+            # gradients in the parameter's own memory order, optimizers see matching layouts
+            self.views.append(torch.as_strided(self.flat, p.shape, p.stride(), storage_offset=off))
             off += p.numel()
 
-    def attach(self, zero=True):
-        """Point p.grad at the views (zeroed: autograd accumulates into them)."""
+    def attach(self, zero=False):
+        """Point p.grad at the views. The native encoder backward overwrites every element, so no
+        zero fill is needed (zero=True only if something accumulates into the views)."""
         if zero:
             self.flat.zero_()
         for p, v in zip(self.params, self.views):

@@ -1,48 +1,334 @@
-"""Encoder execution engine: runs a ResNet parameter container (backbone.py) on the device.
+"""Encoder execution engine: runs a ResNet-18 parameter container (backbone.py) entirely on the
+kernels of libmla_b200.so — forward AND backward (the reference gets its backward from autograd
+over cuDNN, main.py:435).
 
-INTERIM (round 1, first slice): the convolution / batch-norm / pooling arithmetic is issued
-as library calls (cuDNN through torch.nn.functional) while the hand-written sm_100a
-implicit-GEMM kernels are brought up; `BACKEND` names what is running and bench.py reports it.
-The head, GS projection and fusion kernels are already native (libmla_b200.so).
+Data layout: activations NHWC fp32; conv weights [Cout][R][S][Cin], which is the channels_last
+memory of the reference's OIHW parameters (converted in place on first use, after the seeded
+initialisation so that initial values stay bit-identical to the reference's).
+
+Per encoder and input shape a `ResNetPlan` owns every intermediate buffer (nothing is allocated
+in the steady state) and issues the launch sequence:
+  stem   im2col (raw NCHW/NCTHW input, frame fold by index arithmetic) -> tcgen05 GEMM -> BN
+         statistics -> fused BN+ReLU+MaxPool
+  block  conv3x3 (tcgen05 implicit GEMM) -> BN stats -> BN+ReLU -> conv3x3 -> BN stats ->
+         [1x1/2 downsample conv -> BN stats] -> fused BN + residual(+its BN) + ReLU
+  head   global average pool over (T,h,w)
+and the mirrored backward (BN backward = 2-stage reduction + apply, dgrad / wgrad on tcgen05,
+residual gradients accumulated in the dgrad epilogue).
 """
 import torch
-import torch.nn.functional as F
 
-BACKEND = "cudnn-interim"
+from . import _lib
 
-
-def _bn(x, bn, training):
-    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-    return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
+BACKEND = "native-tcgen05"
+_STEM_KP = {1: 64, 3: 192}     # K = 49*Cin padded to a multiple of 64 (tcgen05 K-blocks of 32, N tiles of 64)
 
 
-def resnet_feature_map(net, x):
-    if not x.is_cuda:
-        raise RuntimeError("mla_b200 encoders run on CUDA only (no CPU fallback); got %s" % x.device)
-    training = net.training
-    if net.modality == "visual":
-        B, C, T, H, W = x.shape
-        x = x.permute(0, 2, 1, 3, 4).contiguous().view(B * T, C, H, W)
-    x = F.conv2d(x, net.conv1.weight, None, 2, 3)
-    x = F.relu(_bn(x, net.bn1, training))
-    x = F.max_pool2d(x, 3, 2, 1)
-    for li in range(1, 5):
-        for blk in getattr(net, "layer%d" % li):
-            identity = x
-            out = F.conv2d(x, blk.conv1.weight, None, blk.stride, 1)
-            out = F.relu(_bn(out, blk.bn1, training))
-            out = F.conv2d(out, blk.conv2.weight, None, 1, 1)
-            out = _bn(out, blk.bn2, training)
-            if blk.downsample is not None:
-                identity = F.conv2d(x, blk.downsample[0].weight, None, blk.stride, 0)
-                identity = _bn(identity, blk.downsample[1], training)
-            x = F.relu(out + identity)
-    return x
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(rc, what):
+    if rc != 0:
+        _lib.check(rc, what)
+
+
+def _krsc(p):
+    """Make a conv weight parameter channels_last in place (memory [Cout][R][S][Cin])."""
+    if p.dim() == 4 and not p.data.permute(0, 2, 3, 1).is_contiguous():
+        p.data = p.data.contiguous(memory_format=torch.channels_last)
+    return p
+
+
+def _flatten_params(net):
+    """Re-home every parameter of an encoder into ONE contiguous fp32 buffer (values preserved; conv
+    weights become channels_last = [Cout][R][S][Cin]). One launch then produces the TF32-rounded copy
+    of all weights that the tensor-core convolutions read (`net._mla_wr`), at the same offsets."""
+    flat = net.__dict__.get("_mla_flat")
+    params = list(net.parameters())
+    if flat is not None and all(p.data.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+                                for p in params):
+        return
+    dev = params[0].device
+    sizes = [(p.numel() + 3) // 4 * 4 for p in params]          # 16-byte aligned slots
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    off = 0
+    offsets = {}
+    for p, n in zip(params, sizes):
+        if p.dim() == 4:
+            o, i, r, s = p.shape
+            view = torch.as_strided(flat, p.shape, (r * s * i, 1, s * i, i), storage_offset=off)
+        else:
+            view = torch.as_strided(flat, p.shape, p.data.contiguous().stride(), storage_offset=off)
+        view.copy_(p.data)
+        p.data = view
+        offsets[id(p)] = off
+        off += n
+    net.__dict__["_mla_flat"] = flat
+    net.__dict__["_mla_wr"] = torch.empty_like(flat)
+    net.__dict__["_mla_off"] = offsets
+
+
+def _grad_buffer(p):
+    """The tensor backward writes d(loss)/dp into: the pre-attached p.grad (e.g. a view of the flat
+    all-reduce bucket) when its memory matches p's, otherwise a fresh tensor with p's layout."""
+    g = p.grad
+    if g is None or g.stride() != p.stride() or g.dtype != torch.float32:
+        g = torch.empty_like(p)
+        p.grad = g
+    return g
+
+
+class _BN:
+    def __init__(self, bn, dev):
+        self.bn = bn
+        C = bn.num_features
+        self.C = C
+        self.mean = torch.empty(C, device=dev)
+        self.invstd = torch.empty(C, device=dev)
+        self.scale = torch.empty(C, device=dev)
+        self.shift = torch.empty(C, device=dev)
+
+
+class ResNetPlan:
+    def __init__(self, net, x):
+        self.net = net
+        dev = x.device
+        self.dev = dev
+        if net.modality == "visual":
+            B, Cin, T, H, W = x.shape
+        else:
+            B, Cin, H, W = x.shape
+            T = 1
+        self.B, self.T, self.Cin, self.H, self.W = B, T, Cin, H, W
+        self.N = B * T
+        self.key = tuple(x.shape)
+        self.L = _lib.lib()
+        self._pool = {}
+        N = self.N
+        _flatten_params(net)
+        self.flat, self.wr, self.woff = net._mla_flat, net._mla_wr, net._mla_off
+        # ---- stem
+        self.Kp = _STEM_KP[Cin]
+        self.OH0, self.OW0 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        self.PH, self.PW = (self.OH0 + 2 - 3) // 2 + 1, (self.OW0 + 2 - 3) // 2 + 1
+        self.M0 = N * self.OH0 * self.OW0
+        e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)   # noqa: E731
+        self.col = e(self.M0, self.Kp)
+        self.wpad = e(64, self.Kp)
+        self.dwpad = e(64, self.Kp)
+        self.y0 = e(N, self.OH0, self.OW0, 64)
+        self.p0 = e(N, self.PH, self.PW, 64)
+        self.idx0 = e(N, self.PH, self.PW, 64, dt=torch.uint8)
+        self.bn0 = _BN(net.bn1, dev)
+        # ---- residual blocks
+        self.blocks = []
+        h, w, cin = self.PH, self.PW, 64
+        for li in range(1, 5):
+            for blk in getattr(net, "layer%d" % li):
+                s = blk.stride
+                cout = blk.conv1.out_channels
+                ho, wo = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+                d = dict(blk=blk, stride=s, cin=cin, cout=cout, h=h, w=w, ho=ho, wo=wo,
+                         y1=e(N, ho, wo, cout), a1=e(N, ho, wo, cout), y2=e(N, ho, wo, cout), out=e(N, ho, wo, cout),
+                         bn1=_BN(blk.bn1, dev), bn2=_BN(blk.bn2, dev), yd=None, bnd=None)
+                if blk.downsample is not None:
+                    d["yd"] = e(N, ho, wo, cout)
+                    d["bnd"] = _BN(blk.downsample[1], dev)
+                self.blocks.append(d)
+                h, w, cin = ho, wo, cout
+        self.rows = T * h * w                   # NHWC rows averaged per sample
+        self.C_out = cin
+        self.bns = [self.bn0] + [b[k] for b in self.blocks for k in ("bn1", "bn2", "bnd") if b[k] is not None]
+        self.nbt = [b.bn.num_batches_tracked for b in self.bns if b.bn.num_batches_tracked is not None]
+        nb = max(self.L.mla_bn_workspace_bytes(self.M0, 64),
+                 max(self.L.mla_bn_workspace_bytes(N * b["ho"] * b["wo"], b["cout"]) for b in self.blocks))
+        self.bn_ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        nw = self.L.mla_conv2d_wgrad_workspace_bytes(N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
+        for b in self.blocks:
+            nw = max(nw, self.L.mla_conv2d_wgrad_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3,
+                                                                  b["stride"], 1),
+                     self.L.mla_conv2d_wgrad_workspace_bytes(N, b["ho"], b["wo"], b["cout"], b["cout"], 3, 3, 1, 1))
+        self.wg_ws = torch.empty(max(nw, 256), dtype=torch.uint8, device=dev)
+        self.trained_forward = False
+
+    # ------------------------------------------------------------------ small helpers
+    def tmp(self, slot, shape):
+        k = (slot, tuple(shape))
+        t = self._pool.get(k)
+        if t is None:
+            t = torch.empty(shape, dtype=torch.float32, device=self.dev)
+            self._pool[k] = t
+        return t
+
+    def _wptr(self, w):
+        """Device pointer of the TF32-rounded copy of a parameter (plain buffers: their own pointer)."""
+        off = self.woff.get(id(w))
+        return w.data_ptr() if off is None else self.wr.data_ptr() + 4 * off
+
+    def _conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st):
+        _chk(self.L.mla_conv2d_fprop(_p(x), self._wptr(w), _p(y), N, H, W, Cin, Cout, R, R, stride, pad, st), "mla_conv2d_fprop")
+
+    def _dgrad(self, dy, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
+        _chk(self.L.mla_conv2d_dgrad(_p(dy), self._wptr(w), _p(dx), N, H, W, Cin, Cout, R, R, stride, pad, 1 if acc else 0, st),
+             "mla_conv2d_dgrad")
+
+    def _wgrad(self, x, dy, dw, N, H, W, Cin, Cout, R, stride, pad, st):
+        _chk(self.L.mla_conv2d_wgrad(_p(x), _p(dy), _p(dw), N, H, W, Cin, Cout, R, R, stride, pad, _p(self.wg_ws),
+                                     self.wg_ws.numel(), st), "mla_conv2d_wgrad")
+
+    def _bn_coeffs(self, y, M, b, training, st):
+        bn = b.bn
+        if training:
+            _chk(self.L.mla_bn_train_stats(_p(y), M, b.C, _p(bn.weight), _p(bn.bias), _p(bn.running_mean),
+                                           _p(bn.running_var), float(bn.momentum), float(bn.eps), _p(b.mean),
+                                           _p(b.invstd), _p(b.scale), _p(b.shift), _p(self.bn_ws), self.bn_ws.numel(), st),
+                 "mla_bn_train_stats")
+        else:
+            _chk(self.L.mla_bn_eval_coeffs(_p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
+                                           float(bn.eps), b.C, _p(b.scale), _p(b.shift), st), "mla_bn_eval_coeffs")
+
+    def _bn_bwd(self, dz, z, y, b, M, dy, g_out, st):
+        bn = b.bn
+        dg, db = _grad_buffer(bn.weight), _grad_buffer(bn.bias)
+        _chk(self.L.mla_bn_backward(_p(dz), _p(z), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C, _p(dg), _p(db),
+                                    _p(dy), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st), "mla_bn_backward")
+
+    # ------------------------------------------------------------------------ forward
+    def forward(self, x, training):
+        L, N, st = self.L, self.N, _lib.stream_ptr()
+        net = self.net
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        HW = self.H * self.W
+        if net.modality == "visual":       # [B,3,T,H,W]: n = b*T + t
+            sB, sT, sC = 3 * self.T * HW, HW, self.T * HW
+        else:                              # [B,1,H,W]
+            sB, sT, sC = self.Cin * HW, 0, HW
+        K = 49 * self.Cin
+        _chk(L.mla_round_tf32(_p(self.flat), _p(self.wr), self.flat.numel(), st), "mla_round_tf32")
+        _chk(L.mla_stem_im2col(_p(x), _p(self.col), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp,
+                               st), "mla_stem_im2col")
+        _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
+        self._conv(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st)
+        self._bn_coeffs(self.y0, self.M0, self.bn0, training, st)
+        _chk(L.mla_bn_relu_maxpool(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.idx0), N,
+                                   self.OH0, self.OW0, 64, st), "mla_bn_relu_maxpool")
+        xin = self.p0
+        for b in self.blocks:
+            blk, s, cin, cout = b["blk"], b["stride"], b["cin"], b["cout"]
+            M = N * b["ho"] * b["wo"]
+            self._conv(xin, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, st)
+            self._bn_coeffs(b["y1"], M, b["bn1"], training, st)
+            _chk(L.mla_bn_apply(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(b["a1"]), M,
+                                cout, st), "mla_bn_apply")
+            self._conv(b["a1"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, st)
+            self._bn_coeffs(b["y2"], M, b["bn2"], training, st)
+            if b["yd"] is not None:
+                self._conv(xin, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, st)
+                self._bn_coeffs(b["yd"], M, b["bnd"], training, st)
+                _chk(L.mla_bn_apply(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]), _p(b["bnd"].scale),
+                                    _p(b["bnd"].shift), 1, _p(b["out"]), M, cout, st), "mla_bn_apply")
+            else:
+                _chk(L.mla_bn_apply(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
+                                    _p(b["out"]), M, cout, st), "mla_bn_apply")
+            xin = b["out"]
+        self.x_in0 = None
+        feat = torch.empty(self.B, self.C_out, dtype=torch.float32, device=self.dev)
+        _chk(L.mla_avgpool_forward(_p(xin), _p(feat), self.B, self.rows, self.C_out, st), "mla_avgpool_forward")
+        if training and self.nbt:
+            torch._foreach_add_(self.nbt, 1)
+        self.trained_forward = training
+        return feat
+
+    # ----------------------------------------------------------------------- backward
+    def backward(self, dfeat):
+        if not self.trained_forward:
+            raise RuntimeError("encoder backward needs a training-mode forward on the same plan")
+        L, N, st = self.L, self.N, _lib.stream_ptr()
+        net = self.net
+        dfeat = dfeat.contiguous()
+        last = self.blocks[-1]
+        dout = self.tmp("dXa", last["out"].shape)
+        _chk(L.mla_avgpool_backward(_p(dfeat), _p(dout), self.B, self.rows, self.C_out, st), "mla_avgpool_backward")
+        for i in range(len(self.blocks) - 1, -1, -1):
+            b = self.blocks[i]
+            blk, s, cin, cout = b["blk"], b["stride"], b["cin"], b["cout"]
+            xin = self.blocks[i - 1]["out"] if i > 0 else self.p0
+            M = N * b["ho"] * b["wo"]
+            shp = b["out"].shape
+            g = self.tmp("g%d" % (i & 1), shp)
+            dy2 = self.tmp("dy", shp)
+            self._bn_bwd(dout, b["out"], b["y2"], b["bn2"], M, dy2, g, st)
+            self._wgrad(b["a1"], dy2, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3, 1, 1, st)
+            da1 = self.tmp("da", shp)
+            self._dgrad(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
+            dy1 = dy2                                   # dy2 is dead: reuse its buffer
+            self._bn_bwd(da1, b["a1"], b["y1"], b["bn1"], M, dy1, None, st)
+            self._wgrad(xin, dy1, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1, st)
+            if b["yd"] is not None:
+                dyd = da1                               # da1 is dead
+                self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st)
+                self._wgrad(xin, dyd, _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0, st)
+                dx = self.tmp("dXa", xin.shape)         # xin.shape != out.shape here, so never aliases dout
+                self._dgrad(dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, False, st)
+            else:
+                dx = g                                  # identity shortcut: dX starts as the masked gradient
+            self._dgrad(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
+            dout = dx
+        # stem: maxpool+relu backward, BN backward, weight gradient (no dgrad: the input needs none)
+        g0 = self.tmp("g0", self.y0.shape)
+        _chk(L.mla_maxpool_relu_backward(_p(dout), _p(self.p0), _p(self.idx0), _p(g0), N, self.OH0, self.OW0, 64, st),
+             "mla_maxpool_relu_backward")
+        dy0 = self.tmp("dy0", self.y0.shape)
+        self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, dy0, None, st)
+        self._wgrad(self.col, dy0, self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st)
+        _chk(L.mla_pad_rows(_p(self.dwpad), _p(_grad_buffer(net.conv1.weight)), 64, 49 * self.Cin, self.Kp, 1, st),
+             "mla_pad_rows")
+        self.trained_forward = False
+
+
+class _EncoderFn(torch.autograd.Function):
+    """Bridges a ResNetPlan into autograd: forward returns the pooled feature; backward runs the
+    plan's native backward, which writes parameter gradients in place (p.grad)."""
+
+    @staticmethod
+    def forward(ctx, plan, x, anchor):
+        ctx.plan = plan
+        return plan.forward(x, True)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        ctx.plan.backward(dfeat)
+        return None, None, None
+
+
+def _plan(net, x):
+    plans = net.__dict__.setdefault("_mla_plans", {})
+    key = (tuple(x.shape), x.device)
+    p = plans.get(key)
+    if p is None:
+        if len(plans) >= 4:
+            plans.clear()
+        p = ResNetPlan(net, x)
+        plans[key] = p
+    return p
 
 
 def resnet_pooled(net, x):
-    batch = x.shape[0]
-    fm = resnet_feature_map(net, x)                       # [B*T, 512, h, w]
-    n, c, h, w = fm.shape
-    return fm.view(batch, n // batch, c, h * w).mean(dim=(1, 3))
+    """[B,1,H,W] / [B,3,T,H,W] -> pooled feature [B,512] (backbone + adaptive_avg_pool + flatten)."""
+    if not x.is_cuda:
+        raise RuntimeError("mla_b200 encoders run on CUDA only (no CPU fallback); got %s" % x.device)
+    plan = _plan(net, x)
+    if net.training and torch.is_grad_enabled():
+        return _EncoderFn.apply(plan, x, net.conv1.weight)
+    with torch.no_grad():
+        return plan.forward(x, net.training)
+
+
+def resnet_feature_map(net, x):
+    """Layer4 feature map in the reference's NCHW layout [N,512,h,w] (API completeness; no grad)."""
+    plan = _plan(net, x)
+    with torch.no_grad():
+        plan.forward(x, net.training)
+    return plan.blocks[-1]["out"].permute(0, 3, 1, 2)

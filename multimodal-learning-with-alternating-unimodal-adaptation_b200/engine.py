@@ -93,19 +93,19 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
     model.train()
     print("Start training ... ")
     fc = net.fusion_module.fc_out
-    st = getattr(net, "_mla_turn_state", None)
-    if st is None:
-        st = _TurnState(net)
-        net._mla_turn_state = st
     world = mdist.world_size()
     len_dataloader = len(dataloader)
-    n_mod = len(st.encoders)
+    n_mod = len(encoder_param_groups(net))
     acc = torch.zeros(1 + n_mod, dtype=torch.float64, device=device)      # _loss, _loss_a, _loss_v[, _loss_t]
 
     for batch_step, data_packet in enumerate(dataloader):
         inputs, label = _unpack(args, data_packet, device)
         optimizer.zero_grad()                                              # main.py:164
         feats = model(*inputs)                                             # main.py:421-431
+        st = getattr(net, "_mla_turn_state", None)
+        if st is None:       # after the first forward: the engine has fixed the parameter memory layouts by now
+            st = _TurnState(net)
+            net._mla_turn_state = st
         if len(feats) != n_mod:
             raise RuntimeError("model returned %d features for %d encoders" % (len(feats), n_mod))
         B = feats[0].shape[0]
@@ -114,7 +114,7 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
         for m, feat in enumerate(feats):                                   # a -> v -> (t)
             fdet = feat.detach()
             o = head_turn(fc, fdet, label, grad_scale=inv_global, out=st.head_out)   # main.py:432-435 (head part)
-            st.flat[m].attach(zero=True)
+            st.flat[m].attach()
             feat.backward(o["dfeat"])                                      # main.py:435 (encoder part)
             if world > 1:                                                  # two collectives per turn
                 mdist.allreduce_sum_(st.flat[m].flat)
