@@ -10,12 +10,15 @@
 //   MODE 2  wgrad   dw[co, r,s,ci] = sum_m dy[m, co] * x[pix(m,r,s), ci]           K = N*OH*OW (split)
 //
 // One CTA computes a 128 x BN accumulator tile. Warp roles (192 threads):
-//   warps 0-3  gather producers: one 128-byte channel segment per thread and k-block, copied
-//              with cp.async (zero-fill for padding / stride holes / tails) into the 128B-swizzled
-//              layout the UMMA descriptors expect; afterwards the same warps run the epilogue
-//              (tcgen05.ld 32x32b -> registers -> global).
-//   warp 4     TMA producer for the dense operand (weights, or dy for wgrad): 2-D tiled tensor
-//              map, SWIZZLE_128B, completion on the stage's mbarrier (complete_tx).
+//   warp 4     TMA producer. The dense operand (weights, or dy for wgrad) comes through a 2-D tiled
+//              tensor map; the GATHERED operand (the im2col view of x or dy) comes through an
+//              im2col-mode tensor map (cuTensorMapEncodeIm2col): one cp.async.bulk.tensor.4d...im2col
+//              per k-block loads 128 (or 32) pixels x 32 channels of one filter tap, zero-filling
+//              padding and tails in hardware, straight into the 128B-swizzled layout the UMMA
+//              descriptors expect. Both complete on the stage's mbarrier (complete_tx).
+//   warps 0-3  epilogue (tcgen05.ld 32x32b -> registers -> global). Only for the stride-2 dgrad,
+//              whose gather has holes the im2col walk cannot express, the same warps first act as
+//              cp.async gather producers (one 128-byte channel segment per thread and k-block).
 //   warp 5     TMEM allocation + the single MMA-issuing thread: 4 x tcgen05.mma (K = 8 each)
 //              per 32-wide k-block, tcgen05.commit releases the smem stage / publishes TMEM.
 // K-major operands are [rows][32 tf32]; MN-major operands (weights in dgrad, both operands in
@@ -49,6 +52,9 @@ struct ConvGemmParams {
   int KBtot;         // total k-blocks = ceil(M / 32)
   int splits;
   long long split_stride;  // elements between split partials
+  // im2col-mode TMA gather (IM2COL kernels): base pixel of output position (oh, ow) is
+  // (ow * mul + g_base, oh * mul + g_base); filter offset of tap (r, s) is (s, r), or (S-1-s, R-1-r) if g_flip
+  int g_base, g_flip;
 };
 
 template <bool MN_MAJOR>
@@ -83,8 +89,9 @@ __device__ __forceinline__ void gather_segment(const ConvGemmParams& p, uint32_t
     tc::cp_async16(dst_row + (MN_MAJOR ? tc::swz32(j, row) : tc::swz16(j, row)), src + (bytes ? 4 * j : 0), bytes);
 }
 
-template <int MODE, int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap, ConvGemmParams p) {
+template <int MODE, int BN, int STAGES, bool IM2COL>
+__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                             const __grid_constant__ CUtensorMap tmap_g, ConvGemmParams p) {
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr int LAG = STAGES - 1;
@@ -99,13 +106,16 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(tc::smem_u32(&full_bar[s]), kGatherThreads + 1);
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), IM2COL ? 1 : kGatherThreads + 1);
       tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
     }
     tc::mbar_init(tc::smem_u32(&tmem_full_bar), 1);
     tc::fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap);
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap);
+    if (IM2COL) tc::tma_prefetch_desc(&tmap_g);
+  }
   if (warp == 5) {
     tc::tmem_alloc(tc::smem_u32(&tmem_slot), BN);
     tc::tmem_relinquish();
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   if (warp < 4) {
     // ===================== gather producers =====================
     const int t = threadIdx.x;
-    for (int kb = 0; kb < KB; ++kb) {
+    for (int kb = 0; kb < (IM2COL ? 0 : KB); ++kb) {
       const int s = kb % STAGES;
       tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((kb / STAGES) & 1) ^ 1);
       const uint32_t stage = tiles + s * kStageBytes;
@@ -159,9 +169,11 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         tc::mbar_arrive(tc::smem_u32(&full_bar[(kb - LAG) % STAGES]));
       }
     }
-    tc::cp_async_wait<0>();
-    tc::fence_proxy_async();
-    for (int kb = max(KB - LAG, 0); kb < KB; ++kb) tc::mbar_arrive(tc::smem_u32(&full_bar[kb % STAGES]));
+    if (!IM2COL) {
+      tc::cp_async_wait<0>();
+      tc::fence_proxy_async();
+      for (int kb = max(KB - LAG, 0); kb < KB; ++kb) tc::mbar_arrive(tc::smem_u32(&full_bar[kb % STAGES]));
+    }
 
     // ===================== epilogue =====================
     if (KB > 0) {
@@ -205,26 +217,52 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   } else if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // base pixel of this tile's first GEMM row (fprop / dgrad) in the gathered tensor's coordinates
+      int gw = 0, gh = 0, gn = 0;
+      if (IM2COL && MODE != 2) {
+        const int ow = m0 % p.OW;
+        const int t = m0 / p.OW;
+        gw = ow * p.mul + p.g_base;
+        gh = (t % p.OH) * p.mul + p.g_base;
+        gn = t / p.OH;
+      }
+      const uint32_t tx_gather = IM2COL ? (MODE == 2 ? kBBytes : kABytes) : 0u;
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((kb / STAGES) & 1) ^ 1);
         const uint32_t stage = tiles + s * kStageBytes;
         const uint32_t bar = tc::smem_u32(&full_bar[s]);
-        if (MODE == 0) {
-          tc::mbar_arrive_expect_tx(bar, kBBytes);
-          tc::tma_load_2d(stage + kABytes, &tmap, bar, kb * 32, n0);  // box {32 k, BN rows}
-        } else if (MODE == 1) {
-          tc::mbar_arrive_expect_tx(bar, kBBytes);
+        if (MODE == 0 || MODE == 1) {
           const int tap = kb / p.kcb;
           const int cb = kb - tap * p.kcb;
+          tc::mbar_arrive_expect_tx(bar, kBBytes + tx_gather);
+          if (IM2COL) {
+            const int r = tap / p.S, sx = tap - r * p.S;
+            tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * 32, gw, gh, gn,
+                                   (uint16_t)(p.g_flip ? p.S - 1 - sx : sx), (uint16_t)(p.g_flip ? p.R - 1 - r : r));
+          }
+          if (MODE == 0) {
+            tc::tma_load_2d(stage + kABytes, &tmap, bar, kb * 32, n0);  // box {32 k, BN rows}
+          } else {
 #pragma unroll
-          for (int pnl = 0; pnl < BN / 32; ++pnl)  // box {32 ci, 32 co rows}
-            tc::tma_load_2d(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32);
+            for (int pnl = 0; pnl < BN / 32; ++pnl)  // box {32 ci, 32 co rows}
+              tc::tma_load_2d(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32);
+          }
         } else {
-          tc::mbar_arrive_expect_tx(bar, kABytes);
+          tc::mbar_arrive_expect_tx(bar, kABytes + tx_gather);
 #pragma unroll
           for (int pnl = 0; pnl < 4; ++pnl)  // box {32 co, 32 pixel rows}
             tc::tma_load_2d(stage + pnl * 4096, &tmap, bar, m0 + pnl * 32, (kb_begin + kb) * 32);
+          if (IM2COL) {
+            const int pix = (kb_begin + kb) * 32;
+            const int ow = pix % p.OW;
+            const int t = pix / p.OW;
+            const int w = ow * p.mul + p.g_base, h = (t % p.OH) * p.mul + p.g_base, n = t / p.OH;
+#pragma unroll
+            for (int pnl = 0; pnl < BN / 32; ++pnl)  // 32 pixels x 32 ci of tap (tap_r, tap_s)
+              tc::tma_load_im2col_4d(stage + kABytes + pnl * 4096, &tmap_g, bar, n0 + pnl * 32, w, h, n, (uint16_t)tap_s,
+                                     (uint16_t)tap_r);
+          }
         }
       }
     }
@@ -291,6 +329,50 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn encode_im2col_fn() {
+  static EncodeIm2colFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeIm2colFn>(f);
+  }();
+  return fn;
+}
+
+// im2col-mode map over an NHWC fp32 tensor: 32 channels x `pixels` base pixels per load. Base pixels walk
+// [lower, dim - 1 + upper] in w and h with the traversal stride `stride` (= one GEMM row / K index each);
+// filter taps are added as instruction offsets. Out-of-bounds reads return zero.
+int make_map_im2col(CUtensorMap* m, const float* ptr, int N, int H, int W, int C, int lower, int upper, int stride,
+                    int pixels, bool mn_major) {
+  EncodeIm2colFn fn = encode_im2col_fn();
+  if (!fn) return MLA_E_NODEVICE;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  int lo[2] = {lower, lower}, up[2] = {upper, upper};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, lo, up, 32u,
+                  (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
+}
+
+// MLA_CONV_GATHER=1 forces the cp.async gather kernels everywhere (A/B comparison, bring-up).
+bool force_gather() {
+  static const bool v = [] {
+    const char* e = getenv("MLA_CONV_GATHER");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
+
 // 2-D fp32 row-major [rows][cols] tensor map with a {32 cols (128 B), box_rows} box; 128B swizzle with
 // 16 B chunks (K-major operand tiles) or 32 B chunks (MN-major operand panels).
 int make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols, int box_rows, bool mn_major) {
@@ -308,16 +390,16 @@ int make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols
   return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
 }
 
-template <int MODE, int BN, int STAGES>
-int launch(const CUtensorMap& map, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
+template <int MODE, int BN, int STAGES, bool IM2COL>
+int launch(const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (kABytes + BN * 128) + 1024;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES, IM2COL>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.store(1, std::memory_order_release);
   }
-  conv_gemm_kernel<MODE, BN, STAGES><<<grid, kThreads, smem, st>>>(map, p);
+  conv_gemm_kernel<MODE, BN, STAGES, IM2COL><<<grid, kThreads, smem, st>>>(map, gmap, p);
   MLA_CUDA_TRY(cudaGetLastError());
   mla::count_launch();
   return 0;
@@ -350,7 +432,13 @@ extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N,
   if (rc) return rc;
   dim3 grid((p.M + 127) / 128, Cout / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return BN == 64 ? launch<0, 64, 4>(map, p, grid, st) : launch<0, 128, 3>(map, p, grid, st);
+  if (force_gather()) return BN == 64 ? launch<0, 64, 4, false>(map, map, p, grid, st) : launch<0, 128, 3, false>(map, map, p, grid, st);
+  // gathered operand: x, base pixel (ow*stride - pad, oh*stride - pad), taps as offsets
+  p.g_base = -pad; p.g_flip = 0;
+  CUtensorMap gmap;
+  rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, pad - (R - 1), stride, 128, false);
+  if (rc) return rc;
+  return BN == 64 ? launch<0, 64, 4, true>(map, gmap, p, grid, st) : launch<0, 128, 3, true>(map, gmap, p, grid, st);
 }
 
 extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin, int Cout,
@@ -371,7 +459,15 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
   if (rc) return rc;
   dim3 grid((p.M + 127) / 128, Cin / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return BN == 64 ? launch<1, 64, 4>(map, p, grid, st) : launch<1, 128, 3>(map, p, grid, st);
+  if (stride != 1 || force_gather())   // stride-2 dgrad: the gather has holes -> cp.async gather kernel
+    return BN == 64 ? launch<1, 64, 4, false>(map, map, p, grid, st) : launch<1, 128, 3, false>(map, map, p, grid, st);
+  // stride 1: dgrad is a convolution of dy with the flipped filter: base pixel (w + pad - (S-1), h + pad - (R-1)),
+  // weight tap (r, s) pairs with filter offset (R-1-r, S-1-s)
+  p.g_base = pad - (R - 1); p.g_flip = 1;
+  CUtensorMap gmap;
+  rc = make_map_im2col(&gmap, dy, N, OH, OW, Cout, pad - (R - 1), pad - (R - 1) + (H - OH), 1, 128, false);
+  if (rc) return rc;
+  return BN == 64 ? launch<1, 64, 4, true>(map, gmap, p, grid, st) : launch<1, 128, 3, true>(map, gmap, p, grid, st);
 }
 
 namespace {
@@ -427,7 +523,15 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   if (rc) return rc;
   dim3 grid(Cin / pl.BN, (Cout + 127) / 128, R * S * pl.splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = pl.BN == 64 ? launch<2, 64, 4>(map, p, grid, st) : launch<2, 128, 3>(map, p, grid, st);
+  if (force_gather()) {
+    rc = pl.BN == 64 ? launch<2, 64, 4, false>(map, map, p, grid, st) : launch<2, 128, 3, false>(map, map, p, grid, st);
+  } else {
+    p.g_base = -pad; p.g_flip = 0;
+    CUtensorMap gmap;
+    rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, pad - (R - 1), stride, 32, true);
+    if (rc) return rc;
+    rc = pl.BN == 64 ? launch<2, 64, 4, true>(map, gmap, p, grid, st) : launch<2, 128, 3, true>(map, gmap, p, grid, st);
+  }
   if (rc) return rc;
   if (pl.splits > 1) {
     const long long n4 = p.split_stride / 4;

@@ -130,6 +130,29 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
   }
 }
 
+// Fixed-order sum of the per-block partials of one channel pair (sum a, sum b): blockDim = (32, kFinY);
+// lane x owns channel c, slice y adds blocks y, y+kFinY, ... and the slices are combined in order.
+constexpr int kFinY = 16;
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int nblocks, int C, int c, double& s,
+                                                double& ss) {
+  __shared__ double sh[2][kFinY][33];
+  double a = 0, b = 0;
+  if (c < C) {
+    for (int blk = threadIdx.y; blk < nblocks; blk += kFinY) {
+      a += part[(size_t)blk * 2 * C + c];
+      b += part[(size_t)blk * 2 * C + C + c];
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  s = 0; ss = 0;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int y = 0; y < kFinY; ++y) { s += sh[0][y][threadIdx.x]; ss += sh[1][y][threadIdx.x]; }
+  }
+}
+
 // stats finalize: mean, biased var -> invstd, scale = gamma*invstd, shift = beta - mean*scale;
 // running stats: momentum update with the UNBIASED variance (torch BatchNorm2d semantics).
 __global__ void bn_stats_finalize_kernel(const double* __restrict__ part, int nblocks, long long M, int C,
@@ -138,13 +161,10 @@ __global__ void bn_stats_finalize_kernel(const double* __restrict__ part, int nb
                                          float momentum, float eps, float* __restrict__ mean_out,
                                          float* __restrict__ invstd_out, float* __restrict__ scale_out,
                                          float* __restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0, ss = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += part[(size_t)b * 2 * C + c];
-    ss += part[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, ss;
+  reduce_partials(part, nblocks, C, c, s, ss);
+  if (c >= C || threadIdx.y != 0) return;
   const double mean = s / (double)M;
   double var = ss / (double)M - mean * mean;
   if (var < 0) var = 0;
@@ -195,13 +215,10 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
 // BN backward finalize: dgamma = sum g*xhat, dbeta = sum g (fixed-order over block partials)
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblocks, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ sums /*[2][C]: dbeta, dgamma*/) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0, ss = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += part[(size_t)b * 2 * C + c];
-    ss += part[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, ss;
+  reduce_partials(part, nblocks, C, c, s, ss);
+  if (c >= C || threadIdx.y != 0) return;
   if (dbeta) dbeta[c] = (float)s;
   if (dgamma) dgamma[c] = (float)ss;
   sums[c] = (float)s;
@@ -412,7 +429,7 @@ extern "C" int mla_bn_train_stats(const float* y, long long M, int C, const floa
   channel_reduce_kernel<0><<<pl.nblocks, kRedThreads, pl.smem, st>>>(y, nullptr, nullptr, nullptr, nullptr, M, C,
                                                                     pl.rows_per_block, part);
   MLA_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, pl.nblocks, M, C, gamma, beta, running_mean, running_var,
+  bn_stats_finalize_kernel<<<(C + 31) / 32, dim3(32, kFinY), 0, st>>>(part, pl.nblocks, M, C, gamma, beta, running_mean, running_var,
                                                            momentum, eps, mean_out, invstd_out, scale_out, shift_out);
   MLA_LAUNCH_CHECK();
   return 0;
@@ -457,7 +474,7 @@ extern "C" int mla_bn_backward(const float* dz, const float* z, const float* y, 
   }
   channel_reduce_kernel<1><<<pl.nblocks, kRedThreads, pl.smem, st>>>(y, dz, z, mean, invstd, M, C, pl.rows_per_block, part);
   MLA_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, pl.nblocks, C, dgamma, dbeta, sums);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, kFinY), 0, st>>>(part, pl.nblocks, C, dgamma, dbeta, sums);
   MLA_LAUNCH_CHECK();
   const long long n4 = M * (C / 4);
   bn_bwd_apply_kernel<<<ew_grid(n4, 256), 256, 0, st>>>(dz, z, y, mean, invstd, gamma, sums, 1.f / (float)M, dy, g_out, n4,

@@ -245,7 +245,10 @@ class AVOracle:
     """State + step functions of the CREMA-D AVClassifier path (configs 1/2 of BASELINE.json).
 
     `state` is a dict with the reference's state-dict names WITHOUT the 'module.' prefix
-    (audio_net.*, visual_net.*, fusion_module.fc_out.{weight,bias}); tensors are torch CPU."""
+    (audio_net.*, visual_net.*, fusion_module.fc_out.{weight,bias}); tensors are torch CPU.
+    (Tests may also hand it CUDA tensors: the same torch code then runs the reference's
+    arithmetic as the reference itself would on a GPU — cuDNN convolutions, TF32 under torch's
+    defaults — which calibrates how far ANY TF32 implementation sits from the fp32 fixtures.)"""
 
     def __init__(self, state, lr=1e-3, force_projection=False, gs_mode=0):
         import torch
@@ -270,10 +273,10 @@ class AVOracle:
         loss = F.cross_entropy(out, label)                             # main.py:434
         loss.backward(retain_graph=True)                               # main.py:435
         if self.force_projection:                                      # main.py:437-438 -> utils.py:24-41
-            P1, g1 = gs_before_update(self.Pl, feat.detach().numpy(), W.grad.numpy(), batch_step, len_dl,
+            P1, g1 = gs_before_update(self.Pl, feat.detach().cpu().numpy(), W.grad.cpu().numpy(), batch_step, len_dl,
                                       self.exp_count, mode=self.gs_mode)
             self.Pl = P1
-            W.grad = torch.from_numpy(np.ascontiguousarray(g1))
+            W.grad = torch.from_numpy(np.ascontiguousarray(g1)).to(W.device)
         self.opt.step()                                                # main.py:439
         self.opt.zero_grad()                                           # main.py:440
         self.exp_count += 1                                            # main.py:442
@@ -316,7 +319,7 @@ class AVOracle:
         hits = np.zeros((3, n_classes), np.int64)
         for spec, image, label in batches:
             oa, ov = self.eval_logits(spec, image)
-            r = fuse_eval([oa.numpy(), ov.numpy()], label.numpy(), n_classes, dynamic=dynamic,
+            r = fuse_eval([oa.cpu().numpy(), ov.cpu().numpy()], label.cpu().numpy(), n_classes, dynamic=dynamic,
                           fixed_w=(av_alpha, 1 - av_alpha))
             num += r["num"]
             hits += r["hits"]

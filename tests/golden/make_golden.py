@@ -288,8 +288,12 @@ def make_av(ref_main, ref_utils):
     for tag, fire in (("small_noop", False), ("small_fire", True)):
         for k, v in run_epoch(small, fire).items():
             out["%s_%s" % (tag, k)] = v
+    # single-step epochs: the losses depend on the forward pass and the head update only (no encoder
+    # update has happened yet), so they pin forward parity without the chaotic TF32 trajectory
+    out["small_step1_losses"] = run_epoch(small[:1], False)["losses"]
     # KAT-6: three B=4 batches at the full BASELINE.json size
     full = batches(3, 4, 1, (257, 188), 224)
+    out["full_step1_losses"] = run_epoch(full[:1], False)["losses"]
     for k, v in run_epoch(full, False).items():
         if k in ("losses", "accs_dyn", "accs_fix", "exp_count", "Pl_is_eye"):
             out["full_noop_%s" % k] = v

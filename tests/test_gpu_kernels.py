@@ -181,8 +181,10 @@ def test_fusion_vs_reference_fixture(ops, golden, name, x):
     fused, w, am, ent = ops.fuse_eval(outs, lab, hits=hits, num=num, want_entropy=True)
     assert np.allclose(ent.cpu().numpy(), g[k + "entropy"], rtol=3e-6)
     assert np.abs(w.cpu().numpy() - g[k + "w"]).max() <= w_tol(g[k + "entropy"])
-    assert np.allclose(fused.cpu().numpy(), g[k + "fused"], atol=1e-5)
-    assert np.array_equal(am.cpu().numpy(), g[k + "argmax"])                           # bit-exact predictions
+    # fused = sum_m w_m out_m: a weight shift dw (bounded above) moves it by at most dw * sum_m max|out_m|
+    amax = sum(float(np.abs(g[k + "out%d" % m]).max()) for m in range(M))
+    assert np.allclose(fused.cpu().numpy(), g[k + "fused"], atol=1e-5 + w_tol(g[k + "entropy"]) * amax)
+    assert np.array_equal(am.cpu().numpy(), g[k + "argmax"])                        # bit-exact predictions
     ref = orc.fuse_eval([g[k + "out%d" % m] for m in range(M)], g[k + "label"], C)
     assert np.array_equal(hits.cpu().numpy(), ref["hits"]) and np.array_equal(num.cpu().numpy(), ref["num"])
     # counters accumulate across batches (main.py:659-676)
