@@ -146,7 +146,10 @@ MLA_API int    mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
  * bn_relu_maxpool / maxpool_relu_backward: stem BN+ReLU+MaxPool(3,2,1) fused; idx holds the
  *               argmax window position (uint8 per element).
  * avgpool_*   : feat[b] = mean of `rows` consecutive NHWC rows (h*w, or T*h*w for video).
- * ws for the BN calls: mla_bn_workspace_bytes(M, C).
+ * ws for the BN calls: mla_bn_workspace_bytes(M, C) bytes, ZERO-FILLED by the caller before its first use
+ *               (it holds the completion tickets of the single-launch reductions; every call leaves
+ *               them at zero again, so one buffer serves any sequence of calls on one stream).
+ *               C % 64 == 0. Deterministic: partial sums are combined in block order.
  */
 MLA_API int    mla_stem_im2col(const float* in, float* col, int N, int T, long long sB, long long sT,
                         long long sC, int Cin, int H, int W, int R, int S, int stride, int pad, int Kp,

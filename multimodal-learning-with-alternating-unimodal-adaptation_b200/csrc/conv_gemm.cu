@@ -52,9 +52,15 @@ struct ConvGemmParams {
   int KBtot;         // total k-blocks = ceil(M / 32)
   int splits;
   long long split_stride;  // elements between split partials
-  // im2col-mode TMA gather (IM2COL kernels): base pixel of output position (oh, ow) is
-  // (ow * mul + g_base, oh * mul + g_base); filter offset of tap (r, s) is (s, r), or (S-1-s, R-1-r) if g_flip
-  int g_base, g_flip;
+  // im2col-mode TMA gather (IM2COL kernels): base pixel of GEMM row / K index (oh, ow) is
+  // (ow * mul + g_base_w, oh * mul + g_base_h). The launch iterates nr x ns filter taps: tap (i, j) uses the
+  // weights of filter position (tap_r[i], tap_s[j]) and the instruction offset (off_s[j], off_r[i]).
+  int g_base_w, g_base_h;
+  int nr, ns;
+  signed char tap_r[8], tap_s[8], off_r[8], off_s[8];
+  // output row map (stride-s dgrad, one launch per output parity class): GEMM row (n, i, j) over the OH x OW
+  // sub-grid is written to dx pixel (n, i * o_mul + o_ph, j * o_mul + o_pw) of an o_H x o_W image.
+  int o_mul, o_ph, o_pw, o_H, o_W;
 };
 
 template <bool MN_MAJOR>
@@ -188,7 +194,15 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         orow = p.out + (long long)split * p.split_stride + (long long)co * p.ldo + (tap_r * p.S + tap_s) * p.CinW + n0;
     } else {
       const int m = m0 + row;
-      if (m < p.M) orow = p.out + (long long)m * p.ldo + n0;
+      if (m < p.M) {
+        long long orow_idx = m;
+        if (p.o_mul > 1) {
+          const int j = m % p.OW;
+          const int t = m / p.OW;
+          orow_idx = ((long long)(t / p.OH) * p.o_H + (t % p.OH) * p.o_mul + p.o_ph) * p.o_W + j * p.o_mul + p.o_pw;
+        }
+        orow = p.out + orow_idx * p.ldo + n0;
+      }
     }
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -222,8 +236,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       if (IM2COL && MODE != 2) {
         const int ow = m0 % p.OW;
         const int t = m0 / p.OW;
-        gw = ow * p.mul + p.g_base;
-        gh = (t % p.OH) * p.mul + p.g_base;
+        gw = ow * p.mul + p.g_base_w;
+        gh = (t % p.OH) * p.mul + p.g_base_h;
         gn = t / p.OH;
       }
       const uint32_t tx_gather = IM2COL ? (MODE == 2 ? kBBytes : kABytes) : 0u;
@@ -233,16 +247,16 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         const uint32_t stage = tiles + s * kStageBytes;
         const uint32_t bar = tc::smem_u32(&full_bar[s]);
         if (MODE == 0 || MODE == 1) {
-          const int tap = kb / p.kcb;
+          int tap = kb / p.kcb;
           const int cb = kb - tap * p.kcb;
           tc::mbar_arrive_expect_tx(bar, kBBytes + tx_gather);
           if (IM2COL) {
-            const int r = tap / p.S, sx = tap - r * p.S;
-            tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * 32, gw, gh, gn,
-                                   (uint16_t)(p.g_flip ? p.S - 1 - sx : sx), (uint16_t)(p.g_flip ? p.R - 1 - r : r));
+            const int ti = tap / p.ns, tj = tap - ti * p.ns;
+            tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * 32, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
+            tap = p.tap_r[ti] * p.S + p.tap_s[tj];   // filter position whose weights this k-block multiplies
           }
           if (MODE == 0) {
-            tc::tma_load_2d(stage + kABytes, &tmap, bar, kb * 32, n0);  // box {32 k, BN rows}
+            tc::tma_load_2d(stage + kABytes, &tmap, bar, tap * p.CinW + cb * 32, n0);  // box {32 k, BN rows}
           } else {
 #pragma unroll
             for (int pnl = 0; pnl < BN / 32; ++pnl)  // box {32 ci, 32 co rows}
@@ -257,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
             const int pix = (kb_begin + kb) * 32;
             const int ow = pix % p.OW;
             const int t = pix / p.OW;
-            const int w = ow * p.mul + p.g_base, h = (t % p.OH) * p.mul + p.g_base, n = t / p.OH;
+            const int w = ow * p.mul + p.g_base_w, h = (t % p.OH) * p.mul + p.g_base_h, n = t / p.OH;
 #pragma unroll
             for (int pnl = 0; pnl < BN / 32; ++pnl)  // 32 pixels x 32 ci of tap (tap_r, tap_s)
               tc::tma_load_im2col_4d(stage + kABytes + pnl * 4096, &tmap_g, bar, n0 + pnl * 32, w, h, n, (uint16_t)tap_s,
@@ -349,13 +363,13 @@ EncodeIm2colFn encode_im2col_fn() {
 // im2col-mode map over an NHWC fp32 tensor: 32 channels x `pixels` base pixels per load. Base pixels walk
 // [lower, dim - 1 + upper] in w and h with the traversal stride `stride` (= one GEMM row / K index each);
 // filter taps are added as instruction offsets. Out-of-bounds reads return zero.
-int make_map_im2col(CUtensorMap* m, const float* ptr, int N, int H, int W, int C, int lower, int upper, int stride,
-                    int pixels, bool mn_major) {
+int make_map_im2col(CUtensorMap* m, const float* ptr, int N, int H, int W, int C, int lower_w, int lower_h, int upper_w,
+                    int upper_h, int stride, int pixels, bool mn_major) {
   EncodeIm2colFn fn = encode_im2col_fn();
   if (!fn) return MLA_E_NODEVICE;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  int lo[2] = {lower, lower}, up[2] = {upper, upper};
+  int lo[2] = {lower_w, lower_h}, up[2] = {upper_w, upper_h};   // {W, H} order (as the instruction's offsets)
   cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, lo, up, 32u,
                   (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -405,9 +419,16 @@ int launch(const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams
   return 0;
 }
 
+// all R x S taps: weights of filter position (i, j), instruction offset (i, j) or the flipped one
+void full_taps(ConvGemmParams& p, int R, int S, bool flip) {
+  p.nr = R; p.ns = S;
+  for (int i = 0; i < R; ++i) { p.tap_r[i] = (signed char)i; p.off_r[i] = (signed char)(flip ? R - 1 - i : i); }
+  for (int j = 0; j < S; ++j) { p.tap_s[j] = (signed char)j; p.off_s[j] = (signed char)(flip ? S - 1 - j : j); }
+}
+
 bool conv_shape_ok(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
   return N > 0 && H > 0 && W > 0 && Cin >= 64 && Cin % 64 == 0 && Cout >= 64 && Cout % 64 == 0 && R == S &&
-         (R == 1 || R == 3) && (stride == 1 || stride == 2) && pad >= 0 && pad <= R / 2;
+         (R == 1 || R == 3 || R == 5 || R == 7) && (stride == 1 || stride == 2) && pad >= 0 && pad <= R / 2;
 }
 
 int out_size(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / stride + 1; }
@@ -434,9 +455,10 @@ extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (force_gather()) return BN == 64 ? launch<0, 64, 4, false>(map, map, p, grid, st) : launch<0, 128, 3, false>(map, map, p, grid, st);
   // gathered operand: x, base pixel (ow*stride - pad, oh*stride - pad), taps as offsets
-  p.g_base = -pad; p.g_flip = 0;
+  p.g_base_w = p.g_base_h = -pad;
+  full_taps(p, R, S, false);
   CUtensorMap gmap;
-  rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, pad - (R - 1), stride, 128, false);
+  rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 128, false);
   if (rc) return rc;
   return BN == 64 ? launch<0, 64, 4, true>(map, gmap, p, grid, st) : launch<0, 128, 3, true>(map, gmap, p, grid, st);
 }
@@ -459,15 +481,64 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
   if (rc) return rc;
   dim3 grid((p.M + 127) / 128, Cin / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (stride != 1 || force_gather())   // stride-2 dgrad: the gather has holes -> cp.async gather kernel
+  if (force_gather())
     return BN == 64 ? launch<1, 64, 4, false>(map, map, p, grid, st) : launch<1, 128, 3, false>(map, map, p, grid, st);
-  // stride 1: dgrad is a convolution of dy with the flipped filter: base pixel (w + pad - (S-1), h + pad - (R-1)),
-  // weight tap (r, s) pairs with filter offset (R-1-r, S-1-s)
-  p.g_base = pad - (R - 1); p.g_flip = 1;
-  CUtensorMap gmap;
-  rc = make_map_im2col(&gmap, dy, N, OH, OW, Cout, pad - (R - 1), pad - (R - 1) + (H - OH), 1, 128, false);
-  if (rc) return rc;
-  return BN == 64 ? launch<1, 64, 4, true>(map, gmap, p, grid, st) : launch<1, 128, 3, true>(map, gmap, p, grid, st);
+  if (stride == 1) {
+    // dgrad is a convolution of dy with the flipped filter: base pixel (w + pad - (S-1), h + pad - (R-1)),
+    // weight tap (r, s) pairs with filter offset (R-1-r, S-1-s)
+    p.g_base_w = pad - (S - 1); p.g_base_h = pad - (R - 1);
+    full_taps(p, R, S, true);
+    CUtensorMap gmap;
+    rc = make_map_im2col(&gmap, dy, N, OH, OW, Cout, p.g_base_w, p.g_base_h, p.g_base_w + (W - OW), p.g_base_h + (H - OH),
+                         1, 128, false);
+    if (rc) return rc;
+    return BN == 64 ? launch<1, 64, 4, true>(map, gmap, p, grid, st) : launch<1, 128, 3, true>(map, gmap, p, grid, st);
+  }
+  // stride s: one dense sub-convolution per output parity class (ph, pw). dx[n, i*s+ph, j*s+pw] sums the taps r
+  // with (ph + pad - r) % s == 0, reading dy row i + (ph + pad - r) / s — a stride-1 walk over dy, so the im2col
+  // map applies; rows are scattered to their dx pixels by the epilogue.
+  for (int ph = 0; ph < stride; ++ph) {
+    for (int pw = 0; pw < stride; ++pw) {
+      ConvGemmParams q = p;
+      const int Hs = (H - ph + stride - 1) / stride, Ws = (W - pw + stride - 1) / stride;
+      if (Hs <= 0 || Ws <= 0) continue;
+      q.nr = q.ns = 0;
+      int qr[8], qs[8], lo_h = 1 << 20, lo_w = 1 << 20;
+      for (int r = 0; r < R; ++r) {
+        const int t = ph + pad - r;
+        if (((t % stride) + stride) % stride != 0) continue;
+        qr[q.nr] = (t >= 0 ? t : t - (stride - 1)) / stride;
+        q.tap_r[q.nr] = (signed char)r;
+        lo_h = min(lo_h, qr[q.nr]);
+        ++q.nr;
+      }
+      for (int c = 0; c < S; ++c) {
+        const int t = pw + pad - c;
+        if (((t % stride) + stride) % stride != 0) continue;
+        qs[q.ns] = (t >= 0 ? t : t - (stride - 1)) / stride;
+        q.tap_s[q.ns] = (signed char)c;
+        lo_w = min(lo_w, qs[q.ns]);
+        ++q.ns;
+      }
+      q.OH = Hs; q.OW = Ws; q.M = N * Hs * Ws;
+      q.o_mul = stride; q.o_ph = ph; q.o_pw = pw; q.o_H = H; q.o_W = W;
+      q.KB = q.nr * q.ns * q.kcb;
+      dim3 g((q.M + 127) / 128, Cin / BN);
+      if (q.KB == 0) {
+        if (accumulate) continue;              // nothing to add to these pixels
+        lo_h = lo_w = 0;                       // KB == 0: the kernel only writes zeros
+      }
+      for (int i = 0; i < q.nr; ++i) q.off_r[i] = (signed char)(qr[i] - lo_h);
+      for (int j = 0; j < q.ns; ++j) q.off_s[j] = (signed char)(qs[j] - lo_w);
+      q.g_base_w = lo_w; q.g_base_h = lo_h;
+      CUtensorMap gmap;
+      rc = make_map_im2col(&gmap, dy, N, OH, OW, Cout, lo_w, lo_h, lo_w + Ws - OW, lo_h + Hs - OH, 1, 128, false);
+      if (rc) return rc;
+      rc = BN == 64 ? launch<1, 64, 4, true>(map, gmap, q, g, st) : launch<1, 128, 3, true>(map, gmap, q, g, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
 }
 
 namespace {
@@ -526,9 +597,10 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   if (force_gather()) {
     rc = pl.BN == 64 ? launch<2, 64, 4, false>(map, map, p, grid, st) : launch<2, 128, 3, false>(map, map, p, grid, st);
   } else {
-    p.g_base = -pad; p.g_flip = 0;
+    p.g_base_w = p.g_base_h = -pad;
+    full_taps(p, R, S, false);
     CUtensorMap gmap;
-    rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, pad - (R - 1), stride, 32, true);
+    rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 32, true);
     if (rc) return rc;
     rc = pl.BN == 64 ? launch<2, 64, 4, true>(map, gmap, p, grid, st) : launch<2, 128, 3, true>(map, gmap, p, grid, st);
   }

@@ -74,37 +74,55 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict
 }
 
 // ------------------------------------------------------------------- per-channel reductions
+// One launch per BatchNorm statistic pass: grid (row blocks, 64-channel chunks), block 16 float4 lanes x 16
+// rows. Every block writes its partial sums (double); the LAST block to finish a channel chunk (atomic
+// ticket) adds the partials in block order — fixed order, so the result is deterministic — and runs the
+// finalisation (statistics / running stats, or dgamma / dbeta) for its 64 channels. No second launch.
 // MODE 0: a = x, b = x*x (BN statistics).
 // MODE 1: g = dz * (z > 0 or no mask); a = g, b = g * (y - mean) * invstd (BN backward sums).
+struct BnFinal {
+  long long M;
+  // MODE 0
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var;
+  float momentum, eps;
+  float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
+  // MODE 1
+  float* dgamma; float* dbeta; float* sums;   // sums [2][C]: dbeta, dgamma (read by the apply pass)
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                                      const float* __restrict__ z,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, long long M, int C,
-                                                                     long long rows_per_block, double* __restrict__ part) {
-  extern __shared__ double s_acc[];  // [TY][2][C]
-  const int C4 = C >> 2;
-  const int TY = kRedThreads / C4;
-  const int tx = threadIdx.x % C4, ty = threadIdx.x / C4;
+                                                                     long long rows_per_block, double* __restrict__ part,
+                                                                     unsigned int* __restrict__ counters, BnFinal f) {
+  __shared__ double s_acc[16][2][64];
+  __shared__ double s_fin[2][64];
+  __shared__ int s_last;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int chunk = blockIdx.y, nrb = gridDim.x;
+  const int c0 = chunk * 64 + 4 * tx;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
   double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-  if (ty < TY) {
+  {
     float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
-    if (MODE == 1) { mu = ld4(mean + 4 * tx); is = ld4(invstd + 4 * tx); }
+    if (MODE == 1) { mu = ld4(mean + c0); is = ld4(invstd + c0); }
     long long r = r0 + ty;
     while (r < r1) {
       float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
-      for (int it = 0; it < 32 && r < r1; ++it, r += TY) {   // fp32 for 32 rows, then flush to double
-        const float4 v = ld4(x + r * C + 4 * tx);
+      for (int it = 0; it < 32 && r < r1; ++it, r += 16) {   // fp32 for 32 rows, then flush to double
+        const float4 v = ld4(x + r * C + c0);
         if (MODE == 0) {
           fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
           fb[0] = fmaf(v.x, v.x, fb[0]); fb[1] = fmaf(v.y, v.y, fb[1]);
           fb[2] = fmaf(v.z, v.z, fb[2]); fb[3] = fmaf(v.w, v.w, fb[3]);
         } else {
-          float4 g = ld4(dz + r * C + 4 * tx);
+          float4 g = ld4(dz + r * C + c0);
           if (z != nullptr) {
-            const float4 zz = ld4(z + r * C + 4 * tx);
+            const float4 zz = ld4(z + r * C + c0);
             g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f;
             g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
           }
@@ -118,66 +136,58 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      s_acc[((size_t)ty * 2 + 0) * C + 4 * tx + q] = a[q];
-      s_acc[((size_t)ty * 2 + 1) * C + 4 * tx + q] = b[q];
+      s_acc[ty][0][4 * tx + q] = a[q];
+      s_acc[ty][1][4 * tx + q] = b[q];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kRedThreads) {
-    double s = 0;
-    for (int y = 0; y < TY; ++y) s += s_acc[(size_t)y * 2 * C + i];   // fixed order
-    part[(size_t)blockIdx.x * 2 * C + i] = s;
-  }
-}
-
-// Fixed-order sum of the per-block partials of one channel pair (sum a, sum b): blockDim = (32, kFinY);
-// lane x owns channel c, slice y adds blocks y, y+kFinY, ... and the slices are combined in order.
-constexpr int kFinY = 16;
-__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int nblocks, int C, int c, double& s,
-                                                double& ss) {
-  __shared__ double sh[2][kFinY][33];
-  double a = 0, b = 0;
-  if (c < C) {
-    for (int blk = threadIdx.y; blk < nblocks; blk += kFinY) {
-      a += part[(size_t)blk * 2 * C + c];
-      b += part[(size_t)blk * 2 * C + C + c];
-    }
-  }
-  sh[0][threadIdx.y][threadIdx.x] = a;
-  sh[1][threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  s = 0; ss = 0;
-  if (threadIdx.y == 0) {
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    double sum = 0;
 #pragma unroll
-    for (int y = 0; y < kFinY; ++y) { s += sh[0][y][threadIdx.x]; ss += sh[1][y][threadIdx.x]; }
+    for (int y = 0; y < 16; ++y) sum += s_acc[y][which][c];   // fixed order
+    part[((size_t)chunk * nrb + blockIdx.x) * 128 + threadIdx.x] = sum;
   }
-}
-
-// stats finalize: mean, biased var -> invstd, scale = gamma*invstd, shift = beta - mean*scale;
-// running stats: momentum update with the UNBIASED variance (torch BatchNorm2d semantics).
-__global__ void bn_stats_finalize_kernel(const double* __restrict__ part, int nblocks, long long M, int C,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         float* __restrict__ running_mean, float* __restrict__ running_var,
-                                         float momentum, float eps, float* __restrict__ mean_out,
-                                         float* __restrict__ invstd_out, float* __restrict__ scale_out,
-                                         float* __restrict__ shift_out) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s, ss;
-  reduce_partials(part, nblocks, C, c, s, ss);
-  if (c >= C || threadIdx.y != 0) return;
-  const double mean = s / (double)M;
-  double var = ss / (double)M - mean * mean;
-  if (var < 0) var = 0;
-  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float sc = gamma[c] * invstd;
-  mean_out[c] = (float)mean;
-  invstd_out[c] = invstd;
-  scale_out[c] = sc;
-  shift_out[c] = beta[c] - (float)mean * sc;
-  if (running_mean != nullptr) {
-    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[chunk], 1u) == (unsigned)(nrb - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 128) {
+    const double* pp = part + (size_t)chunk * nrb * 128 + threadIdx.x;
+    double sum = 0;
+#pragma unroll 8
+    for (int blk = 0; blk < nrb; ++blk) sum += __ldcg(pp + (size_t)blk * 128);   // block order: deterministic
+    s_fin[threadIdx.x >> 6][threadIdx.x & 63] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) counters[chunk] = 0;   // leave the workspace reusable
+  if (threadIdx.x >= 64) return;
+  const int c = chunk * 64 + threadIdx.x;
+  const double sa = s_fin[0][threadIdx.x], sb = s_fin[1][threadIdx.x];
+  if (MODE == 0) {
+    // mean, biased var -> invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats: momentum
+    // update with the UNBIASED variance (torch BatchNorm2d semantics)
+    const double mu = sa / (double)f.M;
+    double var = sb / (double)f.M - mu * mu;
+    if (var < 0) var = 0;
+    const float is = (float)(1.0 / sqrt(var + (double)f.eps));
+    const float sc = f.gamma[c] * is;
+    f.mean_out[c] = (float)mu;
+    f.invstd_out[c] = is;
+    f.scale_out[c] = sc;
+    f.shift_out[c] = f.beta[c] - (float)mu * sc;
+    if (f.running_mean != nullptr) {
+      const double unbiased = f.M > 1 ? var * (double)f.M / (double)(f.M - 1) : var;
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * (float)mu;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+    }
+  } else {
+    if (f.dbeta) f.dbeta[c] = (float)sa;
+    if (f.dgamma) f.dgamma[c] = (float)sb;
+    f.sums[c] = (float)sa;
+    f.sums[C + c] = (float)sb;
   }
 }
 
@@ -210,19 +220,6 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     st4(out + 4 * i, tf32r4(o));   // consumers are tcgen05 convolutions (and the residual add / pooling)
   }
-}
-
-// BN backward finalize: dgamma = sum g*xhat, dbeta = sum g (fixed-order over block partials)
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblocks, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ sums /*[2][C]: dbeta, dgamma*/) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s, ss;
-  reduce_partials(part, nblocks, C, c, s, ss);
-  if (c >= C || threadIdx.y != 0) return;
-  if (dbeta) dbeta[c] = (float)s;
-  if (dgamma) dgamma[c] = (float)ss;
-  sums[c] = (float)s;
-  sums[C + c] = (float)ss;
 }
 
 // dy = gamma*invstd * (g - dbeta/M - xhat*dgamma/M), g = dz*(z>0); optionally also writes g.
@@ -352,22 +349,23 @@ int ew_grid(long long n, int threads) {
 }
 
 struct RedPlan {
-  int nblocks;
+  int nrb, chunks;          // row blocks x 64-channel chunks
   long long rows_per_block;
-  size_t smem;
+  size_t off_sums, off_part, bytes;   // workspace layout: [counters | sums 2C floats | partials]
 };
 int red_plan(long long M, int C, RedPlan* pl) {
-  if (M < 1 || C < 16 || (C & 3) || C > 1024 || (kRedThreads % (C / 4)) != 0) return MLA_E_SHAPE;
+  if (M < 1 || C < 64 || (C & 63) || C > 4096) return MLA_E_SHAPE;
   const mla::DeviceInfo& di = mla::device_info();
   if (di.ok != 1) return di.ok;
-  const int TY = kRedThreads / (C / 4);
-  long long nb = (M + (long long)TY * 16 - 1) / ((long long)TY * 16);
-  const long long cap = (long long)di.sm_count * 4;
-  if (nb > cap) nb = cap;
-  if (nb < 1) nb = 1;
-  pl->rows_per_block = (M + nb - 1) / nb;
-  pl->nblocks = (int)((M + pl->rows_per_block - 1) / pl->rows_per_block);
-  pl->smem = (size_t)TY * 2 * C * sizeof(double);
+  pl->chunks = C / 64;
+  long long nrb = (M + 127) / 128;                                   // >= 8 rows per thread
+  const long long cap = max(1, 2 * di.sm_count / pl->chunks);
+  if (nrb > cap) nrb = cap;
+  pl->rows_per_block = (M + nrb - 1) / nrb;
+  pl->nrb = (int)((M + pl->rows_per_block - 1) / pl->rows_per_block);
+  pl->off_sums = mla::align_up((size_t)pl->chunks * sizeof(unsigned int), 256);
+  pl->off_part = pl->off_sums + mla::align_up(2 * (size_t)C * sizeof(float), 256);
+  pl->bytes = pl->off_part + (size_t)pl->chunks * pl->nrb * 128 * sizeof(double);
   return 0;
 }
 
@@ -406,7 +404,7 @@ extern "C" int mla_pad_rows(const float* src, float* dst, int rows, int k, int k
 extern "C" size_t mla_bn_workspace_bytes(long long M, int C) {
   RedPlan pl;
   if (red_plan(M, C, &pl) != 0) return 0;
-  return (size_t)pl.nblocks * 2 * C * sizeof(double) + 2 * (size_t)C * sizeof(float) + 256;
+  return pl.bytes;
 }
 
 extern "C" int mla_bn_train_stats(const float* y, long long M, int C, const float* gamma, const float* beta,
@@ -417,20 +415,15 @@ extern "C" int mla_bn_train_stats(const float* y, long long M, int C, const floa
   RedPlan pl;
   int rc = red_plan(M, C, &pl);
   if (rc) return rc;
-  if (!ws || ws_bytes < mla_bn_workspace_bytes(M, C)) return MLA_E_WORKSPACE;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double* part = static_cast<double*>(ws);
-  static std::atomic<int> cfg{0};
-  if (!cfg.load()) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(channel_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    MLA_CUDA_TRY(cudaFuncSetAttribute(channel_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    cfg.store(1);
-  }
-  channel_reduce_kernel<0><<<pl.nblocks, kRedThreads, pl.smem, st>>>(y, nullptr, nullptr, nullptr, nullptr, M, C,
-                                                                    pl.rows_per_block, part);
-  MLA_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(C + 31) / 32, dim3(32, kFinY), 0, st>>>(part, pl.nblocks, M, C, gamma, beta, running_mean, running_var,
-                                                           momentum, eps, mean_out, invstd_out, scale_out, shift_out);
+  if (!ws || ws_bytes < pl.bytes) return MLA_E_WORKSPACE;
+  char* base = static_cast<char*>(ws);
+  BnFinal f{};
+  f.M = M; f.gamma = gamma; f.beta = beta; f.running_mean = running_mean; f.running_var = running_var;
+  f.momentum = momentum; f.eps = eps; f.mean_out = mean_out; f.invstd_out = invstd_out; f.scale_out = scale_out;
+  f.shift_out = shift_out;
+  channel_reduce_kernel<0><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, nullptr, nullptr, nullptr, nullptr, M, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
+      reinterpret_cast<unsigned int*>(base), f);
   MLA_LAUNCH_CHECK();
   return 0;
 }
@@ -463,18 +456,15 @@ extern "C" int mla_bn_backward(const float* dz, const float* z, const float* y, 
   RedPlan pl;
   int rc = red_plan(M, C, &pl);
   if (rc) return rc;
-  if (!ws || ws_bytes < mla_bn_workspace_bytes(M, C)) return MLA_E_WORKSPACE;
+  if (!ws || ws_bytes < pl.bytes) return MLA_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double* part = static_cast<double*>(ws);
-  float* sums = reinterpret_cast<float*>(static_cast<char*>(ws) + (size_t)pl.nblocks * 2 * C * sizeof(double));
-  static std::atomic<int> cfg{0};
-  if (!cfg.load()) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(channel_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    cfg.store(1);
-  }
-  channel_reduce_kernel<1><<<pl.nblocks, kRedThreads, pl.smem, st>>>(y, dz, z, mean, invstd, M, C, pl.rows_per_block, part);
-  MLA_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, kFinY), 0, st>>>(part, pl.nblocks, C, dgamma, dbeta, sums);
+  char* base = static_cast<char*>(ws);
+  float* sums = reinterpret_cast<float*>(base + pl.off_sums);
+  BnFinal f{};
+  f.M = M; f.dgamma = dgamma; f.dbeta = dbeta; f.sums = sums;
+  channel_reduce_kernel<1><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, st>>>(
+      y, dz, z, mean, invstd, M, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
+      reinterpret_cast<unsigned int*>(base), f);
   MLA_LAUNCH_CHECK();
   const long long n4 = M * (C / 4);
   bn_bwd_apply_kernel<<<ew_grid(n4, 256), 256, 0, st>>>(dz, z, y, mean, invstd, gamma, sums, 1.f / (float)M, dy, g_out, n4,

@@ -143,7 +143,7 @@ class ResNetPlan:
         self.nbt = [b.bn.num_batches_tracked for b in self.bns if b.bn.num_batches_tracked is not None]
         nb = max(self.L.mla_bn_workspace_bytes(self.M0, 64),
                  max(self.L.mla_bn_workspace_bytes(N * b["ho"] * b["wo"], b["cout"]) for b in self.blocks))
-        self.bn_ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        self.bn_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)      # ticket counters start at 0 (mla_b200.h)
         nw = self.L.mla_conv2d_wgrad_workspace_bytes(N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
         for b in self.blocks:
             nw = max(nw, self.L.mla_conv2d_wgrad_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3,
@@ -271,10 +271,13 @@ class ResNetPlan:
                 self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st)
                 self._wgrad(xin, dyd, _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0, st)
                 dx = self.tmp("dXa", xin.shape)         # xin.shape != out.shape here, so never aliases dout
-                self._dgrad(dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, False, st)
+                # the 3x3 dgrad touches every pixel of dx and goes first; the 1x1/2 shortcut then ADDS into the
+                # one output parity class it reaches (its other classes are skipped, not zero-filled)
+                self._dgrad(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, False, st)
+                self._dgrad(dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, True, st)
             else:
                 dx = g                                  # identity shortcut: dX starts as the masked gradient
-            self._dgrad(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
+                self._dgrad(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
             dout = dx
         # stem: maxpool+relu backward, BN backward, weight gradient (no dgrad: the input needs none)
         g0 = self.tmp("g0", self.y0.shape)

@@ -27,7 +27,7 @@ def check_bn(N, H, W, C, relu_mask=True, res=True):
     rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
     rm2, rv2 = rm.clone(), rv.clone()
     mean, invstd, scale, shift = (torch.empty(C, device=dev) for _ in range(4))
-    ws = torch.empty(L.mla_bn_workspace_bytes(M, C), dtype=torch.uint8, device=dev)
+    ws = torch.zeros(L.mla_bn_workspace_bytes(M, C), dtype=torch.uint8, device=dev)
     rc = L.mla_bn_train_stats(P(y), M, C, P(gamma), P(beta), P(rm), P(rv), 0.1, 1e-5, P(mean), P(invstd), P(scale), P(shift),
                               P(ws), ws.numel(), st())
     assert rc == 0, rc
