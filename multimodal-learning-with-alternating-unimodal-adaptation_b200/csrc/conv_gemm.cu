@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     }
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
+      if (MODE == 2 && n0 + c >= p.CinW) break;   // partial last ci tile (Cin % BN == 32)
       uint32_t v[32];
       if (KB > 0) {
         tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
@@ -263,7 +264,9 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
               tc::tma_load_2d(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32);
           }
         } else {
-          tc::mbar_arrive_expect_tx(bar, kABytes + tx_gather);
+          // panels of a partial last ci tile are neither loaded nor stored (their accumulator columns are garbage)
+          const int npnl = IM2COL ? min(BN / 32, (p.CinW - n0) / 32) : BN / 32;
+          tc::mbar_arrive_expect_tx(bar, kABytes + (IM2COL ? (uint32_t)npnl * 4096u : 0u));
 #pragma unroll
           for (int pnl = 0; pnl < 4; ++pnl)  // box {32 co, 32 pixel rows}
             tc::tma_load_2d(stage + pnl * 4096, &tmap, bar, m0 + pnl * 32, (kb_begin + kb) * 32);
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
             const int w = ow * p.mul + p.g_base_w, h = (t % p.OH) * p.mul + p.g_base_h, n = t / p.OH;
 #pragma unroll
             for (int pnl = 0; pnl < BN / 32; ++pnl)  // 32 pixels x 32 ci of tap (tap_r, tap_s)
-              tc::tma_load_im2col_4d(stage + kABytes + pnl * 4096, &tmap_g, bar, n0 + pnl * 32, w, h, n, (uint16_t)tap_s,
+              if (pnl < npnl) tc::tma_load_im2col_4d(stage + kABytes + pnl * 4096, &tmap_g, bar, n0 + pnl * 32, w, h, n, (uint16_t)tap_s,
                                      (uint16_t)tap_r);
           }
         }
@@ -426,8 +429,9 @@ void full_taps(ConvGemmParams& p, int R, int S, bool flip) {
   for (int j = 0; j < S; ++j) { p.tap_s[j] = (signed char)j; p.off_s[j] = (signed char)(flip ? S - 1 - j : j); }
 }
 
-bool conv_shape_ok(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
-  return N > 0 && H > 0 && W > 0 && Cin >= 64 && Cin % 64 == 0 && Cout >= 64 && Cout % 64 == 0 && R == S &&
+// cin_mult: 64 where Cin is tiled as a GEMM N dimension without a tail guard (dgrad), 32 otherwise
+bool conv_shape_ok(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int cin_mult = 64) {
+  return N > 0 && H > 0 && W > 0 && Cin >= cin_mult && Cin % cin_mult == 0 && Cout >= 64 && Cout % 64 == 0 && R == S &&
          (R == 1 || R == 3 || R == 5 || R == 7) && (stride == 1 || stride == 2) && pad >= 0 && pad <= R / 2;
 }
 
@@ -438,7 +442,7 @@ int out_size(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / str
 extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int R,
                                 int S, int stride, int pad, void* stream) {
   if (!x || !w || !y || !mla::aligned16(x) || !mla::aligned16(w) || !mla::aligned16(y)) return MLA_E_BADARG;
-  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad)) return MLA_E_SHAPE;
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad, 32)) return MLA_E_SHAPE;
   const mla::DeviceInfo& di = mla::device_info();
   if (di.ok != 1) return di.ok;
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
@@ -548,7 +552,7 @@ struct WgradPlan {
   size_t ws_bytes;
 };
 int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, WgradPlan* pl) {
-  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad)) return MLA_E_SHAPE;
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad, 32)) return MLA_E_SHAPE;
   const mla::DeviceInfo& di = mla::device_info();
   if (di.ok != 1) return di.ok;
   pl->OH = out_size(H, R, stride, pad);
@@ -557,7 +561,7 @@ int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
   if (pl->OH <= 0 || pl->OW <= 0 || pl->M > 0x7fffffffLL) return MLA_E_SHAPE;
   pl->BN = (Cin % 128 == 0) ? 128 : 64;
   pl->KBtot = (int)((pl->M + 31) / 32);
-  const int tiles = R * S * (Cin / pl->BN) * ((Cout + 127) / 128);
+  const int tiles = R * S * ((Cin + pl->BN - 1) / pl->BN) * ((Cout + 127) / 128);
   int splits = (4 * di.sm_count + tiles - 1) / tiles;       // ~4 CTAs per SM in total
   splits = max(1, min(splits, pl->KBtot / 8 > 0 ? pl->KBtot / 8 : 1));   // >= 8 k-blocks per split
   pl->kb_per_split = (pl->KBtot + splits - 1) / splits;
@@ -592,9 +596,10 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   CUtensorMap map;
   rc = make_map_2d(&map, dy, pl.M, Cout, 32, true);
   if (rc) return rc;
-  dim3 grid(Cin / pl.BN, (Cout + 127) / 128, R * S * pl.splits);
+  dim3 grid((Cin + pl.BN - 1) / pl.BN, (Cout + 127) / 128, R * S * pl.splits);   // last ci tile may be partial
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (force_gather()) {
+    if (Cin % pl.BN != 0) return MLA_E_SHAPE;
     rc = pl.BN == 64 ? launch<2, 64, 4, false>(map, map, p, grid, st) : launch<2, 128, 3, false>(map, map, p, grid, st);
   } else {
     p.g_base_w = p.g_base_h = -pad;

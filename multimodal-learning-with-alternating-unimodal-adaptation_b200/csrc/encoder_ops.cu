@@ -35,27 +35,47 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
 // col[m][k], m = (n, oh, ow), k = (r*S + s)*Cin + ci for k < R*S*Cin, zero for the pad columns.
 // Input element (n, ci, h, w) lives at in[(n / T)*sB + (n % T)*sT + ci*sC + h*W + w] (raw NCHW /
 // NCTHW tensors: the frame fold of backbone.py:144-147 is pure index arithmetic here).
-__global__ void stem_im2col_kernel(const float* __restrict__ in, float* __restrict__ col, int N, int T, long long sB,
-                                   long long sT, long long sC, int Cin, int H, int W, int OH, int OW, int R, int S,
-                                   int stride, int pad, int K, int Kp) {
-  const long long total = (long long)N * OH * OW * Kp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kp);
-    const long long m = i / Kp;
-    float v = 0.f;
+// One block per output row (n, oh): the R input rows of every channel are staged in shared memory
+// (coalesced, zero-padded left/right/top/bottom), a k -> offset table replaces the per-element
+// div/mod, and the row's OW x Kp outputs leave as coalesced float4 stores. HBM-bound by the col write.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ in, float* __restrict__ col, int T,
+                                                          long long sB, long long sT, long long sC, int Cin, int H, int W,
+                                                          int OH, int OW, int R, int S, int stride, int pad, int K, int Kp) {
+  extern __shared__ __align__(16) float sm[];
+  const int Wp = W + 2 * pad + 2;                  // padded row pitch (+2 keeps the last window in range)
+  int* koff = reinterpret_cast<int*>(sm + (((size_t)Cin * R * Wp + 3) & ~(size_t)3));
+  const int n = blockIdx.x / OH, oh = blockIdx.x - n * OH;
+  const float* src = in + (long long)(n / T) * sB + (long long)(n % T) * sT;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    int o = -1;
     if (k < K) {
-      const int ci = k % Cin;
-      const int rs = k / Cin;
-      const int s = rs % S, r = rs / S;
-      const int ow = (int)(m % OW);
-      const long long t = m / OW;
-      const int oh = (int)(t % OH);
-      const int n = (int)(t / OH);
-      const int h = oh * stride + r - pad, w = ow * stride + s - pad;
-      if (h >= 0 && h < H && w >= 0 && w < W)
-        v = in[(long long)(n / T) * sB + (long long)(n % T) * sT + (long long)ci * sC + (long long)h * W + w];
+      const int ci = k % Cin, rs = k / Cin;
+      o = (ci * R + rs / S) * Wp + rs % S;
     }
-    col[i] = tf32r(v);
+    koff[k] = o;
+  }
+  const int rows = Cin * R;
+  for (int i = threadIdx.x; i < rows * Wp; i += blockDim.x) {
+    const int row = i / Wp, wp = i - row * Wp;
+    const int ci = row / R, r = row - ci * R;
+    const int h = oh * stride + r - pad, w = wp - pad;
+    float v = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) v = src[(long long)ci * sC + (long long)h * W + w];
+    sm[i] = tf32r(v);
+  }
+  __syncthreads();
+  const int K4 = Kp >> 2;
+  float* dst = col + (long long)blockIdx.x * OW * Kp;
+  for (int i = threadIdx.x; i < OW * K4; i += blockDim.x) {
+    const int ow = i / K4, k = (i - ow * K4) * 4;
+    const int base = ow * stride;
+    const int4 o = *reinterpret_cast<const int4*>(koff + k);
+    float4 v;
+    v.x = o.x >= 0 ? sm[o.x + base] : 0.f;
+    v.y = o.y >= 0 ? sm[o.y + base] : 0.f;
+    v.z = o.z >= 0 ? sm[o.z + base] : 0.f;
+    v.w = o.w >= 0 ? sm[o.w + base] : 0.f;
+    st4(dst + 4 * (long long)i, v);
   }
 }
 
@@ -377,11 +397,18 @@ int red_plan(long long M, int C, RedPlan* pl) {
 
 extern "C" int mla_stem_im2col(const float* in, float* col, int N, int T, long long sB, long long sT, long long sC, int Cin,
                                int H, int W, int R, int S, int stride, int pad, int Kp, void* stream) {
-  if (!in || !col || N < 1 || T < 1 || Cin < 1 || Kp < R * S * Cin) return MLA_E_BADARG;
+  if (!in || !col || N < 1 || T < 1 || Cin < 1 || Kp < R * S * Cin || (Kp & 3) || !mla::aligned16(col)) return MLA_E_BADARG;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
-  const long long total = (long long)N * OH * OW * Kp;
-  stem_im2col_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, col, N, T, sB, sT, sC, Cin, H, W, OH, OW, R, S, stride, pad, R * S * Cin, Kp);
+  if (OH < 1 || OW < 1) return MLA_E_SHAPE;
+  const size_t smem = ((((size_t)Cin * R * (W + 2 * pad + 2) + 3) & ~(size_t)3) + (size_t)Kp) * sizeof(float);
+  if (smem > 200 * 1024) return MLA_E_SHAPE;
+  static std::atomic<int> cfg{0};
+  if (!cfg.load()) {
+    MLA_CUDA_TRY(cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg.store(1);
+  }
+  stem_im2col_kernel<<<N * OH, 256, smem, static_cast<cudaStream_t>(stream)>>>(in, col, T, sB, sT, sC, Cin, H, W, OH, OW, R, S,
+                                                                              stride, pad, R * S * Cin, Kp);
   MLA_LAUNCH_CHECK();
   return 0;
 }

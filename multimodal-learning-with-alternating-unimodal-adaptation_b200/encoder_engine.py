@@ -21,7 +21,7 @@ import torch
 from . import _lib
 
 BACKEND = "native-tcgen05"
-_STEM_KP = {1: 64, 3: 192}     # K = 49*Cin padded to a multiple of 64 (tcgen05 K-blocks of 32, N tiles of 64)
+_STEM_KP = {1: 64, 3: 160}     # K = 49*Cin padded to a multiple of 32 (tcgen05 k-blocks of 32 tf32)
 
 
 def _p(t):
