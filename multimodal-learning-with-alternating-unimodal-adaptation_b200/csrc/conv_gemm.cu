@@ -95,10 +95,16 @@ __device__ __forceinline__ void gather_segment(const ConvGemmParams& p, uint32_t
     tc::cp_async16(dst_row + (MN_MAJOR ? tc::swz32(j, row) : tc::swz16(j, row)), src + (bytes ? 4 * j : 0), bytes);
 }
 
-template <int MODE, int BN, int STAGES, bool IM2COL>
+// NT > 1 (wgrad only, Cin == BN): one CTA accumulates NT consecutive filter taps side by side — the N tile is
+// NT x BN columns of the flattened (tap, ci) axis of dw, so dy (the A operand) is loaded once for NT taps.
+template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ CUtensorMap tmap_g, ConvGemmParams p) {
-  constexpr uint32_t kBBytes = BN * 128;
+  static_assert(NT == 1 || (MODE == 2 && IM2COL), "multi-tap tiles exist for the im2col wgrad only");
+  constexpr int NTOT = BN * NT;                                     // accumulator columns
+  constexpr uint32_t kTmemCols = NTOT <= 64 ? 64 : (NTOT <= 128 ? 128 : 256);
+  static_assert(NTOT <= 256, "one UMMA covers at most 256 columns");
+  constexpr uint32_t kBBytes = NTOT * 128;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr int LAG = STAGES - 1;
   extern __shared__ uint8_t smem_raw[];
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     if (IM2COL) tc::tma_prefetch_desc(&tmap_g);
   }
   if (warp == 5) {
-    tc::tmem_alloc(tc::smem_u32(&tmem_slot), BN);
+    tc::tmem_alloc(tc::smem_u32(&tmem_slot), kTmemCols);
     tc::tmem_relinquish();
   }
   tc::tc_fence_before();
@@ -136,8 +142,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   if (MODE == 2) {
     n0 = blockIdx.x * BN;    // ci tile
     m0 = blockIdx.y * 128;   // co tile
-    const int tap = blockIdx.z / p.splits;
-    split = blockIdx.z - tap * p.splits;
+    const int tap = (blockIdx.z / p.splits) * NT;   // first of the NT taps of this CTA
+    split = blockIdx.z - (blockIdx.z / p.splits) * p.splits;
     tap_r = tap / p.S;
     tap_s = tap - tap_r * p.S;
     kb_begin = split * p.kb_per_split;
@@ -205,8 +211,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       }
     }
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      if (MODE == 2 && n0 + c >= p.CinW) break;   // partial last ci tile (Cin % BN == 32)
+    for (int c = 0; c < NTOT; c += 32) {
+      if (MODE == 2 && NT == 1 && n0 + c >= p.CinW) break;   // partial last ci tile (Cin % BN == 32)
       uint32_t v[32];
       if (KB > 0) {
         tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
@@ -264,21 +270,29 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
               tc::tma_load_2d(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32);
           }
         } else {
-          // panels of a partial last ci tile are neither loaded nor stored (their accumulator columns are garbage)
+          // panels of a partial last ci tile / of co rows beyond Cout are neither loaded nor stored (their
+          // accumulator columns / rows are garbage that nobody reads)
           const int npnl = IM2COL ? min(BN / 32, (p.CinW - n0) / 32) : BN / 32;
-          tc::mbar_arrive_expect_tx(bar, kABytes + (IM2COL ? (uint32_t)npnl * 4096u : 0u));
+          const int napnl = IM2COL ? min(4, (p.Cout - m0 + 31) / 32) : 4;
+          tc::mbar_arrive_expect_tx(bar, (uint32_t)napnl * 4096u + (IM2COL ? (uint32_t)(npnl * NT) * 4096u : 0u));
 #pragma unroll
           for (int pnl = 0; pnl < 4; ++pnl)  // box {32 co, 32 pixel rows}
-            tc::tma_load_2d(stage + pnl * 4096, &tmap, bar, m0 + pnl * 32, (kb_begin + kb) * 32);
+            if (pnl < napnl) tc::tma_load_2d(stage + pnl * 4096, &tmap, bar, m0 + pnl * 32, (kb_begin + kb) * 32);
           if (IM2COL) {
             const int pix = (kb_begin + kb) * 32;
             const int ow = pix % p.OW;
             const int t = pix / p.OW;
             const int w = ow * p.mul + p.g_base_w, h = (t % p.OH) * p.mul + p.g_base_h, n = t / p.OH;
 #pragma unroll
-            for (int pnl = 0; pnl < BN / 32; ++pnl)  // 32 pixels x 32 ci of tap (tap_r, tap_s)
-              if (pnl < npnl) tc::tma_load_im2col_4d(stage + kABytes + pnl * 4096, &tmap_g, bar, n0 + pnl * 32, w, h, n, (uint16_t)tap_s,
-                                     (uint16_t)tap_r);
+            for (int tp = 0; tp < NT; ++tp) {
+              const int tr = NT == 1 ? tap_r : (tap_r * p.S + tap_s + tp) / p.S;
+              const int ts = NT == 1 ? tap_s : (tap_r * p.S + tap_s + tp) - tr * p.S;
+#pragma unroll
+              for (int pnl = 0; pnl < BN / 32; ++pnl)  // 32 pixels x 32 ci of filter tap (tr, ts)
+                if (pnl < npnl)
+                  tc::tma_load_im2col_4d(stage + kABytes + (tp * (BN / 32) + pnl) * 4096, &tmap_g, bar, n0 + pnl * 32, w, h, n,
+                                         (uint16_t)ts, (uint16_t)tr);
+            }
           }
         }
       }
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   } else {
     // ===================== MMA issuer =====================
     if (lane == 0 && KB > 0) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(128, BN, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0);
+      constexpr uint32_t idesc = tc::make_idesc_tf32(128, NTOT, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0);
       constexpr bool a_mn = (MODE == 2), b_mn = (MODE != 0);
       constexpr uint32_t a_lbo = a_mn ? 4096u : 16u, b_lbo = b_mn ? 4096u : 16u;
       constexpr uint32_t a_sbo = a_mn ? 512u : 1024u, b_sbo = b_mn ? 512u : 1024u;
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, BN);
+  if (warp == 5) tc::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // Fixed-order reduction of split-K partials: dw[i] = sum_s part[s][i].
@@ -407,16 +421,16 @@ int make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols
   return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
 }
 
-template <int MODE, int BN, int STAGES, bool IM2COL>
+template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1>
 int launch(const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (kABytes + BN * 128) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (kABytes + BN * NT * 128) + 1024;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES, IM2COL>,
+    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.store(1, std::memory_order_release);
   }
-  conv_gemm_kernel<MODE, BN, STAGES, IM2COL><<<grid, kThreads, smem, st>>>(map, gmap, p);
+  conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT><<<grid, kThreads, smem, st>>>(map, gmap, p);
   MLA_CUDA_TRY(cudaGetLastError());
   mla::count_launch();
   return 0;
@@ -547,7 +561,7 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
 
 namespace {
 struct WgradPlan {
-  int BN, splits, kb_per_split, KBtot, OH, OW;
+  int BN, NT, splits, kb_per_split, KBtot, OH, OW;
   long long M;
   size_t ws_bytes;
 };
@@ -561,8 +575,12 @@ int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
   if (pl->OH <= 0 || pl->OW <= 0 || pl->M > 0x7fffffffLL) return MLA_E_SHAPE;
   pl->BN = (Cin % 128 == 0) ? 128 : 64;
   pl->KBtot = (int)((pl->M + 31) / 32);
-  const int tiles = R * S * ((Cin + pl->BN - 1) / pl->BN) * ((Cout + 127) / 128);
-  int splits = (4 * di.sm_count + tiles - 1) / tiles;       // ~4 CTAs per SM in total
+  // 64-channel inputs with a 3-wide filter: one CTA takes a whole filter row (3 taps, N = 192)
+  pl->NT = (Cin == 64 && S == 3 && !force_gather()) ? 3 : 1;
+  const int tiles = (R * S / pl->NT) * ((Cin + pl->BN - 1) / pl->BN) * ((Cout + 127) / 128);
+  static const int waves3 = [] { const char* e = getenv("MLA_WGRAD_WAVES"); return e ? atoi(e) : 2; }();
+  const int target = (pl->NT == 3 ? waves3 : 4) * di.sm_count;   // CTAs in total (2 are resident per SM)
+  int splits = (target + tiles - 1) / tiles;
   splits = max(1, min(splits, pl->KBtot / 8 > 0 ? pl->KBtot / 8 : 1));   // >= 8 k-blocks per split
   pl->kb_per_split = (pl->KBtot + splits - 1) / splits;
   pl->splits = (pl->KBtot + pl->kb_per_split - 1) / pl->kb_per_split;
@@ -596,7 +614,7 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   CUtensorMap map;
   rc = make_map_2d(&map, dy, pl.M, Cout, 32, true);
   if (rc) return rc;
-  dim3 grid((Cin + pl.BN - 1) / pl.BN, (Cout + 127) / 128, R * S * pl.splits);   // last ci tile may be partial
+  dim3 grid((Cin + pl.BN - 1) / pl.BN, (Cout + 127) / 128, (R * S / pl.NT) * pl.splits);   // last ci tile may be partial
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (force_gather()) {
     if (Cin % pl.BN != 0) return MLA_E_SHAPE;
@@ -607,7 +625,8 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
     CUtensorMap gmap;
     rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 32, true);
     if (rc) return rc;
-    rc = pl.BN == 64 ? launch<2, 64, 4, true>(map, gmap, p, grid, st) : launch<2, 128, 3, true>(map, gmap, p, grid, st);
+    rc = pl.NT == 3 ? launch<2, 64, 2, true, 3>(map, gmap, p, grid, st)
+         : pl.BN == 64 ? launch<2, 64, 4, true>(map, gmap, p, grid, st) : launch<2, 128, 3, true>(map, gmap, p, grid, st);
   }
   if (rc) return rc;
   if (pl.splits > 1) {

@@ -91,6 +91,15 @@ def all_gather_rows(t):
     return torch.cat(out, dim=0)
 
 
+def broadcast_buffers_(module, src=0):
+    """BatchNorm running statistics are per-rank during training (as under nn.DataParallel, where only replica
+    0's survive, main.py:732); evaluation must use ONE set on every rank: rank `src`'s."""
+    if not is_dist():
+        return
+    for b in module.buffers():
+        dist.broadcast(b, src=src)
+
+
 def params_checksum(t):
     """Order-independent integer checksum of a tensor's bits (cross-rank bit-identity checks)."""
     return int(t.detach().contiguous().view(torch.int32).to(torch.int64).sum().item())

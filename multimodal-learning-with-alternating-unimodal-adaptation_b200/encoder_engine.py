@@ -28,6 +28,29 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+# Optional per-launch timing of the convolution kernels (bench.py's roofline leg): when CONV_TIMING is a
+# list, every conv call is bracketed by CUDA events on the launching stream and appended as
+# (kind, algorithmic FLOPs, start event, end event). Off (None) in normal operation.
+CONV_TIMING = None
+
+
+def _conv_timer_begin():
+    if CONV_TIMING is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _conv_timer_end(e0, kind, N, H, W, Cin, Cout, R, stride, pad):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    CONV_TIMING.append((kind, 2.0 * N * OH * OW * Cout * Cin * R * R, e0, e1))
+
+
 def _chk(rc, what):
     if rc != 0:
         _lib.check(rc, what)
@@ -166,16 +189,22 @@ class ResNetPlan:
         off = self.woff.get(id(w))
         return w.data_ptr() if off is None else self.wr.data_ptr() + 4 * off
 
-    def _conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st):
+    def _conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
+        t = _conv_timer_begin()
         _chk(self.L.mla_conv2d_fprop(_p(x), self._wptr(w), _p(y), N, H, W, Cin, Cout, R, R, stride, pad, st), "mla_conv2d_fprop")
+        _conv_timer_end(t, "fprop", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
 
     def _dgrad(self, dy, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
+        t = _conv_timer_begin()
         _chk(self.L.mla_conv2d_dgrad(_p(dy), self._wptr(w), _p(dx), N, H, W, Cin, Cout, R, R, stride, pad, 1 if acc else 0, st),
              "mla_conv2d_dgrad")
+        _conv_timer_end(t, "dgrad", N, H, W, Cin, Cout, R, stride, pad)
 
-    def _wgrad(self, x, dy, dw, N, H, W, Cin, Cout, R, stride, pad, st):
+    def _wgrad(self, x, dy, dw, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
+        t = _conv_timer_begin()
         _chk(self.L.mla_conv2d_wgrad(_p(x), _p(dy), _p(dw), N, H, W, Cin, Cout, R, R, stride, pad, _p(self.wg_ws),
                                      self.wg_ws.numel(), st), "mla_conv2d_wgrad")
+        _conv_timer_end(t, "wgrad", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
 
     def _bn_coeffs(self, y, M, b, training, st):
         bn = b.bn
@@ -210,7 +239,7 @@ class ResNetPlan:
         _chk(L.mla_stem_im2col(_p(x), _p(self.col), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp,
                                st), "mla_stem_im2col")
         _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
-        self._conv(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st)
+        self._conv(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st, k_alg=K)
         self._bn_coeffs(self.y0, self.M0, self.bn0, training, st)
         _chk(L.mla_bn_relu_maxpool(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.idx0), N,
                                    self.OH0, self.OW0, 64, st), "mla_bn_relu_maxpool")
@@ -285,7 +314,7 @@ class ResNetPlan:
              "mla_maxpool_relu_backward")
         dy0 = self.tmp("dy0", self.y0.shape)
         self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, dy0, None, st)
-        self._wgrad(self.col, dy0, self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st)
+        self._wgrad(self.col, dy0, self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st, k_alg=49 * self.Cin)
         _chk(L.mla_pad_rows(_p(self.dwpad), _p(_grad_buffer(net.conv1.weight)), 64, 49 * self.Cin, self.Kp, 1, st),
              "mla_pad_rows")
         self.trained_forward = False

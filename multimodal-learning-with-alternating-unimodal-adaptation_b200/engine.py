@@ -53,6 +53,44 @@ def _unpack(args, data_packet, device):
     return (spec.unsqueeze(1).float(), image.float()), label.to(device, **nb)
 
 
+def _batches_on_device(args, dataloader, device):
+    """Yields (inputs, label) on `device`. Host batches (pinned) are copied on a side stream ONE BATCH AHEAD,
+    so the H2D transfer of batch i+1 overlaps the compute of batch i (the reference copies synchronously at
+    the top of every iteration, main.py:160-162)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        for pkt in dataloader:
+            yield _unpack(args, pkt, device)
+        return
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+    it = iter(dataloader)
+
+    def load():
+        try:
+            pkt = next(it)
+        except StopIteration:
+            return None
+        if all((not torch.is_tensor(t)) or t.is_cuda for t in pkt):
+            return _unpack(args, pkt, device), None                      # already resident: nothing to overlap
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            out = _unpack(args, pkt, device)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        return out, ev
+
+    nxt = load()
+    while nxt is not None:
+        (inputs, label), ev = nxt
+        if ev is not None:
+            main.wait_event(ev)
+            for t in tuple(inputs) + (label,):
+                t.record_stream(main)
+        nxt = load()
+        yield inputs, label
+
+
 class _TurnState:
     """Per-model buffers reused across steps: packed head buffer and flat encoder grads."""
 
@@ -97,9 +135,13 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
     len_dataloader = len(dataloader)
     n_mod = len(encoder_param_groups(net))
     acc = torch.zeros(1 + n_mod, dtype=torch.float64, device=device)      # _loss, _loss_a, _loss_v[, _loss_t]
+    # the reference reads the losses back every step with .item() (main.py:472-476), stalling the stream; here an
+    # opt-in pinned log receives them by non-blocking copies (args.step_loss_log = True), read after the epoch
+    step_log = None
+    if getattr(args, "step_loss_log", False) and torch.device(device).type == "cuda":
+        step_log = torch.empty(len_dataloader, 1 + n_mod, dtype=torch.float64).pin_memory()
 
-    for batch_step, data_packet in enumerate(dataloader):
-        inputs, label = _unpack(args, data_packet, device)
+    for batch_step, (inputs, label) in enumerate(_batches_on_device(args, dataloader, device)):
         optimizer.zero_grad()                                              # main.py:164
         feats = model(*inputs)                                             # main.py:421-431
         st = getattr(net, "_mla_turn_state", None)
@@ -129,14 +171,17 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
             mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
         else:
             mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
-        acc[0:1] += mix.double()
-        for m in range(n_mod):
-            acc[1 + m:2 + m] += losses[m].double()
+        step_vec = torch.cat([mix] + losses).double()                      # (_loss, _loss_a, _loss_v[, _loss_t]) of this step
+        acc += step_vec
+        if step_log is not None:                                           # per-step device->host read, asynchronous
+            step_log[batch_step].copy_(step_vec, non_blocking=True)
     scheduler.step()                                                       # main.py:481
     if world > 1:
         mdist.allreduce_sum_(acc)
         acc /= world
     vals = (acc / len_dataloader).tolist()                                 # the only device->host sync of the epoch
+    if step_log is not None:
+        train_epoch.last_step_losses = step_log                            # complete: the .tolist() above synchronised
     return tuple(vals)
 
 
@@ -151,6 +196,7 @@ def valid(args, model, device, dataloader, gs_flag=False, av_alpha=0.5,
     n_classes = N_CLASSES[args.dataset]
     net = _unwrap(model)
     model.eval()
+    mdist.broadcast_buffers_(net)                                          # DataParallel keeps replica 0's BN statistics
     fc = net.fusion_module.fc_out
     n_mod = 3 if getattr(args, "modal3", False) else 2
     num = torch.zeros(n_classes, dtype=torch.int64, device=device)
@@ -161,8 +207,7 @@ def valid(args, model, device, dataloader, gs_flag=False, av_alpha=0.5,
         fixed = (a_alpha, v_alpha, t_alpha)                                # main.py:649
     else:
         fixed = (av_alpha, 1 - av_alpha)                                   # main.py:651
-    for data_packet in dataloader:
-        inputs, label = _unpack(args, data_packet, device)
+    for inputs, label in _batches_on_device(args, dataloader, device):
         feats = model(*inputs)                                             # main.py:624-634
         logits = [fc(f.contiguous()) for f in feats]                       # main.py:636-639
         if mdist.is_dist():

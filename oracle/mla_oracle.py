@@ -292,6 +292,30 @@ class AVOracle:
         lv = self._turn(v, label, batch_step, len_dl, "visual_net.")
         return la, lv
 
+    def train_step_dp(self, shards, batch_step=0, len_dl=1):
+        """The same iteration under nn.DataParallel (main.py:732) with one shard per replica: every replica runs
+        the encoders on ITS shard with its own BatchNorm batch statistics (only replica 0's running statistics
+        survive), the features are gathered and the head / loss / GS hook / optimiser see the GLOBAL batch.
+        `shards` = [(spec, image, label), ...]. Returns (loss_a, loss_v). This is what the one-process-per-GPU
+        runtime of the product must reproduce."""
+        torch = self.torch
+        self.opt.zero_grad()
+        feats_a, feats_v, labels = [], [], []
+        stat_keys = [k for k in self.sd if k.endswith(("running_mean", "running_var"))]
+        for r, (spec, image, label) in enumerate(shards):
+            saved = {k: self.sd[k].clone() for k in stat_keys} if r > 0 else None
+            a, v = av_forward(self.sd, spec.unsqueeze(1).float(), image.float(), training=True)
+            if saved is not None:
+                for k in stat_keys:
+                    self.sd[k].copy_(saved[k])
+            feats_a.append(a); feats_v.append(v); labels.append(label)
+        _bump_num_batches(self.sd, "audio_net.")
+        _bump_num_batches(self.sd, "visual_net.")
+        a, v, label = torch.cat(feats_a), torch.cat(feats_v), torch.cat(labels)
+        la = self._turn(a, label, batch_step, len_dl, "audio_net.")
+        lv = self._turn(v, label, batch_step, len_dl, "visual_net.")
+        return la, lv
+
     def train_epoch(self, batches, av_alpha=0.5):
         """main.py:127-484 (gs branch) over a list of (spec, image, label). Returns (loss, loss_a, loss_v)."""
         tot = tot_a = tot_v = 0.0

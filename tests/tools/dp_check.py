@@ -1,0 +1,74 @@
+"""Data-parallel check on real GPUs (run under torchrun, one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/tools/dp_check.py
+
+  1. two alternating steps with the GS projection firing, every rank on its own shard;
+  2. P, the shared head and the encoder weights must be BIT-identical on all ranks (checksums);
+  3. rank 0 re-runs the first step through the oracle's nn.DataParallel restatement (per-replica BatchNorm,
+     gathered features, global-batch head / GS) in fp32 on its GPU and compares the losses (rel 2e-3: forward-level
+     TF32 tolerance on B=8 shards) and the projected head update."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import mla_b200  # noqa: E402
+from mla_b200 import dist as mdist  # noqa: E402
+from oracle import mla_oracle as orc  # noqa: E402
+
+
+def main():
+    rank, world = mdist.init_from_env("nccl")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modulation="Normal", gs_flag=True,
+                              dynamic=True, lorb="base", modal3=False, clip=False)
+    mla_b200.setup_seed(0)
+    net = mla_b200.AVClassifier(args).apply(mla_b200.weight_init)
+    state = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    model = mla_b200.ModuleHolder(net.to(dev))
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    sch = torch.optim.lr_scheduler.StepLR(opt, 70, 0.1)
+    gs = mla_b200.GSPlugin(force_projection=True)
+    B = 8
+    shards = [[orc.synthetic_av_batch(B, 100 * step + r, spec_hw=(129, 96), image_hw=(112, 112)) for r in range(world)]
+              for step in range(2)]
+    mine = [s[rank] + (torch.zeros(B, 1, dtype=torch.long),) for s in shards]
+    losses1 = mla_b200.train_epoch(args, 0, model, dev, mine[:1], opt, sch, gs_plugin=gs, gs_flag=True, av_alpha=0.55)
+    fc_after1 = model.module.fusion_module.fc_out.weight.detach().clone()
+    mla_b200.train_epoch(args, 0, model, dev, mine[1:], opt, sch, gs_plugin=gs, gs_flag=True, av_alpha=0.55)
+    sums = torch.tensor([mdist.params_checksum(gs.Pl), mdist.params_checksum(model.module.fusion_module.fc_out.weight),
+                         mdist.params_checksum(model.module.audio_net.layer3[0].conv1.weight),
+                         mdist.params_checksum(model.module.visual_net.conv1.weight)], device=dev)
+    allsums = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(allsums, sums)
+    for r in range(1, world):
+        assert torch.equal(allsums[0], allsums[r]), "rank %d state differs from rank 0: %s vs %s" % (r, allsums[r], allsums[0])
+    accs = mla_b200.valid(args, model, dev, mine, gs_flag=True, av_alpha=0.55)
+    acc_t = torch.tensor(accs, device=dev, dtype=torch.float64)
+    acc_all = [torch.zeros_like(acc_t) for _ in range(world)]
+    dist.all_gather(acc_all, acc_t)
+    for r in range(1, world):
+        assert torch.equal(acc_all[0], acc_all[r]), "eval accuracies differ across ranks"
+    if rank == 0:
+        torch.backends.cudnn.allow_tf32 = False
+        o = orc.AVOracle({k: v.to(dev) for k, v in state.items()}, force_projection=True)
+        la, lv = o.train_step_dp([tuple(t.to(dev) for t in s) for s in shards[0]], 0, 1)
+        ref = (np.float32(la) * np.float32(0.55) + np.float32(lv) * np.float32(0.45), la, lv)
+        print("step-1 losses: ours", losses1, "DataParallel oracle", ref)
+        assert np.allclose(losses1, ref, rtol=2e-3), (losses1, ref)
+        w_ref = o.sd["fusion_module.fc_out.weight"].detach()
+        w0 = state["fusion_module.fc_out.weight"].to(dev)
+        num = float((fc_after1 - w_ref).norm() / (w_ref - w0).norm())
+        print("head UPDATE after step 1 (audio + visual turn, projection fired): rel-F error vs oracle %.3e" % num)
+        assert num < 2e-2
+        print("dp_check ok: world %d, P / head / encoders bit-identical on all ranks, accs %s" % (world, accs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,7 +34,7 @@ def use_exact_convs():
         # 4-D parameters are logically OIHW whatever their strides; 2-D [Cout][K] buffers are KRSC memory
         return w.detach() if w.dim() == 4 else w.detach().view(Cout, R, R, Cin).permute(0, 3, 1, 2)
 
-    def conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st):
+    def conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
         y.copy_(F.conv2d(nchw(x, N, H, W, Cin), wt(w, Cout, R, Cin), None, stride, pad).permute(0, 2, 3, 1))
 
     def dgrad(self, dy, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
@@ -43,7 +43,7 @@ def use_exact_convs():
         g = g.permute(0, 2, 3, 1)
         dx.view(N, H, W, Cin).copy_(dx.view(N, H, W, Cin) + g if acc else g)
 
-    def wgrad(self, x, dy, dw, N, H, W, Cin, Cout, R, stride, pad, st):
+    def wgrad(self, x, dy, dw, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
         OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
         g = torch.nn.grad.conv2d_weight(nchw(x, N, H, W, Cin), (Cout, Cin, R, R), nchw(dy, N, OH, OW, Cout), stride, pad)
         if dw.dim() == 4:
