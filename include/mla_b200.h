@@ -119,6 +119,12 @@ MLA_API int    mla_fuse_eval(const float* const* logits, int M, int B, int C, in
  */
 MLA_API int    mla_conv2d_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
                         int Cout, int R, int S, int stride, int pad, void* stream);
+/* fprop that also emits BatchNorm partial sums of its output from the fp32 accumulators: stat_part
+ * [mla_conv2d_fprop_stat_tiles(...)][2][Cout] floats = (sum y, sum y^2) per 128-row output tile; feed them to
+ * mla_bn_stats_from_partials (saves the statistics pass over y). */
+MLA_API int    mla_conv2d_fprop_stat_tiles(int N, int H, int W, int R, int S, int stride, int pad);
+MLA_API int    mla_conv2d_fprop_bnstats(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, float* stat_part, void* stream);
 MLA_API int    mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin,
                         int Cout, int R, int S, int stride, int pad, int accumulate, void* stream);
 MLA_API size_t mla_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S,
@@ -160,6 +166,12 @@ MLA_API int    mla_pad_rows(const float* src, float* dst, int rows, int k, int k
 MLA_API size_t mla_bn_workspace_bytes(long long M, int C);
 MLA_API int    mla_bn_train_stats(const float* y, long long M, int C, const float* gamma, const float* beta,
                         float* running_mean, float* running_var, float momentum, float eps,
+                        float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
+                        void* ws, size_t ws_bytes, void* stream);
+/* Same outputs as mla_bn_train_stats from the per-tile partial sums of mla_conv2d_fprop_bnstats (M = number of
+ * pixels the statistics cover; ws: mla_bn_workspace_bytes(ntiles, C), zero-filled like the other BN workspaces). */
+MLA_API int    mla_bn_stats_from_partials(const float* part, int ntiles, long long M, int C, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                         float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
                         void* ws, size_t ws_bytes, void* stream);
 MLA_API int    mla_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,

@@ -34,6 +34,11 @@ _SIGNATURES = {
                                ctypes.POINTER(_c_float), _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "mla_conv2d_fprop": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p]),
+    "mla_conv2d_fprop_stat_tiles": (_c_int, [_c_int] * 7),
+    "mla_conv2d_fprop_bnstats": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_void_p]),
+    "mla_bn_stats_from_partials": (_c_int, [_c_void_p, _c_int, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                            _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                            _c_size_t, _c_void_p]),
     "mla_conv2d_dgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
     "mla_conv2d_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 9),
     "mla_conv2d_wgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),

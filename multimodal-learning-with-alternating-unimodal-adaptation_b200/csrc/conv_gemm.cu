@@ -61,6 +61,9 @@ struct ConvGemmParams {
   // output row map (stride-s dgrad, one launch per output parity class): GEMM row (n, i, j) over the OH x OW
   // sub-grid is written to dx pixel (n, i * o_mul + o_ph, j * o_mul + o_pw) of an o_H x o_W image.
   int o_mul, o_ph, o_pw, o_H, o_W;
+  // fprop only: per-M-tile BatchNorm partial sums of the OUTPUT, stat_part[m tile][2][Cout] = (sum y, sum y*y)
+  // over the tile's 128 rows, taken from the fp32 accumulators (NULL = off)
+  float* stat_part;
 };
 
 template <bool MN_MAJOR>
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_stat[MODE == 0 ? 4 * 2 * BN : 1];   // [warp][sum | sumsq][column] (fprop BN statistics)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -233,6 +237,38 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
           }
           dst[j] = o;
         }
+      }
+      if (MODE == 0 && p.stat_part != nullptr) {
+        // column sums over this warp's 32 rows (rows past M are exact zeros): butterfly transpose-reduce, lane j
+        // ends up with column c + j. Fixed shuffle tree -> deterministic.
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(v[j]); b[j] = a[j] * a[j]; }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float sa = up ? a[i] : a[i + off], ka = up ? a[i + off] : a[i];
+            const float sb = up ? b[i] : b[i + off], kb2 = up ? b[i + off] : b[i];
+            a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+            b[i] = kb2 + __shfl_xor_sync(0xffffffffu, sb, off);
+          }
+        }
+        s_stat[(warp * 2 + 0) * BN + c + lane] = a[0];
+        s_stat[(warp * 2 + 1) * BN + c + lane] = b[0];
+      }
+    }
+    if (MODE == 0 && p.stat_part != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+      const int t = threadIdx.x;
+      if (t < BN) {
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { sa += s_stat[(w * 2 + 0) * BN + t]; sb += s_stat[(w * 2 + 1) * BN + t]; }
+        float* dstp = p.stat_part + (size_t)blockIdx.x * 2 * p.Cout + n0 + t;
+        dstp[0] = sa;
+        dstp[p.Cout] = sb;
       }
     }
   } else if (warp == 4) {
@@ -453,8 +489,28 @@ int out_size(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / str
 
 }  // namespace
 
+static int conv2d_fprop_impl(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int R, int S,
+                            int stride, int pad, float* stat_part, void* stream);
+
 extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int R,
                                 int S, int stride, int pad, void* stream) {
+  return conv2d_fprop_impl(x, w, y, N, H, W, Cin, Cout, R, S, stride, pad, nullptr, stream);
+}
+
+extern "C" int mla_conv2d_fprop_stat_tiles(int N, int H, int W, int R, int S, int stride, int pad) {
+  const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
+  if (N < 1 || OH < 1 || OW < 1) return 0;
+  return (int)(((long long)N * OH * OW + 127) / 128);
+}
+
+extern "C" int mla_conv2d_fprop_bnstats(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout,
+                                        int R, int S, int stride, int pad, float* stat_part, void* stream) {
+  if (!stat_part || !mla::aligned16(stat_part)) return MLA_E_BADARG;
+  return conv2d_fprop_impl(x, w, y, N, H, W, Cin, Cout, R, S, stride, pad, stat_part, stream);
+}
+
+static int conv2d_fprop_impl(const float* x, const float* w, float* y, int N, int H, int W, int Cin, int Cout, int R, int S,
+                            int stride, int pad, float* stat_part, void* stream) {
   if (!x || !w || !y || !mla::aligned16(x) || !mla::aligned16(w) || !mla::aligned16(y)) return MLA_E_BADARG;
   if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad, 32)) return MLA_E_SHAPE;
   const mla::DeviceInfo& di = mla::device_info();
@@ -464,7 +520,7 @@ extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N,
   ConvGemmParams p{};
   p.src = x; p.Hs = H; p.Ws = W; p.Cs = Cin; p.OH = OH; p.OW = OW; p.M = N * OH * OW; p.R = R; p.S = S;
   p.mul = stride; p.sgn = 1; p.off = -pad; p.div = 1; p.kcb = Cin / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
-  p.out = y; p.ldo = Cout; p.accumulate = 0; p.Cout = Cout;
+  p.out = y; p.ldo = Cout; p.accumulate = 0; p.Cout = Cout; p.stat_part = stat_part;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   CUtensorMap map;
   int rc = make_map_2d(&map, w, Cout, (long long)R * S * Cin, BN, false);

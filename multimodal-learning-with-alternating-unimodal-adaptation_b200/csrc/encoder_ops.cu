@@ -100,6 +100,8 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict
 // finalisation (statistics / running stats, or dgamma / dbeta) for its 64 channels. No second launch.
 // MODE 0: a = x, b = x*x (BN statistics).
 // MODE 1: g = dz * (z > 0 or no mask); a = g, b = g * (y - mean) * invstd (BN backward sums).
+// MODE 2: x = per-tile partial sums [rows = tiles][2][C] written by the fprop epilogue: a = x[r][0][c],
+//         b = x[r][1][c]; finalised like MODE 0 (f.M = the real number of pixels).
 struct BnFinal {
   long long M;
   // MODE 0
@@ -133,9 +135,13 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
     long long r = r0 + ty;
     while (r < r1) {
       float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
-      for (int it = 0; it < 32 && r < r1; ++it, r += 16) {   // fp32 for 32 rows, then flush to double
-        const float4 v = ld4(x + r * C + c0);
-        if (MODE == 0) {
+      for (int it = 0; it < (MODE == 2 ? 2 : 32) && r < r1; ++it, r += 16) {   // a few rows in fp32, then flush to double
+        const float4 v = ld4(x + r * (MODE == 2 ? 2 * C : C) + c0);
+        if (MODE == 2) {
+          const float4 q = ld4(x + r * 2 * C + C + c0);
+          fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
+          fb[0] += q.x; fb[1] += q.y; fb[2] += q.z; fb[3] += q.w;
+        } else if (MODE == 0) {
           fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
           fb[0] = fmaf(v.x, v.x, fb[0]); fb[1] = fmaf(v.y, v.y, fb[1]);
           fb[2] = fmaf(v.z, v.z, fb[2]); fb[3] = fmaf(v.w, v.w, fb[3]);
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
   if (threadIdx.x >= 64) return;
   const int c = chunk * 64 + threadIdx.x;
   const double sa = s_fin[0][threadIdx.x], sb = s_fin[1][threadIdx.x];
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 2) {
     // mean, biased var -> invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats: momentum
     // update with the UNBIASED variance (torch BatchNorm2d semantics)
     const double mu = sa / (double)f.M;
@@ -450,6 +456,28 @@ extern "C" int mla_bn_train_stats(const float* y, long long M, int C, const floa
   f.shift_out = shift_out;
   channel_reduce_kernel<0><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       y, nullptr, nullptr, nullptr, nullptr, M, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
+      reinterpret_cast<unsigned int*>(base), f);
+  MLA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mla_bn_stats_from_partials(const float* part, int ntiles, long long M, int C, const float* gamma,
+                                          const float* beta, float* running_mean, float* running_var, float momentum,
+                                          float eps, float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
+                                          void* ws, size_t ws_bytes, void* stream) {
+  if (!part || !gamma || !beta || !mean_out || !invstd_out || !scale_out || !shift_out || ntiles < 1 || M < 1)
+    return MLA_E_BADARG;
+  RedPlan pl;
+  int rc = red_plan(ntiles, C, &pl);
+  if (rc) return rc;
+  if (!ws || ws_bytes < pl.bytes) return MLA_E_WORKSPACE;
+  char* base = static_cast<char*>(ws);
+  BnFinal f{};
+  f.M = M; f.gamma = gamma; f.beta = beta; f.running_mean = running_mean; f.running_var = running_var;
+  f.momentum = momentum; f.eps = eps; f.mean_out = mean_out; f.invstd_out = invstd_out; f.scale_out = scale_out;
+  f.shift_out = shift_out;
+  channel_reduce_kernel<2><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      part, nullptr, nullptr, nullptr, nullptr, ntiles, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
       reinterpret_cast<unsigned int*>(base), f);
   MLA_LAUNCH_CHECK();
   return 0;

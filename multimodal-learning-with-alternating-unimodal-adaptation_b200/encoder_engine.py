@@ -166,6 +166,9 @@ class ResNetPlan:
         self.nbt = [b.bn.num_batches_tracked for b in self.bns if b.bn.num_batches_tracked is not None]
         nb = max(self.L.mla_bn_workspace_bytes(self.M0, 64),
                  max(self.L.mla_bn_workspace_bytes(N * b["ho"] * b["wo"], b["cout"]) for b in self.blocks))
+        self.stat_part = torch.empty(max([(self.M0 + 127) // 128 * 2 * 64] +
+                                         [(N * b["ho"] * b["wo"] + 127) // 128 * 2 * b["cout"] for b in self.blocks]),
+                                     dtype=torch.float32, device=dev)          # per-tile BN partial sums (fprop epilogue)
         self.bn_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)      # ticket counters start at 0 (mla_b200.h)
         nw = self.L.mla_conv2d_wgrad_workspace_bytes(N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
         for b in self.blocks:
@@ -193,6 +196,26 @@ class ResNetPlan:
         t = _conv_timer_begin()
         _chk(self.L.mla_conv2d_fprop(_p(x), self._wptr(w), _p(y), N, H, W, Cin, Cout, R, R, stride, pad, st), "mla_conv2d_fprop")
         _conv_timer_end(t, "fprop", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
+
+    def _conv_bn(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, b, training, st, k_alg=None):
+        """Convolution + BatchNorm coefficients of its output. Training: the conv epilogue emits per-tile
+        (sum, sum^2) partials from its fp32 accumulators and one small launch finalises them (no statistics
+        pass over y). Eval: plain conv + coefficients from the running statistics."""
+        if not training:
+            self._conv(x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=k_alg)
+            self._bn_coeffs(y, 0, b, False, st)
+            return
+        t = _conv_timer_begin()
+        _chk(self.L.mla_conv2d_fprop_bnstats(_p(x), self._wptr(w), _p(y), N, H, W, Cin, Cout, R, R, stride, pad,
+                                              _p(self.stat_part), st), "mla_conv2d_fprop_bnstats")
+        _conv_timer_end(t, "fprop", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
+        OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+        M = N * OH * OW
+        bn = b.bn
+        _chk(self.L.mla_bn_stats_from_partials(_p(self.stat_part), (M + 127) // 128, M, b.C, _p(bn.weight), _p(bn.bias),
+                                               _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps),
+                                               _p(b.mean), _p(b.invstd), _p(b.scale), _p(b.shift), _p(self.bn_ws),
+                                               self.bn_ws.numel(), st), "mla_bn_stats_from_partials")
 
     def _dgrad(self, dy, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
         t = _conv_timer_begin()
@@ -239,23 +262,22 @@ class ResNetPlan:
         _chk(L.mla_stem_im2col(_p(x), _p(self.col), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp,
                                st), "mla_stem_im2col")
         _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
-        self._conv(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st, k_alg=K)
-        self._bn_coeffs(self.y0, self.M0, self.bn0, training, st)
+        self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
+                      k_alg=K)
         _chk(L.mla_bn_relu_maxpool(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.idx0), N,
                                    self.OH0, self.OW0, 64, st), "mla_bn_relu_maxpool")
         xin = self.p0
         for b in self.blocks:
             blk, s, cin, cout = b["blk"], b["stride"], b["cin"], b["cout"]
             M = N * b["ho"] * b["wo"]
-            self._conv(xin, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, st)
-            self._bn_coeffs(b["y1"], M, b["bn1"], training, st)
+            self._conv_bn(xin, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, b["bn1"], training, st)
             _chk(L.mla_bn_apply(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(b["a1"]), M,
                                 cout, st), "mla_bn_apply")
-            self._conv(b["a1"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, st)
-            self._bn_coeffs(b["y2"], M, b["bn2"], training, st)
+            self._conv_bn(b["a1"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, b["bn2"], training,
+                          st)
             if b["yd"] is not None:
-                self._conv(xin, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, st)
-                self._bn_coeffs(b["yd"], M, b["bnd"], training, st)
+                self._conv_bn(xin, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, b["bnd"],
+                              training, st)
                 _chk(L.mla_bn_apply(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]), _p(b["bnd"].scale),
                                     _p(b["bnd"].shift), 1, _p(b["out"]), M, cout, st), "mla_bn_apply")
             else:

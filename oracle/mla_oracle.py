@@ -303,11 +303,12 @@ class AVOracle:
         feats_a, feats_v, labels = [], [], []
         stat_keys = [k for k in self.sd if k.endswith(("running_mean", "running_var"))]
         for r, (spec, image, label) in enumerate(shards):
-            saved = {k: self.sd[k].clone() for k in stat_keys} if r > 0 else None
-            a, v = av_forward(self.sd, spec.unsqueeze(1).float(), image.float(), training=True)
-            if saved is not None:
+            sd = self.sd
+            if r > 0:                      # replicas > 0 update throw-away copies of the running statistics
+                sd = dict(self.sd)
                 for k in stat_keys:
-                    self.sd[k].copy_(saved[k])
+                    sd[k] = self.sd[k].clone()
+            a, v = av_forward(sd, spec.unsqueeze(1).float(), image.float(), training=True)
             feats_a.append(a); feats_v.append(v); labels.append(label)
         _bump_num_batches(self.sd, "audio_net.")
         _bump_num_batches(self.sd, "visual_net.")

@@ -34,7 +34,7 @@ def use_exact_convs():
         # 4-D parameters are logically OIHW whatever their strides; 2-D [Cout][K] buffers are KRSC memory
         return w.detach() if w.dim() == 4 else w.detach().view(Cout, R, R, Cin).permute(0, 3, 1, 2)
 
-    def conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
+    def conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):  # noqa: D401
         y.copy_(F.conv2d(nchw(x, N, H, W, Cin), wt(w, Cout, R, Cin), None, stride, pad).permute(0, 2, 3, 1))
 
     def dgrad(self, dy, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
@@ -50,7 +50,12 @@ def use_exact_convs():
             dw.copy_(g)
         else:
             dw.view(Cout, R, R, Cin).copy_(g.permute(0, 2, 3, 1))
+    def conv_bn(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, b, training, st, k_alg=None):
+        conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st)
+        OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+        self._bn_coeffs(y, N * OH * OW, b, training, st)
     ee.ResNetPlan._conv, ee.ResNetPlan._dgrad, ee.ResNetPlan._wgrad = conv, dgrad, wgrad
+    ee.ResNetPlan._conv_bn = conv_bn
 
 
 def run(B, hw, img, seed=3, verbose=False):
