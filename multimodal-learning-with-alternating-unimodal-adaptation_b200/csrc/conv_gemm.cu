@@ -100,14 +100,27 @@ __device__ __forceinline__ void gather_segment(const ConvGemmParams& p, uint32_t
 
 // NT > 1 (wgrad only, Cin == BN): one CTA accumulates NT consecutive filter taps side by side — the N tile is
 // NT x BN columns of the flattened (tap, ci) axis of dw, so dy (the A operand) is loaded once for NT taps.
-template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1>
+// CL > 1 (fprop / dgrad, im2col): CL CTAs with consecutive M tiles and the SAME weight tile form a thread-block
+// cluster; each loads 1/CL of the weight tile per k-block and TMA-multicasts it into all CL shared memories, so
+// the weights cross L2->SM once per cluster instead of once per CTA. A stage is released cluster-wide: every
+// CTA's tcgen05.commit arrives on the stage's empty barrier of all CL CTAs.
+// PAIR (fprop / dgrad, im2col): two CTAs with consecutive M tiles form a tcgen05 CTA pair (cta_group::2): one
+// 256 x BN MMA per k-step, issued by the leader, reads each CTA's own 128 A rows and HALF of the weight tile from
+// each CTA's shared memory — every SM ingests BN/2 weight rows instead of BN. Loads of both CTAs complete on the
+// leader's full barrier; its tcgen05.commit releases the stage in both CTAs.
+template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1, int CL = 1, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ CUtensorMap tmap_g, ConvGemmParams p) {
   static_assert(NT == 1 || (MODE == 2 && IM2COL), "multi-tap tiles exist for the im2col wgrad only");
+  static_assert(CL == 1 || (MODE != 2 && IM2COL && NT == 1), "weight multicast exists for the im2col fprop / dgrad only");
+  static_assert(CL == 1 || MODE == 0 || (BN / 32) % CL == 0, "dgrad splits whole 32-column weight panels");
+  static_assert(!PAIR || (CL == 1 && NT == 1 && IM2COL && MODE != 2), "CTA pairs exist for the im2col fprop / dgrad only");
+  constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1);
+  constexpr int kCluster = PAIR ? 2 : CL;
   constexpr int NTOT = BN * NT;                                     // accumulator columns
   constexpr uint32_t kTmemCols = NTOT <= 64 ? 64 : (NTOT <= 128 ? 128 : 256);
   static_assert(NTOT <= 256, "one UMMA covers at most 256 columns");
-  constexpr uint32_t kBBytes = NTOT * 128;
+  constexpr uint32_t kBBytes = (PAIR ? NTOT / 2 : NTOT) * 128;      // weight bytes per stage held by THIS CTA
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr int LAG = STAGES - 1;
   extern __shared__ uint8_t smem_raw[];
@@ -116,6 +129,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_stat[MODE == 0 ? 4 * 2 * BN : 1];   // [warp][sum | sumsq][column] (fprop BN statistics)
+  static_assert(BN <= 256, "tile width");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -123,7 +137,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(tc::smem_u32(&full_bar[s]), IM2COL ? 1 : kGatherThreads + 1);
-      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), CL);
     }
     tc::mbar_init(tc::smem_u32(&tmem_full_bar), 1);
     tc::fence_mbar_init();
@@ -133,13 +147,20 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     if (IM2COL) tc::tma_prefetch_desc(&tmap_g);
   }
   if (warp == 5) {
-    tc::tmem_alloc(tc::smem_u32(&tmem_slot), kTmemCols);
-    tc::tmem_relinquish();
+    if (PAIR) {
+      tc::tmem_alloc2(tc::smem_u32(&tmem_slot), kTmemCols);
+      tc::tmem_relinquish2();
+    } else {
+      tc::tmem_alloc(tc::smem_u32(&tmem_slot), kTmemCols);
+      tc::tmem_relinquish();
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) tc::cluster_sync();   // every CTA's barriers are initialised before any remote arrive / multicast
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const uint32_t cl_rank = kCluster > 1 ? tc::cluster_ctarank() : 0u;
 
   // tile coordinates
   int m0 = 0, n0 = 0, tap_r = 0, tap_s = 0, kb_begin = 0, KB = p.KB, split = 0;
@@ -261,8 +282,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     }
     if (MODE == 0 && p.stat_part != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
-      const int t = threadIdx.x;
-      if (t < BN) {
+      for (int t = threadIdx.x; t < BN && m0 < p.M; t += 128) {
         float sa = 0.f, sb = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) { sa += s_stat[(w * 2 + 0) * BN + t]; sb += s_stat[(w * 2 + 1) * BN + t]; }
@@ -292,18 +312,44 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         if (MODE == 0 || MODE == 1) {
           int tap = kb / p.kcb;
           const int cb = kb - tap * p.kcb;
-          tc::mbar_arrive_expect_tx(bar, kBBytes + tx_gather);
+          if (PAIR) {
+            if (cl_rank == 0) tc::mbar_arrive_expect_tx(bar, 2u * (kABytes + kBBytes));   // both CTAs' bytes land here
+          } else {
+            tc::mbar_arrive_expect_tx(bar, kBBytes + tx_gather);
+          }
           if (IM2COL) {
             const int ti = tap / p.ns, tj = tap - ti * p.ns;
-            tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * 32, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
+            if (PAIR)
+              tc::tma_load_im2col_4d_2sm(stage, &tmap_g, bar, cb * 32, gw, gh, gn, (uint16_t)p.off_s[tj],
+                                         (uint16_t)p.off_r[ti]);
+            else
+              tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * 32, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
             tap = p.tap_r[ti] * p.S + p.tap_s[tj];   // filter position whose weights this k-block multiplies
           }
           if (MODE == 0) {
-            tc::tma_load_2d(stage + kABytes, &tmap, bar, tap * p.CinW + cb * 32, n0);  // box {32 k, BN rows}
+            if (PAIR) {   // box {32 k, BN / 2 rows}: this CTA's half of the weight tile
+              tc::tma_load_2d_2sm(stage + kABytes, &tmap, bar, tap * p.CinW + cb * 32, n0 + (int)cl_rank * (BN / 2));
+            } else if (CL == 1) {
+              tc::tma_load_2d(stage + kABytes, &tmap, bar, tap * p.CinW + cb * 32, n0);  // box {32 k, BN rows}
+            } else {   // box {32 k, BN / CL rows}: this CTA's slice of the weight tile, delivered to the whole cluster
+              tc::tma_load_2d_mc(stage + kABytes + cl_rank * (BN / CL) * 128, &tmap, bar, tap * p.CinW + cb * 32,
+                                 n0 + (int)cl_rank * (BN / CL), kClMask);
+            }
           } else {
+            if (PAIR) {
 #pragma unroll
-            for (int pnl = 0; pnl < BN / 32; ++pnl)  // box {32 ci, 32 co rows}
-              tc::tma_load_2d(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32);
+              for (int pnl = 0; pnl < BN / 64; ++pnl)  // this CTA's half of the 32-column weight panels
+                tc::tma_load_2d_2sm(stage + kABytes + pnl * 4096, &tmap, bar,
+                                    tap * p.CinW + n0 + ((int)cl_rank * (BN / 64) + pnl) * 32, cb * 32);
+            } else {
+#pragma unroll
+              for (int pnl = 0; pnl < BN / 32; ++pnl) {  // box {32 ci, 32 co rows}
+                if (CL == 1)
+                  tc::tma_load_2d(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32);
+                else if ((pnl % CL) == (int)cl_rank)
+                  tc::tma_load_2d_mc(stage + kABytes + pnl * 4096, &tmap, bar, tap * p.CinW + n0 + pnl * 32, cb * 32, kClMask);
+              }
+            }
           }
         } else {
           // panels of a partial last ci tile / of co rows beyond Cout are neither loaded nor stored (their
@@ -335,8 +381,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     }
   } else {
     // ===================== MMA issuer =====================
-    if (lane == 0 && KB > 0) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(128, NTOT, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0);
+    if (lane == 0 && KB > 0 && (!PAIR || cl_rank == 0)) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(PAIR ? 256 : 128, NTOT, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0);
       constexpr bool a_mn = (MODE == 2), b_mn = (MODE != 0);
       constexpr uint32_t a_lbo = a_mn ? 4096u : 16u, b_lbo = b_mn ? 4096u : 16u;
       constexpr uint32_t a_sbo = a_mn ? 512u : 1024u, b_sbo = b_mn ? 512u : 1024u;
@@ -352,17 +398,25 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = tc::make_smem_desc(stage + k * a_kstep, a_lbo, a_sbo, a_lay);
           const uint64_t bd = tc::make_smem_desc(stage + kABytes + k * b_kstep, b_lbo, b_sbo, b_lay);
-          tc::umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (PAIR) tc::umma_tf32_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          else tc::umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+        if (PAIR) tc::umma_commit_2sm(tc::smem_u32(&empty_bar[s]), (uint16_t)3);
+        else if (CL == 1) tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+        else tc::umma_commit_mc(tc::smem_u32(&empty_bar[s]), kClMask);
       }
-      tc::umma_commit(tc::smem_u32(&tmem_full_bar));
+      if (PAIR) tc::umma_commit_2sm(tc::smem_u32(&tmem_full_bar), (uint16_t)3);
+      else tc::umma_commit(tc::smem_u32(&tmem_full_bar));
     }
   }
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (kCluster > 1) tc::cluster_sync();   // no CTA exits while a peer can still signal its barriers
+  if (warp == 5) {
+    if (PAIR) tc::tmem_dealloc2(tmem_base, kTmemCols);
+    else tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // Fixed-order reduction of split-K partials: dw[i] = sum_s part[s][i].
@@ -431,6 +485,18 @@ int make_map_im2col(CUtensorMap* m, const float* ptr, int N, int H, int W, int C
   return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
 }
 
+// MLA_CONV_CLUSTER = 1 | 2 | 4: CTAs per weight-multicast cluster in fprop / dgrad.
+int conv_cluster() {
+  static const int v = [] {
+    const char* e = getenv("MLA_CONV_CLUSTER");
+    const int c = e ? atoi(e) : 1;
+    return (c == 2 || c == 4) ? c : 1;
+  }();
+  return v;
+}
+
+// MLA_CONV_PAIR = 0 | 1 | 2: tcgen05 CTA pairs (cta_group::2) in fprop / dgrad; 2 = also 256-column tiles where the
+// channel count allows.
 // MLA_CONV_GATHER=1 forces the cp.async gather kernels everywhere (A/B comparison, bring-up).
 bool force_gather() {
   static const bool v = [] {
@@ -438,6 +504,26 @@ bool force_gather() {
     return e != nullptr && e[0] == '1';
   }();
   return v;
+}
+
+// Unset = auto (measured on the ResNet-18 shapes, profiles/r1_conv_variants.md): pairs pay once the N tile is >= 128
+// columns (256-column tiles for 256 channels, 128-column tiles otherwise); 64-column tiles stay single-CTA.
+int conv_pair_env() {
+  static const int v = [] {
+    const char* e = getenv("MLA_CONV_PAIR");
+    return e ? atoi(e) : -1;
+  }();
+  return v;
+}
+// tile width for `nch` output columns of the GEMM, or 0 = no pairing
+int conv_pair_bn(int nch) {
+  const int e = conv_pair_env();
+  if (e == 0 || force_gather()) return 0;
+  const int bn = (nch % 128 == 0) ? 128 : 64;
+  if (e == 1) return bn;
+  if (e >= 2) return nch % 256 == 0 ? 256 : bn;
+  if (nch % 128 != 0) return 0;          // auto
+  return nch == 256 ? 256 : 128;
 }
 
 // 2-D fp32 row-major [rows][cols] tensor map with a {32 cols (128 B), box_rows} box; 128B swizzle with
@@ -457,16 +543,29 @@ int make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols
   return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
 }
 
-template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1>
+template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1, int CL = 1, bool PAIR = false>
 int launch(const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (kABytes + BN * NT * 128) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (kABytes + (PAIR ? BN / 2 : BN * NT) * 128) + 1024;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT>,
+    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.store(1, std::memory_order_release);
   }
-  conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT><<<grid, kThreads, smem, st>>>(map, gmap, p);
+  constexpr int kCluster = PAIR ? 2 : CL;
+  if (kCluster > 1) {
+    grid.x = (grid.x + kCluster - 1) / kCluster * kCluster;   // whole clusters; padding CTAs load like the others, store nothing
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR>, map, gmap, p));
+    mla::count_launch();
+    return 0;
+  }
+  conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR><<<grid, kThreads, smem, st>>>(map, gmap, p);
   MLA_CUDA_TRY(cudaGetLastError());
   mla::count_launch();
   return 0;
@@ -500,6 +599,10 @@ extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N,
 extern "C" int mla_conv2d_fprop_stat_tiles(int N, int H, int W, int R, int S, int stride, int pad) {
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (N < 1 || OH < 1 || OW < 1) return 0;
+  if (!force_gather()) {
+    const mla::StripPlan sp = mla::strip_plan(N, H, W, R, S, stride, pad);
+    if (sp.tiles > 0) return sp.tiles;
+  }
   return (int)(((long long)N * OH * OW + 127) / 128);
 }
 
@@ -517,6 +620,10 @@ static int conv2d_fprop_impl(const float* x, const float* w, float* y, int N, in
   if (di.ok != 1) return di.ok;
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (OH <= 0 || OW <= 0 || (long long)N * OH * OW > 0x7fffffffLL) return MLA_E_SHAPE;
+  if (!force_gather()) {   // 3x3 / stride 1: halo-resident strip kernel (9 taps from one shared-memory copy of the input)
+    const mla::StripPlan sp = mla::strip_plan(N, H, W, R, S, stride, pad);
+    if (sp.tiles > 0) return mla::conv_strip_run(0, x, w, y, N, H, W, Cin, Cout, 0, stat_part, sp, stream);
+  }
   ConvGemmParams p{};
   p.src = x; p.Hs = H; p.Ws = W; p.Cs = Cin; p.OH = OH; p.OW = OW; p.M = N * OH * OW; p.R = R; p.S = S;
   p.mul = stride; p.sgn = 1; p.off = -pad; p.div = 1; p.kcb = Cin / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
@@ -534,8 +641,46 @@ static int conv2d_fprop_impl(const float* x, const float* w, float* y, int N, in
   CUtensorMap gmap;
   rc = make_map_im2col(&gmap, x, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 128, false);
   if (rc) return rc;
+  if (const int BNp = conv_pair_bn(Cout)) {   // CTA pairs: each CTA holds half of the weight tile -> box {32 k, BNp / 2 rows}
+    rc = make_map_2d(&map, w, Cout, (long long)R * S * Cin, BNp / 2, false);
+    if (rc) return rc;
+    dim3 gp((p.M + 127) / 128, Cout / BNp);
+    if (BNp == 256) return launch<0, 256, 3, true, 1, 1, true>(map, gmap, p, gp, st);
+    if (BNp == 128) return launch<0, 128, 4, true, 1, 1, true>(map, gmap, p, gp, st);
+    return launch<0, 64, 4, true, 1, 1, true>(map, gmap, p, gp, st);
+  }
+  const int cl = conv_cluster();
+  if (cl > 1) {   // weight tile split over the cluster: box {32 k, BN / cl rows}
+    rc = make_map_2d(&map, w, Cout, (long long)R * S * Cin, BN / cl, false);
+    if (rc) return rc;
+    if (cl == 2) return BN == 64 ? launch<0, 64, 4, true, 1, 2>(map, gmap, p, grid, st) : launch<0, 128, 3, true, 1, 2>(map, gmap, p, grid, st);
+    return BN == 64 ? launch<0, 64, 4, true, 1, 4>(map, gmap, p, grid, st) : launch<0, 128, 3, true, 1, 4>(map, gmap, p, grid, st);
+  }
+  static const int occ3 = [] { const char* e = getenv("MLA_CONV_OCC3"); return e ? atoi(e) : 0; }();
+  if (occ3) return BN == 64 ? launch<0, 64, 3, true>(map, gmap, p, grid, st) : launch<0, 128, 2, true>(map, gmap, p, grid, st);
   return BN == 64 ? launch<0, 64, 4, true>(map, gmap, p, grid, st) : launch<0, 128, 3, true>(map, gmap, p, grid, st);
 }
+
+namespace {
+// im2col dgrad launch with the configured weight-multicast cluster (64-column tiles have 2 weight panels: <= 2)
+int launch_dgrad(int BN, const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams& p, dim3 grid,
+                 cudaStream_t st) {
+  if (const int BNp = conv_pair_bn(p.CinW)) {
+    grid.y = p.CinW / BNp;
+    if (BNp == 256) return launch<1, 256, 3, true, 1, 1, true>(map, gmap, p, grid, st);
+    if (BNp == 128) return launch<1, 128, 4, true, 1, 1, true>(map, gmap, p, grid, st);
+    return launch<1, 64, 4, true, 1, 1, true>(map, gmap, p, grid, st);
+  }
+  const int cl = conv_cluster();
+  if (BN == 64) {
+    if (cl >= 2) return launch<1, 64, 4, true, 1, 2>(map, gmap, p, grid, st);
+    return launch<1, 64, 4, true>(map, gmap, p, grid, st);
+  }
+  if (cl == 2) return launch<1, 128, 3, true, 1, 2>(map, gmap, p, grid, st);
+  if (cl == 4) return launch<1, 128, 3, true, 1, 4>(map, gmap, p, grid, st);
+  return launch<1, 128, 3, true>(map, gmap, p, grid, st);
+}
+}  // namespace
 
 extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin, int Cout,
                                 int R, int S, int stride, int pad, int accumulate, void* stream) {
@@ -545,6 +690,10 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
   if (di.ok != 1) return di.ok;
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (OH <= 0 || OW <= 0 || (long long)N * H * W > 0x7fffffffLL) return MLA_E_SHAPE;
+  if (!force_gather()) {
+    const mla::StripPlan sp = mla::strip_plan(N, H, W, R, S, stride, pad);
+    if (sp.tiles > 0) return mla::conv_strip_run(1, dy, w, dx, N, H, W, Cin, Cout, accumulate ? 1 : 0, nullptr, sp, stream);
+  }
   ConvGemmParams p{};
   p.src = dy; p.Hs = OH; p.Ws = OW; p.Cs = Cout; p.OH = H; p.OW = W; p.M = N * H * W; p.R = R; p.S = S;
   p.mul = 1; p.sgn = -1; p.off = pad; p.div = stride; p.kcb = Cout / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
@@ -566,7 +715,7 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
     rc = make_map_im2col(&gmap, dy, N, OH, OW, Cout, p.g_base_w, p.g_base_h, p.g_base_w + (W - OW), p.g_base_h + (H - OH),
                          1, 128, false);
     if (rc) return rc;
-    return BN == 64 ? launch<1, 64, 4, true>(map, gmap, p, grid, st) : launch<1, 128, 3, true>(map, gmap, p, grid, st);
+    return launch_dgrad(BN, map, gmap, p, grid, st);
   }
   // stride s: one dense sub-convolution per output parity class (ph, pw). dx[n, i*s+ph, j*s+pw] sums the taps r
   // with (ph + pad - r) % s == 0, reading dy row i + (ph + pad - r) / s — a stride-1 walk over dy, so the im2col
@@ -608,7 +757,7 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
       CUtensorMap gmap;
       rc = make_map_im2col(&gmap, dy, N, OH, OW, Cout, lo_w, lo_h, lo_w + Ws - OW, lo_h + Hs - OH, 1, 128, false);
       if (rc) return rc;
-      rc = BN == 64 ? launch<1, 64, 4, true>(map, gmap, q, g, st) : launch<1, 128, 3, true>(map, gmap, q, g, st);
+      rc = launch_dgrad(BN, map, gmap, q, g, st);
       if (rc) return rc;
     }
   }

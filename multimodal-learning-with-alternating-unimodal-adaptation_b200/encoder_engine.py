@@ -166,8 +166,11 @@ class ResNetPlan:
         self.nbt = [b.bn.num_batches_tracked for b in self.bns if b.bn.num_batches_tracked is not None]
         nb = max(self.L.mla_bn_workspace_bytes(self.M0, 64),
                  max(self.L.mla_bn_workspace_bytes(N * b["ho"] * b["wo"], b["cout"]) for b in self.blocks))
-        self.stat_part = torch.empty(max([(self.M0 + 127) // 128 * 2 * 64] +
-                                         [(N * b["ho"] * b["wo"] + 127) // 128 * 2 * b["cout"] for b in self.blocks]),
+        tl = self.L.mla_conv2d_fprop_stat_tiles
+        self.stat_part = torch.empty(max([tl(N, self.OH0, self.OW0, 1, 1, 1, 0) * 2 * 64] +
+                                         [max(tl(N, b["h"], b["w"], 3, 3, b["stride"], 1), tl(N, b["ho"], b["wo"], 3, 3, 1, 1),
+                                              tl(N, b["h"], b["w"], 1, 1, b["stride"], 0)) * 2 * b["cout"]
+                                          for b in self.blocks]),
                                      dtype=torch.float32, device=dev)          # per-tile BN partial sums (fprop epilogue)
         self.bn_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)      # ticket counters start at 0 (mla_b200.h)
         nw = self.L.mla_conv2d_wgrad_workspace_bytes(N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
@@ -212,7 +215,8 @@ class ResNetPlan:
         OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
         M = N * OH * OW
         bn = b.bn
-        _chk(self.L.mla_bn_stats_from_partials(_p(self.stat_part), (M + 127) // 128, M, b.C, _p(bn.weight), _p(bn.bias),
+        ntiles = self.L.mla_conv2d_fprop_stat_tiles(N, H, W, R, R, stride, pad)
+        _chk(self.L.mla_bn_stats_from_partials(_p(self.stat_part), ntiles, M, b.C, _p(bn.weight), _p(bn.bias),
                                                _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps),
                                                _p(b.mean), _p(b.invstd), _p(b.scale), _p(b.shift), _p(self.bn_ws),
                                                self.bn_ws.numel(), st), "mla_bn_stats_from_partials")
