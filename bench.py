@@ -256,9 +256,25 @@ def run_native(a, rank, world):
         t_eval = timed(lambda: mla_b200.valid(args, model, dev, [resident[i % 2] for i in range(a.steps)],
                                               gs_flag=True, av_alpha=0.55))
     clocks = sampler.stop() if rank == 0 else None
+    # host cost of enqueueing one step (Python + ctypes + launches): the same launch sequence on a tiny batch, where
+    # the GPU work is negligible — shows how far the step is from being launch-bound
+    host_ms = None
+    if rank == 0 and world == 1:
+        tiny = SyntheticAVLoader(2, 2, seed=99, spec_hw=(65, 48), image_hw=(64, 64)).batches
+        tiny = [tuple(t.to(dev) for t in b) for b in tiny]
+        with quiet:
+            epoch(tiny, 3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            epoch(tiny, 10)
+            torch.cuda.synchronize()
+            host_ms = (time.perf_counter() - t0) * 1e3 / 10
     # roofline leg: the SAME K steps once more with every convolution launch bracketed by CUDA events on the
     # launching stream (kept out of the headline timed region so that the event records cannot perturb it)
     conv = None
+    from mla_b200 import basic_model
+    overlap = basic_model.OVERLAP_ENCODERS
+    basic_model.OVERLAP_ENCODERS = False     # one stream: per-launch durations must not include a co-running kernel
     if rank == 0:
         encoder_engine.CONV_TIMING = []
         with quiet:
@@ -281,6 +297,7 @@ def run_native(a, rank, world):
     elif world > 1:
         with quiet:
             epoch(resident, a.steps)
+    basic_model.OVERLAP_ENCODERS = overlap
     if rank != 0:
         return
     samples = BATCH * world * a.steps
@@ -292,11 +309,12 @@ def run_native(a, rank, world):
            "dtype": "tf32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                       "encoder_backend": encoder_engine.BACKEND, "gs_projection": "fires (force_projection)",
+                      "streams": "audio / visual encoders on two CUDA streams" if overlap else "single stream",
                       "l2": "2 alternating input batches (179 MB) + >1 GB of activations per step exceed the 126 MB L2; no explicit flush"},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * t_e2e / a.steps},
-           "eval_samples_per_s": samples / t_eval,
+           "eval_samples_per_s": samples / t_eval, "host_enqueue_ms_per_step": host_ms,
            "encoder_tflops": FLOP_PER_SAMPLE_STEP * samples / t_dev / 1e12}
     prof = profile_summary()
     if conv is not None and conv["seconds"] > 0:

@@ -180,6 +180,15 @@ MLA_API int    mla_bn_eval_coeffs(const float* gamma, const float* beta, const f
 MLA_API int    mla_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
                         const float* res_scale, const float* res_shift, int relu, float* out,
                         long long M, int C, void* stream);
+/* Same as mla_bn_apply, additionally writing the sign of the output as a bitmask (1 bit per element, element e =
+ * bit e % 32 of word e / 32; M*C/32 words, C % 32 == 0): mla_bn_backward_mask reads it in place of the 32x larger
+ * activation z when it masks the gradient of the ReLU. */
+MLA_API int    mla_bn_apply_mask(const float* y, const float* scale, const float* shift, const float* res,
+                        const float* res_scale, const float* res_shift, int relu, float* out,
+                        unsigned int* relu_mask, long long M, int C, void* stream);
+MLA_API int    mla_bn_backward_mask(const float* dz, const unsigned int* relu_mask, const float* y, const float* mean,
+                        const float* invstd, const float* gamma, long long M, int C, float* dgamma,
+                        float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream);
 MLA_API int    mla_bn_backward(const float* dz, const float* z, const float* y, const float* mean,
                         const float* invstd, const float* gamma, long long M, int C, float* dgamma,
                         float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream);

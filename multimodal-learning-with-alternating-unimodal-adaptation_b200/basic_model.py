@@ -6,12 +6,16 @@ creation order follow the reference so state dicts and seeded initialisation are
 Only the concat head under --gs_flag is in scope (QMF / film / gated / sum are
 out of scope and raise).
 """
+import os
+
+import torch
 import torch.nn as nn
 
 from .backbone import resnet18
 from .fusion_modules import ConcatFusion
 
 _N_CLASSES = {"CREMAD": 6}
+OVERLAP_ENCODERS = os.environ.get("MLA_OVERLAP", "1") != "0"     # audio / visual encoder work on two CUDA streams
 
 
 class AVClassifier(nn.Module):
@@ -32,8 +36,22 @@ class AVClassifier(nn.Module):
         self.args = args
 
     def forward(self, audio, visual):
-        a = self.audio_net.pooled(audio)        # backbone + adaptive_avg_pool2d + flatten
-        v = self.visual_net.pooled(visual)      # backbone + adaptive_avg_pool3d over (T,H,W) + flatten
+        if audio.is_cuda and OVERLAP_ENCODERS:
+            # the two encoders are independent: the audio one runs on a side stream, concurrently with the visual one
+            cur = torch.cuda.current_stream(audio.device)
+            side = self.__dict__.get("_mla_side_stream")
+            if side is None:
+                side = torch.cuda.Stream(audio.device)
+                self.__dict__["_mla_side_stream"] = side
+            side.wait_stream(cur)               # inputs and the latest parameter update are ready
+            with torch.cuda.stream(side):
+                a = self.audio_net.pooled(audio)
+            v = self.visual_net.pooled(visual)
+            cur.wait_stream(side)
+            a.record_stream(cur)
+        else:
+            a = self.audio_net.pooled(audio)        # backbone + adaptive_avg_pool2d + flatten
+            v = self.visual_net.pooled(visual)      # backbone + adaptive_avg_pool3d over (T,H,W) + flatten
         if not self.args.gs_flag:
             return self.fusion_module(a, v)
         return a, v

@@ -419,15 +419,24 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   }
 }
 
-// Fixed-order reduction of split-K partials: dw[i] = sum_s part[s][i].
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4, int splits,
-                                     long long stride4) {
+// Fixed-order reduction of split-K partials: dw[i] = sum_s part[s][i]. Eight partials are loaded before they are
+// added (memory-level parallelism); the additions keep the order s = 0, 1, 2, ... (deterministic).
+__global__ void __launch_bounds__(64) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                            long long n4, int splits, long long stride4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  const float4* p4 = reinterpret_cast<const float4*>(part);
-  float4 acc = p4[i];
-  for (int s = 1; s < splits; ++s) {
-    const float4 v = p4[i + (long long)s * stride4];
+  const float4* p4 = reinterpret_cast<const float4*>(part) + i;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(p4 + (long long)(s + u) * stride4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+  for (; s < splits; ++s) {
+    const float4 v = __ldcs(p4 + (long long)s * stride4);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   reinterpret_cast<float4*>(out)[i] = acc;
@@ -836,7 +845,7 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   if (rc) return rc;
   if (pl.splits > 1) {
     const long long n4 = p.split_stride / 4;
-    splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
+    splitk_reduce_kernel<<<(unsigned)((n4 + 63) / 64), 64, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
     MLA_CUDA_TRY(cudaGetLastError());
     mla::count_launch();
   }

@@ -31,6 +31,13 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
     st4(dst + 4 * i, tf32r4(ld4(src + 4 * i)));
 }
 
+// ReLU sign bitmask: bit e of the mask belongs to element e of the [M][C] tensor, i.e. float4 number i owns the nibble
+// (mask[i / 8] >> 4 * (i % 8)) & 15 (bit q = component q is > 0). Written by the forward BN-apply, read by the two
+// BN-backward passes instead of the 32x larger activation itself.
+__device__ __forceinline__ unsigned relu_nibble(const unsigned int* __restrict__ mask, long long i) {
+  return (__ldg(mask + (i >> 3)) >> (4 * (int)(i & 7))) & 15u;
+}
+
 // ------------------------------------------------------------------------------ stem im2col
 // col[m][k], m = (n, oh, ow), k = (r*S + s)*Cin + ci for k < R*S*Cin, zero for the pad columns.
 // Input element (n, ci, h, w) lives at in[(n / T)*sB + (n % T)*sT + ci*sC + h*W + w] (raw NCHW /
@@ -119,7 +126,8 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, long long M, int C,
                                                                      long long rows_per_block, double* __restrict__ part,
-                                                                     unsigned int* __restrict__ counters, BnFinal f) {
+                                                                     unsigned int* __restrict__ counters, BnFinal f,
+                                                                     const unsigned int* __restrict__ mask) {
   __shared__ double s_acc[16][2][64];
   __shared__ double s_fin[2][64];
   __shared__ int s_last;
@@ -132,34 +140,67 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
   {
     float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
     if (MODE == 1) { mu = ld4(mean + c0); is = ld4(invstd + c0); }
-    long long r = r0 + ty;
-    while (r < r1) {
-      float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
-      for (int it = 0; it < (MODE == 2 ? 2 : 32) && r < r1; ++it, r += 16) {   // a few rows in fp32, then flush to double
-        const float4 v = ld4(x + r * (MODE == 2 ? 2 * C : C) + c0);
-        if (MODE == 2) {
-          const float4 q = ld4(x + r * 2 * C + C + c0);
-          fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
-          fb[0] += q.x; fb[1] += q.y; fb[2] += q.z; fb[3] += q.w;
-        } else if (MODE == 0) {
-          fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
-          fb[0] = fmaf(v.x, v.x, fb[0]); fb[1] = fmaf(v.y, v.y, fb[1]);
-          fb[2] = fmaf(v.z, v.z, fb[2]); fb[3] = fmaf(v.w, v.w, fb[3]);
-        } else {
-          float4 g = ld4(dz + r * C + c0);
-          if (z != nullptr) {
-            const float4 zz = ld4(z + r * C + c0);
-            g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f;
-            g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
-          }
-          fa[0] += g.x; fa[1] += g.y; fa[2] += g.z; fa[3] += g.w;
-          fb[0] = fmaf(g.x, (v.x - mu.x) * is.x, fb[0]); fb[1] = fmaf(g.y, (v.y - mu.y) * is.y, fb[1]);
-          fb[2] = fmaf(g.z, (v.z - mu.z) * is.z, fb[2]); fb[3] = fmaf(g.w, (v.w - mu.w) * is.w, fb[3]);
+    // this thread's rows: r0 + ty + 16 * i, i < n. Four rows per step with all their loads issued first (memory-level
+    // parallelism); fp32 accumulation over at most 32 rows, then flushed to double.
+    const long long n = (r1 - r0 - ty + 15) / 16;
+    const long long rs = (MODE == 2) ? 2LL * C : (long long)C;   // row stride in floats
+    const float* xp = x + (r0 + ty) * rs + c0;
+    const float* dzp = (MODE == 1) ? dz + (r0 + ty) * rs + c0 : nullptr;
+    const float* zp = (MODE == 1 && z != nullptr) ? z + (r0 + ty) * rs + c0 : nullptr;
+    float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
+    auto flush = [&]() {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] += (double)fa[q]; b[q] += (double)fb[q]; fa[q] = 0.f; fb[q] = 0.f; }
+    };
+    auto row = [&](const float4& v, const float4& w, const float4& zz) {
+      if (MODE == 2) {          // w = the second half of the partial row (sum of squares)
+        fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
+        fb[0] += w.x; fb[1] += w.y; fb[2] += w.z; fb[3] += w.w;
+      } else if (MODE == 0) {
+        fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
+        fb[0] = fmaf(v.x, v.x, fb[0]); fb[1] = fmaf(v.y, v.y, fb[1]);
+        fb[2] = fmaf(v.z, v.z, fb[2]); fb[3] = fmaf(v.w, v.w, fb[3]);
+      } else {                  // w = dz, zz = the ReLU output (mask) or +1
+        const float gx = zz.x > 0.f ? w.x : 0.f, gy = zz.y > 0.f ? w.y : 0.f;
+        const float gz = zz.z > 0.f ? w.z : 0.f, gw = zz.w > 0.f ? w.w : 0.f;
+        fa[0] += gx; fa[1] += gy; fa[2] += gz; fa[3] += gw;
+        fb[0] = fmaf(gx, (v.x - mu.x) * is.x, fb[0]); fb[1] = fmaf(gy, (v.y - mu.y) * is.y, fb[1]);
+        fb[2] = fmaf(gz, (v.z - mu.z) * is.z, fb[2]); fb[3] = fmaf(gw, (v.w - mu.w) * is.w, fb[3]);
+      }
+    };
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+    const int kFlush = (MODE == 2) ? 1 : 8;     // steps of 4 rows between flushes
+    long long i = 0;
+    int since = 0;
+    for (; i + 4 <= n; i += 4) {
+      float4 v[4], w[4], zz[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long o = (i + u) * 16 * rs;
+        v[u] = ld4(xp + o);
+        w[u] = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
+        zz[u] = (zp != nullptr) ? ld4(zp + o) : one;
+        if (MODE == 1 && mask != nullptr) {
+          const unsigned nb = relu_nibble(mask, ((r0 + ty + (i + u) * 16) * C + c0) >> 2);
+          zz[u] = make_float4((nb & 1u) ? 1.f : 0.f, (nb & 2u) ? 1.f : 0.f, (nb & 4u) ? 1.f : 0.f, (nb & 8u) ? 1.f : 0.f);
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { a[q] += (double)fa[q]; b[q] += (double)fb[q]; }
+      for (int u = 0; u < 4; ++u) row(v[u], w[u], zz[u]);
+      if (++since == kFlush) { flush(); since = 0; }
     }
+    for (; i < n; ++i) {
+      const long long o = i * 16 * rs;
+      const float4 v = ld4(xp + o);
+      const float4 w = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
+      float4 zz = (zp != nullptr) ? ld4(zp + o) : one;
+      if (MODE == 1 && mask != nullptr) {
+        const unsigned nb = relu_nibble(mask, ((r0 + ty + i * 16) * C + c0) >> 2);
+        zz = make_float4((nb & 1u) ? 1.f : 0.f, (nb & 2u) ? 1.f : 0.f, (nb & 4u) ? 1.f : 0.f, (nb & 8u) ? 1.f : 0.f);
+      }
+      row(v, w, zz);
+    }
+    flush();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       s_acc[ty][0][4 * tx + q] = a[q];
@@ -180,12 +221,18 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x < 128) {
-    const double* pp = part + (size_t)chunk * nrb * 128 + threadIdx.x;
+  {
+    // column (threadIdx.x & 127) of the partial rows; the two halves of the block take alternate partial rows and are
+    // combined in a fixed order (deterministic)
+    __shared__ double s_half[128];
+    const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const double* pp = part + (size_t)chunk * nrb * 128 + col;
     double sum = 0;
 #pragma unroll 8
-    for (int blk = 0; blk < nrb; ++blk) sum += __ldcg(pp + (size_t)blk * 128);   // block order: deterministic
-    s_fin[threadIdx.x >> 6][threadIdx.x & 63] = sum;
+    for (int blk = half; blk < nrb; blk += 2) sum += __ldcg(pp + (size_t)blk * 128);
+    if (half == 1) s_half[col] = sum;
+    __syncthreads();
+    if (half == 0) s_fin[col >> 6][col & 63] = sum + s_half[col];
   }
   __syncthreads();
   if (threadIdx.x == 0) counters[chunk] = 0;   // leave the workspace reusable
@@ -227,24 +274,55 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
   shift[c] = beta[c] - rm[c] * sc;
 }
 
-// out = relu?( y*scale + shift + (res ? res*rscale + rshift : 0) )
-__global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                                const float* __restrict__ res, const float* __restrict__ rscale,
-                                const float* __restrict__ rshift, int relu, float* __restrict__ out, long long n4, int C4) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    const float4 v = ld4(y + 4 * i), sc = ld4(scale + c), sh = ld4(shift + c);
-    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-    if (res != nullptr) {
-      float4 r = ld4(res + 4 * i);
-      if (rscale != nullptr) {
-        const float4 rs = ld4(rscale + c), rb = ld4(rshift + c);
-        r = make_float4(fmaf(r.x, rs.x, rb.x), fmaf(r.y, rs.y, rb.y), fmaf(r.z, rs.z, rb.z), fmaf(r.w, rs.w, rb.w));
+// out = relu?( y*scale + shift + (res ? res*rscale + rshift : 0) ). Four float4 per thread and step, loads first.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const float* __restrict__ res,
+                                                       const float* __restrict__ rscale, const float* __restrict__ rshift,
+                                                       int relu, float* __restrict__ out, long long n4, int C4,
+                                                       unsigned int* __restrict__ mask_out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // the loop bound is warp-uniform (i0 - lane), so all 32 lanes stay together for the mask shuffles
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 - (threadIdx.x & 31) < n4; i0 += 4 * stride) {
+    float4 v[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        v[u] = ld4(y + 4 * i);
+        if (res != nullptr) r[u] = ld4(res + 4 * i);
       }
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    st4(out + 4 * i, tf32r4(o));   // consumers are tcgen05 convolutions (and the residual add / pooling)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i - (threadIdx.x & 31) >= n4) break;     // warp-uniform
+      const bool live = i < n4;                    // tail lanes of the last warp only take part in the shuffles
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const int c = (int)(i % C4) * 4;
+        const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+        o = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z),
+                        fmaf(v[u].w, sc.w, sh.w));
+        if (res != nullptr) {
+          float4 rr = r[u];
+          if (rscale != nullptr) {
+            const float4 rs = ld4(rscale + c), rb = ld4(rshift + c);
+            rr = make_float4(fmaf(rr.x, rs.x, rb.x), fmaf(rr.y, rs.y, rb.y), fmaf(rr.z, rs.z, rb.z), fmaf(rr.w, rs.w, rb.w));
+          }
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        st4(out + 4 * i, tf32r4(o));   // consumers are tcgen05 convolutions (and the residual add / pooling)
+      }
+      if (mask_out != nullptr) {       // 8 lanes = 8 float4 = one 32-bit mask word
+        unsigned w = ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u))
+                     << (4 * (threadIdx.x & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if (live && (threadIdx.x & 7) == 0) mask_out[i >> 3] = w;
+      }
+    }
   }
 }
 
@@ -252,7 +330,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums, float inv_m,
-                                    float* __restrict__ dy, float* __restrict__ g_out, long long n4, int C4) {
+                                    float* __restrict__ dy, float* __restrict__ g_out, long long n4, int C4,
+                                    const unsigned int* __restrict__ mask) {
   const int C = C4 * 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
@@ -261,6 +340,10 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
       const float4 zz = ld4(z + 4 * i);
       g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f;
       g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
+    } else if (mask != nullptr) {
+      const unsigned nb = relu_nibble(mask, i);
+      g.x = (nb & 1u) ? g.x : 0.f; g.y = (nb & 2u) ? g.y : 0.f;
+      g.z = (nb & 4u) ? g.z : 0.f; g.w = (nb & 8u) ? g.w : 0.f;
     }
     if (g_out != nullptr) st4(g_out + 4 * i, g);
     const float4 v = ld4(y + 4 * i), mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c);
@@ -385,7 +468,7 @@ int red_plan(long long M, int C, RedPlan* pl) {
   if (di.ok != 1) return di.ok;
   pl->chunks = C / 64;
   long long nrb = (M + 127) / 128;                                   // >= 8 rows per thread
-  const long long cap = max(1, 2 * di.sm_count / pl->chunks);
+  const long long cap = max(1, 4 * di.sm_count / pl->chunks);
   if (nrb > cap) nrb = cap;
   pl->rows_per_block = (M + nrb - 1) / nrb;
   pl->nrb = (int)((M + pl->rows_per_block - 1) / pl->rows_per_block);
@@ -456,7 +539,7 @@ extern "C" int mla_bn_train_stats(const float* y, long long M, int C, const floa
   f.shift_out = shift_out;
   channel_reduce_kernel<0><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       y, nullptr, nullptr, nullptr, nullptr, M, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
-      reinterpret_cast<unsigned int*>(base), f);
+      reinterpret_cast<unsigned int*>(base), f, nullptr);
   MLA_LAUNCH_CHECK();
   return 0;
 }
@@ -478,7 +561,7 @@ extern "C" int mla_bn_stats_from_partials(const float* part, int ntiles, long lo
   f.shift_out = shift_out;
   channel_reduce_kernel<2><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       part, nullptr, nullptr, nullptr, nullptr, ntiles, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
-      reinterpret_cast<unsigned int*>(base), f);
+      reinterpret_cast<unsigned int*>(base), f, nullptr);
   MLA_LAUNCH_CHECK();
   return 0;
 }
@@ -494,19 +577,26 @@ extern "C" int mla_bn_eval_coeffs(const float* gamma, const float* beta, const f
   return 0;
 }
 
-extern "C" int mla_bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
-                            const float* res_shift, int relu, float* out, long long M, int C, void* stream) {
+extern "C" int mla_bn_apply_mask(const float* y, const float* scale, const float* shift, const float* res,
+                                 const float* res_scale, const float* res_shift, int relu, float* out,
+                                 unsigned int* relu_mask, long long M, int C, void* stream) {
   if (!y || !scale || !shift || !out || M < 1 || C < 4 || (C & 3)) return MLA_E_BADARG;
+  if (relu_mask != nullptr && (C & 31)) return MLA_E_SHAPE;    // whole mask words per row group
   const long long n4 = M * (C / 4);
-  bn_apply_kernel<<<ew_grid(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, scale, shift, res, res_scale,
-                                                                                  res_shift, relu, out, n4, C / 4);
+  bn_apply_kernel<<<ew_grid((n4 + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, scale, shift, res, res_scale, res_shift, relu, out, n4, C / 4, relu_mask);
   MLA_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int mla_bn_backward(const float* dz, const float* z, const float* y, const float* mean, const float* invstd,
-                               const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* g_out,
-                               void* ws, size_t ws_bytes, void* stream) {
+extern "C" int mla_bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
+                            const float* res_shift, int relu, float* out, long long M, int C, void* stream) {
+  return mla_bn_apply_mask(y, scale, shift, res, res_scale, res_shift, relu, out, nullptr, M, C, stream);
+}
+
+static int bn_backward_impl(const float* dz, const float* z, const unsigned int* mask, const float* y, const float* mean,
+                            const float* invstd, const float* gamma, long long M, int C, float* dgamma, float* dbeta,
+                            float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream) {
   if (!dz || !y || !mean || !invstd || !gamma || !dy) return MLA_E_BADARG;
   RedPlan pl;
   int rc = red_plan(M, C, &pl);
@@ -519,13 +609,27 @@ extern "C" int mla_bn_backward(const float* dz, const float* z, const float* y, 
   f.M = M; f.dgamma = dgamma; f.dbeta = dbeta; f.sums = sums;
   channel_reduce_kernel<1><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, st>>>(
       y, dz, z, mean, invstd, M, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
-      reinterpret_cast<unsigned int*>(base), f);
+      reinterpret_cast<unsigned int*>(base), f, mask);
   MLA_LAUNCH_CHECK();
   const long long n4 = M * (C / 4);
   bn_bwd_apply_kernel<<<ew_grid(n4, 256), 256, 0, st>>>(dz, z, y, mean, invstd, gamma, sums, 1.f / (float)M, dy, g_out, n4,
-                                                       C / 4);
+                                                       C / 4, mask);
   MLA_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mla_bn_backward(const float* dz, const float* z, const float* y, const float* mean, const float* invstd,
+                               const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* g_out,
+                               void* ws, size_t ws_bytes, void* stream) {
+  return bn_backward_impl(dz, z, nullptr, y, mean, invstd, gamma, M, C, dgamma, dbeta, dy, g_out, ws, ws_bytes, stream);
+}
+
+extern "C" int mla_bn_backward_mask(const float* dz, const unsigned int* relu_mask, const float* y, const float* mean,
+                                    const float* invstd, const float* gamma, long long M, int C, float* dgamma,
+                                    float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream) {
+  if (!relu_mask) return MLA_E_BADARG;
+  return bn_backward_impl(dz, nullptr, relu_mask, y, mean, invstd, gamma, M, C, dgamma, dbeta, dy, g_out, ws, ws_bytes,
+                          stream);
 }
 
 extern "C" int mla_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* out, unsigned char* idx,

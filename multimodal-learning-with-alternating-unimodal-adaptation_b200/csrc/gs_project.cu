@@ -111,7 +111,20 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     const float* src = p.P + (size_t)(row0 + lr) * D;
     float* dst = s_P + (size_t)lr * D;
     float acc = 0.f;
-    for (int j4 = lane; j4 < D4; j4 += 32) {
+    int j4 = lane;
+    for (; j4 + 7 * 32 < D4; j4 += 8 * 32) {      // 8 independent 512-byte row segments in flight per warp
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ld4(src + 4 * (j4 + 32 * u));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 r = ld4(s_r + 4 * (j4 + 32 * u));
+        st4(dst + 4 * (j4 + 32 * u), v[u]);
+        acc = fmaf(v[u].x, r.x, acc); acc = fmaf(v[u].y, r.y, acc);
+        acc = fmaf(v[u].z, r.z, acc); acc = fmaf(v[u].w, r.w, acc);
+      }
+    }
+    for (; j4 < D4; j4 += 32) {
       float4 v = ld4(src + 4 * j4);
       float4 r = ld4(s_r + 4 * j4);
       st4(dst + 4 * j4, v);

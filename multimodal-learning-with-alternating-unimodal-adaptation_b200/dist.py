@@ -70,6 +70,11 @@ class FlatGrads:
         for p, v in zip(self.params, self.views):
             p.grad = v
 
+    def detach(self):
+        """Hide the gradients from the optimiser (p.grad = None) without touching the flat buffer."""
+        for p in self.params:
+            p.grad = None
+
     def allreduce_avg(self):
         if is_dist():
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)

@@ -20,7 +20,10 @@ import torch
 
 from . import _lib
 
+import os
+
 BACKEND = "native-tcgen05"
+_USE_RELU_MASK = os.environ.get("MLA_RELU_MASK", "1") != "0"      # A/B switch (bitmask vs reading the activation)
 _STEM_KP = {1: 64, 3: 160}     # K = 49*Cin padded to a multiple of 32 (tcgen05 k-blocks of 32 tf32)
 
 
@@ -154,6 +157,8 @@ class ResNetPlan:
                 ho, wo = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
                 d = dict(blk=blk, stride=s, cin=cin, cout=cout, h=h, w=w, ho=ho, wo=wo,
                          y1=e(N, ho, wo, cout), a1=e(N, ho, wo, cout), y2=e(N, ho, wo, cout), out=e(N, ho, wo, cout),
+                         # ReLU sign bitmasks of a1 / out (1 bit per element): what BN backward reads instead of them
+                         m1=e(N * ho * wo * cout // 32, dt=torch.int32), m2=e(N * ho * wo * cout // 32, dt=torch.int32),
                          bn1=_BN(blk.bn1, dev), bn2=_BN(blk.bn2, dev), yd=None, bnd=None)
                 if blk.downsample is not None:
                     d["yd"] = e(N, ho, wo, cout)
@@ -244,9 +249,14 @@ class ResNetPlan:
             _chk(self.L.mla_bn_eval_coeffs(_p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
                                            float(bn.eps), b.C, _p(b.scale), _p(b.shift), st), "mla_bn_eval_coeffs")
 
-    def _bn_bwd(self, dz, z, y, b, M, dy, g_out, st):
+    def _bn_bwd(self, dz, z, y, b, M, dy, g_out, st, mask=None):
         bn = b.bn
         dg, db = _grad_buffer(bn.weight), _grad_buffer(bn.bias)
+        if mask is not None:
+            _chk(self.L.mla_bn_backward_mask(_p(dz), _p(mask), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C,
+                                             _p(dg), _p(db), _p(dy), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st),
+                 "mla_bn_backward_mask")
+            return
         _chk(self.L.mla_bn_backward(_p(dz), _p(z), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C, _p(dg), _p(db),
                                     _p(dy), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st), "mla_bn_backward")
 
@@ -275,18 +285,20 @@ class ResNetPlan:
             blk, s, cin, cout = b["blk"], b["stride"], b["cin"], b["cout"]
             M = N * b["ho"] * b["wo"]
             self._conv_bn(xin, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, b["bn1"], training, st)
-            _chk(L.mla_bn_apply(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(b["a1"]), M,
-                                cout, st), "mla_bn_apply")
+            mk1, mk2 = (_p(b["m1"]), _p(b["m2"])) if training else (None, None)
+            _chk(L.mla_bn_apply_mask(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(b["a1"]),
+                                     mk1, M, cout, st), "mla_bn_apply")
             self._conv_bn(b["a1"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, b["bn2"], training,
                           st)
             if b["yd"] is not None:
                 self._conv_bn(xin, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, b["bnd"],
                               training, st)
-                _chk(L.mla_bn_apply(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]), _p(b["bnd"].scale),
-                                    _p(b["bnd"].shift), 1, _p(b["out"]), M, cout, st), "mla_bn_apply")
+                _chk(L.mla_bn_apply_mask(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]),
+                                         _p(b["bnd"].scale), _p(b["bnd"].shift), 1, _p(b["out"]), mk2, M, cout, st),
+                     "mla_bn_apply")
             else:
-                _chk(L.mla_bn_apply(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
-                                    _p(b["out"]), M, cout, st), "mla_bn_apply")
+                _chk(L.mla_bn_apply_mask(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
+                                         _p(b["out"]), mk2, M, cout, st), "mla_bn_apply")
             xin = b["out"]
         self.x_in0 = None
         feat = torch.empty(self.B, self.C_out, dtype=torch.float32, device=self.dev)
@@ -314,12 +326,18 @@ class ResNetPlan:
             shp = b["out"].shape
             g = self.tmp("g%d" % (i & 1), shp)
             dy2 = self.tmp("dy", shp)
-            self._bn_bwd(dout, b["out"], b["y2"], b["bn2"], M, dy2, g, st)
+            if _USE_RELU_MASK:
+                self._bn_bwd(dout, None, b["y2"], b["bn2"], M, dy2, g, st, mask=b["m2"])
+            else:
+                self._bn_bwd(dout, b["out"], b["y2"], b["bn2"], M, dy2, g, st)
             self._wgrad(b["a1"], dy2, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3, 1, 1, st)
             da1 = self.tmp("da", shp)
             self._dgrad(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
             dy1 = dy2                                   # dy2 is dead: reuse its buffer
-            self._bn_bwd(da1, b["a1"], b["y1"], b["bn1"], M, dy1, None, st)
+            if _USE_RELU_MASK:
+                self._bn_bwd(da1, None, b["y1"], b["bn1"], M, dy1, None, st, mask=b["m1"])
+            else:
+                self._bn_bwd(da1, b["a1"], b["y1"], b["bn1"], M, dy1, None, st)
             self._wgrad(xin, dy1, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1, st)
             if b["yd"] is not None:
                 dyd = da1                               # da1 is dead
@@ -379,7 +397,9 @@ def resnet_pooled(net, x):
         raise RuntimeError("mla_b200 encoders run on CUDA only (no CPU fallback); got %s" % x.device)
     plan = _plan(net, x)
     if net.training and torch.is_grad_enabled():
-        return _EncoderFn.apply(plan, x, net.conv1.weight)
+        out = _EncoderFn.apply(plan, x, net.conv1.weight)
+        out._mla_plan = plan          # lets train_epoch run the native backward directly, on a stream of its choice
+        return out
     with torch.no_grad():
         return plan.forward(x, net.training)
 

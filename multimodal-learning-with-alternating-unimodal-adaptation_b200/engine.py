@@ -12,6 +12,7 @@ Out of scope (raises): the joint-training branch without --gs_flag (main.py:165-
 import torch
 import torch.nn as nn
 
+from . import basic_model
 from . import dist as mdist
 from . import ops
 from .fusion_modules import head_turn
@@ -54,9 +55,10 @@ def _unpack(args, data_packet, device):
 
 
 def _batches_on_device(args, dataloader, device):
-    """Yields (inputs, label) on `device`. Host batches (pinned) are copied on a side stream ONE BATCH AHEAD,
-    so the H2D transfer of batch i+1 overlaps the compute of batch i (the reference copies synchronously at
-    the top of every iteration, main.py:160-162)."""
+    """Yields (inputs, label) on `device`. Host batches (pinned) are copied on a side stream ONE BATCH AHEAD into
+    two alternating sets of preallocated device buffers, so the H2D transfer of batch i+1 overlaps the compute of
+    batch i and nothing is allocated per step (the reference copies synchronously at the top of every iteration,
+    main.py:160-162)."""
     dev = torch.device(device)
     if dev.type != "cuda":
         for pkt in dataloader:
@@ -65,6 +67,8 @@ def _batches_on_device(args, dataloader, device):
     main = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(dev)
     it = iter(dataloader)
+    bufs = [None, None]
+    count = [0]
 
     def load():
         try:
@@ -73,20 +77,26 @@ def _batches_on_device(args, dataloader, device):
             return None
         if all((not torch.is_tensor(t)) or t.is_cuda for t in pkt):
             return _unpack(args, pkt, device), None                      # already resident: nothing to overlap
+        k = count[0] & 1
+        count[0] += 1
+        if bufs[k] is None or any(torch.is_tensor(t) and (b.shape != t.shape or b.dtype != t.dtype)
+                                  for t, b in zip(pkt, bufs[k])):
+            bufs[k] = [torch.empty(t.shape, dtype=t.dtype, device=dev) if torch.is_tensor(t) else t for t in pkt]
+        # buffer set k was last read by the step before the one now being enqueued: everything on `main` so far
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            out = _unpack(args, pkt, device)
+            for t, b in zip(pkt, bufs[k]):
+                if torch.is_tensor(t):
+                    b.copy_(t, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(side)
-        return out, ev
+        return _unpack(args, tuple(bufs[k]), device), ev
 
     nxt = load()
     while nxt is not None:
         (inputs, label), ev = nxt
         if ev is not None:
             main.wait_event(ev)
-            for t in tuple(inputs) + (label,):
-                t.record_stream(main)
         nxt = load()
         yield inputs, label
 
@@ -106,6 +116,24 @@ class _TurnState:
                          "feat_sum": self.packed[o_fs:o_fs + D]}
         self.encoders = encoder_param_groups(net)
         self.flat = [mdist.FlatGrads(g) for g in self.encoders]
+        self._dfeat = {}
+        self._side = {}
+
+    def dfeat_buffer(self, m, feat):
+        """d(loss)/d(feature) of modality m: its own buffer, because the encoder backward that reads it may still be
+        running on a side stream when the next modality's head turn writes its dfeat."""
+        t = self._dfeat.get(m)
+        if t is None or t.shape != feat.shape or t.device != feat.device:
+            t = torch.empty_like(feat)
+            self._dfeat[m] = t
+        return t
+
+    def side_stream(self, m):
+        s = self._side.get(m)
+        if s is None:
+            s = torch.cuda.Stream()
+            self._side[m] = s
+        return s
 
 
 def encoder_param_groups(net):
@@ -153,13 +181,36 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
         B = feats[0].shape[0]
         inv_global = 1.0 / (B * world)
         losses = []
+        pending = []
         for m, feat in enumerate(feats):                                   # a -> v -> (t)
             fdet = feat.detach()
+            st.head_out["dfeat"] = st.dfeat_buffer(m, fdet)                # one dfeat buffer per modality (see below)
             o = head_turn(fc, fdet, label, grad_scale=inv_global, out=st.head_out)   # main.py:432-435 (head part)
-            st.flat[m].attach()
-            feat.backward(o["dfeat"])                                      # main.py:435 (encoder part)
-            if world > 1:                                                  # two collectives per turn
-                mdist.allreduce_sum_(st.flat[m].flat)
+            plan = getattr(feat, "_mla_plan", None)
+            if plan is not None:
+                # main.py:435 (encoder part), native backward launched directly. Every encoder but the last runs its
+                # backward (and gradient all-reduce) on its own side stream, concurrently with the next turns: this
+                # turn's optimizer.step() then only sees the head; the encoder's own SGD update follows when its
+                # gradients are complete (same arithmetic: SGD treats parameters independently, and the next turns
+                # never read this encoder's parameters).
+                deferred = basic_model.OVERLAP_ENCODERS and m < n_mod - 1
+                stream = st.side_stream(m) if deferred else torch.cuda.current_stream()
+                if deferred:
+                    stream.wait_stream(torch.cuda.current_stream())        # dfeat is ready
+                with torch.cuda.stream(stream):
+                    st.flat[m].attach()
+                    plan.backward(o["dfeat"])
+                    if world > 1:                                          # encoder-gradient all-reduce
+                        mdist.allreduce_sum_(st.flat[m].flat)
+                if deferred:
+                    st.flat[m].detach()
+                    pending.append((m, stream))
+            else:
+                st.flat[m].attach()
+                feat.backward(o["dfeat"])
+                if world > 1:
+                    mdist.allreduce_sum_(st.flat[m].flat)
+            if world > 1:                                                  # the small head all-reduce
                 mdist.allreduce_sum_(st.packed)
             gs_plugin.before_update(fc, fdet, batch_step, len_dataloader, gs_plugin.exp_count,
                                     feat_sum=o["feat_sum"], inv_batch=inv_global)     # main.py:437-438
@@ -167,6 +218,12 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
             optimizer.zero_grad()                                          # main.py:440
             gs_plugin.exp_count += 1                                       # main.py:442
             losses.append(o["loss"].clone())
+        if pending:                                                        # deferred encoder updates (main.py:439)
+            for m, stream in pending:
+                torch.cuda.current_stream().wait_stream(stream)
+                st.flat[m].attach()
+            optimizer.step()
+            optimizer.zero_grad()
         if n_mod == 2:                                                     # main.py:472 (fp32, like the reference)
             mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
         else:
