@@ -275,6 +275,8 @@ def run_native(a, rank, world):
     from mla_b200 import basic_model
     overlap = basic_model.OVERLAP_ENCODERS
     basic_model.OVERLAP_ENCODERS = False     # one stream: per-launch durations must not include a co-running kernel
+    overlap_w = encoder_engine._OVERLAP_WGRAD
+    encoder_engine._OVERLAP_WGRAD = False
     if rank == 0:
         encoder_engine.CONV_TIMING = []
         with quiet:
@@ -298,6 +300,7 @@ def run_native(a, rank, world):
         with quiet:
             epoch(resident, a.steps)
     basic_model.OVERLAP_ENCODERS = overlap
+    encoder_engine._OVERLAP_WGRAD = overlap_w
     if rank != 0:
         return
     samples = BATCH * world * a.steps
@@ -309,7 +312,8 @@ def run_native(a, rank, world):
            "dtype": "tf32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                       "encoder_backend": encoder_engine.BACKEND, "gs_projection": "fires (force_projection)",
-                      "streams": "audio / visual encoders on two CUDA streams" if overlap else "single stream",
+                      "streams": ("audio / visual encoders on two CUDA streams" if overlap else "single stream") +
+                                 ("; weight gradients on a third/fourth" if overlap_w else ""),
                       "l2": "2 alternating input batches (179 MB) + >1 GB of activations per step exceed the 126 MB L2; no explicit flush"},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
@@ -346,8 +350,22 @@ def run_native(a, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def start_watchdog(limit_s):
+    """A wedged GPU must not turn into a silent hang: if the run has not finished after `limit_s` seconds, say so on
+    stderr and leave with a non-zero exit code."""
+    def fire():
+        sys.stderr.write("bench.py watchdog: no result after %d s, aborting\n" % limit_s)
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(limit_s, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     a = parse()
+    start_watchdog(900 if a.impl == "reference" else 600)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":

@@ -515,12 +515,16 @@ bool force_gather() {
   return v;
 }
 
-// Unset = auto (measured on the ResNet-18 shapes, profiles/r1_conv_variants.md): pairs pay once the N tile is >= 128
-// columns (256-column tiles for 256 channels, 128-column tiles otherwise); 64-column tiles stay single-CTA.
+// MLA_CONV_PAIR = 1 | 2 | 3 enables tcgen05 CTA pairs (cta_group::2) in fprop / dgrad: 1 = same tile widths, 2 = also
+// 256-column tiles, 3 = the measured-best mix (profiles/r1_conv_variants.md: pairs for N tiles >= 128 columns, 256-column
+// tiles for exactly 256 channels). OFF BY DEFAULT: the host runtime runs the two encoders (and their weight
+// gradients) on concurrent CUDA streams, and two different pair kernels co-resident on one SM pair can dead-lock in
+// tcgen05.alloc.cta_group::2 (each holds one SM's allocation while waiting for the other's) — observed once as a hung
+// bench on B200. Single-CTA allocations cannot form such a cycle. Pairs are only safe on a single stream.
 int conv_pair_env() {
   static const int v = [] {
     const char* e = getenv("MLA_CONV_PAIR");
-    return e ? atoi(e) : -1;
+    return e ? atoi(e) : 0;
   }();
   return v;
 }
@@ -530,8 +534,8 @@ int conv_pair_bn(int nch) {
   if (e == 0 || force_gather()) return 0;
   const int bn = (nch % 128 == 0) ? 128 : 64;
   if (e == 1) return bn;
-  if (e >= 2) return nch % 256 == 0 ? 256 : bn;
-  if (nch % 128 != 0) return 0;          // auto
+  if (e == 2) return nch % 256 == 0 ? 256 : bn;
+  if (nch % 128 != 0) return 0;          // 3: measured-best mix
   return nch == 256 ? 256 : 128;
 }
 

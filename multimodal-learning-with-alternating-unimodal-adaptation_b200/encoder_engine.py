@@ -23,6 +23,7 @@ from . import _lib
 import os
 
 BACKEND = "native-tcgen05"
+_OVERLAP_WGRAD = os.environ.get("MLA_OVERLAP_WGRAD", "1") != "0"    # wgrad kernels on a side stream of the plan
 _USE_RELU_MASK = os.environ.get("MLA_RELU_MASK", "1") != "0"      # A/B switch (bitmask vs reading the activation)
 _STEM_KP = {1: 64, 3: 160}     # K = 49*Cin padded to a multiple of 32 (tcgen05 k-blocks of 32 tf32)
 
@@ -185,6 +186,8 @@ class ResNetPlan:
                      self.L.mla_conv2d_wgrad_workspace_bytes(N, b["ho"], b["wo"], b["cout"], b["cout"], 3, 3, 1, 1))
         self.wg_ws = torch.empty(max(nw, 256), dtype=torch.uint8, device=dev)
         self.trained_forward = False
+        self.wstream = None            # side stream of the weight-gradient kernels (created on first backward)
+        self._slot_events = {}         # (buffer slot, shape) -> event of the last wgrad that read it
 
     # ------------------------------------------------------------------ small helpers
     def tmp(self, slot, shape):
@@ -315,6 +318,35 @@ class ResNetPlan:
         L, N, st = self.L, self.N, _lib.stream_ptr()
         net = self.net
         dfeat = dfeat.contiguous()
+        # Weight gradients leave the critical path: every wgrad (and its split-K reduction) runs on the plan's own side
+        # stream as soon as its dy exists, concurrently with the BN-backward / dgrad chain that continues on `cur`.
+        # A dy buffer is only rewritten after the wgrad that read it has finished (events per buffer slot).
+        cur = torch.cuda.current_stream()
+        if self.wstream is None:
+            self.wstream = torch.cuda.Stream()
+        wsm = self.wstream if _OVERLAP_WGRAD else cur
+        wst = wsm.cuda_stream
+        wsm.wait_stream(cur)
+        events = self._slot_events
+
+        def buf(slot, shape):                       # a buffer about to be overwritten on `cur`
+            ev = events.pop((slot, tuple(shape)), None)
+            if ev is not None:
+                cur.wait_event(ev)
+            return self.tmp(slot, shape)
+
+        def wgrad_async(x, dy, slot, dw, *geom, k_alg=None):
+            if wsm is not cur:
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                wsm.wait_event(ready)
+            with torch.cuda.stream(wsm):
+                self._wgrad(x, dy, dw, *geom, wst, k_alg=k_alg)
+            if wsm is not cur:
+                done = torch.cuda.Event()
+                done.record(wsm)
+                events[(slot, tuple(dy.shape))] = done
+
         last = self.blocks[-1]
         dout = self.tmp("dXa", last["out"].shape)
         _chk(L.mla_avgpool_backward(_p(dfeat), _p(dout), self.B, self.rows, self.C_out, st), "mla_avgpool_backward")
@@ -324,25 +356,26 @@ class ResNetPlan:
             xin = self.blocks[i - 1]["out"] if i > 0 else self.p0
             M = N * b["ho"] * b["wo"]
             shp = b["out"].shape
-            g = self.tmp("g%d" % (i & 1), shp)
-            dy2 = self.tmp("dy", shp)
+            par = i & 1
+            g = self.tmp("g%d" % par, shp)
+            dy2 = buf("dy2_%d" % par, shp)
             if _USE_RELU_MASK:
                 self._bn_bwd(dout, None, b["y2"], b["bn2"], M, dy2, g, st, mask=b["m2"])
             else:
                 self._bn_bwd(dout, b["out"], b["y2"], b["bn2"], M, dy2, g, st)
-            self._wgrad(b["a1"], dy2, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3, 1, 1, st)
+            wgrad_async(b["a1"], dy2, "dy2_%d" % par, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3, 1, 1)
             da1 = self.tmp("da", shp)
             self._dgrad(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
-            dy1 = dy2                                   # dy2 is dead: reuse its buffer
+            dy1 = buf("dy1_%d" % par, shp)
             if _USE_RELU_MASK:
                 self._bn_bwd(da1, None, b["y1"], b["bn1"], M, dy1, None, st, mask=b["m1"])
             else:
                 self._bn_bwd(da1, b["a1"], b["y1"], b["bn1"], M, dy1, None, st)
-            self._wgrad(xin, dy1, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1, st)
+            wgrad_async(xin, dy1, "dy1_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1)
             if b["yd"] is not None:
-                dyd = da1                               # da1 is dead
+                dyd = buf("dyd", shp)
                 self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st)
-                self._wgrad(xin, dyd, _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0, st)
+                wgrad_async(xin, dyd, "dyd", _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0)
                 dx = self.tmp("dXa", xin.shape)         # xin.shape != out.shape here, so never aliases dout
                 # the 3x3 dgrad touches every pixel of dx and goes first; the 1x1/2 shortcut then ADDS into the
                 # one output parity class it reaches (its other classes are skipped, not zero-filled)
@@ -356,11 +389,13 @@ class ResNetPlan:
         g0 = self.tmp("g0", self.y0.shape)
         _chk(L.mla_maxpool_relu_backward(_p(dout), _p(self.p0), _p(self.idx0), _p(g0), N, self.OH0, self.OW0, 64, st),
              "mla_maxpool_relu_backward")
-        dy0 = self.tmp("dy0", self.y0.shape)
+        dy0 = buf("dy0", self.y0.shape)
         self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, dy0, None, st)
-        self._wgrad(self.col, dy0, self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, st, k_alg=49 * self.Cin)
-        _chk(L.mla_pad_rows(_p(self.dwpad), _p(_grad_buffer(net.conv1.weight)), 64, 49 * self.Cin, self.Kp, 1, st),
-             "mla_pad_rows")
+        wgrad_async(self.col, dy0, "dy0", self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, k_alg=49 * self.Cin)
+        with torch.cuda.stream(wsm):
+            _chk(L.mla_pad_rows(_p(self.dwpad), _p(_grad_buffer(net.conv1.weight)), 64, 49 * self.Cin, self.Kp, 1, wst),
+                 "mla_pad_rows")
+        cur.wait_stream(wsm)                            # every parameter gradient is complete on `cur`
         self.trained_forward = False
 
 
