@@ -376,6 +376,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     from mla_b200 import dist as mdist
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the ONE JSON line
         mdist.init_from_env("nccl")
     else:
         torch.cuda.set_device(0)

@@ -186,6 +186,8 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
             fdet = feat.detach()
             st.head_out["dfeat"] = st.dfeat_buffer(m, fdet)                # one dfeat buffer per modality (see below)
             o = head_turn(fc, fdet, label, grad_scale=inv_global, out=st.head_out)   # main.py:432-435 (head part)
+            if world > 1:                                                  # SURVEY §8e: the small head all-reduce
+                mdist.allreduce_sum_(st.packed)
             plan = getattr(feat, "_mla_plan", None)
             if plan is not None:
                 # main.py:435 (encoder part), native backward launched directly. Every encoder but the last runs its
@@ -200,9 +202,12 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                 with torch.cuda.stream(stream):
                     st.flat[m].attach()
                     plan.backward(o["dfeat"])
-                    if world > 1:                                          # encoder-gradient all-reduce
+                    if world > 1 and not deferred:                         # encoder-gradient all-reduce
                         mdist.allreduce_sum_(st.flat[m].flat)
                 if deferred:
+                    # its all-reduce is issued with the deferred update below: collectives of one communicator run in
+                    # issue order, so issuing it here would park the NEXT turn's small head all-reduce behind this
+                    # whole backward pass and serialise the two encoders again
                     st.flat[m].detach()
                     pending.append((m, stream))
             else:
@@ -210,8 +215,6 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                 feat.backward(o["dfeat"])
                 if world > 1:
                     mdist.allreduce_sum_(st.flat[m].flat)
-            if world > 1:                                                  # SURVEY §8e: the small head all-reduce
-                mdist.allreduce_sum_(st.packed)
             gs_plugin.before_update(fc, fdet, batch_step, len_dataloader, gs_plugin.exp_count,
                                     feat_sum=o["feat_sum"], inv_batch=inv_global)     # main.py:437-438
             optimizer.step()                                               # main.py:439
@@ -221,6 +224,8 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
         if pending:                                                        # deferred encoder updates (main.py:439)
             for m, stream in pending:
                 torch.cuda.current_stream().wait_stream(stream)
+                if world > 1:
+                    mdist.allreduce_sum_(st.flat[m].flat)
                 st.flat[m].attach()
             optimizer.step()
             optimizer.zero_grad()
