@@ -239,10 +239,10 @@ def run_native(a, rank, world):
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + encoder_engine.GRAPH_LAUNCHES
     with quiet:
         t_dev = timed(lambda: epoch(resident, a.steps))
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() + encoder_engine.GRAPH_LAUNCHES - l0     # eager launches + graph-replayed kernel nodes
     # end to end: host (pinned) buffers in, H2D every step, losses read back to the host every step
     with quiet:
         epoch(host, min(2, a.warmup))
@@ -313,7 +313,8 @@ def run_native(a, rank, world):
            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                       "encoder_backend": encoder_engine.BACKEND, "gs_projection": "fires (force_projection)",
                       "streams": ("audio / visual encoders on two CUDA streams" if overlap else "single stream") +
-                                 ("; weight gradients on a third/fourth" if overlap_w else ""),
+                                 ("; weight gradients on a third/fourth" if overlap_w else "") +
+                                 ("; encoder launch sequences replayed as CUDA graphs" if encoder_engine.USE_GRAPHS else ""),
                       "l2": "2 alternating input batches (179 MB) + >1 GB of activations per step exceed the 126 MB L2; no explicit flush"},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),

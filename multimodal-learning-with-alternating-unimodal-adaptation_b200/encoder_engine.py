@@ -23,6 +23,7 @@ from . import _lib
 import os
 
 BACKEND = "native-tcgen05"
+USE_GRAPHS = os.environ.get("MLA_GRAPHS", "1") != "0"               # replay the plans' launch sequences as CUDA graphs
 _OVERLAP_WGRAD = os.environ.get("MLA_OVERLAP_WGRAD", "1") != "0"    # wgrad kernels on a side stream of the plan
 _USE_RELU_MASK = os.environ.get("MLA_RELU_MASK", "1") != "0"      # A/B switch (bitmask vs reading the activation)
 _STEM_KP = {1: 64, 3: 160}     # K = 49*Cin padded to a multiple of 32 (tcgen05 k-blocks of 32 tf32)
@@ -36,6 +37,7 @@ def _p(t):
 # list, every conv call is bracketed by CUDA events on the launching stream and appended as
 # (kind, algorithmic FLOPs, start event, end event). Off (None) in normal operation.
 CONV_TIMING = None
+GRAPH_LAUNCHES = 0        # kernel launches replayed through CUDA graphs (the library's own counter only sees eager ones)
 
 
 def _conv_timer_begin():
@@ -135,6 +137,7 @@ class ResNetPlan:
         N = self.N
         _flatten_params(net)
         self.flat, self.wr, self.woff = net._mla_flat, net._mla_wr, net._mla_off
+        self._params = list(net.parameters())
         # ---- stem
         self.Kp = _STEM_KP[Cin]
         self.OH0, self.OW0 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
@@ -186,6 +189,9 @@ class ResNetPlan:
                      self.L.mla_conv2d_wgrad_workspace_bytes(N, b["ho"], b["wo"], b["cout"], b["cout"], 3, 3, 1, 1))
         self.wg_ws = torch.empty(max(nw, 256), dtype=torch.uint8, device=dev)
         self.trained_forward = False
+        self.feat_static = torch.empty(self.B, self.C_out, dtype=torch.float32, device=dev)    # pooled feature (graph output)
+        self.dfeat_static = torch.empty(self.B, self.C_out, dtype=torch.float32, device=dev)   # its gradient (graph input)
+        self._graphs, self._warm = {}, {}
         self.wstream = None            # side stream of the weight-gradient kernels (created on first backward)
         self._slot_events = {}         # (buffer slot, shape) -> event of the last wgrad that read it
 
@@ -263,6 +269,38 @@ class ResNetPlan:
         _chk(self.L.mla_bn_backward(_p(dz), _p(z), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C, _p(dg), _p(db),
                                     _p(dy), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st), "mla_bn_backward")
 
+    # ------------------------------------------------------------------------ CUDA graphs
+    def _run(self, key, fn):
+        """Run `fn` (a fixed launch sequence over buffers this plan owns) — eagerly the first time (function
+        attributes, lazy allocations), then captured once into a CUDA graph and replayed: one launch instead of
+        ~80-250, so the host never delays the streams (the two encoders and the weight gradients run on concurrent
+        streams and every microsecond of enqueue latency on one of them is exposed)."""
+        if not USE_GRAPHS or CONV_TIMING is not None:
+            return fn()
+        g = self._graphs.get(key)
+        if g is None:
+            if self._warm.get(key, 0) < 1:
+                self._warm[key] = 1
+                return fn()
+            try:
+                g = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    fn()
+                g.mla_nodes = _lib.launch_count() - n0      # kernels of ours inside the graph
+            except Exception as e:                      # capture unsupported for some reason: stay eager, loudly
+                import warnings
+                warnings.warn("mla_b200: CUDA graph capture of %s failed (%s); running eagerly" % (key, e))
+                self._graphs[key] = False
+                torch.cuda.synchronize()
+                return fn()
+            self._graphs[key] = g
+        if g is False:
+            return fn()
+        g.replay()
+        global GRAPH_LAUNCHES
+        GRAPH_LAUNCHES += g.mla_nodes
+
     # ------------------------------------------------------------------------ forward
     def forward(self, x, training):
         L, N, st = self.L, self.N, _lib.stream_ptr()
@@ -274,10 +312,18 @@ class ResNetPlan:
             sB, sT, sC = 3 * self.T * HW, HW, self.T * HW
         else:                              # [B,1,H,W]
             sB, sT, sC = self.Cin * HW, 0, HW
-        K = 49 * self.Cin
-        _chk(L.mla_round_tf32(_p(self.flat), _p(self.wr), self.flat.numel(), st), "mla_round_tf32")
+        # the only launch that reads the caller's buffer (its address changes from batch to batch): outside the graph
         _chk(L.mla_stem_im2col(_p(x), _p(self.col), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp,
                                st), "mla_stem_im2col")
+        self._run(("fwd", bool(training)), lambda: self._forward_body(training))
+        self.trained_forward = training
+        return self.feat_static.clone()
+
+    def _forward_body(self, training):
+        L, N, st = self.L, self.N, _lib.stream_ptr()
+        net = self.net
+        K = 49 * self.Cin
+        _chk(L.mla_round_tf32(_p(self.flat), _p(self.wr), self.flat.numel(), st), "mla_round_tf32")
         _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
         self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
                       k_alg=K)
@@ -303,21 +349,33 @@ class ResNetPlan:
                 _chk(L.mla_bn_apply_mask(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
                                          _p(b["out"]), mk2, M, cout, st), "mla_bn_apply")
             xin = b["out"]
-        self.x_in0 = None
-        feat = torch.empty(self.B, self.C_out, dtype=torch.float32, device=self.dev)
-        _chk(L.mla_avgpool_forward(_p(xin), _p(feat), self.B, self.rows, self.C_out, st), "mla_avgpool_forward")
+        _chk(L.mla_avgpool_forward(_p(xin), _p(self.feat_static), self.B, self.rows, self.C_out, st), "mla_avgpool_forward")
         if training and self.nbt:
             torch._foreach_add_(self.nbt, 1)
-        self.trained_forward = training
-        return feat
 
     # ----------------------------------------------------------------------- backward
     def backward(self, dfeat):
         if not self.trained_forward:
             raise RuntimeError("encoder backward needs a training-mode forward on the same plan")
+        self.dfeat_static.copy_(dfeat)
+        params = self._params
+        if params[0].grad is not None and params[-1].grad is not None:
+            # gradient buffers pre-attached by the caller (train_epoch: views of the flat all-reduce bucket): their
+            # addresses are stable, so the launch sequence can be replayed as a graph keyed on them
+            for p in params:
+                _grad_buffer(p)
+            if len(self._graphs) > 8:
+                self._graphs.clear(); self._warm.clear()
+            self._run(("bwd", params[0].grad.data_ptr(), params[-1].grad.data_ptr()), self._backward_body)
+        else:
+            self._backward_body()                        # fresh gradient tensors every call (plain autograd use): eager
+        self.trained_forward = False
+
+    def _backward_body(self):
         L, N, st = self.L, self.N, _lib.stream_ptr()
         net = self.net
-        dfeat = dfeat.contiguous()
+        dfeat = self.dfeat_static
+        self._slot_events.clear()                        # only events of THIS pass order its buffer reuse
         # Weight gradients leave the critical path: every wgrad (and its split-K reduction) runs on the plan's own side
         # stream as soon as its dy exists, concurrently with the BN-backward / dgrad chain that continues on `cur`.
         # A dy buffer is only rewritten after the wgrad that read it has finished (events per buffer slot).
@@ -396,7 +454,6 @@ class ResNetPlan:
             _chk(L.mla_pad_rows(_p(self.dwpad), _p(_grad_buffer(net.conv1.weight)), 64, 49 * self.Cin, self.Kp, 1, wst),
                  "mla_pad_rows")
         cur.wait_stream(wsm)                            # every parameter gradient is complete on `cur`
-        self.trained_forward = False
 
 
 class _EncoderFn(torch.autograd.Function):
