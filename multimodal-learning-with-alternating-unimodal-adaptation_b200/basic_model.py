@@ -35,23 +35,37 @@ class AVClassifier(nn.Module):
         self.visual_net = resnet18(modality="visual")
         self.args = args
 
+    def _streams(self, device):
+        st = self.__dict__.get("_mla_streams")
+        if st is None:
+            st = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+            self.__dict__["_mla_streams"] = st
+        return st
+
+    def forward_streams(self, audio, visual):
+        """Both encoders launched on their own CUDA streams, NOT joined: returns [(a, stream_a), (v, stream_v)].
+        The caller waits on a modality's stream when it needs that feature — train_epoch runs the whole audio turn
+        (head, GS, audio backward) while the longer visual forward is still in flight. `forward` is this + a join."""
+        cur = torch.cuda.current_stream(audio.device)
+        sa, sv = self._streams(audio.device)
+        sa.wait_stream(cur)                     # inputs and the latest parameter update are ready
+        sv.wait_stream(cur)
+        with torch.cuda.stream(sv):
+            v = self.visual_net.pooled(visual)      # backbone + adaptive_avg_pool3d over (T,H,W) + flatten
+        with torch.cuda.stream(sa):
+            a = self.audio_net.pooled(audio)        # backbone + adaptive_avg_pool2d + flatten
+        return [(a, sa), (v, sv)]
+
     def forward(self, audio, visual):
         if audio.is_cuda and OVERLAP_ENCODERS:
-            # the two encoders are independent: the audio one runs on a side stream, concurrently with the visual one
             cur = torch.cuda.current_stream(audio.device)
-            side = self.__dict__.get("_mla_side_stream")
-            if side is None:
-                side = torch.cuda.Stream(audio.device)
-                self.__dict__["_mla_side_stream"] = side
-            side.wait_stream(cur)               # inputs and the latest parameter update are ready
-            with torch.cuda.stream(side):
-                a = self.audio_net.pooled(audio)
-            v = self.visual_net.pooled(visual)
-            cur.wait_stream(side)
-            a.record_stream(cur)
+            (a, sa), (v, sv) = self.forward_streams(audio, visual)
+            for t, s in ((a, sa), (v, sv)):
+                cur.wait_stream(s)
+                t.record_stream(cur)
         else:
-            a = self.audio_net.pooled(audio)        # backbone + adaptive_avg_pool2d + flatten
-            v = self.visual_net.pooled(visual)      # backbone + adaptive_avg_pool3d over (T,H,W) + flatten
+            a = self.audio_net.pooled(audio)
+            v = self.visual_net.pooled(visual)
         if not self.args.gs_flag:
             return self.fusion_module(a, v)
         return a, v

@@ -171,7 +171,11 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
 
     for batch_step, (inputs, label) in enumerate(_batches_on_device(args, dataloader, device)):
         optimizer.zero_grad()                                              # main.py:164
-        feats = model(*inputs)                                             # main.py:421-431
+        if basic_model.OVERLAP_ENCODERS and hasattr(net, "forward_streams") and inputs[0].is_cuda:
+            pairs = net.forward_streams(*inputs)                           # main.py:421-431, one stream per encoder
+            feats, feat_streams = [f for f, _ in pairs], [s for _, s in pairs]
+        else:
+            feats, feat_streams = model(*inputs), None                     # main.py:421-431
         st = getattr(net, "_mla_turn_state", None)
         if st is None:       # after the first forward: the engine has fixed the parameter memory layouts by now
             st = _TurnState(net)
@@ -183,6 +187,9 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
         losses = []
         pending = []
         for m, feat in enumerate(feats):                                   # a -> v -> (t)
+            if feat_streams is not None:           # this turn starts as soon as ITS encoder's forward has finished
+                torch.cuda.current_stream().wait_stream(feat_streams[m])
+                feat.record_stream(torch.cuda.current_stream())
             fdet = feat.detach()
             st.head_out["dfeat"] = st.dfeat_buffer(m, fdet)                # one dfeat buffer per modality (see below)
             o = head_turn(fc, fdet, label, grad_scale=inv_global, out=st.head_out)   # main.py:432-435 (head part)
