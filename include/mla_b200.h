@@ -127,6 +127,19 @@ MLA_API int    mla_conv2d_fprop_bnstats(const float* x, const float* w, float* y
                         int Cout, int R, int S, int stride, int pad, float* stat_part, void* stream);
 MLA_API int    mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin,
                         int Cout, int R, int S, int stride, int pad, int accumulate, void* stream);
+/* 2-byte operand variants (tcgen05 kind::f16, fp32 accumulate; half the k-blocks, MMA instructions and operand bytes):
+ *   fprop16: x16 [N,H,W,Cin] fp16, w16 [Cout,R,S,Cin] fp16 -> y fp32 (+ optional BN partial sums as fprop_bnstats).
+ *            fp16 carries TF32's 10-bit mantissa: the products are those of the TF32 path. Cin % 64 == 0.
+ *   dgrad16: dy16 [N,OH,OW,Cout] bf16, wt16 [Cin,R,S,Cout] bf16 (the filter TRANSPOSED, mla_filter_transpose16; the
+ *            hardware rejects mixed fp16 x bf16 operands) -> dx fp32 (accumulate != 0: +=). Cout, Cin % 64 == 0. */
+MLA_API int    mla_conv2d_fprop16(const void* x16, const void* w16, float* y, int N, int H, int W, int Cin, int Cout,
+                        int R, int S, int stride, int pad, float* stat_part, void* stream);
+MLA_API int    mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx, int N, int H, int W, int Cin, int Cout,
+                        int R, int S, int stride, int pad, int accumulate, void* stream);
+/* dst16[i] = fp16(src[i]) (bf16 != 0: bfloat16), n % 4 == 0. */
+MLA_API int    mla_cast16(const float* src, void* dst16, long long n, int bf16, void* stream);
+/* wt16 [Cin,RS,Cout] fp16 (bf16 != 0: bfloat16) = transpose of w [Cout,RS,Cin] fp32. */
+MLA_API int    mla_filter_transpose16(const float* w, void* wt16, int Cout, int RS, int Cin, int bf16, void* stream);
 MLA_API size_t mla_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S,
                         int stride, int pad);
 MLA_API int    mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin,

@@ -39,6 +39,10 @@ _SIGNATURES = {
     "mla_bn_stats_from_partials": (_c_int, [_c_void_p, _c_int, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                             _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                             _c_size_t, _c_void_p]),
+    "mla_conv2d_fprop16": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_void_p]),
+    "mla_conv2d_dgrad16": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
+    "mla_cast16": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p]),
+    "mla_filter_transpose16": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "mla_conv2d_dgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
     "mla_conv2d_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 9),
     "mla_conv2d_wgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),

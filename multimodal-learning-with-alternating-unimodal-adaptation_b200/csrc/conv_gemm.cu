@@ -108,13 +108,18 @@ __device__ __forceinline__ void gather_segment(const ConvGemmParams& p, uint32_t
 // 256 x BN MMA per k-step, issued by the leader, reads each CTA's own 128 A rows and HALF of the weight tile from
 // each CTA's shared memory — every SM ingests BN/2 weight rows instead of BN. Loads of both CTAs complete on the
 // leader's full barrier; its tcgen05.commit releases the stage in both CTAs.
-template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1, int CL = 1, bool PAIR = false>
+// ET != 0 (MODE 0, im2col): 2-byte operands through kind::f16 — ET 1: A fp16, B fp16; 2: A bf16, B bf16; 3: A bf16,
+// B fp16. A 128-byte operand row then holds 64 channels, so a k-block is 64 channels deep: half the k-blocks, MMA
+// instructions and bytes of the TF32 path for the same convolution. Layouts, swizzles and k-steps are byte-identical.
+template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1, int CL = 1, bool PAIR = false, int ET = 0>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ CUtensorMap tmap_g, ConvGemmParams p) {
   static_assert(NT == 1 || (MODE == 2 && IM2COL), "multi-tap tiles exist for the im2col wgrad only");
   static_assert(CL == 1 || (MODE != 2 && IM2COL && NT == 1), "weight multicast exists for the im2col fprop / dgrad only");
   static_assert(CL == 1 || MODE == 0 || (BN / 32) % CL == 0, "dgrad splits whole 32-column weight panels");
   static_assert(!PAIR || (CL == 1 && NT == 1 && IM2COL && MODE != 2), "CTA pairs exist for the im2col fprop / dgrad only");
+  static_assert(ET == 0 || (MODE == 0 && IM2COL && NT == 1 && CL == 1 && !PAIR), "2-byte operands: plain im2col MODE 0 only");
+  constexpr int KE = ET == 0 ? 32 : 64;   // elements of K per 128-byte operand row = per k-block
   constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1);
   constexpr int kCluster = PAIR ? 2 : CL;
   constexpr int NTOT = BN * NT;                                     // accumulator columns
@@ -323,14 +328,14 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
               tc::tma_load_im2col_4d_2sm(stage, &tmap_g, bar, cb * 32, gw, gh, gn, (uint16_t)p.off_s[tj],
                                          (uint16_t)p.off_r[ti]);
             else
-              tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * 32, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
+              tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * KE, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
             tap = p.tap_r[ti] * p.S + p.tap_s[tj];   // filter position whose weights this k-block multiplies
           }
           if (MODE == 0) {
             if (PAIR) {   // box {32 k, BN / 2 rows}: this CTA's half of the weight tile
               tc::tma_load_2d_2sm(stage + kABytes, &tmap, bar, tap * p.CinW + cb * 32, n0 + (int)cl_rank * (BN / 2));
             } else if (CL == 1) {
-              tc::tma_load_2d(stage + kABytes, &tmap, bar, tap * p.CinW + cb * 32, n0);  // box {32 k, BN rows}
+              tc::tma_load_2d(stage + kABytes, &tmap, bar, tap * p.CinW + cb * KE, n0);  // box {KE k, BN rows}
             } else {   // box {32 k, BN / CL rows}: this CTA's slice of the weight tile, delivered to the whole cluster
               tc::tma_load_2d_mc(stage + kABytes + cl_rank * (BN / CL) * 128, &tmap, bar, tap * p.CinW + cb * 32,
                                  n0 + (int)cl_rank * (BN / CL), kClMask);
@@ -382,7 +387,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   } else {
     // ===================== MMA issuer =====================
     if (lane == 0 && KB > 0 && (!PAIR || cl_rank == 0)) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(PAIR ? 256 : 128, NTOT, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0);
+      constexpr uint32_t idesc = ET == 0 ? tc::make_idesc_tf32(PAIR ? 256 : 128, NTOT, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0)
+                                         : tc::make_idesc_f16(128, NTOT, ET >= 2 ? 1 : 0, ET == 2 ? 1 : 0, 0, 0);
       constexpr bool a_mn = (MODE == 2), b_mn = (MODE != 0);
       constexpr uint32_t a_lbo = a_mn ? 4096u : 16u, b_lbo = b_mn ? 4096u : 16u;
       constexpr uint32_t a_sbo = a_mn ? 512u : 1024u, b_sbo = b_mn ? 512u : 1024u;
@@ -399,6 +405,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
           const uint64_t ad = tc::make_smem_desc(stage + k * a_kstep, a_lbo, a_sbo, a_lay);
           const uint64_t bd = tc::make_smem_desc(stage + kABytes + k * b_kstep, b_lbo, b_sbo, b_lay);
           if (PAIR) tc::umma_tf32_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          else if (ET != 0) tc::umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           else tc::umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         if (PAIR) tc::umma_commit_2sm(tc::smem_u32(&empty_bar[s]), (uint16_t)3);
@@ -494,6 +501,21 @@ int make_map_im2col(CUtensorMap* m, const float* ptr, int N, int H, int W, int C
   return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
 }
 
+// 2-byte variants (fp16 / bf16: `bf16` selects the TMA data type; the bytes move identically): 64 elements per row.
+int make_map_im2col16(CUtensorMap* m, const void* ptr, bool bf16, int N, int H, int W, int C, int lower_w, int lower_h,
+                      int upper_w, int upper_h, int stride, int pixels) {
+  EncodeIm2colFn fn = encode_im2col_fn();
+  if (!fn) return MLA_E_NODEVICE;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lo[2] = {lower_w, lower_h}, up[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims,
+                  strides, lo, up, 64u, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
+}
+
 // MLA_CONV_CLUSTER = 1 | 2 | 4: CTAs per weight-multicast cluster in fprop / dgrad.
 int conv_cluster() {
   static const int v = [] {
@@ -556,12 +578,25 @@ int make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols
   return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
 }
 
-template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1, int CL = 1, bool PAIR = false>
+int make_map_2d16(CUtensorMap* m, const void* ptr, bool bf16, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return MLA_E_NODEVICE;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
+}
+
+template <int MODE, int BN, int STAGES, bool IM2COL, int NT = 1, int CL = 1, bool PAIR = false, int ET = 0>
 int launch(const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (kABytes + (PAIR ? BN / 2 : BN * NT) * 128) + 1024;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR>,
+    MLA_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR, ET>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.store(1, std::memory_order_release);
   }
@@ -574,11 +609,11 @@ int launch(const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR>, map, gmap, p));
+    MLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR, ET>, map, gmap, p));
     mla::count_launch();
     return 0;
   }
-  conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR><<<grid, kThreads, smem, st>>>(map, gmap, p);
+  conv_gemm_kernel<MODE, BN, STAGES, IM2COL, NT, CL, PAIR, ET><<<grid, kThreads, smem, st>>>(map, gmap, p);
   MLA_CUDA_TRY(cudaGetLastError());
   mla::count_launch();
   return 0;
@@ -771,6 +806,110 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
       rc = make_map_im2col(&gmap, dy, N, OH, OW, Cout, lo_w, lo_h, lo_w + Ws - OW, lo_h + Hs - OH, 1, 128, false);
       if (rc) return rc;
       rc = launch_dgrad(BN, map, gmap, q, g, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 2-byte operand convolutions (kind::f16, fp32 accumulate). fprop16: x fp16, w fp16 [Cout][R][S][Cin]. dgrad16: dy bf16,
+// wt bf16 = the TRANSPOSED filter [Cin][R][S][Cout], which makes dgrad the same K-major GEMM as fprop (flipped taps,
+// stride-2 by output parity classes) — no MN-major operand. fp16 has TF32's 10-bit mantissa, so fprop16 multiplies
+// the same operand values as the TF32 path; dy in bf16 (8-bit mantissa, fp32 range) sits far below the ~10 % noise TF32
+// ReLU-mask flips already put on the encoder gradients.
+extern "C" int mla_conv2d_fprop16(const void* x16, const void* w16, float* y, int N, int H, int W, int Cin, int Cout, int R,
+                                  int S, int stride, int pad, float* stat_part, void* stream) {
+  if (!x16 || !w16 || !y || !mla::aligned16(x16) || !mla::aligned16(w16) || !mla::aligned16(y)) return MLA_E_BADARG;
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad, 64)) return MLA_E_SHAPE;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
+  if (OH <= 0 || OW <= 0 || (long long)N * OH * OW > 0x7fffffffLL) return MLA_E_SHAPE;
+  ConvGemmParams p{};
+  p.OH = OH; p.OW = OW; p.M = N * OH * OW; p.R = R; p.S = S; p.mul = stride;
+  p.kcb = Cin / 64; p.KB = R * S * p.kcb; p.CinW = Cin;
+  p.out = y; p.ldo = Cout; p.accumulate = 0; p.Cout = Cout; p.stat_part = stat_part;
+  p.g_base_w = p.g_base_h = -pad;
+  full_taps(p, R, S, false);
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  CUtensorMap map, gmap;
+  int rc = make_map_2d16(&map, w16, false, Cout, (long long)R * S * Cin, BN);
+  if (rc) return rc;
+  rc = make_map_im2col16(&gmap, x16, false, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 128);
+  if (rc) return rc;
+  dim3 grid((p.M + 127) / 128, Cout / BN);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 1>(map, gmap, p, grid, st)
+                  : launch<0, 128, 3, true, 1, 1, false, 1>(map, gmap, p, grid, st);
+}
+
+extern "C" int mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx, int N, int H, int W, int Cin, int Cout,
+                                  int R, int S, int stride, int pad, int accumulate, void* stream) {
+  if (!dy16 || !wt16 || !dx || !mla::aligned16(dy16) || !mla::aligned16(wt16) || !mla::aligned16(dx)) return MLA_E_BADARG;
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad)) return MLA_E_SHAPE;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
+  if (OH <= 0 || OW <= 0 || (long long)N * H * W > 0x7fffffffLL) return MLA_E_SHAPE;
+  ConvGemmParams p{};
+  p.OH = H; p.OW = W; p.M = N * H * W; p.R = R; p.S = S; p.mul = 1;
+  p.kcb = Cout / 64; p.CinW = Cout;      // GEMM K = dy channels; a filter tap spans Cout columns of the transposed filter
+  p.out = dx; p.ldo = Cin; p.accumulate = accumulate ? 1 : 0; p.Cout = Cin;
+  const int BN = (Cin % 128 == 0) ? 128 : 64;
+  CUtensorMap map, gmap;
+  int rc = make_map_2d16(&map, wt16, true, Cin, (long long)R * S * Cout, BN);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto go = [&](const ConvGemmParams& q, dim3 g) {
+    return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 2>(map, gmap, q, g, st)
+                    : launch<0, 128, 3, true, 1, 1, false, 2>(map, gmap, q, g, st);
+  };
+  if (stride == 1) {
+    p.KB = R * S * p.kcb;
+    p.g_base_w = pad - (S - 1); p.g_base_h = pad - (R - 1);
+    full_taps(p, R, S, true);
+    rc = make_map_im2col16(&gmap, dy16, true, N, OH, OW, Cout, p.g_base_w, p.g_base_h, p.g_base_w + (W - OW),
+                           p.g_base_h + (H - OH), 1, 128);
+    if (rc) return rc;
+    return go(p, dim3((p.M + 127) / 128, Cin / BN));
+  }
+  for (int ph = 0; ph < stride; ++ph) {      // one dense sub-convolution per output parity class (see mla_conv2d_dgrad)
+    for (int pw = 0; pw < stride; ++pw) {
+      ConvGemmParams q = p;
+      const int Hs = (H - ph + stride - 1) / stride, Ws = (W - pw + stride - 1) / stride;
+      if (Hs <= 0 || Ws <= 0) continue;
+      q.nr = q.ns = 0;
+      int qr[8], qs[8], lo_h = 1 << 20, lo_w = 1 << 20;
+      for (int r = 0; r < R; ++r) {
+        const int t = ph + pad - r;
+        if (((t % stride) + stride) % stride != 0) continue;
+        qr[q.nr] = (t >= 0 ? t : t - (stride - 1)) / stride;
+        q.tap_r[q.nr] = (signed char)r;
+        lo_h = min(lo_h, qr[q.nr]);
+        ++q.nr;
+      }
+      for (int c = 0; c < S; ++c) {
+        const int t = pw + pad - c;
+        if (((t % stride) + stride) % stride != 0) continue;
+        qs[q.ns] = (t >= 0 ? t : t - (stride - 1)) / stride;
+        q.tap_s[q.ns] = (signed char)c;
+        lo_w = min(lo_w, qs[q.ns]);
+        ++q.ns;
+      }
+      q.OH = Hs; q.OW = Ws; q.M = N * Hs * Ws;
+      q.o_mul = stride; q.o_ph = ph; q.o_pw = pw; q.o_H = H; q.o_W = W;
+      q.KB = q.nr * q.ns * q.kcb;
+      if (q.KB == 0) {
+        if (accumulate) continue;
+        lo_h = lo_w = 0;
+      }
+      for (int i = 0; i < q.nr; ++i) q.off_r[i] = (signed char)(qr[i] - lo_h);
+      for (int j = 0; j < q.ns; ++j) q.off_s[j] = (signed char)(qs[j] - lo_w);
+      q.g_base_w = lo_w; q.g_base_h = lo_h;
+      rc = make_map_im2col16(&gmap, dy16, true, N, OH, OW, Cout, lo_w, lo_h, lo_w + Ws - OW, lo_h + Hs - OH, 1, 128);
+      if (rc) return rc;
+      rc = go(q, dim3((q.M + 127) / 128, Cin / BN));
       if (rc) return rc;
     }
   }

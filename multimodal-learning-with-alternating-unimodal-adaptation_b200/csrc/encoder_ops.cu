@@ -6,6 +6,9 @@
 //   their backward passes, global average pool fwd/bwd            basic_model.py:61-65
 // All reductions are two-stage with a fixed order (deterministic); per-channel sums are carried
 // in double across threads/blocks so mean/variance match torch's to fp32 rounding.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -36,6 +39,46 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
 // BN-backward passes instead of the 32x larger activation itself.
 __device__ __forceinline__ unsigned relu_nibble(const unsigned int* __restrict__ mask, long long i) {
   return (__ldg(mask + (i >> 3)) >> (4 * (int)(i & 7))) & 15u;
+}
+
+// ------------------------------------------------------------------------------ 2-byte copies
+__device__ __forceinline__ uint2 pack_h4(float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const unsigned int*>(&a), *reinterpret_cast<const unsigned int*>(&b));
+}
+__device__ __forceinline__ uint2 pack_b4(float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const unsigned int*>(&a), *reinterpret_cast<const unsigned int*>(&b));
+}
+
+__global__ void cast16_kernel(const float* __restrict__ src, uint2* __restrict__ dst, long long n4, int bf16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ld4(src + 4 * i);
+    dst[i] = bf16 ? pack_b4(v) : pack_h4(v);
+  }
+}
+
+// wt[ci][rs][co] = fp16 or bf16 (w[co][rs][ci]); one block per (rs, 32x32 tile), transposed through shared memory
+__global__ void filter_transpose16_kernel(const float* __restrict__ w, unsigned short* __restrict__ wt, int Cout, int RS,
+                                          int Cin, int bf16) {
+  __shared__ float tile[32][33];
+  const int rs = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int co = co0 + j, ci = ci0 + tx;
+    tile[j][tx] = (co < Cout && ci < Cin) ? w[((long long)co * RS + rs) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int ci = ci0 + j, co = co0 + tx;
+    if (ci < Cin && co < Cout) {
+      const float v = tile[tx][j];
+      unsigned short bits;
+      if (bf16) { const __nv_bfloat16 h = __float2bfloat16_rn(v); bits = *reinterpret_cast<const unsigned short*>(&h); }
+      else { const __half h = __float2half_rn(v); bits = *reinterpret_cast<const unsigned short*>(&h); }
+      wt[((long long)ci * RS + rs) * Cout + co] = bits;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ stem im2col
@@ -505,6 +548,22 @@ extern "C" int mla_stem_im2col(const float* in, float* col, int N, int T, long l
 extern "C" int mla_round_tf32(const float* src, float* dst, long long n, void* stream) {
   if (!src || !dst || n < 4 || (n & 3) || !mla::aligned16(src) || !mla::aligned16(dst)) return MLA_E_BADARG;
   round_tf32_kernel<<<ew_grid(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n / 4);
+  MLA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mla_cast16(const float* src, void* dst16, long long n, int bf16, void* stream) {
+  if (!src || !dst16 || n < 4 || (n & 3) || !mla::aligned16(src) || (reinterpret_cast<uintptr_t>(dst16) & 7u)) return MLA_E_BADARG;
+  cast16_kernel<<<ew_grid(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<uint2*>(dst16), n / 4, bf16);
+  MLA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mla_filter_transpose16(const float* w, void* wt16, int Cout, int RS, int Cin, int bf16, void* stream) {
+  if (!w || !wt16 || Cout < 1 || RS < 1 || Cin < 1) return MLA_E_BADARG;
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, RS);
+  filter_transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<unsigned short*>(wt16), Cout, RS,
+                                                                              Cin, bf16);
   MLA_LAUNCH_CHECK();
   return 0;
 }
