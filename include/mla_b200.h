@@ -202,6 +202,17 @@ MLA_API int    mla_bn_apply_mask(const float* y, const float* scale, const float
 MLA_API int    mla_bn_backward_mask(const float* dz, const unsigned int* relu_mask, const float* y, const float* mean,
                         const float* invstd, const float* gamma, long long M, int C, float* dgamma,
                         float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream);
+/* The same three passes with 2-byte side outputs for the kind::f16 convolutions (any of relu_mask / out16 / dy16 / z may
+ * be NULL): out16 = fp16 copy of the activation (fprop16 operand), dy16 = bf16 copy of the gradient (dgrad16 operand). */
+MLA_API int    mla_bn_apply_ex(const float* y, const float* scale, const float* shift, const float* res,
+                        const float* res_scale, const float* res_shift, int relu, float* out,
+                        unsigned int* relu_mask, void* out16, long long M, int C, void* stream);
+MLA_API int    mla_bn_backward_ex(const float* dz, const float* z, const unsigned int* relu_mask, const float* y,
+                        const float* mean, const float* invstd, const float* gamma, long long M, int C,
+                        float* dgamma, float* dbeta, float* dy, void* dy16, float* g_out, void* ws,
+                        size_t ws_bytes, void* stream);
+MLA_API int    mla_bn_relu_maxpool_ex(const float* y, const float* scale, const float* shift, float* out, void* out16,
+                        unsigned char* idx, int N, int H, int W, int C, void* stream);
 MLA_API int    mla_bn_backward(const float* dz, const float* z, const float* y, const float* mean,
                         const float* invstd, const float* gamma, long long M, int C, float* dgamma,
                         float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream);

@@ -57,6 +57,9 @@ _SIGNATURES = {
     "mla_bn_apply": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_ll, _c_int, _c_void_p]),
     "mla_bn_apply_mask": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p]),
     "mla_bn_backward_mask": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
+    "mla_bn_apply_ex": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p]),
+    "mla_bn_backward_ex": (_c_int, [_c_void_p] * 7 + [_c_ll, _c_int] + [_c_void_p] * 6 + [_c_size_t, _c_void_p]),
+    "mla_bn_relu_maxpool_ex": (_c_int, [_c_void_p] * 6 + [_c_int] * 4 + [_c_void_p]),
     "mla_bn_backward": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
     "mla_bn_relu_maxpool": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
     "mla_maxpool_relu_backward": (_c_int, [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p]),

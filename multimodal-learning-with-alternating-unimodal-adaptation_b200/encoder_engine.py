@@ -23,6 +23,7 @@ from . import _lib
 import os
 
 BACKEND = "native-tcgen05"
+USE_F16 = os.environ.get("MLA_F16", "1") != "0"                     # 2-byte conv operands: fp16 fprop, bf16 dgrad (kind::f16)
 USE_GRAPHS = os.environ.get("MLA_GRAPHS", "1") != "0"               # replay the plans' launch sequences as CUDA graphs
 _OVERLAP_WGRAD = os.environ.get("MLA_OVERLAP_WGRAD", "1") != "0"    # wgrad kernels on a side stream of the plan
 _USE_RELU_MASK = os.environ.get("MLA_RELU_MASK", "1") != "0"      # A/B switch (bitmask vs reading the activation)
@@ -149,6 +150,11 @@ class ResNetPlan:
         self.dwpad = e(64, self.Kp)
         self.y0 = e(N, self.OH0, self.OW0, 64)
         self.p0 = e(N, self.PH, self.PW, 64)
+        self.f16 = USE_F16
+        half = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)          # noqa: E731
+        self.p0_16 = half(N, self.PH, self.PW, 64) if self.f16 else None
+        self.w16 = torch.empty(self.flat.numel(), dtype=torch.float16, device=dev) if self.f16 else None     # fp16 weights
+        self.wt16 = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=dev) if self.f16 else None   # transposed, bf16
         self.idx0 = e(N, self.PH, self.PW, 64, dt=torch.uint8)
         self.bn0 = _BN(net.bn1, dev)
         # ---- residual blocks
@@ -163,6 +169,8 @@ class ResNetPlan:
                          y1=e(N, ho, wo, cout), a1=e(N, ho, wo, cout), y2=e(N, ho, wo, cout), out=e(N, ho, wo, cout),
                          # ReLU sign bitmasks of a1 / out (1 bit per element): what BN backward reads instead of them
                          m1=e(N * ho * wo * cout // 32, dt=torch.int32), m2=e(N * ho * wo * cout // 32, dt=torch.int32),
+                         # fp16 copies of a1 / out: the operands of the kind::f16 forward convolutions
+                         a1_16=half(N, ho, wo, cout) if self.f16 else None, out_16=half(N, ho, wo, cout) if self.f16 else None,
                          bn1=_BN(blk.bn1, dev), bn2=_BN(blk.bn2, dev), yd=None, bnd=None)
                 if blk.downsample is not None:
                     d["yd"] = e(N, ho, wo, cout)
@@ -208,6 +216,35 @@ class ResNetPlan:
         """Device pointer of the TF32-rounded copy of a parameter (plain buffers: their own pointer)."""
         off = self.woff.get(id(w))
         return w.data_ptr() if off is None else self.wr.data_ptr() + 4 * off
+
+    def _w16ptr(self, w):
+        return self.w16.data_ptr() + 2 * self.woff[id(w)]
+
+    def _wt16ptr(self, w):
+        return self.wt16.data_ptr() + 2 * self.woff[id(w)]
+
+    def _conv_bn16(self, x16, w, y, N, H, W, Cin, Cout, R, stride, pad, b, training, st):
+        """fp16 x fp16 forward convolution (+ BN partial sums in training), then the BN coefficients."""
+        t = _conv_timer_begin()
+        _chk(self.L.mla_conv2d_fprop16(_p(x16), self._w16ptr(w), _p(y), N, H, W, Cin, Cout, R, R, stride, pad,
+                                       _p(self.stat_part) if training else None, st), "mla_conv2d_fprop16")
+        _conv_timer_end(t, "fprop", N, H, W, Cin, Cout, R, stride, pad)
+        if not training:
+            self._bn_coeffs(y, 0, b, False, st)
+            return
+        OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+        M = N * OH * OW
+        bn = b.bn
+        _chk(self.L.mla_bn_stats_from_partials(_p(self.stat_part), (M + 127) // 128, M, b.C, _p(bn.weight), _p(bn.bias),
+                                               _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps),
+                                               _p(b.mean), _p(b.invstd), _p(b.scale), _p(b.shift), _p(self.bn_ws),
+                                               self.bn_ws.numel(), st), "mla_bn_stats_from_partials")
+
+    def _dgrad16(self, dy16, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
+        t = _conv_timer_begin()
+        _chk(self.L.mla_conv2d_dgrad16(_p(dy16), self._wt16ptr(w), _p(dx), N, H, W, Cin, Cout, R, R, stride, pad,
+                                       1 if acc else 0, st), "mla_conv2d_dgrad16")
+        _conv_timer_end(t, "dgrad", N, H, W, Cin, Cout, R, stride, pad)
 
     def _conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
         t = _conv_timer_begin()
@@ -258,16 +295,20 @@ class ResNetPlan:
             _chk(self.L.mla_bn_eval_coeffs(_p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
                                            float(bn.eps), b.C, _p(b.scale), _p(b.shift), st), "mla_bn_eval_coeffs")
 
-    def _bn_bwd(self, dz, z, y, b, M, dy, g_out, st, mask=None):
+    def _bn_bwd(self, dz, z, y, b, M, dy, g_out, st, mask=None, dy16=None):
         bn = b.bn
         dg, db = _grad_buffer(bn.weight), _grad_buffer(bn.bias)
-        if mask is not None:
-            _chk(self.L.mla_bn_backward_mask(_p(dz), _p(mask), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C,
-                                             _p(dg), _p(db), _p(dy), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st),
-                 "mla_bn_backward_mask")
-            return
-        _chk(self.L.mla_bn_backward(_p(dz), _p(z), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C, _p(dg), _p(db),
-                                    _p(dy), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st), "mla_bn_backward")
+        _chk(self.L.mla_bn_backward_ex(_p(dz), _p(z), _p(mask), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C,
+                                       _p(dg), _p(db), _p(dy), _p(dy16), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st),
+             "mla_bn_backward")
+
+    def tmp16(self, slot, shape):
+        k = (slot, tuple(shape), "bf16")
+        t = self._pool.get(k)
+        if t is None:
+            t = torch.empty(shape, dtype=torch.bfloat16, device=self.dev)
+            self._pool[k] = t
+        return t
 
     # ------------------------------------------------------------------------ CUDA graphs
     def _run(self, key, fn):
@@ -327,28 +368,42 @@ class ResNetPlan:
         _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
         self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
                       k_alg=K)
-        _chk(L.mla_bn_relu_maxpool(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.idx0), N,
-                                   self.OH0, self.OW0, 64, st), "mla_bn_relu_maxpool")
-        xin = self.p0
+        _chk(L.mla_bn_relu_maxpool_ex(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.p0_16),
+                                      _p(self.idx0), N, self.OH0, self.OW0, 64, st), "mla_bn_relu_maxpool")
+        f16 = self.f16
+        if f16:      # fp16 copy of every parameter (same offsets as the flat buffer): the B operand of fprop16
+            _chk(L.mla_cast16(_p(self.flat), _p(self.w16), self.flat.numel(), 0, st), "mla_cast16")
+        xin, xin16 = self.p0, self.p0_16
         for b in self.blocks:
             blk, s, cin, cout = b["blk"], b["stride"], b["cin"], b["cout"]
             M = N * b["ho"] * b["wo"]
-            self._conv_bn(xin, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, b["bn1"], training, st)
-            mk1, mk2 = (_p(b["m1"]), _p(b["m2"])) if training else (None, None)
-            _chk(L.mla_bn_apply_mask(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(b["a1"]),
-                                     mk1, M, cout, st), "mla_bn_apply")
-            self._conv_bn(b["a1"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, b["bn2"], training,
-                          st)
-            if b["yd"] is not None:
-                self._conv_bn(xin, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, b["bnd"],
-                              training, st)
-                _chk(L.mla_bn_apply_mask(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]),
-                                         _p(b["bnd"].scale), _p(b["bnd"].shift), 1, _p(b["out"]), mk2, M, cout, st),
-                     "mla_bn_apply")
+            if f16:
+                self._conv_bn16(xin16, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, b["bn1"], training, st)
             else:
-                _chk(L.mla_bn_apply_mask(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
-                                         _p(b["out"]), mk2, M, cout, st), "mla_bn_apply")
-            xin = b["out"]
+                self._conv_bn(xin, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, b["bn1"], training, st)
+            mk1, mk2 = (_p(b["m1"]), _p(b["m2"])) if training else (None, None)
+            _chk(L.mla_bn_apply_ex(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(b["a1"]),
+                                   mk1, _p(b["a1_16"]), M, cout, st), "mla_bn_apply")
+            if f16:
+                self._conv_bn16(b["a1_16"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, b["bn2"],
+                                training, st)
+            else:
+                self._conv_bn(b["a1"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, b["bn2"],
+                              training, st)
+            if b["yd"] is not None:
+                if f16:
+                    self._conv_bn16(xin16, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, b["bnd"],
+                                    training, st)
+                else:
+                    self._conv_bn(xin, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, b["bnd"],
+                                  training, st)
+                _chk(L.mla_bn_apply_ex(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]),
+                                       _p(b["bnd"].scale), _p(b["bnd"].shift), 1, _p(b["out"]), mk2, _p(b["out_16"]), M, cout,
+                                       st), "mla_bn_apply")
+            else:
+                _chk(L.mla_bn_apply_ex(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
+                                       _p(b["out"]), mk2, _p(b["out_16"]), M, cout, st), "mla_bn_apply")
+            xin, xin16 = b["out"], b["out_16"]
         _chk(L.mla_avgpool_forward(_p(xin), _p(self.feat_static), self.B, self.rows, self.C_out, st), "mla_avgpool_forward")
         if training and self.nbt:
             torch._foreach_add_(self.nbt, 1)
@@ -405,6 +460,15 @@ class ResNetPlan:
                 done.record(wsm)
                 events[(slot, tuple(dy.shape))] = done
 
+        f16 = self.f16
+        if f16:      # transposed bf16 filters: the K-major B operand of dgrad16 (weights are those of this step's forward)
+            for b in self.blocks:
+                blk = b["blk"]
+                ws_ = [(blk.conv1.weight, b["cout"], 9, b["cin"]), (blk.conv2.weight, b["cout"], 9, b["cout"])]
+                if b["yd"] is not None:
+                    ws_.append((blk.downsample[0].weight, b["cout"], 1, b["cin"]))
+                for w, co, rs, ci in ws_:
+                    _chk(L.mla_filter_transpose16(_p(w), self._wt16ptr(w), co, rs, ci, 1, st), "mla_filter_transpose16")
         last = self.blocks[-1]
         dout = self.tmp("dXa", last["out"].shape)
         _chk(L.mla_avgpool_backward(_p(dfeat), _p(dout), self.B, self.rows, self.C_out, st), "mla_avgpool_backward")
@@ -417,31 +481,34 @@ class ResNetPlan:
             par = i & 1
             g = self.tmp("g%d" % par, shp)
             dy2 = buf("dy2_%d" % par, shp)
-            if _USE_RELU_MASK:
-                self._bn_bwd(dout, None, b["y2"], b["bn2"], M, dy2, g, st, mask=b["m2"])
-            else:
-                self._bn_bwd(dout, b["out"], b["y2"], b["bn2"], M, dy2, g, st)
+            dy2h = self.tmp16("dy2h", shp) if f16 else None      # bf16 copies (dgrad16 operands) live on `cur` only
+            z2, mk2 = (None, b["m2"]) if _USE_RELU_MASK else (b["out"], None)
+            self._bn_bwd(dout, z2, b["y2"], b["bn2"], M, dy2, g, st, mask=mk2, dy16=dy2h)
             wgrad_async(b["a1"], dy2, "dy2_%d" % par, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3, 1, 1)
             da1 = self.tmp("da", shp)
-            self._dgrad(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
-            dy1 = buf("dy1_%d" % par, shp)
-            if _USE_RELU_MASK:
-                self._bn_bwd(da1, None, b["y1"], b["bn1"], M, dy1, None, st, mask=b["m1"])
+            if f16:
+                self._dgrad16(dy2h, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
             else:
-                self._bn_bwd(da1, b["a1"], b["y1"], b["bn1"], M, dy1, None, st)
+                self._dgrad(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
+            dy1 = buf("dy1_%d" % par, shp)
+            dy1h = self.tmp16("dy1h", shp) if f16 else None
+            z1, mk1 = (None, b["m1"]) if _USE_RELU_MASK else (b["a1"], None)
+            self._bn_bwd(da1, z1, b["y1"], b["bn1"], M, dy1, None, st, mask=mk1, dy16=dy1h)
             wgrad_async(xin, dy1, "dy1_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1)
+            dg = self._dgrad16 if f16 else self._dgrad
             if b["yd"] is not None:
                 dyd = buf("dyd", shp)
-                self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st)
+                dydh = self.tmp16("dydh", shp) if f16 else None
+                self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st, dy16=dydh)
                 wgrad_async(xin, dyd, "dyd", _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0)
                 dx = self.tmp("dXa", xin.shape)         # xin.shape != out.shape here, so never aliases dout
                 # the 3x3 dgrad touches every pixel of dx and goes first; the 1x1/2 shortcut then ADDS into the
                 # one output parity class it reaches (its other classes are skipped, not zero-filled)
-                self._dgrad(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, False, st)
-                self._dgrad(dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, True, st)
+                dg(dy1h if f16 else dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, False, st)
+                dg(dydh if f16 else dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, True, st)
             else:
                 dx = g                                  # identity shortcut: dX starts as the masked gradient
-                self._dgrad(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
+                dg(dy1h if f16 else dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
             dout = dx
         # stem: maxpool+relu backward, BN backward, weight gradient (no dgrad: the input needs none)
         g0 = self.tmp("g0", self.y0.shape)

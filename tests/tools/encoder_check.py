@@ -55,6 +55,7 @@ def use_exact_convs():
         OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
         self._bn_coeffs(y, N * OH * OW, b, training, st)
     ee.USE_GRAPHS = False          # torch convolutions inside the launch sequence are not graph-captured here
+    ee.USE_F16 = False             # the patched launchers are the fp32-operand ones
     ee.ResNetPlan._conv, ee.ResNetPlan._dgrad, ee.ResNetPlan._wgrad = conv, dgrad, wgrad
     ee.ResNetPlan._conv_bn = conv_bn
 
