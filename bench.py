@@ -294,8 +294,8 @@ def run_native(a, rank, world):
             d = by.setdefault(kind, [0, 0.0, 0.0])
             d[0] += 1; d[1] += f; d[2] += e0.elapsed_time(e1) * 1e-3
         conv = {"launches": len(recs), "seconds": tot_t, "flops": tot_f,
-                "by_kind": {k: {"launches": v[0], "tflops": v[1] / v[2] / 1e12, "ms_per_step": 1e3 * v[2] / a.steps}
-                            for k, v in by.items()},
+                "by_kind": {k: {"launches": v[0], "tflops": v[1] / v[2] / 1e12, "ms_per_step": 1e3 * v[2] / a.steps,
+                                "flops": v[1]} for k, v in by.items()},
                 "instrumented_ms_per_step": None if t_inst is None else 1e3 * t_inst / a.steps}
     elif world > 1:
         with quiet:
@@ -310,7 +310,7 @@ def run_native(a, rank, world):
     out = {"metric": "MLA train samples/sec (CREMA-D AV, ResNet-18)", "value": value, "unit": "samples/s",
            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "tf32", "data": "synthetic",
+           "dtype": "f16+tf32" if encoder_engine.USE_F16 else "tf32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                       "encoder_backend": encoder_engine.BACKEND, "gs_projection": "fires (force_projection)",
                       "streams": ("audio / visual encoders on two CUDA streams" if overlap else "single stream") +
@@ -324,22 +324,27 @@ def run_native(a, rank, world):
            "encoder_tflops": FLOP_PER_SAMPLE_STEP * samples / t_dev / 1e12}
     prof = profile_summary()
     if conv is not None and conv["seconds"] > 0:
-        # dominant kernel of the step: conv_gemm_kernel (tcgen05 TF32 implicit GEMM; fprop + dgrad + wgrad launches).
+        # dominant kernel of the step: conv_gemm_kernel (tcgen05 implicit GEMM; fprop + dgrad + wgrad launches).
         # achieved = algorithmic FLOPs (2*M*Cout*Cin*R*S per launch, stem with its true K=49*Cin) / CUDA-event time.
-        # peak: MEASURED_PEAKS.json holds bf16 only; kind::tf32 runs at half the bf16 rate on sm_100 (1.1 vs 2.25
-        # PFLOP/s nominal), so the denominator is HALF the measured SUSTAINED bf16 figure (kernel timed inside a step).
-        peak = pk["bf16_sustained"] / 2
+        # peak: the measured SUSTAINED bf16 figure (kernel timed inside a step) for the kind::f16 launches (fp16 / bf16
+        # operands); HALF of it for the kind::tf32 launches (MEASURED_PEAKS.json has no TF32 figure; TF32 runs at half the
+        # bf16 rate on sm_100: 1.1 vs 2.25 PFLOP/s nominal). The reported peak is the FLOP-weighted blend
+        # sum(flops) / sum(flops_i / peak_i), i.e. frac = (time at peak) / (measured time).
+        t_ideal = sum(v["flops"] / (pk["bf16_sustained"] * (1.0 if k.endswith("16") else 0.5) * 1e12)
+                      for k, v in conv["by_kind"].items())
+        peak = conv["flops"] / t_ideal / 1e12
         ach = conv["flops"] / conv["seconds"] / 1e12
-        out["roofline"] = {"kernel": "conv_gemm_kernel (tcgen05 kind::tf32 implicit GEMM, im2col-TMA fed)",
+        out["roofline"] = {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, im2col-TMA fed; kind::f16 fprop/dgrad, kind::tf32 wgrad/stem)",
                            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                            "traffic": prof.get("conv_traffic"),
-                           "peak_source": "0.5 x bf16_tflops_sustained, " + pk["source"],
+                           "peak_source": "FLOP-weighted blend of bf16_tflops_sustained (f16 launches) and 0.5x (tf32 launches), "
+                                          + pk["source"],
                            "launches_per_step": conv["launches"] / a.steps,
                            "avg_launch_us": 1e6 * conv["seconds"] / conv["launches"],
                            "flops_per_step": conv["flops"] / a.steps,
                            "share_of_step": (conv["seconds"] / a.steps) / (conv["instrumented_ms_per_step"] * 1e-3
                                                                            if conv["instrumented_ms_per_step"] else t_dev / a.steps),
-                           "by_kind": conv["by_kind"],
+                           "by_kind": {k: {kk: vv for kk, vv in v.items() if kk != "flops"} for k, v in conv["by_kind"].items()},
                            "instrumented_ms_per_step": conv["instrumented_ms_per_step"]}
     if not a.no_sweep:
         pts = gs_sweep(torch, ops, pk)

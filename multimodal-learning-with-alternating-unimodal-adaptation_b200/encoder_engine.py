@@ -228,7 +228,7 @@ class ResNetPlan:
         t = _conv_timer_begin()
         _chk(self.L.mla_conv2d_fprop16(_p(x16), self._w16ptr(w), _p(y), N, H, W, Cin, Cout, R, R, stride, pad,
                                        _p(self.stat_part) if training else None, st), "mla_conv2d_fprop16")
-        _conv_timer_end(t, "fprop", N, H, W, Cin, Cout, R, stride, pad)
+        _conv_timer_end(t, "fprop16", N, H, W, Cin, Cout, R, stride, pad)
         if not training:
             self._bn_coeffs(y, 0, b, False, st)
             return
@@ -244,7 +244,7 @@ class ResNetPlan:
         t = _conv_timer_begin()
         _chk(self.L.mla_conv2d_dgrad16(_p(dy16), self._wt16ptr(w), _p(dx), N, H, W, Cin, Cout, R, R, stride, pad,
                                        1 if acc else 0, st), "mla_conv2d_dgrad16")
-        _conv_timer_end(t, "dgrad", N, H, W, Cin, Cout, R, stride, pad)
+        _conv_timer_end(t, "dgrad16", N, H, W, Cin, Cout, R, stride, pad)
 
     def _conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
         t = _conv_timer_begin()
