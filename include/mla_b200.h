@@ -136,6 +136,11 @@ MLA_API int    mla_conv2d_fprop16(const void* x16, const void* w16, float* y, in
                         int R, int S, int stride, int pad, float* stat_part, void* stream);
 MLA_API int    mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx, int N, int H, int W, int Cin, int Cout,
                         int R, int S, int stride, int pad, int accumulate, void* stream);
+/*   wgrad16: x16 [N,H,W,Cin] bf16, dy16 [N,OH,OW,Cout] bf16 -> dw fp32 [Cout,R,S,Cin]; Cin, Cout % 64 == 0. */
+MLA_API size_t mla_conv2d_wgrad16_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                        int pad);
+MLA_API int    mla_conv2d_wgrad16(const void* x16, const void* dy16, float* dw, int N, int H, int W, int Cin, int Cout,
+                        int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
 /* dst16[i] = fp16(src[i]) (bf16 != 0: bfloat16), n % 4 == 0. */
 MLA_API int    mla_cast16(const float* src, void* dst16, long long n, int bf16, void* stream);
 /* wt16 [Cin,RS,Cout] fp16 (bf16 != 0: bfloat16) = transpose of w [Cout,RS,Cin] fp32. */
@@ -202,17 +207,18 @@ MLA_API int    mla_bn_apply_mask(const float* y, const float* scale, const float
 MLA_API int    mla_bn_backward_mask(const float* dz, const unsigned int* relu_mask, const float* y, const float* mean,
                         const float* invstd, const float* gamma, long long M, int C, float* dgamma,
                         float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream);
-/* The same three passes with 2-byte side outputs for the kind::f16 convolutions (any of relu_mask / out16 / dy16 / z may
- * be NULL): out16 = fp16 copy of the activation (fprop16 operand), dy16 = bf16 copy of the gradient (dgrad16 operand). */
+/* The same three passes with 2-byte side outputs for the kind::f16 convolutions. Any of relu_mask / out16 / out16b /
+ * dy16 / z may be NULL, and so may the fp32 out / dy when a 2-byte output is given: out16 = fp16 copy of the activation
+ * (fprop16 operand), out16b = bf16 copy (wgrad16 x operand), dy16 = bf16 gradient (dgrad16 / wgrad16 operand). */
 MLA_API int    mla_bn_apply_ex(const float* y, const float* scale, const float* shift, const float* res,
                         const float* res_scale, const float* res_shift, int relu, float* out,
-                        unsigned int* relu_mask, void* out16, long long M, int C, void* stream);
+                        unsigned int* relu_mask, void* out16, void* out16b, long long M, int C, void* stream);
 MLA_API int    mla_bn_backward_ex(const float* dz, const float* z, const unsigned int* relu_mask, const float* y,
                         const float* mean, const float* invstd, const float* gamma, long long M, int C,
                         float* dgamma, float* dbeta, float* dy, void* dy16, float* g_out, void* ws,
                         size_t ws_bytes, void* stream);
 MLA_API int    mla_bn_relu_maxpool_ex(const float* y, const float* scale, const float* shift, float* out, void* out16,
-                        unsigned char* idx, int N, int H, int W, int C, void* stream);
+                        void* out16b, unsigned char* idx, int N, int H, int W, int C, void* stream);
 MLA_API int    mla_bn_backward(const float* dz, const float* z, const float* y, const float* mean,
                         const float* invstd, const float* gamma, long long M, int C, float* dgamma,
                         float* dbeta, float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream);

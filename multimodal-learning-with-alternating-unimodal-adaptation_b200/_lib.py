@@ -41,6 +41,8 @@ _SIGNATURES = {
                                             _c_size_t, _c_void_p]),
     "mla_conv2d_fprop16": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_void_p]),
     "mla_conv2d_dgrad16": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
+    "mla_conv2d_wgrad16_workspace_bytes": (_c_size_t, [_c_int] * 9),
+    "mla_conv2d_wgrad16": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),
     "mla_cast16": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p]),
     "mla_filter_transpose16": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "mla_conv2d_dgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
@@ -57,9 +59,10 @@ _SIGNATURES = {
     "mla_bn_apply": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_ll, _c_int, _c_void_p]),
     "mla_bn_apply_mask": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p]),
     "mla_bn_backward_mask": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
-    "mla_bn_apply_ex": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_void_p]),
+    "mla_bn_apply_ex": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int,
+                                _c_void_p]),
     "mla_bn_backward_ex": (_c_int, [_c_void_p] * 7 + [_c_ll, _c_int] + [_c_void_p] * 6 + [_c_size_t, _c_void_p]),
-    "mla_bn_relu_maxpool_ex": (_c_int, [_c_void_p] * 6 + [_c_int] * 4 + [_c_void_p]),
+    "mla_bn_relu_maxpool_ex": (_c_int, [_c_void_p] * 7 + [_c_int] * 4 + [_c_void_p]),
     "mla_bn_backward": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
     "mla_bn_relu_maxpool": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p]),
     "mla_maxpool_relu_backward": (_c_int, [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p]),

@@ -118,7 +118,11 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   static_assert(CL == 1 || (MODE != 2 && IM2COL && NT == 1), "weight multicast exists for the im2col fprop / dgrad only");
   static_assert(CL == 1 || MODE == 0 || (BN / 32) % CL == 0, "dgrad splits whole 32-column weight panels");
   static_assert(!PAIR || (CL == 1 && NT == 1 && IM2COL && MODE != 2), "CTA pairs exist for the im2col fprop / dgrad only");
-  static_assert(ET == 0 || (MODE == 0 && IM2COL && NT == 1 && CL == 1 && !PAIR), "2-byte operands: plain im2col MODE 0 only");
+  static_assert(ET == 0 || (MODE != 1 && IM2COL && CL == 1 && !PAIR), "2-byte operands: im2col fprop-type and wgrad only");
+  static_assert(ET == 0 || MODE == 0 || ET == 2, "the 2-byte wgrad takes bf16 x bf16");
+  // MN-major panels (wgrad): [K rows = pixels][128 B along M/N]; 32 tf32 or 64 2-byte elements wide, 32 / 64 pixels deep
+  constexpr int PW = ET == 0 ? 32 : 64;
+  constexpr uint32_t kPanel = ET == 0 ? 4096u : 8192u;
   constexpr int KE = ET == 0 ? 32 : 64;   // elements of K per 128-byte operand row = per k-block
   constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1);
   constexpr int kCluster = PAIR ? 2 : CL;
@@ -359,14 +363,14 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         } else {
           // panels of a partial last ci tile / of co rows beyond Cout are neither loaded nor stored (their
           // accumulator columns / rows are garbage that nobody reads)
-          const int npnl = IM2COL ? min(BN / 32, (p.CinW - n0) / 32) : BN / 32;
-          const int napnl = IM2COL ? min(4, (p.Cout - m0 + 31) / 32) : 4;
-          tc::mbar_arrive_expect_tx(bar, (uint32_t)napnl * 4096u + (IM2COL ? (uint32_t)(npnl * NT) * 4096u : 0u));
+          const int npnl = IM2COL ? min(BN / PW, (p.CinW - n0) / PW) : BN / PW;
+          const int napnl = IM2COL ? min(128 / PW, (p.Cout - m0 + PW - 1) / PW) : 128 / PW;
+          tc::mbar_arrive_expect_tx(bar, (uint32_t)napnl * kPanel + (IM2COL ? (uint32_t)(npnl * NT) * kPanel : 0u));
 #pragma unroll
-          for (int pnl = 0; pnl < 4; ++pnl)  // box {32 co, 32 pixel rows}
-            if (pnl < napnl) tc::tma_load_2d(stage + pnl * 4096, &tmap, bar, m0 + pnl * 32, (kb_begin + kb) * 32);
+          for (int pnl = 0; pnl < 128 / PW; ++pnl)  // box {PW co, PW pixel rows}
+            if (pnl < napnl) tc::tma_load_2d(stage + pnl * kPanel, &tmap, bar, m0 + pnl * PW, (kb_begin + kb) * PW);
           if (IM2COL) {
-            const int pix = (kb_begin + kb) * 32;
+            const int pix = (kb_begin + kb) * PW;
             const int ow = pix % p.OW;
             const int t = pix / p.OW;
             const int w = ow * p.mul + p.g_base_w, h = (t % p.OH) * p.mul + p.g_base_h, n = t / p.OH;
@@ -375,9 +379,9 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
               const int tr = NT == 1 ? tap_r : (tap_r * p.S + tap_s + tp) / p.S;
               const int ts = NT == 1 ? tap_s : (tap_r * p.S + tap_s + tp) - tr * p.S;
 #pragma unroll
-              for (int pnl = 0; pnl < BN / 32; ++pnl)  // 32 pixels x 32 ci of filter tap (tr, ts)
+              for (int pnl = 0; pnl < BN / PW; ++pnl)  // PW pixels x PW ci of filter tap (tr, ts)
                 if (pnl < npnl)
-                  tc::tma_load_im2col_4d(stage + kABytes + (tp * (BN / 32) + pnl) * 4096, &tmap_g, bar, n0 + pnl * 32, w, h, n,
+                  tc::tma_load_im2col_4d(stage + kABytes + (tp * (BN / PW) + pnl) * kPanel, &tmap_g, bar, n0 + pnl * PW, w, h, n,
                                          (uint16_t)ts, (uint16_t)tr);
             }
           }
@@ -388,13 +392,18 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     // ===================== MMA issuer =====================
     if (lane == 0 && KB > 0 && (!PAIR || cl_rank == 0)) {
       constexpr uint32_t idesc = ET == 0 ? tc::make_idesc_tf32(PAIR ? 256 : 128, NTOT, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0)
-                                         : tc::make_idesc_f16(128, NTOT, ET >= 2 ? 1 : 0, ET == 2 ? 1 : 0, 0, 0);
+                                         : tc::make_idesc_f16(128, NTOT, ET >= 2 ? 1 : 0, ET == 2 ? 1 : 0, MODE == 2 ? 1 : 0,
+                                                              MODE == 2 ? 1 : 0);
       constexpr bool a_mn = (MODE == 2), b_mn = (MODE != 0);
-      constexpr uint32_t a_lbo = a_mn ? 4096u : 16u, b_lbo = b_mn ? 4096u : 16u;
-      constexpr uint32_t a_sbo = a_mn ? 512u : 1024u, b_sbo = b_mn ? 512u : 1024u;
-      constexpr uint32_t a_lay = a_mn ? tc::kLayoutSw128Base32 : tc::kLayoutSw128;
-      constexpr uint32_t b_lay = b_mn ? tc::kLayoutSw128Base32 : tc::kLayoutSw128;
-      constexpr uint32_t a_kstep = a_mn ? 1024u : 32u, b_kstep = b_mn ? 1024u : 32u;
+      // MN-major operands: tf32 -> SWIZZLE_128B_BASE32B panels (4-row atoms); 2-byte -> plain SWIZZLE_128B panels (8-row
+      // atoms, LBO = panel stride, SBO = 1024, 16 K rows per instruction; profiles/r1_umma_mn16_probe.txt)
+      constexpr uint32_t a_lbo = a_mn ? kPanel : 16u, b_lbo = b_mn ? kPanel : 16u;
+      constexpr uint32_t mn_sbo = ET == 0 ? 512u : 1024u, mn_kstep = ET == 0 ? 1024u : 2048u;
+      constexpr uint32_t mn_lay = ET == 0 ? tc::kLayoutSw128Base32 : tc::kLayoutSw128;
+      constexpr uint32_t a_sbo = a_mn ? mn_sbo : 1024u, b_sbo = b_mn ? mn_sbo : 1024u;
+      constexpr uint32_t a_lay = a_mn ? mn_lay : tc::kLayoutSw128;
+      constexpr uint32_t b_lay = b_mn ? mn_lay : tc::kLayoutSw128;
+      constexpr uint32_t a_kstep = a_mn ? mn_kstep : 32u, b_kstep = b_mn ? mn_kstep : 32u;
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         tc::mbar_wait(tc::smem_u32(&full_bar[s]), (kb / STAGES) & 1);
@@ -922,8 +931,9 @@ struct WgradPlan {
   long long M;
   size_t ws_bytes;
 };
-int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, WgradPlan* pl) {
-  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad, 32)) return MLA_E_SHAPE;
+// kp = pixels per k-block: 32 (tf32) or 64 (2-byte operands, which also need Cin % 64 == 0)
+int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, WgradPlan* pl, int kp = 32) {
+  if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad, kp)) return MLA_E_SHAPE;
   const mla::DeviceInfo& di = mla::device_info();
   if (di.ok != 1) return di.ok;
   pl->OH = out_size(H, R, stride, pad);
@@ -931,14 +941,15 @@ int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
   pl->M = (long long)N * pl->OH * pl->OW;
   if (pl->OH <= 0 || pl->OW <= 0 || pl->M > 0x7fffffffLL) return MLA_E_SHAPE;
   pl->BN = (Cin % 128 == 0) ? 128 : 64;
-  pl->KBtot = (int)((pl->M + 31) / 32);
+  pl->KBtot = (int)((pl->M + kp - 1) / kp);
   // 64-channel inputs with a 3-wide filter: one CTA takes a whole filter row (3 taps, N = 192)
   pl->NT = (Cin == 64 && S == 3 && !force_gather()) ? 3 : 1;
   const int tiles = (R * S / pl->NT) * ((Cin + pl->BN - 1) / pl->BN) * ((Cout + 127) / 128);
   static const int waves3 = [] { const char* e = getenv("MLA_WGRAD_WAVES"); return e ? atoi(e) : 2; }();
   const int target = (pl->NT == 3 ? waves3 : 4) * di.sm_count;   // CTAs in total (2 are resident per SM)
   int splits = (target + tiles - 1) / tiles;
-  splits = max(1, min(splits, pl->KBtot / 8 > 0 ? pl->KBtot / 8 : 1));   // >= 8 k-blocks per split
+  const int min_kb = kp == 32 ? 8 : 4;                                    // >= 256 pixels per split
+  splits = max(1, min(splits, pl->KBtot / min_kb > 0 ? pl->KBtot / min_kb : 1));
   pl->kb_per_split = (pl->KBtot + splits - 1) / splits;
   pl->splits = (pl->KBtot + pl->kb_per_split - 1) / pl->kb_per_split;
   pl->ws_bytes = pl->splits > 1 ? (size_t)pl->splits * Cout * R * S * Cin * sizeof(float) : 0;
@@ -985,6 +996,51 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
     rc = pl.NT == 3 ? launch<2, 64, 2, true, 3>(map, gmap, p, grid, st)
          : pl.BN == 64 ? launch<2, 64, 4, true>(map, gmap, p, grid, st) : launch<2, 128, 3, true>(map, gmap, p, grid, st);
   }
+  if (rc) return rc;
+  if (pl.splits > 1) {
+    const long long n4 = p.split_stride / 4;
+    splitk_reduce_kernel<<<(unsigned)((n4 + 63) / 64), 64, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
+    MLA_CUDA_TRY(cudaGetLastError());
+    mla::count_launch();
+  }
+  return 0;
+}
+
+// wgrad with 2-byte operands: x16 [N,H,W,Cin] bf16, dy16 [N,OH,OW,Cout] bf16 (both MN-major: K = pixels) -> dw fp32
+// [Cout,R,S,Cin]. 64-pixel k-blocks, plain SWIZZLE_128B panels; same split-K / multi-tap structure as the TF32 wgrad.
+extern "C" size_t mla_conv2d_wgrad16_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                                                     int pad) {
+  WgradPlan pl;
+  if (wgrad_plan(N, H, W, Cin, Cout, R, S, stride, pad, &pl, 64) != 0) return 0;
+  return pl.ws_bytes + 256;
+}
+
+extern "C" int mla_conv2d_wgrad16(const void* x16, const void* dy16, float* dw, int N, int H, int W, int Cin, int Cout,
+                                  int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream) {
+  if (!x16 || !dy16 || !dw || !mla::aligned16(x16) || !mla::aligned16(dy16) || !mla::aligned16(dw) || !mla::aligned16(ws))
+    return MLA_E_BADARG;
+  WgradPlan pl;
+  int rc = wgrad_plan(N, H, W, Cin, Cout, R, S, stride, pad, &pl, 64);
+  if (rc) return rc;
+  if (pl.splits > 1 && (ws == nullptr || ws_bytes < pl.ws_bytes)) return MLA_E_WORKSPACE;
+  ConvGemmParams p{};
+  p.OH = pl.OH; p.OW = pl.OW; p.M = (int)pl.M; p.R = R; p.S = S; p.mul = stride; p.CinW = Cin;
+  p.ldo = (long long)R * S * Cin; p.accumulate = 0; p.Cout = Cout;
+  p.kb_per_split = pl.kb_per_split; p.KBtot = pl.KBtot; p.splits = pl.splits;
+  p.split_stride = (long long)Cout * R * S * Cin;
+  p.out = pl.splits > 1 ? static_cast<float*>(ws) : dw;
+  p.g_base_w = p.g_base_h = -pad;
+  full_taps(p, R, S, false);
+  CUtensorMap map, gmap;
+  rc = make_map_2d16(&map, dy16, true, pl.M, Cout, 64);                       // box {64 co, 64 pixel rows}
+  if (rc) return rc;
+  rc = make_map_im2col16(&gmap, x16, true, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 64);
+  if (rc) return rc;
+  dim3 grid(Cin / pl.BN, (Cout + 127) / 128, (R * S / pl.NT) * pl.splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = pl.NT == 3 ? launch<2, 64, 2, true, 3, 1, false, 2>(map, gmap, p, grid, st)
+       : pl.BN == 64 ? launch<2, 64, 4, true, 1, 1, false, 2>(map, gmap, p, grid, st)
+                     : launch<2, 128, 3, true, 1, 1, false, 2>(map, gmap, p, grid, st);
   if (rc) return rc;
   if (pl.splits > 1) {
     const long long n4 = p.split_stride / 4;

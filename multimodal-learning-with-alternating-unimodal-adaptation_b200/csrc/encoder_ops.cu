@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ shift, const float* __restrict__ res,
                                                        const float* __restrict__ rscale, const float* __restrict__ rshift,
                                                        int relu, float* __restrict__ out, long long n4, int C4,
-                                                       unsigned int* __restrict__ mask_out, uint2* __restrict__ out16) {
+                                                       unsigned int* __restrict__ mask_out, uint2* __restrict__ out16,
+                                                       uint2* __restrict__ out16b) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   // the loop bound is warp-uniform (i0 - lane), so all 32 lanes stay together for the mask shuffles
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 - (threadIdx.x & 31) < n4; i0 += 4 * stride) {
@@ -355,8 +356,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
           o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
         }
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        st4(out + 4 * i, tf32r4(o));   // consumers are tcgen05 convolutions (and the residual add / pooling)
-        if (out16 != nullptr) out16[i] = pack_h4(o);   // fp16 copy: the operand of the kind::f16 forward convolutions
+        if (out != nullptr) st4(out + 4 * i, tf32r4(o));   // fp32 copy: residual add / pooling / TF32 convolutions
+        if (out16 != nullptr) out16[i] = pack_h4(o);       // fp16 copy: the operand of the kind::f16 forward convolutions
+        if (out16b != nullptr) out16b[i] = pack_b4(o);     // bf16 copy: the x operand of the kind::f16 wgrad
       }
       if (mask_out != nullptr) {       // 8 lanes = 8 float4 = one 32-bit mask word
         unsigned w = ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u))
@@ -397,7 +399,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
     o.y = ga.y * is.y * (g.y - db.y * inv_m - (v.y - mu.y) * is.y * dg.y * inv_m);
     o.z = ga.z * is.z * (g.z - db.z * inv_m - (v.z - mu.z) * is.z * dg.z * inv_m);
     o.w = ga.w * is.w * (g.w - db.w * inv_m - (v.w - mu.w) * is.w * dg.w * inv_m);
-    st4(dy + 4 * i, tf32r4(o));    // dy only feeds dgrad / wgrad
+    if (dy != nullptr) st4(dy + 4 * i, tf32r4(o));    // dy only feeds dgrad / wgrad
     if (dy16 != nullptr) dy16[i] = pack_b4(o);    // bf16 copy: the operand of the kind::f16 dgrad
   }
 }
@@ -406,7 +408,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
 __global__ void bn_relu_maxpool_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                                        const float* __restrict__ shift, float* __restrict__ out,
                                        unsigned char* __restrict__ idx, int N, int H, int W, int C4, int OH, int OW,
-                                       uint2* __restrict__ out16) {
+                                       uint2* __restrict__ out16, uint2* __restrict__ out16b) {
   const long long total = (long long)N * OH * OW * C4;
   const int C = C4 * 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -436,6 +438,7 @@ __global__ void bn_relu_maxpool_kernel(const float* __restrict__ y, const float*
     }
     st4(out + 4 * i, tf32r4(make_float4(best[0], best[1], best[2], best[3])));
     if (out16 != nullptr) out16[i] = pack_h4(make_float4(best[0], best[1], best[2], best[3]));
+    if (out16b != nullptr) out16b[i] = pack_b4(make_float4(best[0], best[1], best[2], best[3]));
     reinterpret_cast<uchar4*>(idx)[i] = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1], (unsigned char)bi[2],
                                                     (unsigned char)bi[3]);
   }
@@ -642,12 +645,13 @@ extern "C" int mla_bn_eval_coeffs(const float* gamma, const float* beta, const f
 
 extern "C" int mla_bn_apply_ex(const float* y, const float* scale, const float* shift, const float* res,
                                const float* res_scale, const float* res_shift, int relu, float* out,
-                               unsigned int* relu_mask, void* out16, long long M, int C, void* stream) {
-  if (!y || !scale || !shift || !out || M < 1 || C < 4 || (C & 3)) return MLA_E_BADARG;
+                               unsigned int* relu_mask, void* out16, void* out16b, long long M, int C, void* stream) {
+  if (!y || !scale || !shift || (!out && !out16 && !out16b) || M < 1 || C < 4 || (C & 3)) return MLA_E_BADARG;
   if (relu_mask != nullptr && (C & 31)) return MLA_E_SHAPE;    // whole mask words per row group
   const long long n4 = M * (C / 4);
   bn_apply_kernel<<<ew_grid((n4 + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y, scale, shift, res, res_scale, res_shift, relu, out, n4, C / 4, relu_mask, static_cast<uint2*>(out16));
+      y, scale, shift, res, res_scale, res_shift, relu, out, n4, C / 4, relu_mask, static_cast<uint2*>(out16),
+      static_cast<uint2*>(out16b));
   MLA_LAUNCH_CHECK();
   return 0;
 }
@@ -655,7 +659,8 @@ extern "C" int mla_bn_apply_ex(const float* y, const float* scale, const float* 
 extern "C" int mla_bn_apply_mask(const float* y, const float* scale, const float* shift, const float* res,
                                  const float* res_scale, const float* res_shift, int relu, float* out,
                                  unsigned int* relu_mask, long long M, int C, void* stream) {
-  return mla_bn_apply_ex(y, scale, shift, res, res_scale, res_shift, relu, out, relu_mask, nullptr, M, C, stream);
+  if (!out) return MLA_E_BADARG;
+  return mla_bn_apply_ex(y, scale, shift, res, res_scale, res_shift, relu, out, relu_mask, nullptr, nullptr, M, C, stream);
 }
 
 extern "C" int mla_bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* res_scale,
@@ -666,7 +671,7 @@ extern "C" int mla_bn_apply(const float* y, const float* scale, const float* shi
 static int bn_backward_impl(const float* dz, const float* z, const unsigned int* mask, const float* y, const float* mean,
                             const float* invstd, const float* gamma, long long M, int C, float* dgamma, float* dbeta,
                             float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream, void* dy16 = nullptr) {
-  if (!dz || !y || !mean || !invstd || !gamma || !dy) return MLA_E_BADARG;
+  if (!dz || !y || !mean || !invstd || !gamma || (!dy && !dy16)) return MLA_E_BADARG;
   RedPlan pl;
   int rc = red_plan(M, C, &pl);
   if (rc) return rc;
@@ -710,19 +715,19 @@ extern "C" int mla_bn_backward_mask(const float* dz, const unsigned int* relu_ma
 }
 
 extern "C" int mla_bn_relu_maxpool_ex(const float* y, const float* scale, const float* shift, float* out, void* out16,
-                                      unsigned char* idx, int N, int H, int W, int C, void* stream) {
+                                      void* out16b, unsigned char* idx, int N, int H, int W, int C, void* stream) {
   if (!y || !scale || !shift || !out || !idx || (C & 3)) return MLA_E_BADARG;
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * OH * OW * (C / 4);
   bn_relu_maxpool_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y, scale, shift, out, idx, N, H, W, C / 4, OH, OW, static_cast<uint2*>(out16));
+      y, scale, shift, out, idx, N, H, W, C / 4, OH, OW, static_cast<uint2*>(out16), static_cast<uint2*>(out16b));
   MLA_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int mla_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* out, unsigned char* idx,
                                    int N, int H, int W, int C, void* stream) {
-  return mla_bn_relu_maxpool_ex(y, scale, shift, out, nullptr, idx, N, H, W, C, stream);
+  return mla_bn_relu_maxpool_ex(y, scale, shift, out, nullptr, nullptr, idx, N, H, W, C, stream);
 }
 
 extern "C" int mla_maxpool_relu_backward(const float* dp, const float* p, const unsigned char* idx, float* g, int N, int H,

@@ -152,7 +152,9 @@ class ResNetPlan:
         self.p0 = e(N, self.PH, self.PW, 64)
         self.f16 = USE_F16
         half = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)          # noqa: E731
+        bhalf = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)        # noqa: E731
         self.p0_16 = half(N, self.PH, self.PW, 64) if self.f16 else None
+        self.p0_b = bhalf(N, self.PH, self.PW, 64) if self.f16 else None            # bf16 copy: wgrad16 x operand
         self.w16 = torch.empty(self.flat.numel(), dtype=torch.float16, device=dev) if self.f16 else None     # fp16 weights
         self.wt16 = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=dev) if self.f16 else None   # transposed, bf16
         self.idx0 = e(N, self.PH, self.PW, 64, dt=torch.uint8)
@@ -171,6 +173,8 @@ class ResNetPlan:
                          m1=e(N * ho * wo * cout // 32, dt=torch.int32), m2=e(N * ho * wo * cout // 32, dt=torch.int32),
                          # fp16 copies of a1 / out: the operands of the kind::f16 forward convolutions
                          a1_16=half(N, ho, wo, cout) if self.f16 else None, out_16=half(N, ho, wo, cout) if self.f16 else None,
+                         # bf16 copies: the x operands of the kind::f16 weight gradients
+                         a1_b=bhalf(N, ho, wo, cout) if self.f16 else None, out_b=bhalf(N, ho, wo, cout) if self.f16 else None,
                          bn1=_BN(blk.bn1, dev), bn2=_BN(blk.bn2, dev), yd=None, bnd=None)
                 if blk.downsample is not None:
                     d["yd"] = e(N, ho, wo, cout)
@@ -195,6 +199,11 @@ class ResNetPlan:
             nw = max(nw, self.L.mla_conv2d_wgrad_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3,
                                                                   b["stride"], 1),
                      self.L.mla_conv2d_wgrad_workspace_bytes(N, b["ho"], b["wo"], b["cout"], b["cout"], 3, 3, 1, 1))
+        if self.f16:
+            for b in self.blocks:
+                nw = max(nw, self.L.mla_conv2d_wgrad16_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3, b["stride"], 1),
+                         self.L.mla_conv2d_wgrad16_workspace_bytes(N, b["ho"], b["wo"], b["cout"], b["cout"], 3, 3, 1, 1),
+                         self.L.mla_conv2d_wgrad16_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 1, 1, b["stride"], 0))
         self.wg_ws = torch.empty(max(nw, 256), dtype=torch.uint8, device=dev)
         self.trained_forward = False
         self.feat_static = torch.empty(self.B, self.C_out, dtype=torch.float32, device=dev)    # pooled feature (graph output)
@@ -284,6 +293,12 @@ class ResNetPlan:
                                      self.wg_ws.numel(), st), "mla_conv2d_wgrad")
         _conv_timer_end(t, "wgrad", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
 
+    def _wgrad16(self, x16b, dy16, dw, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
+        t = _conv_timer_begin()
+        _chk(self.L.mla_conv2d_wgrad16(_p(x16b), _p(dy16), _p(dw), N, H, W, Cin, Cout, R, R, stride, pad, _p(self.wg_ws),
+                                       self.wg_ws.numel(), st), "mla_conv2d_wgrad16")
+        _conv_timer_end(t, "wgrad16", N, H, W, Cin, Cout, R, stride, pad)
+
     def _bn_coeffs(self, y, M, b, training, st):
         bn = b.bn
         if training:
@@ -369,7 +384,8 @@ class ResNetPlan:
         self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
                       k_alg=K)
         _chk(L.mla_bn_relu_maxpool_ex(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.p0_16),
-                                      _p(self.idx0), N, self.OH0, self.OW0, 64, st), "mla_bn_relu_maxpool")
+                                      _p(self.p0_b) if training else None, _p(self.idx0), N, self.OH0, self.OW0, 64, st),
+             "mla_bn_relu_maxpool")
         f16 = self.f16
         if f16:      # fp16 copy of every parameter (same offsets as the flat buffer): the B operand of fprop16
             _chk(L.mla_cast16(_p(self.flat), _p(self.w16), self.flat.numel(), 0, st), "mla_cast16")
@@ -382,8 +398,10 @@ class ResNetPlan:
             else:
                 self._conv_bn(xin, blk.conv1.weight, b["y1"], N, b["h"], b["w"], cin, cout, 3, s, 1, b["bn1"], training, st)
             mk1, mk2 = (_p(b["m1"]), _p(b["m2"])) if training else (None, None)
-            _chk(L.mla_bn_apply_ex(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(b["a1"]),
-                                   mk1, _p(b["a1_16"]), M, cout, st), "mla_bn_apply")
+            # a1 in fp32 is only read by the TF32 wgrad / the unmasked BN backward: not written on the 2-byte path
+            a1_32 = None if (f16 and _USE_RELU_MASK) else b["a1"]
+            _chk(L.mla_bn_apply_ex(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(a1_32),
+                                   mk1, _p(b["a1_16"]), _p(b["a1_b"]) if training else None, M, cout, st), "mla_bn_apply")
             if f16:
                 self._conv_bn16(b["a1_16"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, b["bn2"],
                                 training, st)
@@ -398,11 +416,12 @@ class ResNetPlan:
                     self._conv_bn(xin, blk.downsample[0].weight, b["yd"], N, b["h"], b["w"], cin, cout, 1, s, 0, b["bnd"],
                                   training, st)
                 _chk(L.mla_bn_apply_ex(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]),
-                                       _p(b["bnd"].scale), _p(b["bnd"].shift), 1, _p(b["out"]), mk2, _p(b["out_16"]), M, cout,
-                                       st), "mla_bn_apply")
+                                       _p(b["bnd"].scale), _p(b["bnd"].shift), 1, _p(b["out"]), mk2, _p(b["out_16"]),
+                                       _p(b["out_b"]) if training else None, M, cout, st), "mla_bn_apply")
             else:
                 _chk(L.mla_bn_apply_ex(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
-                                       _p(b["out"]), mk2, _p(b["out_16"]), M, cout, st), "mla_bn_apply")
+                                       _p(b["out"]), mk2, _p(b["out_16"]), _p(b["out_b"]) if training else None, M, cout, st),
+                     "mla_bn_apply")
             xin, xin16 = b["out"], b["out_16"]
         _chk(L.mla_avgpool_forward(_p(xin), _p(self.feat_static), self.B, self.rows, self.C_out, st), "mla_avgpool_forward")
         if training and self.nbt:
@@ -448,13 +467,22 @@ class ResNetPlan:
                 cur.wait_event(ev)
             return self.tmp(slot, shape)
 
-        def wgrad_async(x, dy, slot, dw, *geom, k_alg=None):
+        def buf16(slot, shape):                     # same for the bf16 gradient buffers (dgrad16 / wgrad16 operands)
+            ev = events.pop((slot, tuple(shape)), None)
+            if ev is not None:
+                cur.wait_event(ev)
+            return self.tmp16(slot, shape)
+
+        def wgrad_async(x, dy, slot, dw, *geom, k_alg=None, two_byte=False):
             if wsm is not cur:
                 ready = torch.cuda.Event()
                 ready.record(cur)
                 wsm.wait_event(ready)
             with torch.cuda.stream(wsm):
-                self._wgrad(x, dy, dw, *geom, wst, k_alg=k_alg)
+                if two_byte:
+                    self._wgrad16(x, dy, dw, *geom, wst)
+                else:
+                    self._wgrad(x, dy, dw, *geom, wst, k_alg=k_alg)
             if wsm is not cur:
                 done = torch.cuda.Event()
                 done.record(wsm)
@@ -480,35 +508,48 @@ class ResNetPlan:
             shp = b["out"].shape
             par = i & 1
             g = self.tmp("g%d" % par, shp)
-            dy2 = buf("dy2_%d" % par, shp)
-            dy2h = self.tmp16("dy2h", shp) if f16 else None      # bf16 copies (dgrad16 operands) live on `cur` only
+            xin_b = (self.blocks[i - 1]["out_b"] if i > 0 else self.p0_b) if f16 else None
             z2, mk2 = (None, b["m2"]) if _USE_RELU_MASK else (b["out"], None)
-            self._bn_bwd(dout, z2, b["y2"], b["bn2"], M, dy2, g, st, mask=mk2, dy16=dy2h)
-            wgrad_async(b["a1"], dy2, "dy2_%d" % par, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3, 1, 1)
+            z1, mk1 = (None, b["m1"]) if _USE_RELU_MASK else (b["a1"], None)
             da1 = self.tmp("da", shp)
             if f16:
-                self._dgrad16(dy2h, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
+                # 2-byte path: the gradients exist in bf16 only; wgrad16 reads (x bf16, dy bf16), dgrad16 (dy bf16, w^T bf16)
+                dy2 = buf16("dy2h_%d" % par, shp)
+                self._bn_bwd(dout, z2, b["y2"], b["bn2"], M, None, g, st, mask=mk2, dy16=dy2)
+                wgrad_async(b["a1_b"], dy2, "dy2h_%d" % par, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3,
+                            1, 1, two_byte=True)
+                self._dgrad16(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
+                dy1 = buf16("dy1h_%d" % par, shp)
+                self._bn_bwd(da1, z1, b["y1"], b["bn1"], M, None, None, st, mask=mk1, dy16=dy1)
+                wgrad_async(xin_b, dy1, "dy1h_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1,
+                            two_byte=True)
             else:
+                dy2 = buf("dy2_%d" % par, shp)
+                self._bn_bwd(dout, z2, b["y2"], b["bn2"], M, dy2, g, st, mask=mk2)
+                wgrad_async(b["a1"], dy2, "dy2_%d" % par, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3, 1, 1)
                 self._dgrad(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
-            dy1 = buf("dy1_%d" % par, shp)
-            dy1h = self.tmp16("dy1h", shp) if f16 else None
-            z1, mk1 = (None, b["m1"]) if _USE_RELU_MASK else (b["a1"], None)
-            self._bn_bwd(da1, z1, b["y1"], b["bn1"], M, dy1, None, st, mask=mk1, dy16=dy1h)
-            wgrad_async(xin, dy1, "dy1_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1)
+                dy1 = buf("dy1_%d" % par, shp)
+                self._bn_bwd(da1, z1, b["y1"], b["bn1"], M, dy1, None, st, mask=mk1)
+                wgrad_async(xin, dy1, "dy1_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1)
             dg = self._dgrad16 if f16 else self._dgrad
             if b["yd"] is not None:
-                dyd = buf("dyd", shp)
-                dydh = self.tmp16("dydh", shp) if f16 else None
-                self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st, dy16=dydh)
-                wgrad_async(xin, dyd, "dyd", _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0)
+                if f16:
+                    dyd = buf16("dydh", shp)
+                    self._bn_bwd(g, None, b["yd"], b["bnd"], M, None, None, st, dy16=dyd)
+                    wgrad_async(xin_b, dyd, "dydh", _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0,
+                                two_byte=True)
+                else:
+                    dyd = buf("dyd", shp)
+                    self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st)
+                    wgrad_async(xin, dyd, "dyd", _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0)
                 dx = self.tmp("dXa", xin.shape)         # xin.shape != out.shape here, so never aliases dout
                 # the 3x3 dgrad touches every pixel of dx and goes first; the 1x1/2 shortcut then ADDS into the
                 # one output parity class it reaches (its other classes are skipped, not zero-filled)
-                dg(dy1h if f16 else dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, False, st)
-                dg(dydh if f16 else dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, True, st)
+                dg(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, False, st)
+                dg(dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, True, st)
             else:
                 dx = g                                  # identity shortcut: dX starts as the masked gradient
-                dg(dy1h if f16 else dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
+                dg(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
             dout = dx
         # stem: maxpool+relu backward, BN backward, weight gradient (no dgrad: the input needs none)
         g0 = self.tmp("g0", self.y0.shape)

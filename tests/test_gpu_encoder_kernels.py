@@ -106,6 +106,17 @@ def test_conv_2byte_operands(L, case):
     assert relf(dx.permute(0, 3, 1, 2), dxr) < 2e-5
     # fp16 operands carry TF32's mantissa: against the unrounded fp32 convolution the error is the TF32 one
     assert relf(y.permute(0, 3, 1, 2), F.conv2d(x, w, None, stride, pad)) < 2e-3
+    # wgrad16: bf16 x bf16, both operands MN-major (K = pixels)
+    xb = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    dw = torch.empty(Cout, R, R, Cin, device="cuda")
+    nb = L.mla_conv2d_wgrad16_workspace_bytes(N, H, W, Cin, Cout, R, R, stride, pad)
+    assert nb > 0
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    assert L.mla_conv2d_wgrad16(P(xb), P(dy16), P(dw), N, H, W, Cin, Cout, R, R, stride, pad, P(ws), nb, st()) == 0
+    torch.cuda.synchronize()
+    dwr = torch.nn.grad.conv2d_weight(xb.float().permute(0, 3, 1, 2), (Cout, Cin, R, R), dy16.float().permute(0, 3, 1, 2),
+                                      stride, pad)
+    assert relf(dw.permute(0, 3, 1, 2), dwr) < 2e-5
 
 
 @pytest.mark.parametrize("N,H,W,C,relu,res", [(2, 5, 3, 64, True, True), (4, 9, 6, 512, True, True),
@@ -133,8 +144,9 @@ def test_batchnorm_forward_backward(L, N, H, W, C, relu, res):
     out = torch.empty(M, C, device=dev)
     mask = torch.zeros(M * C // 32, dtype=torch.int32, device=dev)
     out16 = torch.empty(M, C, dtype=torch.float16, device=dev)
+    out16b = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
     assert L.mla_bn_apply_ex(P(y), P(scale), P(shift), P(idn) if res else None, None, None, 1 if relu else 0, P(out), P(mask),
-                             P(out16), M, C, st()) == 0
+                             P(out16), P(out16b), M, C, st()) == 0
     dz = torch.randn(M, C, device=dev, generator=g0)
     z.backward(dz)
     dy, g = torch.empty(M, C, device=dev), torch.empty(M, C, device=dev)
@@ -145,6 +157,7 @@ def test_batchnorm_forward_backward(L, N, H, W, C, relu, res):
     assert relf(mean, y.mean(0)) < 1e-5 and relf(rm, rm2) < 1e-5 and relf(rv, rv2) < 1e-5     # torch running-stat semantics
     assert relf(out, z.detach()) < 1e-3                                  # stored TF32-rounded
     assert relf(out16.float(), z.detach()) < 1e-3                        # fp16 copy = the same 10-bit mantissa
+    assert relf(out16b.float(), z.detach()) < 4e-3                       # bf16 copy: 8-bit mantissa
     assert relf(dg, gt.grad) < 1e-4 and relf(db, bt.grad) < 1e-4
     assert relf(dy, yt.grad) < 1e-3
     assert relf(g, dz * (z.detach() > 0) if relu else dz) < 1e-6
@@ -161,6 +174,11 @@ def test_batchnorm_forward_backward(L, N, H, W, C, relu, res):
         torch.cuda.synchronize()
         assert torch.equal(dy2, dy) and torch.equal(g2, g) and torch.equal(dg2, dg) and torch.equal(db2, db)
         assert relf(dy16.float(), dy) < 4e-3                              # bf16: 8-bit mantissa
+        dy16b = torch.empty_like(dy16)                                    # 2-byte output only (no fp32 dy)
+        assert L.mla_bn_backward_ex(P(dz), None, P(mask), P(y), P(mean), P(invstd), P(gamma), M, C, P(dg2), P(db2), None,
+                                    P(dy16b), None, P(ws), ws.numel(), st()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(dy16b, dy16)
 
 
 @pytest.mark.parametrize("B,T,Cin,H,W", [(2, 1, 1, 65, 48), (2, 2, 3, 64, 64), (1, 1, 1, 257, 188)])
@@ -187,7 +205,7 @@ def test_stem_im2col_conv_maxpool(L, B, T, Cin, H, W):
     p = torch.empty(N, PH, PW, 64, device=dev)
     p16 = torch.empty(N, PH, PW, 64, dtype=torch.float16, device=dev)
     idx = torch.empty(N, PH, PW, 64, dtype=torch.uint8, device=dev)
-    assert L.mla_bn_relu_maxpool_ex(P(y), P(scale), P(shift), P(p), P(p16), P(idx), N, OH, OW, 64, st()) == 0
+    assert L.mla_bn_relu_maxpool_ex(P(y), P(scale), P(shift), P(p), P(p16), None, P(idx), N, OH, OW, 64, st()) == 0
     yr = y.permute(0, 3, 1, 2).clone().requires_grad_(True)
     pr = F.max_pool2d(F.relu(yr * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)), 3, 2, 1)
     dp = torch.randn_like(pr)

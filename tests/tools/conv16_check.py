@@ -52,12 +52,25 @@ def case(N, H, W, Cin, Cout, R, stride, time_it=False):
     msg = "N%d %dx%d Cin%d Cout%d k%d s%d: fprop16=%.2e dgrad16=%.2e dgrad16_acc=%.2e transpose_ok=%s" % (
         N, H, W, Cin, Cout, R, stride, relf(y.permute(0, 3, 1, 2), yr), relf(dx.permute(0, 3, 1, 2), dxr),
         relf((acc - 1).permute(0, 3, 1, 2), dxr), wt_ok)
+    xb = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    dw = torch.empty(Cout, R, R, Cin, device="cuda")
+    nb = L.mla_conv2d_wgrad16_workspace_bytes(N, H, W, Cin, Cout, R, R, stride, pad)
+    wsb = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    rc = L.mla_conv2d_wgrad16(xb.data_ptr(), dy16.data_ptr(), dw.data_ptr(), N, H, W, Cin, Cout, R, R, stride, pad, wsb.data_ptr(),
+                              nb, st())
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    dwr = torch.nn.grad.conv2d_weight(xb.float().permute(0, 3, 1, 2), (Cout, Cin, R, R), dy16.float().permute(0, 3, 1, 2),
+                                      stride, pad)
+    msg += " wgrad16=%.2e" % relf(dw.permute(0, 3, 1, 2), dwr)
     if time_it:
         flops = 2.0 * y.numel() * Cin * R * R
         for name, fn in (("fprop16", lambda: L.mla_conv2d_fprop16(x16.data_ptr(), w16.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout,
                                                                     R, R, stride, pad, None, st())),
                          ("dgrad16", lambda: L.mla_conv2d_dgrad16(dy16.data_ptr(), wt16.data_ptr(), dx.data_ptr(), N, H, W, Cin,
-                                                                    Cout, R, R, stride, pad, 0, st()))):
+                                                                    Cout, R, R, stride, pad, 0, st())),
+                         ("wgrad16", lambda: L.mla_conv2d_wgrad16(xb.data_ptr(), dy16.data_ptr(), dw.data_ptr(), N, H, W, Cin,
+                                                                    Cout, R, R, stride, pad, wsb.data_ptr(), nb, st()))):
             for _ in range(3):
                 fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
