@@ -164,7 +164,7 @@ struct BnFinal {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+__global__ void __launch_bounds__(kRedThreads, 4) channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                                      const float* __restrict__ z,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, long long M, int C,
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
 #pragma unroll
       for (int q = 0; q < 4; ++q) { a[q] += (double)fa[q]; b[q] += (double)fb[q]; fa[q] = 0.f; fb[q] = 0.f; }
     };
-    auto row = [&](const float4& v, const float4& w, const float4& zz) {
+    auto row = [&](const float4& v, const float4& w, unsigned nb) {   // nb: bit q = component q passes the ReLU mask
       if (MODE == 2) {          // w = the second half of the partial row (sum of squares)
         fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
         fb[0] += w.x; fb[1] += w.y; fb[2] += w.z; fb[3] += w.w;
@@ -203,45 +203,46 @@ __global__ void __launch_bounds__(kRedThreads) channel_reduce_kernel(const float
         fa[0] += v.x; fa[1] += v.y; fa[2] += v.z; fa[3] += v.w;
         fb[0] = fmaf(v.x, v.x, fb[0]); fb[1] = fmaf(v.y, v.y, fb[1]);
         fb[2] = fmaf(v.z, v.z, fb[2]); fb[3] = fmaf(v.w, v.w, fb[3]);
-      } else {                  // w = dz, zz = the ReLU output (mask) or +1
-        const float gx = zz.x > 0.f ? w.x : 0.f, gy = zz.y > 0.f ? w.y : 0.f;
-        const float gz = zz.z > 0.f ? w.z : 0.f, gw = zz.w > 0.f ? w.w : 0.f;
+      } else {                  // w = dz
+        const float gx = (nb & 1u) ? w.x : 0.f, gy = (nb & 2u) ? w.y : 0.f;
+        const float gz = (nb & 4u) ? w.z : 0.f, gw = (nb & 8u) ? w.w : 0.f;
         fa[0] += gx; fa[1] += gy; fa[2] += gz; fa[3] += gw;
         fb[0] = fmaf(gx, (v.x - mu.x) * is.x, fb[0]); fb[1] = fmaf(gy, (v.y - mu.y) * is.y, fb[1]);
         fb[2] = fmaf(gz, (v.z - mu.z) * is.z, fb[2]); fb[3] = fmaf(gw, (v.w - mu.w) * is.w, fb[3]);
       }
+    };
+    auto bits = [&](long long o, long long rowidx) -> unsigned {   // ReLU pass bits of the float4 at row offset o
+      if (MODE != 1) return 15u;
+      if (mask != nullptr) return relu_nibble(mask, (rowidx * C + c0) >> 2);
+      if (zp != nullptr) {
+        const float4 zz = ld4(zp + o);
+        return (zz.x > 0.f ? 1u : 0u) | (zz.y > 0.f ? 2u : 0u) | (zz.z > 0.f ? 4u : 0u) | (zz.w > 0.f ? 8u : 0u);
+      }
+      return 15u;
     };
     const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
     const int kFlush = (MODE == 2) ? 1 : 8;     // steps of 4 rows between flushes
     long long i = 0;
     int since = 0;
     for (; i + 4 <= n; i += 4) {
-      float4 v[4], w[4], zz[4];
+      float4 v[4], w[4];
+      unsigned nb[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long o = (i + u) * 16 * rs;
         v[u] = ld4(xp + o);
         w[u] = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
-        zz[u] = (zp != nullptr) ? ld4(zp + o) : one;
-        if (MODE == 1 && mask != nullptr) {
-          const unsigned nb = relu_nibble(mask, ((r0 + ty + (i + u) * 16) * C + c0) >> 2);
-          zz[u] = make_float4((nb & 1u) ? 1.f : 0.f, (nb & 2u) ? 1.f : 0.f, (nb & 4u) ? 1.f : 0.f, (nb & 8u) ? 1.f : 0.f);
-        }
+        nb[u] = bits(o, r0 + ty + (i + u) * 16);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) row(v[u], w[u], zz[u]);
+      for (int u = 0; u < 4; ++u) row(v[u], w[u], nb[u]);
       if (++since == kFlush) { flush(); since = 0; }
     }
     for (; i < n; ++i) {
       const long long o = i * 16 * rs;
       const float4 v = ld4(xp + o);
       const float4 w = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
-      float4 zz = (zp != nullptr) ? ld4(zp + o) : one;
-      if (MODE == 1 && mask != nullptr) {
-        const unsigned nb = relu_nibble(mask, ((r0 + ty + i * 16) * C + c0) >> 2);
-        zz = make_float4((nb & 1u) ? 1.f : 0.f, (nb & 2u) ? 1.f : 0.f, (nb & 4u) ? 1.f : 0.f, (nb & 8u) ? 1.f : 0.f);
-      }
-      row(v, w, zz);
+      row(v, w, bits(o, r0 + ty + i * 16));
     }
     flush();
 #pragma unroll
