@@ -5,7 +5,7 @@ The directory name contains hyphens, so import it through the `mla_b200` alias p
 repo root (`import mla_b200`). Names mirror the reference's modules:
     GSPlugin, setup_seed, weight_init            (utils/utils.py)
     calculate_entropy, calculate_gating_weights[3], train_epoch, valid, get_arguments (main.py)
-    AVClassifier                                 (models/basic_model.py)
+    AVClassifier, M3AEClassifier                 (models/basic_model.py, models/m3ae.py)
     ConcatFusion, ConcatFusion3                  (models/fusion_modules.py)
     resnet18                                     (models/backbone.py)
 """
@@ -15,6 +15,7 @@ from .fusion import calculate_entropy, calculate_gating_weights, calculate_gatin
 from .fusion_modules import ConcatFusion, ConcatFusion3, head_turn  # noqa: F401
 from .backbone import resnet18  # noqa: F401
 from .basic_model import AVClassifier  # noqa: F401
+from .m3ae import M3AEClassifier  # noqa: F401
 from .utils import setup_seed, weight_init  # noqa: F401
 from .engine import ModuleHolder, train_epoch, valid  # noqa: F401
 from .main import get_arguments  # noqa: F401

@@ -217,8 +217,8 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                     # whole backward pass and serialise the two encoders again
                     st.flat[m].detach()
                     pending.append((m, stream))
-            else:
-                st.flat[m].attach()
+            else:                                  # autograd encoders (m3ae): gradients ACCUMULATE into the views
+                st.flat[m].attach(zero=True)
                 feat.backward(o["dfeat"])
                 if world > 1:
                     mdist.allreduce_sum_(st.flat[m].flat)

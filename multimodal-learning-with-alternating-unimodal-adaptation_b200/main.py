@@ -18,6 +18,7 @@ from . import dist as mdist
 from .basic_model import AVClassifier
 from .engine import ModuleHolder, train_epoch, valid
 from .gs_plugin import GSPlugin
+from .m3ae import M3AEClassifier
 from .utils import setup_seed, weight_init
 
 
@@ -90,13 +91,43 @@ class SyntheticAVLoader:
             yield self.batches[i % len(self.batches)]
 
 
+class SyntheticTextImageLoader:
+    """len()-able iterable of Food-101-shaped m3ae batches (token [B,1,L] int64, padding_mask [B,1,L], image
+    [B,3,256,256], label, idx), pinned host memory, seeded per rank (dataset layout: dataset/*.py __getitem__)."""
+
+    def __init__(self, batch_size, steps, seed, text_len=512, image_hw=(256, 256), n_classes=101, vocab=30522, distinct=2):
+        g = torch.Generator().manual_seed(seed)
+        self.batches = []
+        for _ in range(min(distinct, steps)):
+            token = torch.randint(0, vocab, (batch_size, 1, text_len), generator=g)
+            n_valid = torch.randint(max(1, text_len // 4), text_len + 1, (batch_size,), generator=g)
+            pm = (torch.arange(text_len)[None, :] >= n_valid[:, None]).long()[:, None, :]
+            image = torch.randn(batch_size, 3, *image_hw, generator=g)
+            label = torch.randint(0, n_classes, (batch_size,), generator=g)
+            idx = torch.zeros(batch_size, 1, dtype=torch.long)
+            if torch.cuda.is_available():
+                token, pm, image, label = token.pin_memory(), pm.pin_memory(), image.pin_memory(), label.pin_memory()
+            self.batches.append((token, pm, image, label, idx))
+        self.steps = steps
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self):
+        for i in range(self.steps):
+            yield self.batches[i % len(self.batches)]
+
+
 def build_model(args, device):
     """main.py:707-734 for the paths in scope."""
-    if args.lorb in ("large", "m3ae") or args.clip:
-        raise NotImplementedError("round 1 implements --lorb base (AVClassifier); m3ae / modal3 encoders are the "
-                                  "next rows of SURVEY.md §8")
-    model = AVClassifier(args)
-    model.apply(weight_init)
+    if args.lorb == "large" or args.clip or (args.lorb == "m3ae" and args.modal3):
+        raise NotImplementedError("implemented: --lorb base (AVClassifier) and --lorb m3ae (M3AEClassifier); the CAV-MAE "
+                                  "/ CLIP / three-modality encoders are the next rows of SURVEY.md §8")
+    if args.lorb == "m3ae":
+        model = M3AEClassifier(args)                             # main.py:709-713 (no weight_init, like the reference)
+    else:
+        model = AVClassifier(args)
+        model.apply(weight_init)
     if args.ckpt_load_path_train:
         loaded = torch.load(args.ckpt_load_path_train, map_location="cpu")["model"]
         state = {k[7:]: v for k, v in loaded.items()}            # strip 'module.' (main.py:723)
@@ -117,8 +148,9 @@ def main(av_alpha=0.5):
     model = build_model(args, device)
     optimizer = optim.SGD(model.parameters(), lr=args.learning_rate, momentum=0.9, weight_decay=1e-4)   # main.py:749
     scheduler = optim.lr_scheduler.StepLR(optimizer, args.lr_decay_step, args.lr_decay_ratio)           # main.py:760
-    train_loader = SyntheticAVLoader(args.batch_size, args.steps, seed=1 + rank)
-    test_loader = SyntheticAVLoader(args.batch_size, max(1, args.steps // 2), seed=1001 + rank)
+    Loader = SyntheticTextImageLoader if args.lorb == "m3ae" else SyntheticAVLoader
+    train_loader = Loader(args.batch_size, args.steps, seed=1 + rank)
+    test_loader = Loader(args.batch_size, max(1, args.steps // 2), seed=1001 + rank)
     gs = GSPlugin(force_projection=args.force_projection) if args.gs_flag else None                     # main.py:819
     if args.train:
         best_acc = 0.0

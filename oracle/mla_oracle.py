@@ -12,6 +12,7 @@ It restates, on the CPU, what the reference computes on the path named by BASELI
   * ResNet-18 encoders / AVClassifier models/backbone.py:142-160, basic_model.py:52-77 (torch CPU fp32)
   * the alternating gs train step     main.py:419-476               (torch CPU fp32 + autograd + SGD)
   * valid() gs branch                 main.py:622-679
+  * m3ae encoders / M3AEClassifier    models/m3ae.py:65-224,337-370, basic_model.py:184-200 (torch CPU fp32)
 
 Pinning: the reference ships no tests or golden vectors, so this oracle is
 pinned against OUTPUTS OF THE REFERENCE ITSELF, executed in the build container under torch
@@ -350,6 +351,135 @@ class AVOracle:
             hits += r["hits"]
         tot = float(num.sum())
         return hits[0].sum() / tot, hits[1].sum() / tot, hits[2].sum() / tot
+
+
+# --------------------------------------------------------------------------------------------
+# m3ae encoders / M3AEClassifier — models/m3ae.py:86-179,181-224,337-370, models/basic_model.py:184-200
+# --------------------------------------------------------------------------------------------
+def sincos_1d(embed_dim, pos):
+    """m3ae.py:181-194: [sin(pos * w_i) | cos(pos * w_i)], w_i = 10000^(-i / (D/2)), float32 throughout."""
+    omega = np.arange(embed_dim // 2, dtype=np.float32)
+    omega /= embed_dim / 2.
+    omega = 1. / 10000 ** omega
+    out = np.einsum("m,d->md", np.asarray(pos, np.float32).reshape(-1), omega)
+    return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+
+def sincos_2d(embed_dim, length):
+    """m3ae.py:207-224: first half of the channels from meshgrid(w, h)[0] (the column index), second half from the row."""
+    g = int(length ** 0.5)
+    assert g * g == length
+    grid = np.stack(np.meshgrid(np.arange(g, dtype=np.float32), np.arange(g, dtype=np.float32)), axis=0)
+    return np.concatenate([sincos_1d(embed_dim // 2, grid[0]), sincos_1d(embed_dim // 2, grid[1])], axis=1)
+
+
+def m3ae_representation(sd, prefix, image, text, text_padding_mask, num_heads):
+    """MaskedMultimodalAutoencoder.forward_representation (m3ae.py:337-370) + Transformer/Block/Attention/TransformerMLP
+    (m3ae.py:65-179), functional over a state dict. DropPath is the identity (as published it returns None and
+    the forward raises; the configured rate is 0), dropout rates are 0."""
+    import torch
+    import torch.nn.functional as F
+    cls = sd[prefix + "cls_token"]
+    D = cls.shape[-1]
+    B = image.shape[0] if image is not None else text.shape[0]
+    dev = cls.device
+    xs = [cls.expand(B, 1, D)]
+    masks = [torch.zeros(B, 1, dtype=torch.float32, device=dev)]
+    if image is not None:
+        pe = torch.from_numpy(sincos_2d(D, image.shape[1])[None]).to(dev)
+        xs.append(F.linear(image, sd[prefix + "image_embedding.weight"], sd[prefix + "image_embedding.bias"]) + pe
+                  + sd[prefix + "encoder_image_type_embedding"])
+        masks.append(torch.zeros(B, image.shape[1], dtype=torch.float32, device=dev))
+    if text is not None:
+        pe = torch.from_numpy(sincos_1d(D, np.arange(text.shape[1], dtype=np.float32))[None]).to(dev)
+        xs.append(F.embedding(text, sd[prefix + "text_embedding.weight"]) + pe + sd[prefix + "encoder_text_type_embedding"])
+        masks.append(text_padding_mask)
+    x = torch.cat(xs, dim=1)
+    mask = torch.cat(masks, dim=1)
+    S = x.shape[1]
+    depth = 1 + max(int(k[len(prefix) + 15:].split(".")[0]) for k in sd if k.startswith(prefix + "encoder.blocks."))
+    scale = (D // num_heads) ** -0.5
+    for i in range(depth):
+        p = "%sencoder.blocks.%d." % (prefix, i)
+        h = F.layer_norm(x, (D,), sd[p + "layer_norm1.weight"], sd[p + "layer_norm1.bias"])
+        qkv = F.linear(h, sd[p + "attention.qkv_linear.weight"], sd[p + "attention.qkv_linear.bias"])
+        qkv = qkv.view(B, S, 3, num_heads, D // num_heads).permute(2, 0, 3, 1, 4)
+        att = torch.matmul(qkv[0], qkv[1].transpose(-2, -1)) * scale
+        att = torch.where(mask[:, None, None, :].expand(att.shape) > 0, torch.tensor(-1e7, device=dev), att)
+        att = F.softmax(att, dim=-1)
+        h = torch.matmul(att, qkv[2]).permute(0, 2, 1, 3).reshape(B, S, D)
+        x = x + F.linear(h, sd[p + "attention.fc.weight"], sd[p + "attention.fc.bias"])
+        h = F.layer_norm(x, (D,), sd[p + "layer_norm2.weight"], sd[p + "layer_norm2.bias"])
+        h = F.gelu(F.linear(h, sd[p + "transformer_mlp.fc1.weight"], sd[p + "transformer_mlp.fc1.bias"]))
+        x = x + F.linear(h, sd[p + "transformer_mlp.fc2.weight"], sd[p + "transformer_mlp.fc2.bias"])
+    return F.layer_norm(x, (D,), sd[prefix + "encoder.layer_norm.weight"], sd[prefix + "encoder.layer_norm.bias"])
+
+
+def m3ae_forward(sd, token, padding_mask, visual, num_heads):
+    """M3AEClassifier.forward (basic_model.py:184-200): 16x16 patches 'b c (h p1) (w p2) -> b (h w) (c p1 p2)', text through
+    mae_a, patches through mae_v, mean over ALL tokens (CLS and padded ones included)."""
+    B, C, H, W = visual.shape
+    patches = visual.reshape(B, C, H // 16, 16, W // 16, 16).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // 16) * (W // 16), C * 256)
+    a = m3ae_representation(sd, "mae_a.", None, token.squeeze(1), padding_mask.squeeze(1), num_heads)
+    v = m3ae_representation(sd, "mae_v.", patches, None, None, num_heads)
+    return a.mean(dim=1), v.mean(dim=1)
+
+
+class M3AEOracle(AVOracle):
+    """The same alternating step (main.py:419-476) with the m3ae packet layout (token, padding_mask, image, label)."""
+
+    def __init__(self, state, num_heads, **kw):
+        super().__init__(state, **kw)
+        self.num_heads = num_heads
+
+    def train_step(self, token, padding_mask, image, label, batch_step=0, len_dl=1):
+        self.opt.zero_grad()
+        a, v = m3ae_forward(self.sd, token, padding_mask, image, self.num_heads)          # main.py:428
+        la = self._turn(a, label, batch_step, len_dl, "mae_a.")
+        lv = self._turn(v, label, batch_step, len_dl, "mae_v.")
+        return la, lv
+
+    def train_epoch(self, batches, av_alpha=0.5):
+        tot = tot_a = tot_v = 0.0
+        for step, b in enumerate(batches):
+            la, lv = self.train_step(b[0], b[1], b[2], b[3], step, len(batches))
+            tot += float(np.float32(np.float32(la) * np.float32(av_alpha)) + np.float32(np.float32(lv) * np.float32(1 - av_alpha)))
+            tot_a += la
+            tot_v += lv
+        n = len(batches)
+        return tot / n, tot_a / n, tot_v / n
+
+    def eval_logits(self, token, padding_mask, image):
+        torch = self.torch
+        import torch.nn.functional as F
+        with torch.no_grad():
+            a, v = m3ae_forward(self.sd, token, padding_mask, image, self.num_heads)
+            W, b = self.sd["fusion_module.fc_out.weight"], self.sd["fusion_module.fc_out.bias"]
+            return F.linear(a, W, b), F.linear(v, W, b)
+
+    def valid(self, batches, n_classes=101, dynamic=True, av_alpha=0.5):
+        num = np.zeros(n_classes, np.int64)
+        hits = np.zeros((3, n_classes), np.int64)
+        for b in batches:
+            oa, ov = self.eval_logits(b[0], b[1], b[2])
+            r = fuse_eval([oa.cpu().numpy(), ov.cpu().numpy()], b[3].cpu().numpy(), n_classes, dynamic=dynamic,
+                          fixed_w=(av_alpha, 1 - av_alpha))
+            num += r["num"]
+            hits += r["hits"]
+        tot = float(num.sum())
+        return hits[0].sum() / tot, hits[1].sum() / tot, hits[2].sum() / tot
+
+
+def synthetic_m3ae_batch(batch, seed, text_len=512, image_hw=(256, 256), n_classes=101, vocab=30522):
+    """(token [B,1,L] int64, padding_mask [B,1,L] int64 with a random padded tail, image [B,3,H,W], label)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    token = torch.randint(0, vocab, (batch, 1, text_len), generator=g)
+    n_valid = torch.randint(max(1, text_len // 4), text_len + 1, (batch,), generator=g)
+    padding_mask = (torch.arange(text_len)[None, :] >= n_valid[:, None]).long()[:, None, :]
+    image = torch.randn(batch, 3, *image_hw, generator=g)
+    label = torch.randint(0, n_classes, (batch,), generator=g)
+    return token, padding_mask, image, label
 
 
 def synthetic_av_batch(batch, seed, spec_hw=(257, 188), frames=2, image_hw=(224, 224), n_classes=6):

@@ -300,14 +300,128 @@ def make_av(ref_main, ref_utils):
     np.savez_compressed(os.path.join(OUT, "av_classifier.npz"), **out)
 
 
+M3AE_TINY = dict(model_type=None, emb_dim=64, depth=2, num_heads=2)
+M3AE_VOCAB = 512
+
+
+def m3ae_batches(n, B, seed, L=12, img=32, n_classes=101, vocab=M3AE_VOCAB):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    res = []
+    for _ in range(n):
+        token = torch.randint(0, vocab, (B, 1, L), generator=g)
+        n_valid = torch.randint(3, L + 1, (B,), generator=g)
+        pm = (torch.arange(L)[None, :] >= n_valid[:, None]).long()[:, None, :]
+        image = torch.randn(B, 3, img, img, generator=g)
+        label = torch.randint(0, n_classes, (B,), generator=g)
+        res.append((token, pm, image, label, torch.zeros(B, 1, dtype=torch.long)))
+    return res
+
+
+def make_m3ae(ref_main, ref_utils):
+    """--lorb m3ae --gs_flag (BASELINE.json configs[2]) on a tiny encoder configuration (emb 64, depth 2, 2 heads,
+    vocabulary 512), executed by the reference's own M3AEClassifier.forward / MaskedMultimodalAutoencoder /
+    train_epoch / valid. Shims (generator only): DropPath.forward -> identity (it returns None), tensors
+    sent `.to(cuda:0)` stay on the CPU, the classifier object is assembled without its __init__ (which torch.load()s
+    hard-coded placeholder checkpoint paths and fixes the head at 768)."""
+    import torch
+    import torch.nn as nn
+    from torch.optim import SGD
+    from torch.optim.lr_scheduler import StepLR
+    from models import m3ae as ref_m3ae
+    from models import basic_model as ref_bm
+    from models.fusion_modules import ConcatFusion
+    ref_m3ae.DropPath.forward = lambda self, input, deterministic=False: input
+    real_to = torch.Tensor.to
+
+    def cpu_to(self, *a, **k):
+        a = tuple(torch.device("cpu") if isinstance(x, torch.device) and x.type == "cuda" else x for x in a)
+        return real_to(self, *a, **k)
+    torch.Tensor.to = cpu_to
+    out = {}
+    args = ref_main.get_arguments()
+    args.dataset, args.lorb, args.gs_flag, args.dynamic = "Food101", "m3ae", True, True
+    args.fusion_method, args.modulation, args.modal3, args.clip = "concat", "Normal", False, False
+    cfg = sys.modules["ml_collections"].ConfigDict(M3AE_TINY)
+
+    def build():
+        ref_utils.setup_seed(0)
+        model = ref_bm.M3AEClassifier.__new__(ref_bm.M3AEClassifier)
+        nn.Module.__init__(model)
+        model.fusion_module = ConcatFusion(input_dim=M3AE_TINY["emb_dim"], output_dim=101)      # basic_model.py:150
+        model.mae_a = ref_m3ae.MaskedMultimodalAutoencoder(text_vocab_size=M3AE_VOCAB, config_updates=cfg)
+        model.mae_v = ref_m3ae.MaskedMultimodalAutoencoder(text_vocab_size=M3AE_VOCAB, config_updates=cfg)
+        model.args = args
+        return model
+
+    model = build()
+    sd = model.state_dict()
+    for k, v in sd.items():
+        out["state/" + k] = v.numpy().copy()
+    # the positional tables
+    out["pos1d_64_12"] = ref_m3ae.get_1d_sincos_pos_embed(64, 12)
+    out["pos2d_64_4"] = ref_m3ae.get_2d_sincos_pos_embed(64, 4)
+    out["pos2d_768_256"] = ref_m3ae.get_2d_sincos_pos_embed(768, 256)[:, ::17, ::5]
+    (token, pm, image, label, _), = m3ae_batches(1, 4, 31)
+    a, v = model(token, pm, image)
+    out["fwd_a"], out["fwd_v"] = a.detach().numpy(), v.detach().numpy()
+    # encoder-output gradients of a fixed scalar (pins the backward of the restatement)
+    (a.square().sum() + v.square().sum()).backward()
+    for k in ("mae_a.encoder.blocks.0.attention.qkv_linear.weight", "mae_v.image_embedding.weight",
+              "mae_v.encoder.blocks.1.transformer_mlp.fc2.weight", "mae_a.cls_token", "mae_v.encoder.layer_norm.weight"):
+        out["grad/" + k] = dict(model.named_parameters())[k].grad.numpy().copy()
+    out["grad_text_embedding_rows"] = model.mae_a.text_embedding.weight.grad.abs().sum(1).numpy()
+
+    def run_epoch(bl):
+        model = build()
+        dp = nn.DataParallel(model, device_ids=[])
+        opt = SGD(dp.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+        sch = StepLR(opt, 70, 0.1)
+        gs = ref_utils.GSPlugin.__new__(ref_utils.GSPlugin)
+        gs.Pl = torch.eye(M3AE_TINY["emb_dim"])
+        gs.exp_count = 0
+        losses = ref_main.train_epoch(args, 0, dp, torch.device("cpu"), bl, opt, sch, gs_plugin=gs, gs_flag=True,
+                                      av_alpha=0.55)
+        accs_dyn = ref_main.valid(args, dp, torch.device("cpu"), bl, gs_flag=True, av_alpha=0.55)
+        args.dynamic = False
+        accs_fix = ref_main.valid(args, dp, torch.device("cpu"), bl, gs_flag=True, av_alpha=0.55)
+        args.dynamic = True
+        fin = model.state_dict()
+        return dict(losses=np.array(losses), accs_dyn=np.array(accs_dyn), accs_fix=np.array(accs_fix),
+                    exp_count=np.array(gs.exp_count), fc_w=fin["fusion_module.fc_out.weight"].numpy().copy(),
+                    qkv0_a=fin["mae_a.encoder.blocks.0.attention.qkv_linear.weight"].numpy().copy(),
+                    fc2_v=fin["mae_v.encoder.blocks.1.transformer_mlp.fc2.weight"].numpy().copy())
+
+    bl = m3ae_batches(3, 8, 7)
+    for k, v in run_epoch(bl[:1]).items():
+        out["step1_" + k] = v
+    for k, v in run_epoch(bl).items():
+        out["step3_" + k] = v
+    torch.Tensor.to = real_to
+    np.savez_compressed(os.path.join(OUT, "m3ae.npz"), **out)
+
+    # seeded initialisation of the full-size 'base' encoder: per-tensor sums only (the module must draw the same
+    # random numbers in the same order to reproduce them)
+    ref_utils.setup_seed(0)
+    enc = ref_m3ae.MaskedMultimodalAutoencoder(text_vocab_size=30522,
+                                               config_updates=sys.modules["ml_collections"].ConfigDict(dict(model_type="base")))
+    sd = enc.state_dict()
+    np.savez_compressed(os.path.join(OUT, "m3ae_base_init.npz"), names=np.array(list(sd.keys())),
+                        shapes=np.array([str(tuple(v.shape)) for v in sd.values()]),
+                        sums=np.array([float(v.double().sum()) for v in sd.values()]),
+                        abs_sums=np.array([float(v.double().abs().sum()) for v in sd.values()]))
+
+
 if __name__ == "__main__":
     ref_main, ref_utils = import_reference()
     import torch
     torch.set_num_threads(8)
-    make_gs(ref_utils)
-    make_fusion(ref_main)
-    make_head()
-    make_av(ref_main, ref_utils)
+    if "--only-m3ae" not in sys.argv[1:] and not os.environ.get("MLA_GOLDEN_ONLY_M3AE"):
+        make_gs(ref_utils)
+        make_fusion(ref_main)
+        make_head()
+        make_av(ref_main, ref_utils)
+    make_m3ae(ref_main, ref_utils)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

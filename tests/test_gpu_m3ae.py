@@ -1,0 +1,202 @@
+"""--lorb m3ae --gs_flag (BASELINE.json configs[2]) through the public API against the
+reference fixtures (tests/golden/m3ae.npz, produced by executing the reference) and the oracle.
+
+Tolerance: the encoder GEMMs multiply operands with a 10-bit mantissa (fp16 forward, TF32 backward; fp32 accumulate)
+where the reference multiplies in fp32: north_star's fp32/TF32 tolerance, rel 1e-3 (Frobenius), on features, losses and
+weights after a step; gradients of a single Linear 1e-3 as well. The optional bf16 backward gets 4e-3 on gradients."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mla_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TINY = dict(model_type=None, emb_dim=64, depth=2, num_heads=2)
+
+
+def relf(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _args(dynamic=True):
+    return argparse.Namespace(dataset="Food101", fusion_method="concat", modulation="Normal", gs_flag=True,
+                              dynamic=dynamic, lorb="m3ae", modal3=False, clip=False)
+
+
+def _state(g):
+    return {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+
+
+def _batches(n, B, seed, L=12, img=32, n_classes=101, vocab=512):
+    gen = torch.Generator().manual_seed(seed)
+    res = []
+    for _ in range(n):
+        token = torch.randint(0, vocab, (B, 1, L), generator=gen)
+        n_valid = torch.randint(3, L + 1, (B,), generator=gen)
+        pm = (torch.arange(L)[None, :] >= n_valid[:, None]).long()[:, None, :]
+        image = torch.randn(B, 3, img, img, generator=gen)
+        label = torch.randint(0, n_classes, (B,), generator=gen)
+        res.append((token, pm, image, label, torch.zeros(B, 1, dtype=torch.long)))
+    return res
+
+
+def _tiny_model(built_lib, g):
+    import mla_b200
+    net = mla_b200.M3AEClassifier(_args(), model_config=TINY, text_vocab_size=512)
+    net.load_state_dict(_state(g), strict=True)
+    return mla_b200.ModuleHolder(net.cuda())
+
+
+@pytest.mark.parametrize("M,K,N", [(257 * 3, 768, 2304), (513 * 2, 3072, 768), (48, 64, 192), (4 * 513, 768, 768),
+                                   (130, 768, 64), (1, 64, 64)])
+@pytest.mark.parametrize("bf16_bwd", [False, True])
+def test_native_linear_forward_backward(built_lib, M, K, N, bf16_bwd):
+    """One Linear on the tcgen05 GEMM kernels (ragged row counts: the 128-row tiles and the 32/64-row k-blocks of the
+    weight gradient end inside a tile) against torch fp64."""
+    from mla_b200 import m3ae
+    gen = torch.Generator().manual_seed(M + K + N)
+    lin = m3ae.NativeLinear(K, N).cuda()
+    x = torch.randn(M, K, generator=gen).cuda().requires_grad_(True)
+    dy = torch.randn(M, N, generator=gen).cuda()
+    prev = m3ae.BACKWARD_BF16
+    m3ae.BACKWARD_BF16 = bf16_bwd
+    try:
+        y = lin(x)
+        y.backward(dy)
+    finally:
+        m3ae.BACKWARD_BF16 = prev
+    torch.cuda.synchronize()
+    xd, wd, bd, dyd = x.detach().double(), lin.weight.detach().double(), lin.bias.detach().double(), dy.double()
+    ry = xd @ wd.t() + bd
+    tol = 4e-3 if bf16_bwd else 1e-3
+    e = (relf(y.detach().cpu(), ry.cpu()), relf(x.grad.cpu(), (dyd @ wd).cpu()), relf(lin.weight.grad.cpu(), (dyd.t() @ xd).cpu()),
+         relf(lin.bias.grad.cpu(), dyd.sum(0).cpu()))
+    print("linear M=%d K=%d N=%d bf16_bwd=%s: rel-F y %.2e dx %.2e dW %.2e db %.2e" % ((M, K, N, bf16_bwd) + e))
+    assert e[0] < 1e-3 and e[1] < tol and e[2] < tol and e[3] < 1e-5
+
+
+def test_native_linear_has_no_cpu_path(built_lib):
+    from mla_b200 import m3ae
+    with pytest.raises(RuntimeError):
+        m3ae.NativeLinear(64, 64)(torch.zeros(2, 64))
+
+
+def test_forward_matches_reference_fixture(built_lib, golden):
+    g = golden("m3ae")
+    model = _tiny_model(built_lib, g)
+    (token, pm, image, _, _), = _batches(1, 4, 31)
+    a, v = model(token.cuda(), pm.cuda(), image.cuda())
+    assert a.shape == (4, 64) and a.requires_grad and v.requires_grad
+    ea, ev = relf(a.detach().cpu(), g["fwd_a"]), relf(v.detach().cpu(), g["fwd_v"])
+    print("m3ae feature rel-F error vs the reference fixture:", ea, ev)
+    assert ea < 1e-3 and ev < 1e-3
+    # gradients of the fixture's scalar through the native backward
+    (a.square().sum() + v.square().sum()).backward()
+    params = dict(model.module.named_parameters())
+    for k in g.files:
+        if k.startswith("grad/"):
+            e = relf(params[k[5:]].grad.cpu(), g[k])
+            print("  grad %-60s rel-F %.2e" % (k[5:], e))
+            assert e < 2e-3, k
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+def test_train_epoch_and_valid_match_reference_fixture(built_lib, golden, steps):
+    import mla_b200
+    g = golden("m3ae")
+    tag = "step%d_" % steps
+    model = _tiny_model(built_lib, g)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    sch = torch.optim.lr_scheduler.StepLR(opt, 70, 0.1)
+    gs = mla_b200.GSPlugin()
+    batches = _batches(3, 8, 7)[:steps]
+    dev = torch.device("cuda")
+    losses = mla_b200.train_epoch(_args(), 0, model, dev, batches, opt, sch, gs_plugin=gs, gs_flag=True, av_alpha=0.55)
+    print("m3ae %d-step losses" % steps, losses, "fixture", g[tag + "losses"])
+    assert np.allclose(losses, g[tag + "losses"], rtol=1e-3)
+    assert gs.exp_count == int(g[tag + "exp_count"])
+    sd = model.module.state_dict()
+    for name, key in (("fusion_module.fc_out.weight", "fc_w"), ("mae_a.encoder.blocks.0.attention.qkv_linear.weight", "qkv0_a"),
+                      ("mae_v.encoder.blocks.1.transformer_mlp.fc2.weight", "fc2_v")):
+        w0 = g["state/" + name].astype(np.float64)
+        upd, ref = sd[name].cpu().numpy().astype(np.float64) - w0, g[tag + key].astype(np.float64) - w0
+        e = relf(sd[name].cpu(), g[tag + key])
+        cos = float((upd * ref).sum() / (np.linalg.norm(upd) * np.linalg.norm(ref)))
+        print("  %-55s rel-F %.2e, update cosine %.5f, |update| ratio %.4f" % (name, e, cos,
+                                                                               np.linalg.norm(upd) / np.linalg.norm(ref)))
+        assert e < 1e-3 and cos > 0.999
+    accs = mla_b200.valid(_args(True), model, dev, batches, gs_flag=True, av_alpha=0.55)
+    accs_fix = mla_b200.valid(_args(False), model, dev, batches, gs_flag=True, av_alpha=0.55)
+    n = 8.0 * steps
+    assert np.abs(np.array(accs) - g[tag + "accs_dyn"]).max() <= 1 / n + 1e-9
+    assert np.abs(np.array(accs_fix) - g[tag + "accs_fix"]).max() <= 1 / n + 1e-9
+
+
+def test_step_with_projection_vs_oracle(built_lib, golden):
+    """Two steps with the GS projection firing ("what the paper meant") against the fp32 CPU oracle."""
+    import mla_b200
+    g = golden("m3ae")
+    model = _tiny_model(built_lib, g)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    sch = torch.optim.lr_scheduler.StepLR(opt, 70, 0.1)
+    gs = mla_b200.GSPlugin(force_projection=True)
+    batches = _batches(2, 8, 19)
+    losses = mla_b200.train_epoch(_args(), 0, model, torch.device("cuda"), batches, opt, sch, gs_plugin=gs, gs_flag=True,
+                                  av_alpha=0.55)
+    o = orc.M3AEOracle(_state(g), num_heads=2, force_projection=True)
+    ref = o.train_epoch([b[:4] for b in batches], av_alpha=0.55)
+    print("m3ae 2-step losses with projection", losses, "oracle", ref)
+    assert np.allclose(losses, ref, rtol=1e-3)
+    # P itself is ill-conditioned on SIGNED (LayerNorm) features: the elementwise denominator alpha + k_i r_j
+    # crosses zero, so fp32 runs of the same update diverge from each other (the kernel-level GS tests carry
+    # the calibrated criterion). Here: P stays normalised and finite, and the projected head update agrees.
+    e_p = relf(gs.Pl.cpu(), o.Pl)
+    e_w = relf(model.module.fusion_module.fc_out.weight.detach().cpu(), o.sd["fusion_module.fc_out.weight"].detach())
+    print("  P rel-F deviation %.2e (ill-conditioned, informational), |P|_F %.6f, head weight rel-F %.2e" % (
+        e_p, float(gs.Pl.norm()), e_w))
+    assert bool(torch.isfinite(gs.Pl).all()) and abs(float(gs.Pl.norm()) - 1) < 1e-4
+    assert not bool(torch.equal(gs.Pl, torch.eye(64, device="cuda")))
+    assert e_w < 1e-3
+
+
+def test_base_encoder_full_size_vs_oracle(built_lib):
+    """The 'base' encoders (768 wide, 12 blocks, 12 heads) at the Food-101 shapes (512 tokens, 256x256 image, B=2): features
+    and one training step against the oracle's restatement run in fp32 on this GPU (TF32 off)."""
+    import mla_b200
+    mla_b200.setup_seed(0)
+    net = mla_b200.M3AEClassifier(_args())
+    state = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    model = mla_b200.ModuleHolder(net.cuda())
+    token, pm, image, label = orc.synthetic_m3ae_batch(2, 5)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        o = orc.M3AEOracle({k: v.cuda() for k, v in state.items()}, num_heads=12)
+        with torch.no_grad():
+            ra, rv = orc.m3ae_forward(o.sd, token.cuda(), pm.cuda(), image.cuda(), 12)
+        a, v = model(token.cuda(), pm.cuda(), image.cuda())
+        ea, ev = relf(a.detach().cpu(), ra.cpu()), relf(v.detach().cpu(), rv.cpu())
+        print("base m3ae feature rel-F error:", ea, ev)
+        assert a.shape == (2, 768) and ea < 1e-3 and ev < 1e-3
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+        sch = torch.optim.lr_scheduler.StepLR(opt, 70, 0.1)
+        gs = mla_b200.GSPlugin()
+        batch = [(token, pm, image, label, torch.zeros(2, 1, dtype=torch.long))]
+        losses = mla_b200.train_epoch(_args(), 0, model, torch.device("cuda"), batch, opt, sch, gs_plugin=gs, gs_flag=True,
+                                      av_alpha=0.55)
+        ref = o.train_epoch([(token.cuda(), pm.cuda(), image.cuda(), label.cuda())], av_alpha=0.55)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    print("base m3ae step losses", losses, "oracle(fp32, GPU)", ref)
+    assert np.allclose(losses, ref, rtol=1e-3)
+    for name in ("mae_a.encoder.blocks.11.transformer_mlp.fc1.weight", "mae_v.image_embedding.weight",
+                 "mae_a.encoder.blocks.0.attention.qkv_linear.weight"):
+        w0 = state[name].double()
+        upd = model.module.state_dict()[name].cpu().double() - w0
+        rupd = o.sd[name].detach().cpu().double() - w0
+        e = float((upd - rupd).norm() / rupd.norm())
+        print("  %-55s weight-update rel-F error %.2e" % (name, e))
+        assert e < 5e-3

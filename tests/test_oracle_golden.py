@@ -180,3 +180,98 @@ def test_kat6_full_size_losses_are_recorded(golden):
     g = golden("av_classifier")
     assert np.allclose(g["full_noop_losses"], [1.5840, 1.5922, 1.5740], atol=1e-4)   # SURVEY KAT-6
     assert list(g["kat4_shapes"]) == [1, 512, 9, 6, 2, 512, 7, 7]                      # SURVEY KAT-4
+
+
+# ------------------------------------------------------------------------------------------------
+# --lorb m3ae (BASELINE.json configs[2]): fixtures from the reference's own M3AEClassifier.forward /
+# MaskedMultimodalAutoencoder / train_epoch / valid on a tiny encoder configuration (make_golden.make_m3ae)
+# ------------------------------------------------------------------------------------------------
+def _m3ae_state(g):
+    return {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+
+
+def _m3ae_batches(n, B, seed, L=12, img=32, n_classes=101, vocab=512):
+    gen = torch.Generator().manual_seed(seed)
+    res = []
+    for _ in range(n):
+        token = torch.randint(0, vocab, (B, 1, L), generator=gen)
+        n_valid = torch.randint(3, L + 1, (B,), generator=gen)
+        pm = (torch.arange(L)[None, :] >= n_valid[:, None]).long()[:, None, :]
+        image = torch.randn(B, 3, img, img, generator=gen)
+        label = torch.randint(0, n_classes, (B,), generator=gen)
+        res.append((token, pm, image, label))
+    return res
+
+
+def test_m3ae_position_tables_match_reference(golden):
+    g = golden("m3ae")
+    assert np.array_equal(orc.sincos_1d(64, np.arange(12, dtype=np.float32))[None], g["pos1d_64_12"])
+    assert np.array_equal(orc.sincos_2d(64, 4)[None], g["pos2d_64_4"])
+    assert np.array_equal(orc.sincos_2d(768, 256)[None][:, ::17, ::5], g["pos2d_768_256"])
+    from mla_b200 import m3ae
+    assert np.array_equal(m3ae.sincos_1d(64, np.arange(12))[None], g["pos1d_64_12"])
+    assert np.array_equal(m3ae.sincos_2d(64, 4)[None], g["pos2d_64_4"])
+    assert np.array_equal(m3ae.sincos_2d(768, 256)[None][:, ::17, ::5], g["pos2d_768_256"])
+
+
+def test_m3ae_oracle_forward_and_gradients_match_reference(golden):
+    g = golden("m3ae")
+    o = orc.M3AEOracle(_m3ae_state(g), num_heads=2)
+    (token, pm, image, _), = _m3ae_batches(1, 4, 31)
+    a, v = orc.m3ae_forward(o.sd, token, pm, image, 2)
+    assert a.shape == (4, 64)
+    assert np.allclose(a.detach().numpy(), g["fwd_a"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(v.detach().numpy(), g["fwd_v"], rtol=1e-5, atol=1e-6)
+    (a.square().sum() + v.square().sum()).backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert relf(o.sd[k[5:]].grad.numpy(), g[k]) < 1e-5, k
+    rows = o.sd["mae_a.text_embedding.weight"].grad.abs().sum(1).numpy()
+    assert np.allclose(rows, g["grad_text_embedding_rows"], rtol=1e-4, atol=1e-6)
+    assert (rows > 0).sum() <= 4 * 12                     # only looked-up tokens (padded ones included) get gradient
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+def test_m3ae_oracle_train_epoch_and_valid_match_reference(golden, steps):
+    g = golden("m3ae")
+    tag = "step%d_" % steps
+    o = orc.M3AEOracle(_m3ae_state(g), num_heads=2)
+    batches = _m3ae_batches(3, 8, 7)[:steps]
+    losses = o.train_epoch(batches, av_alpha=0.55)
+    assert np.allclose(losses, g[tag + "losses"], rtol=1e-5), (losses, g[tag + "losses"])
+    assert o.exp_count == int(g[tag + "exp_count"]) == 2 * steps
+    assert np.array_equal(o.Pl, np.eye(64, dtype=np.float32))                        # as published: the hook never fires
+    assert relf(o.sd["fusion_module.fc_out.weight"].detach().numpy(), g[tag + "fc_w"]) < 1e-5
+    assert relf(o.sd["mae_a.encoder.blocks.0.attention.qkv_linear.weight"].detach().numpy(), g[tag + "qkv0_a"]) < 1e-6
+    assert relf(o.sd["mae_v.encoder.blocks.1.transformer_mlp.fc2.weight"].detach().numpy(), g[tag + "fc2_v"]) < 1e-6
+    assert np.allclose(o.valid(batches, dynamic=True, av_alpha=0.55), g[tag + "accs_dyn"], atol=1e-9)
+    assert np.allclose(o.valid(batches, dynamic=False, av_alpha=0.55), g[tag + "accs_fix"], atol=1e-9)
+
+
+def test_m3ae_seeded_init_is_bit_identical_to_reference(golden):
+    """The host mirror creates the encoder's parameters in the reference's order with the reference's initialisers:
+    under the same seed every tensor of the 'base' encoder has the reference's sum and |sum|."""
+    import mla_b200
+    from mla_b200 import m3ae
+    g = golden("m3ae_base_init")
+    mla_b200.setup_seed(0)
+    enc = m3ae.MaskedMultimodalAutoencoder(30522, {"model_type": "base"})
+    sd = enc.state_dict()
+    assert list(sd.keys()) == list(g["names"])
+    assert [str(tuple(v.shape)) for v in sd.values()] == list(g["shapes"])
+    assert np.array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["sums"])
+    assert np.array_equal(np.array([float(v.double().abs().sum()) for v in sd.values()]), g["abs_sums"])
+    assert (enc.emb_dim, enc.depth, enc.num_heads) == (768, 12, 12)
+
+
+def test_m3ae_tiny_state_loads_into_host_mirror(golden):
+    import argparse
+    from mla_b200 import m3ae
+    g = golden("m3ae")
+    args = argparse.Namespace(dataset="Food101", fusion_method="concat", modulation="Normal", gs_flag=True, dynamic=True,
+                              lorb="m3ae", modal3=False, clip=False)
+    net = m3ae.M3AEClassifier(args, model_config=dict(model_type=None, emb_dim=64, depth=2, num_heads=2), text_vocab_size=512)
+    missing, unexpected = net.load_state_dict(_m3ae_state(g), strict=True)
+    assert not missing and not unexpected
+    with pytest.raises(RuntimeError):                                                  # no CPU fallback
+        net(*_m3ae_batches(1, 2, 3)[0][:3])
