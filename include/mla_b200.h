@@ -151,6 +151,24 @@ MLA_API int    mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
                         int Cout, int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * m3ae transformer encoders (reference models/m3ae.py:86-179). The Linears run on the
+ * convolution GEMMs above as 1x1 convolutions over an N=1 image of M x 1 pixels.
+ *
+ * Fused attention core (m3ae.py:103-121): out = softmax(scale * q k^T, padded keys FILLED with -1e7) v, per head.
+ *   qkv [B, S, 3, H, Dh] fp32 (the qkv_linear output), key_mask [B, S] fp32 (> 0: padded key) or NULL,
+ *   out [B, S, H*Dh] fp32, stats [B, H, S, 2] fp32 (row max, row sum of exp), qkv16 [B, S, 3, H, Dh] fp16 (written by
+ *   the forward; stats and qkv16 are what the backward needs). Dh = 32 or 64. fp16 operands (10-bit mantissa, like
+ *   TF32), fp32 accumulate and softmax; the S x S matrix is never written.
+ * backward: dqkv [B, S, 3, H, Dh] fp32 (every element written); dout is rescaled by a power of two internally so that
+ *   fp16 holds it; ws from mla_attention_backward_workspace_bytes. Deterministic (no atomics on the results). */
+MLA_API int    mla_attention_forward(const float* qkv, const float* key_mask, float* out, float* stats, void* qkv16,
+                        int B, int S, int H, int Dh, float scale, void* stream);
+MLA_API size_t mla_attention_backward_workspace_bytes(int B, int S, int H, int Dh);
+MLA_API int    mla_attention_backward(const void* qkv16, const float* key_mask, const float* out, const float* dout,
+                        const float* stats, float* dqkv, int B, int S, int H, int Dh, float scale, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Memory-bound encoder pieces (NHWC fp32) — models/backbone.py:142-160 (ResNet.forward),
  * :36-52 (BasicBlock.forward), nn.BatchNorm2d / nn.MaxPool2d semantics, basic_model.py:56-65
  * (global average pool), and their backward passes.

@@ -48,6 +48,9 @@ _SIGNATURES = {
     "mla_conv2d_dgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p]),
     "mla_conv2d_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 9),
     "mla_conv2d_wgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),
+    "mla_attention_forward": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_float, _c_void_p]),
+    "mla_attention_backward_workspace_bytes": (_c_size_t, [_c_int] * 4),
+    "mla_attention_backward": (_c_int, [_c_void_p] * 6 + [_c_int] * 4 + [_c_float, _c_void_p, _c_size_t, _c_void_p]),
     "mla_stem_im2col": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_ll, _c_ll] + [_c_int] * 8 + [_c_void_p]),
     "mla_round_tf32": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_void_p]),
     "mla_pad_rows": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

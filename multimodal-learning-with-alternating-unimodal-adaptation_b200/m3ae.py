@@ -9,8 +9,10 @@ and its state dicts load. What runs where:
   * every Linear of the encoder (patch embedding, qkv, attention output, fc1, fc2 — >99 % of the FLOPs) runs on the
     library's tcgen05 GEMMs: the 1x1 case of the implicit-GEMM convolution kernels, fp16 x fp16 forward, bf16 x bf16 for
     dx = dy W and dW = dy^T x (`NativeLinear`, csrc/conv_gemm.cu);
-  * LayerNorm, exact GELU, the S x S attention core (softmax with the -1e7 key-padding fill), the embedding lookup and
-    the token mean still go through ATen ops on the same stream (interim; native kernels are the next step).
+  * the attention core (scores, -1e7 key-padding fill, softmax, weighted sum; forward and backward) is one fused
+    tensor-core kernel per pass (fp16 operands, fp32 softmax) that never writes the S x S matrix (csrc/attention.cu);
+  * LayerNorm, exact GELU, bias adds, the embedding lookup and the token mean still go through ATen ops on the same
+    stream (interim; native kernels are the next step).
 
 Reference behaviours kept: DropPath is the identity (the only configured rate is 0; as published its forward returns
 None and the model cannot run); the token mean includes CLS and padded tokens (basic_model.py:193-194).
@@ -122,6 +124,40 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+class _AttentionFn(torch.autograd.Function):
+    """softmax(scale * q k^T, padded keys filled with -1e7) v for every head, fused (csrc/attention.cu). qkv [B, S, 3*H*Dh]
+    as produced by qkv_linear, mask [B, S] float (> 0: padded key) or None -> [B, S, H*Dh]."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, num_heads, scale):
+        B, S, C3 = qkv.shape
+        Dh = C3 // (3 * num_heads)
+        qkv = qkv.contiguous()
+        dev = qkv.device
+        out = torch.empty(B, S, num_heads * Dh, dtype=torch.float32, device=dev)
+        stats = torch.empty(B, num_heads, S, 2, dtype=torch.float32, device=dev)
+        qkv16 = torch.empty(B, S, C3, dtype=torch.float16, device=dev)
+        _lib.check(_lib.lib().mla_attention_forward(qkv.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                                    out.data_ptr(), stats.data_ptr(), qkv16.data_ptr(), B, S, num_heads, Dh,
+                                                    scale, _lib.stream_ptr()), "mla_attention_forward")
+        ctx.save_for_backward(qkv16, mask, out, stats)
+        ctx.cfg = (B, S, num_heads, Dh, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv16, mask, out, stats = ctx.saved_tensors
+        B, S, H, Dh, scale = ctx.cfg
+        L = _lib.lib()
+        dout = dout.contiguous()
+        dqkv = torch.empty(B, S, 3 * H * Dh, dtype=torch.float32, device=dout.device)
+        ws = torch.empty(L.mla_attention_backward_workspace_bytes(B, S, H, Dh), dtype=torch.uint8, device=dout.device)
+        _lib.check(L.mla_attention_backward(qkv16.data_ptr(), mask.data_ptr() if mask is not None else None, out.data_ptr(),
+                                            dout.data_ptr(), stats.data_ptr(), dqkv.data_ptr(), B, S, H, Dh, scale,
+                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mla_attention_backward")
+        return dqkv, None, None, None
+
+
 class NativeLinear(nn.Linear):
     """nn.Linear (same parameters, same default init) whose CUDA forward / backward are the library's GEMM kernels."""
 
@@ -156,14 +192,9 @@ class Attention(nn.Module):                            # m3ae.py:86-125
         self.fc = NativeLinear(dim, dim)
 
     def forward(self, x, padding_mask=None):
-        B, S, C = x.shape
-        qkv = self.qkv_linear(x).view(B, S, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
-        q, k, v = qkv[0], qkv[1], qkv[2]
-        att = torch.matmul(q, k.transpose(-2, -1)) * self.scale
-        if padding_mask is not None:                   # keys of padded tokens are FILLED with -1e7 (not added)
-            att = torch.where(padding_mask[:, None, None, :] > 0, att.new_tensor(-1e7), att)
-        att = F.softmax(att, dim=-1)
-        out = torch.matmul(att, v).permute(0, 2, 1, 3).reshape(B, S, C)
+        if padding_mask is not None:
+            padding_mask = padding_mask.float().contiguous()
+        out = _AttentionFn.apply(self.qkv_linear(x), padding_mask, self.num_heads, self.scale)
         return self.fc(out)
 
 

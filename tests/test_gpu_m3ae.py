@@ -200,3 +200,52 @@ def test_base_encoder_full_size_vs_oracle(built_lib):
         e = float((upd - rupd).norm() / rupd.norm())
         print("  %-55s weight-update rel-F error %.2e" % (name, e))
         assert e < 5e-3
+
+
+def _attention_ref(qkv, mask, H, scale):
+    """The reference's attention core (m3ae.py:103-121) in fp64."""
+    B, S, C3 = qkv.shape
+    Dh = C3 // (3 * H)
+    q, k, v = qkv.view(B, S, 3, H, Dh).permute(2, 0, 3, 1, 4)
+    att = torch.matmul(q, k.transpose(-2, -1)) * scale
+    if mask is not None:
+        att = torch.where(mask[:, None, None, :].expand(att.shape) > 0, torch.tensor(-1e7, dtype=att.dtype, device=att.device),
+                          att)
+    att = torch.softmax(att, dim=-1)
+    return torch.matmul(att, v).permute(0, 2, 1, 3).reshape(B, S, H * Dh)
+
+
+@pytest.mark.parametrize("B,S,H,Dh,masked", [(2, 513, 12, 64, True), (3, 257, 12, 64, False), (4, 13, 2, 32, True),
+                                             (1, 64, 1, 64, True), (2, 65, 3, 32, False), (1, 1, 2, 64, False),
+                                             (2, 130, 4, 64, "all")])
+def test_fused_attention_forward_backward(built_lib, B, S, H, Dh, masked):
+    """csrc/attention.cu against the reference formulation in fp64: ragged sequence lengths (tiles of 64), padded keys
+    (filled with -1e7, no gradient to their scores), a batch row whose keys are ALL padded (uniform weights, like the
+    reference), both head widths."""
+    from mla_b200 import m3ae
+    gen = torch.Generator().manual_seed(B * 1000 + S)
+    qkv = (torch.randn(B, S, 3 * H * Dh, generator=gen) * 0.8).cuda().requires_grad_(True)
+    dout = torch.randn(B, S, H * Dh, generator=gen).cuda()
+    mask = None
+    if masked:
+        n_valid = torch.randint(1, S + 1, (B,), generator=gen)
+        if masked == "all":
+            n_valid[0] = 0
+        mask = (torch.arange(S)[None, :] >= n_valid[:, None]).float().cuda()
+    scale = Dh ** -0.5
+    out = m3ae._AttentionFn.apply(qkv, mask, H, scale)
+    out.backward(dout)
+    torch.cuda.synchronize()
+    q64 = qkv.detach().double().requires_grad_(True)
+    ref = _attention_ref(q64, mask.double() if mask is not None else None, H, scale)
+    ref.backward(dout.double())
+    e_o, e_g = relf(out.detach().cpu(), ref.detach().cpu()), relf(qkv.grad.cpu(), q64.grad.cpu())
+    g3 = qkv.grad.view(B, S, 3, H * Dh).cpu().double()
+    r3 = q64.grad.view(B, S, 3, H * Dh).cpu()
+    # per-part error relative to the largest part (dq = dk = 0 exactly when there is a single key)
+    den = max(float(r3[:, :, i].norm()) for i in range(3))
+    parts = [float((g3[:, :, i] - r3[:, :, i]).norm()) / den for i in range(3)]
+    print("attention B=%d S=%d H=%d Dh=%d masked=%s: rel-F out %.2e dqkv %.2e (dq %.2e dk %.2e dv %.2e)" % (
+        B, S, H, Dh, masked, e_o, e_g, parts[0], parts[1], parts[2]))
+    assert e_o < 1e-3 and e_g < 1e-3 and max(parts) < 2e-3
+    assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(qkv.grad).all())
