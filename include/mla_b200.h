@@ -168,6 +168,28 @@ MLA_API int    mla_attention_backward(const void* qkv16, const float* key_mask, 
                         const float* stats, float* dqkv, int B, int S, int H, int Dh, float scale, void* ws,
                         size_t ws_bytes, void* stream);
 
+/* Linear layer on the tcgen05 GEMM: y [M, N] = x16 [M, K] (fp16) * w16 [N, K]^T (fp16) + bias [N] + resid [M, N]
+ * (bias / resid may be NULL; the adds happen in the GEMM epilogue). K, N % 64 == 0. nn.Linear of m3ae.py:72-73,98-99. */
+MLA_API int    mla_linear_forward16(const void* x16, const void* w16, const float* bias, const float* resid, float* y,
+                        int M, int K, int N, void* stream);
+/* nn.LayerNorm over the last dimension D (D % 4 == 0, D <= 1280), biased variance, as torch. Outputs (each may be NULL):
+ * y fp32, y16 fp16 (the operand of the next GEMM), y_r fp32 rounded to TF32 (the operand of that GEMM's weight
+ * gradient); mean / rstd [M] are kept for the backward pass. */
+MLA_API int    mla_layernorm_forward(const float* x, const float* gamma, const float* beta, float eps, long long M, int D,
+                        float* y, void* y16, float* y_r, float* mean, float* rstd, void* stream);
+/* dx = resid + dLN/dx (resid may be NULL: the residual branch's gradient), dgamma, dbeta [D]. Deterministic. */
+MLA_API size_t mla_layernorm_backward_workspace_bytes(long long M, int D);
+MLA_API int    mla_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* resid, long long M, int D, float* dx, float* dgamma,
+                        float* dbeta, void* ws, size_t ws_bytes, void* stream);
+/* x16 = fp16(f(x)), x_r = tf32(f(x)); f = identity, or exact (erf) GELU when gelu != 0. n % 4 == 0. */
+MLA_API int    mla_cast_round(const float* x, void* x16, float* x_r, long long n, int gelu, void* stream);
+/* out_r [M, N] = tf32(dy) (u == NULL) or tf32(dy * gelu'(u)) — the dy operand of a Linear's gradient GEMMs — and
+ * colsum [N] = its column sums (the bias gradient), taken before rounding. Deterministic. */
+MLA_API size_t mla_round_colsum_workspace_bytes(long long M, int N);
+MLA_API int    mla_round_colsum(const float* dy, const float* u, float* out_r, float* colsum, long long M, int N, void* ws,
+                        size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Memory-bound encoder pieces (NHWC fp32) — models/backbone.py:142-160 (ResNet.forward),
  * :36-52 (BasicBlock.forward), nn.BatchNorm2d / nn.MaxPool2d semantics, basic_model.py:56-65

@@ -51,6 +51,13 @@ _SIGNATURES = {
     "mla_attention_forward": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_float, _c_void_p]),
     "mla_attention_backward_workspace_bytes": (_c_size_t, [_c_int] * 4),
     "mla_attention_backward": (_c_int, [_c_void_p] * 6 + [_c_int] * 4 + [_c_float, _c_void_p, _c_size_t, _c_void_p]),
+    "mla_linear_forward16": (_c_int, [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p]),
+    "mla_layernorm_forward": (_c_int, [_c_void_p] * 3 + [_c_float, _c_ll, _c_int] + [_c_void_p] * 6),
+    "mla_layernorm_backward_workspace_bytes": (_c_size_t, [_c_ll, _c_int]),
+    "mla_layernorm_backward": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 4 + [_c_size_t, _c_void_p]),
+    "mla_cast_round": (_c_int, [_c_void_p] * 3 + [_c_ll, _c_int, _c_void_p]),
+    "mla_round_colsum_workspace_bytes": (_c_size_t, [_c_ll, _c_int]),
+    "mla_round_colsum": (_c_int, [_c_void_p] * 4 + [_c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "mla_stem_im2col": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_ll, _c_ll] + [_c_int] * 8 + [_c_void_p]),
     "mla_round_tf32": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_void_p]),
     "mla_pad_rows": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

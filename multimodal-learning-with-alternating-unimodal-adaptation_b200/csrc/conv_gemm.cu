@@ -64,6 +64,9 @@ struct ConvGemmParams {
   // fprop only: per-M-tile BatchNorm partial sums of the OUTPUT, stat_part[m tile][2][Cout] = (sum y, sum y*y)
   // over the tile's 128 rows, taken from the fp32 accumulators (NULL = off)
   float* stat_part;
+  // fprop-type launches only (Linear layers): out = acc + bias[column] + resid[row][column] (either may be NULL)
+  const float* bias;
+  const float* resid;
 };
 
 template <bool MN_MAJOR>
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         orow = p.out + orow_idx * p.ldo + n0;
       }
     }
+    const float* rrow = (MODE == 0 && p.resid != nullptr && orow != nullptr) ? p.resid + (long long)(m0 + row) * p.ldo + n0 : nullptr;
 #pragma unroll 1
     for (int c = 0; c < NTOT; c += 32) {
       if (MODE == 2 && NT == 1 && n0 + c >= p.CinW) break;   // partial last ci tile (Cin % BN == 32)
@@ -264,6 +268,14 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
           if (p.accumulate) {
             const float4 old = dst[j];
             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          if (MODE == 0 && p.bias != nullptr) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j);
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          }
+          if (MODE == 0 && rrow != nullptr) {
+            const float4 rv = reinterpret_cast<const float4*>(rrow + c)[j];
+            o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
           }
           dst[j] = o;
         }
@@ -848,6 +860,33 @@ extern "C" int mla_conv2d_fprop16(const void* x16, const void* w16, float* y, in
   rc = make_map_im2col16(&gmap, x16, false, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 128);
   if (rc) return rc;
   dim3 grid((p.M + 127) / 128, Cout / BN);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 1>(map, gmap, p, grid, st)
+                  : launch<0, 128, 3, true, 1, 1, false, 1>(map, gmap, p, grid, st);
+}
+
+// y [M, N] = x16 [M, K] (fp16) w16 [N, K]^T (fp16) + bias [N] + resid [M, N]: a Linear layer = the 1x1 case of fprop16
+// over an N=1 image of M x 1 pixels, with the bias / residual adds in the epilogue. K, N % 64 == 0.
+extern "C" int mla_linear_forward16(const void* x16, const void* w16, const float* bias, const float* resid, float* y, int M,
+                                    int K, int N, void* stream) {
+  if (!x16 || !w16 || !y || !mla::aligned16(x16) || !mla::aligned16(w16) || !mla::aligned16(y) || !mla::aligned16(bias) ||
+      !mla::aligned16(resid))
+    return MLA_E_BADARG;
+  if (!conv_shape_ok(1, M, 1, K, N, 1, 1, 1, 0, 64)) return MLA_E_SHAPE;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  ConvGemmParams p{};
+  p.OH = M; p.OW = 1; p.M = M; p.R = 1; p.S = 1; p.mul = 1;
+  p.kcb = K / 64; p.KB = p.kcb; p.CinW = K;
+  p.out = y; p.ldo = N; p.accumulate = 0; p.Cout = N; p.bias = bias; p.resid = resid;
+  full_taps(p, 1, 1, false);
+  const int BN = (N % 128 == 0) ? 128 : 64;
+  CUtensorMap map, gmap;
+  int rc = make_map_2d16(&map, w16, false, N, K, BN);
+  if (rc) return rc;
+  rc = make_map_im2col16(&gmap, x16, false, 1, M, 1, K, 0, 0, 0, 0, 1, 128);
+  if (rc) return rc;
+  dim3 grid((M + 127) / 128, N / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 1>(map, gmap, p, grid, st)
                   : launch<0, 128, 3, true, 1, 1, false, 1>(map, gmap, p, grid, st);

@@ -11,8 +11,10 @@ and its state dicts load. What runs where:
     dx = dy W and dW = dy^T x (`NativeLinear`, csrc/conv_gemm.cu);
   * the attention core (scores, -1e7 key-padding fill, softmax, weighted sum; forward and backward) is one fused
     tensor-core kernel per pass (fp16 operands, fp32 softmax) that never writes the S x S matrix (csrc/attention.cu);
-  * LayerNorm, exact GELU, bias adds, the embedding lookup and the token mean still go through ATen ops on the same
-    stream (interim; native kernels are the next step).
+  * LayerNorm (forward / backward), exact GELU, the fp16 / TF32 operand copies and the bias gradients are fused
+    single-pass kernels (csrc/transformer_ops.cu); bias and residual adds ride in the GEMM epilogues; a whole block is one
+    autograd node with a hand-written backward (`_BlockFn`);
+  * what is left to ATen: the embedding lookup, the positional / type-embedding adds, the token mean and the optimiser.
 
 Reference behaviours kept: DropPath is the identity (the only configured rate is 0; as published its forward returns
 None and the model cannot run); the token mean includes CLS and padded tokens (basic_model.py:193-194).
@@ -158,6 +160,185 @@ class _AttentionFn(torch.autograd.Function):
         return dqkv, None, None, None
 
 
+# One autograd node per transformer block (forward and hand-written backward over the C ABI) instead of one per op: every
+# activation is produced directly in the formats its consumers need (fp16 GEMM operand, TF32-rounded weight-gradient operand),
+# bias / residual adds ride in the GEMM epilogues, LayerNorm / GELU / bias-gradient work is fused into single passes
+# (csrc/transformer_ops.cu). False: the per-module path above (same arithmetic up to summation order), which also offers
+# BACKWARD_BF16.
+FUSED_BLOCK = True
+
+
+def _scratch(nbytes, dev):
+    return _Workspace.get(nbytes, dev)
+
+
+def _ln_fwd(x2, w, b, eps, want_y=False):
+    L = _lib.lib()
+    M, D = x2.shape
+    dev = x2.device
+    y = torch.empty(M, D, dtype=torch.float32, device=dev) if want_y else None
+    y16 = None if want_y else torch.empty(M, D, dtype=torch.float16, device=dev)
+    y_r = None if want_y else torch.empty(M, D, dtype=torch.float32, device=dev)
+    mean = torch.empty(M, dtype=torch.float32, device=dev)
+    rstd = torch.empty(M, dtype=torch.float32, device=dev)
+    _lib.check(L.mla_layernorm_forward(x2.data_ptr(), w.data_ptr(), b.data_ptr(), eps, M, D,
+                                       y.data_ptr() if want_y else None, None if want_y else y16.data_ptr(),
+                                       None if want_y else y_r.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                       _lib.stream_ptr()), "mla_layernorm_forward")
+    return y, y16, y_r, mean, rstd
+
+
+def _ln_bwd(dy2, x2, mean, rstd, w, resid):
+    L = _lib.lib()
+    M, D = x2.shape
+    dev = x2.device
+    dx = torch.empty(M, D, dtype=torch.float32, device=dev)
+    dw = torch.empty(D, dtype=torch.float32, device=dev)
+    db = torch.empty(D, dtype=torch.float32, device=dev)
+    ws = _scratch(L.mla_layernorm_backward_workspace_bytes(M, D), dev)
+    _lib.check(L.mla_layernorm_backward(dy2.data_ptr(), x2.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w.data_ptr(),
+                                        resid.data_ptr() if resid is not None else None, M, D, dx.data_ptr(), dw.data_ptr(),
+                                        db.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mla_layernorm_backward")
+    return dx, dw, db
+
+
+def _linear16(x16, w, bias, resid, M, K, N):
+    """y = x16 w^T + bias (+ resid) with the adds in the GEMM epilogue; w fp32 [N, K] is cast here (small)."""
+    y = torch.empty(M, N, dtype=torch.float32, device=x16.device)
+    w16 = _cast16(w, False)
+    _lib.check(_lib.lib().mla_linear_forward16(x16.data_ptr(), w16.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                               resid.data_ptr() if resid is not None else None, y.data_ptr(), M, K, N,
+                                               _lib.stream_ptr()), "mla_linear_forward16")
+    return y
+
+
+def _cast_round(x2, gelu):
+    x16 = torch.empty(x2.shape, dtype=torch.float16, device=x2.device)
+    x_r = torch.empty_like(x2)
+    _lib.check(_lib.lib().mla_cast_round(x2.data_ptr(), x16.data_ptr(), x_r.data_ptr(), x2.numel(), 1 if gelu else 0,
+                                         _lib.stream_ptr()), "mla_cast_round")
+    return x16, x_r
+
+
+def _round_colsum(dy2, u):
+    """TF32-rounded dy (times gelu'(u) when u is given) and its column sums (the bias gradient)."""
+    L = _lib.lib()
+    M, N = dy2.shape
+    out = torch.empty_like(dy2)
+    col = torch.empty(N, dtype=torch.float32, device=dy2.device)
+    ws = _scratch(L.mla_round_colsum_workspace_bytes(M, N), dy2.device)
+    _lib.check(L.mla_round_colsum(dy2.data_ptr(), u.data_ptr() if u is not None else None, out.data_ptr(), col.data_ptr(), M, N,
+                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mla_round_colsum")
+    return out, col
+
+
+def _linear_grads(x_r, dy_r, w, M, K, N):
+    """dx [M, K] = dy_r w, dw [N, K] = dy_r^T x_r on the TF32 tcgen05 kernels (operands already TF32-rounded)."""
+    L = _lib.lib()
+    dev = dy_r.device
+    st = _lib.stream_ptr()
+    w_r = _round_tf32(w)
+    dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+    _lib.check(L.mla_conv2d_dgrad(dy_r.data_ptr(), w_r.data_ptr(), dx.data_ptr(), 1, M, 1, K, N, 1, 1, 1, 0, 0, st),
+               "mla_conv2d_dgrad")
+    dw = torch.empty(N, K, dtype=torch.float32, device=dev)
+    ws = _scratch(L.mla_conv2d_wgrad_workspace_bytes(1, M, 1, K, N, 1, 1, 1, 0), dev)
+    _lib.check(L.mla_conv2d_wgrad(x_r.data_ptr(), dy_r.data_ptr(), dw.data_ptr(), 1, M, 1, K, N, 1, 1, 1, 0, ws.data_ptr(),
+                                  ws.numel(), st), "mla_conv2d_wgrad")
+    return dx, dw
+
+
+class _BlockFn(torch.autograd.Function):
+    """x + attention(LN1(x)), then + MLP(LN2(.)) — reference Block.forward, m3ae.py:143-154 — as one node."""
+
+    @staticmethod
+    def forward(ctx, x, mask, H, scale, eps1, eps2, g1, b1, wq, bq, wo, bo, g2, b2, w1, c1, w2, c2):
+        L = _lib.lib()
+        B, S, D = x.shape
+        M, Dh = B * S, D // H
+        dev = x.device
+        x2 = x.reshape(M, D)
+        if x2.dtype != torch.float32 or not x2.is_contiguous():
+            x2 = x2.float().contiguous()
+        _, h16, h_r, mu1, rs1 = _ln_fwd(x2, g1, b1, eps1)
+        qkv = _linear16(h16, wq, bq, None, M, D, 3 * D)
+        del h16
+        ao = torch.empty(M, D, dtype=torch.float32, device=dev)
+        stats = torch.empty(B, H, S, 2, dtype=torch.float32, device=dev)
+        qkv16 = torch.empty(M, 3 * D, dtype=torch.float16, device=dev)
+        _lib.check(L.mla_attention_forward(qkv.data_ptr(), mask.data_ptr() if mask is not None else None, ao.data_ptr(),
+                                           stats.data_ptr(), qkv16.data_ptr(), B, S, H, Dh, scale, _lib.stream_ptr()),
+                   "mla_attention_forward")
+        del qkv
+        ao16, ao_r = _cast_round(ao, False)
+        x1 = _linear16(ao16, wo, bo, x2, M, D, D)
+        del ao16
+        _, h2_16, h2_r, mu2, rs2 = _ln_fwd(x1, g2, b2, eps2)
+        u = _linear16(h2_16, w1, c1, None, M, D, 4 * D)
+        del h2_16
+        g16, g_r = _cast_round(u, True)
+        y = _linear16(g16, w2, c2, x1, M, 4 * D, D)
+        ctx.save_for_backward(x2, mask, mu1, rs1, h_r, qkv16, stats, ao, ao_r, x1, mu2, rs2, h2_r, u, g_r,
+                              g1, wq, wo, g2, w1, w2)
+        ctx.cfg = (B, S, D, H, scale)
+        return y.view(B, S, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2, mask, mu1, rs1, h_r, qkv16, stats, ao, ao_r, x1, mu2, rs2, h2_r, u, g_r, g1, wq, wo, g2, w1, w2) = ctx.saved_tensors
+        B, S, D, H, scale = ctx.cfg
+        L = _lib.lib()
+        M, Dh = B * S, D // H
+        dev = dy.device
+        dy2 = dy.reshape(M, D)
+        if dy2.dtype != torch.float32 or not dy2.is_contiguous():
+            dy2 = dy2.float().contiguous()
+        # MLP: y = x1 + fc2(gelu(fc1(LN2(x1))))
+        dy_r, dc2 = _round_colsum(dy2, None)
+        dg, dw2 = _linear_grads(g_r, dy_r, w2, M, 4 * D, D)
+        du_r, dc1 = _round_colsum(dg, u)
+        del dg
+        dh2, dw1 = _linear_grads(h2_r, du_r, w1, M, D, 4 * D)
+        del du_r
+        dx1, dg2, db2 = _ln_bwd(dh2, x1, mu2, rs2, g2, dy2)
+        # attention: x1 = x + fc(attn(qkv(LN1(x))))
+        d_r, dbo = _round_colsum(dx1, None)
+        dao, dwo = _linear_grads(ao_r, d_r, wo, M, D, D)
+        dqkv = torch.empty(M, 3 * D, dtype=torch.float32, device=dev)
+        ws = torch.empty(L.mla_attention_backward_workspace_bytes(B, S, H, Dh), dtype=torch.uint8, device=dev)
+        _lib.check(L.mla_attention_backward(qkv16.data_ptr(), mask.data_ptr() if mask is not None else None, ao.data_ptr(),
+                                            dao.data_ptr(), stats.data_ptr(), dqkv.data_ptr(), B, S, H, Dh, scale,
+                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mla_attention_backward")
+        dq_r, dbq = _round_colsum(dqkv, None)
+        del dqkv
+        dh1, dwq = _linear_grads(h_r, dq_r, wq, M, D, 3 * D)
+        dx, dg1, db1 = _ln_bwd(dh1, x2, mu1, rs1, g1, dx1)
+        return (dx.view(B, S, D), None, None, None, None, None, dg1, db1, dwq, dbq, dwo, dbo, dg2, db2, dw1, dc1, dw2, dc2)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension on the native kernels (the encoder's final layer_norm)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        if x2.dtype != torch.float32 or not x2.is_contiguous():
+            x2 = x2.float().contiguous()
+        y, _, _, mean, rstd = _ln_fwd(x2, w, b, eps, want_y=True)
+        ctx.save_for_backward(x2, mean, rstd, w)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, w = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape)
+        if dy2.dtype != torch.float32 or not dy2.is_contiguous():
+            dy2 = dy2.float().contiguous()
+        dx, dw, db = _ln_bwd(dy2, x2, mean, rstd, w, None)
+        return dx.view(dy.shape), dw, db, None
+
+
 class NativeLinear(nn.Linear):
     """nn.Linear (same parameters, same default init) whose CUDA forward / backward are the library's GEMM kernels."""
 
@@ -207,6 +388,15 @@ class Block(nn.Module):                                # m3ae.py:128-154 (pre-LN
         self.transformer_mlp = TransformerMLP(emb_dim, emb_dim)
 
     def forward(self, x, padding_mask=None):
+        if FUSED_BLOCK:
+            if not x.is_cuda:
+                raise RuntimeError("mla_b200 m3ae encoders run on CUDA only (no CPU fallback); got %s" % x.device)
+            a, m = self.attention, self.transformer_mlp
+            mask = padding_mask.float().contiguous() if padding_mask is not None else None
+            return _BlockFn.apply(x, mask, a.num_heads, a.scale, self.layer_norm1.eps, self.layer_norm2.eps,
+                                  self.layer_norm1.weight, self.layer_norm1.bias, a.qkv_linear.weight, a.qkv_linear.bias,
+                                  a.fc.weight, a.fc.bias, self.layer_norm2.weight, self.layer_norm2.bias,
+                                  m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
         x = x + self.attention(self.layer_norm1(x), padding_mask)
         return x + self.transformer_mlp(self.layer_norm2(x))
 
@@ -220,6 +410,8 @@ class Transformer(nn.Module):                          # m3ae.py:157-179
     def forward(self, x, padding_mask=None):
         for blk in self.blocks:
             x = blk(x, padding_mask)
+        if FUSED_BLOCK and x.is_cuda:
+            return _LayerNormFn.apply(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
         return self.layer_norm(x)
 
 

@@ -92,10 +92,10 @@ class SyntheticAVLoader:
 
 
 class SyntheticTextImageLoader:
-    """len()-able iterable of Food-101-shaped m3ae batches (token [B,1,L] int64, padding_mask [B,1,L], image
+    """len()-able iterable of Food-101-shaped m3ae batches (token [B,1,256] int64, padding_mask [B,1,L], image
     [B,3,256,256], label, idx), pinned host memory, seeded per rank (dataset layout: dataset/*.py __getitem__)."""
 
-    def __init__(self, batch_size, steps, seed, text_len=512, image_hw=(256, 256), n_classes=101, vocab=30522, distinct=2):
+    def __init__(self, batch_size, steps, seed, text_len=256, image_hw=(256, 256), n_classes=101, vocab=30522, distinct=2):
         g = torch.Generator().manual_seed(seed)
         self.batches = []
         for _ in range(min(distinct, steps)):

@@ -470,7 +470,7 @@ class M3AEOracle(AVOracle):
         return hits[0].sum() / tot, hits[1].sum() / tot, hits[2].sum() / tot
 
 
-def synthetic_m3ae_batch(batch, seed, text_len=512, image_hw=(256, 256), n_classes=101, vocab=30522):
+def synthetic_m3ae_batch(batch, seed, text_len=256, image_hw=(256, 256), n_classes=101, vocab=30522):
     """(token [B,1,L] int64, padding_mask [B,1,L] int64 with a random padded tail, image [B,3,H,W], label)."""
     import torch
     g = torch.Generator().manual_seed(seed)

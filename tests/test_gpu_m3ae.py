@@ -249,3 +249,129 @@ def test_fused_attention_forward_backward(built_lib, B, S, H, Dh, masked):
         B, S, H, Dh, masked, e_o, e_g, parts[0], parts[1], parts[2]))
     assert e_o < 1e-3 and e_g < 1e-3 and max(parts) < 2e-3
     assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(qkv.grad).all())
+
+
+@pytest.mark.parametrize("M,D", [(1, 64), (37, 384), (1000, 768), (130, 1024), (9, 1280), (513, 32)])
+def test_layernorm_kernels(built_lib, M, D):
+    """csrc/transformer_ops.cu LayerNorm forward (fp32 / fp16 / TF32-rounded outputs) and backward (dx with the residual
+    add, dgamma, dbeta) against torch in fp64."""
+    from mla_b200 import m3ae
+    gen = torch.Generator().manual_seed(M * 7 + D)
+    x = (torch.randn(M, D, generator=gen) * 1.7 + 0.3).cuda()
+    w = (torch.rand(D, generator=gen) + 0.5).cuda()
+    b = torch.randn(D, generator=gen).cuda()
+    dy = torch.randn(M, D, generator=gen).cuda()
+    resid = torch.randn(M, D, generator=gen).cuda()
+    y, _, _, mean, rstd = m3ae._ln_fwd(x, w, b, 1e-5, want_y=True)
+    _, y16, y_r, _, _ = m3ae._ln_fwd(x, w, b, 1e-5)
+    dx, dw, db = m3ae._ln_bwd(dy, x, mean, rstd, w, resid)
+    dx0, _, _ = m3ae._ln_bwd(dy, x, mean, rstd, w, None)
+    torch.cuda.synchronize()
+    x64 = x.double().requires_grad_(True)
+    w64, b64 = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(x64, (D,), w64, b64, 1e-5)
+    ref.backward(dy.double())
+    assert relf(y.cpu(), ref.detach().cpu()) < 1e-6
+    assert relf(y16.float().cpu(), ref.detach().cpu()) < 6e-4 and relf(y_r.cpu(), ref.detach().cpu()) < 6e-4
+    assert bool((y_r.view(torch.int32) & 0x1fff).eq(0).all())                   # TF32: low 13 mantissa bits clear
+    assert relf(dx0.cpu(), x64.grad.cpu()) < 1e-5 and relf(dx.cpu(), (x64.grad + resid.double()).cpu()) < 1e-5
+    assert relf(dw.cpu(), w64.grad.cpu()) < 1e-5 and relf(db.cpu(), b64.grad.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N", [(1, 64), (771, 768), (1026, 3072), (50, 2304), (17, 192)])
+def test_elementwise_operand_kernels(built_lib, M, N):
+    """cast_round (with and without GELU), round_colsum (with and without the GELU derivative)."""
+    from mla_b200 import m3ae
+    gen = torch.Generator().manual_seed(M + N)
+    u = (torch.randn(M, N, generator=gen) * 1.5).cuda()
+    dy = torch.randn(M, N, generator=gen).cuda()
+    u16, u_r = m3ae._cast_round(u, False)
+    g16, g_r = m3ae._cast_round(u, True)
+    d_r, col = m3ae._round_colsum(dy, None)
+    du_r, colu = m3ae._round_colsum(dy, u)
+    torch.cuda.synchronize()
+    u64 = u.double().requires_grad_(True)
+    g = torch.nn.functional.gelu(u64)
+    g.backward(dy.double())
+    assert torch.equal(u16, u.half()) and relf(u_r.cpu(), u.cpu()) < 4e-4
+    assert relf(g16.float().cpu(), g.detach().cpu()) < 4e-4 and relf(g_r.cpu(), g.detach().cpu()) < 4e-4
+    assert relf(d_r.cpu(), dy.cpu()) < 4e-4 and relf(col.cpu(), dy.double().sum(0).cpu()) < 1e-5
+    assert relf(du_r.cpu(), u64.grad.cpu()) < 4e-4 and relf(colu.cpu(), u64.grad.sum(0).cpu()) < 1e-5
+    for t in (u_r, g_r, d_r, du_r):
+        assert bool((t.view(torch.int32) & 0x1fff).eq(0).all())
+
+
+@pytest.mark.parametrize("M,K,N", [(771, 768, 2304), (130, 3072, 768), (5, 64, 64)])
+def test_linear_epilogue_bias_and_residual(built_lib, M, K, N):
+    from mla_b200 import m3ae
+    gen = torch.Generator().manual_seed(M + K + N)
+    x16 = torch.randn(M, K, generator=gen).cuda().half()
+    w = (torch.randn(N, K, generator=gen) * 0.05).cuda()
+    bias = torch.randn(N, generator=gen).cuda()
+    resid = torch.randn(M, N, generator=gen).cuda()
+    ref = x16.double() @ w.half().double().t()
+    y0 = m3ae._linear16(x16, w, None, None, M, K, N)
+    y1 = m3ae._linear16(x16, w, bias, None, M, K, N)
+    y2 = m3ae._linear16(x16, w, bias, resid, M, K, N)
+    torch.cuda.synchronize()
+    assert relf(y0.cpu(), ref.cpu()) < 1e-5
+    assert relf(y1.cpu(), (ref + bias.double()).cpu()) < 1e-5
+    assert relf(y2.cpu(), (ref + bias.double() + resid.double()).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("B,S,D,H,masked", [(2, 513, 768, 12, True), (3, 17, 64, 2, False)])
+def test_fused_block_matches_per_module_path(built_lib, B, S, D, H, masked):
+    """_BlockFn (one node, hand-written backward) against the per-module autograd path of the same Block and against the
+    oracle's fp32 restatement of the block on this GPU: output, input gradient and every parameter gradient."""
+    from mla_b200 import m3ae
+    torch.manual_seed(B + S + D)
+    blk = m3ae.Block(D, H).cuda()
+    for p_ in blk.parameters():                    # non-trivial LayerNorm affine / biases
+        if p_.dim() == 1:
+            p_.data.add_(torch.randn_like(p_) * 0.1)
+    x = torch.randn(B, S, D, device="cuda")
+    dy = torch.randn(B, S, D, device="cuda")
+    mask = None
+    if masked:
+        n_valid = torch.randint(1, S + 1, (B,))
+        mask = (torch.arange(S)[None, :] >= n_valid[:, None]).float().cuda()
+
+    def run(fused):
+        prev = m3ae.FUSED_BLOCK
+        m3ae.FUSED_BLOCK = fused
+        try:
+            blk.zero_grad()
+            xi = x.clone().requires_grad_(True)
+            y = blk(xi, mask)
+            y.backward(dy)
+            torch.cuda.synchronize()
+            return y.detach(), xi.grad.clone(), {k: v.grad.clone() for k, v in blk.named_parameters()}
+        finally:
+            m3ae.FUSED_BLOCK = prev
+
+    yf, dxf, gf = run(True)
+    ym, dxm, gm = run(False)
+    # fp32 reference: the oracle's block arithmetic via torch ops (matmul TF32 off)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        import torch.nn.functional as F
+        ps = {k: v.detach().clone().requires_grad_(True) for k, v in blk.named_parameters()}
+        xi = x.clone().requires_grad_(True)
+        h = F.layer_norm(xi, (D,), ps["layer_norm1.weight"], ps["layer_norm1.bias"])
+        qkv = F.linear(h, ps["attention.qkv_linear.weight"], ps["attention.qkv_linear.bias"])
+        a = _attention_ref(qkv, mask, H, (D // H) ** -0.5)
+        x1 = xi + F.linear(a, ps["attention.fc.weight"], ps["attention.fc.bias"])
+        h = F.layer_norm(x1, (D,), ps["layer_norm2.weight"], ps["layer_norm2.bias"])
+        h = F.gelu(F.linear(h, ps["transformer_mlp.fc1.weight"], ps["transformer_mlp.fc1.bias"]))
+        yr = x1 + F.linear(h, ps["transformer_mlp.fc2.weight"], ps["transformer_mlp.fc2.bias"])
+        yr.backward(dy)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    e = {"y": (relf(yf.cpu(), yr.detach().cpu()), relf(ym.cpu(), yr.detach().cpu())),
+         "dx": (relf(dxf.cpu(), xi.grad.cpu()), relf(dxm.cpu(), xi.grad.cpu()))}
+    for k in gf:
+        e[k] = (relf(gf[k].cpu(), ps[k].grad.cpu()), relf(gm[k].cpu(), ps[k].grad.cpu()))
+    for k, (a_, b_) in e.items():
+        print("  %-32s fused %.2e  per-module %.2e" % (k, a_, b_))
+    assert max(v[0] for v in e.values()) < 1e-3 and max(v[1] for v in e.values()) < 1e-3
