@@ -5,7 +5,7 @@ The directory name contains hyphens, so import it through the `mla_b200` alias p
 repo root (`import mla_b200`). Names mirror the reference's modules:
     GSPlugin, setup_seed, weight_init            (utils/utils.py)
     calculate_entropy, calculate_gating_weights[3], train_epoch, valid, get_arguments (main.py)
-    AVClassifier, M3AEClassifier                 (models/basic_model.py, models/m3ae.py)
+    AVClassifier, M3AEClassifier, Modal3Classifier (models/basic_model.py, models/m3ae.py, models/cav_mae.py)
     ConcatFusion, ConcatFusion3                  (models/fusion_modules.py)
     resnet18                                     (models/backbone.py)
 """
@@ -16,6 +16,7 @@ from .fusion_modules import ConcatFusion, ConcatFusion3, head_turn  # noqa: F401
 from .backbone import resnet18  # noqa: F401
 from .basic_model import AVClassifier  # noqa: F401
 from .m3ae import M3AEClassifier  # noqa: F401
+from .cav_mae import Modal3Classifier  # noqa: F401
 from .utils import setup_seed, weight_init  # noqa: F401
 from .engine import ModuleHolder, train_epoch, valid  # noqa: F401
 from .main import get_arguments  # noqa: F401

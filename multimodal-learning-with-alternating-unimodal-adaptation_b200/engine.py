@@ -145,7 +145,9 @@ def encoder_param_groups(net):
             break
     if not names:
         raise RuntimeError("model has no known encoders (audio_net/visual_net or mae_a/mae_v[/mae_t])")
-    return [[p for p in getattr(net, n).parameters()] for n in names]
+    # an encoder may name the parameters its forward really reads (CAVMAEFT carries an unused visual branch): the others
+    # keep grad None and the optimiser skips them, as in the reference
+    return [[p for p in getattr(getattr(net, n), "hot_parameters", getattr(net, n).parameters)()] for n in names]
 
 
 def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,

@@ -19,6 +19,7 @@ from .basic_model import AVClassifier
 from .engine import ModuleHolder, train_epoch, valid
 from .gs_plugin import GSPlugin
 from .m3ae import M3AEClassifier
+from .cav_mae import Modal3Classifier
 from .utils import setup_seed, weight_init
 
 
@@ -93,9 +94,11 @@ class SyntheticAVLoader:
 
 class SyntheticTextImageLoader:
     """len()-able iterable of Food-101-shaped m3ae batches (token [B,1,256] int64, padding_mask [B,1,L], image
-    [B,3,256,256], label, idx), pinned host memory, seeded per rank (dataset layout: dataset/*.py __getitem__)."""
+    [B,3,256,256], label, idx), pinned host memory, seeded per rank (dataset layout: dataset/*.py __getitem__).
+    audio_len > 0: IEMOCAP-shaped three-modality batches (token, padding_mask, image, spec [B,audio_len,128], label, idx)."""
 
-    def __init__(self, batch_size, steps, seed, text_len=256, image_hw=(256, 256), n_classes=101, vocab=30522, distinct=2):
+    def __init__(self, batch_size, steps, seed, text_len=256, image_hw=(256, 256), n_classes=101, vocab=30522, distinct=2,
+                 audio_len=0):
         g = torch.Generator().manual_seed(seed)
         self.batches = []
         for _ in range(min(distinct, steps)):
@@ -105,9 +108,11 @@ class SyntheticTextImageLoader:
             image = torch.randn(batch_size, 3, *image_hw, generator=g)
             label = torch.randint(0, n_classes, (batch_size,), generator=g)
             idx = torch.zeros(batch_size, 1, dtype=torch.long)
+            spec = torch.randn(batch_size, audio_len, 128, generator=g) if audio_len else None
             if torch.cuda.is_available():
                 token, pm, image, label = token.pin_memory(), pm.pin_memory(), image.pin_memory(), label.pin_memory()
-            self.batches.append((token, pm, image, label, idx))
+                spec = spec.pin_memory() if audio_len else None
+            self.batches.append((token, pm, image, spec, label, idx) if audio_len else (token, pm, image, label, idx))
         self.steps = steps
 
     def __len__(self):
@@ -120,11 +125,12 @@ class SyntheticTextImageLoader:
 
 def build_model(args, device):
     """main.py:707-734 for the paths in scope."""
-    if args.lorb == "large" or args.clip or (args.lorb == "m3ae" and args.modal3):
-        raise NotImplementedError("implemented: --lorb base (AVClassifier) and --lorb m3ae (M3AEClassifier); the CAV-MAE "
-                                  "/ CLIP / three-modality encoders are the next rows of SURVEY.md §8")
-    if args.lorb == "m3ae":
-        model = M3AEClassifier(args)                             # main.py:709-713 (no weight_init, like the reference)
+    if args.lorb == "large" or args.clip:
+        raise NotImplementedError("implemented: --lorb base (AVClassifier), --lorb m3ae (M3AEClassifier) and --lorb m3ae "
+                                  "--modal3 (Modal3Classifier); CAVClassifier / CLIPClassifier are out of scope "
+                                  "(SURVEY.md section 2)")
+    if args.lorb == "m3ae":                                      # main.py:708-712 (no weight_init, like the reference)
+        model = Modal3Classifier(args) if args.modal3 else M3AEClassifier(args)
     else:
         model = AVClassifier(args)
         model.apply(weight_init)
@@ -148,7 +154,11 @@ def main(av_alpha=0.5):
     model = build_model(args, device)
     optimizer = optim.SGD(model.parameters(), lr=args.learning_rate, momentum=0.9, weight_decay=1e-4)   # main.py:749
     scheduler = optim.lr_scheduler.StepLR(optimizer, args.lr_decay_step, args.lr_decay_ratio)           # main.py:760
-    Loader = SyntheticTextImageLoader if args.lorb == "m3ae" else SyntheticAVLoader
+    if args.lorb == "m3ae" and args.modal3:
+        def Loader(b, n, seed):
+            return SyntheticTextImageLoader(b, n, seed, n_classes=4, audio_len=1024)
+    else:
+        Loader = SyntheticTextImageLoader if args.lorb == "m3ae" else SyntheticAVLoader
     train_loader = Loader(args.batch_size, args.steps, seed=1 + rank)
     test_loader = Loader(args.batch_size, max(1, args.steps // 2), seed=1001 + rank)
     gs = GSPlugin(force_projection=args.force_projection) if args.gs_flag else None                     # main.py:819

@@ -13,6 +13,8 @@ It restates, on the CPU, what the reference computes on the path named by BASELI
   * the alternating gs train step     main.py:419-476               (torch CPU fp32 + autograd + SGD)
   * valid() gs branch                 main.py:622-679
   * m3ae encoders / M3AEClassifier    models/m3ae.py:65-224,337-370, basic_model.py:184-200 (torch CPU fp32)
+  * CAV-MAE audio / Modal3Classifier  models/cav_mae.py:69-151,337-351, basic_model.py:252-275 (torch CPU fp32; the
+                                      block's Attention / Mlp come from un-vendored timm==0.4.5: those two UNPINNED)
 
 Pinning: the reference ships no tests or golden vectors, so this oracle is
 pinned against OUTPUTS OF THE REFERENCE ITSELF, executed in the build container under torch
@@ -373,6 +375,25 @@ def sincos_2d(embed_dim, length):
     return np.concatenate([sincos_1d(embed_dim // 2, grid[0]), sincos_1d(embed_dim // 2, grid[1])], axis=1)
 
 
+def preln_block(x, mask, num_heads, g1, b1, wq, bq, wo, bo, g2, b2, w1, c1, w2, c2):
+    """One pre-LN transformer block: m3ae.py:128-154 (Block) with :86-125 (Attention: scores * scale, padded keys FILLED
+    with -1e7, softmax) and :65-83 (MLP, exact GELU); also cav_mae.py:86-113 with timm 0.4.5's Attention / Mlp (mask None)."""
+    import torch
+    import torch.nn.functional as F
+    B, S, D = x.shape
+    scale = (D // num_heads) ** -0.5
+    h = F.layer_norm(x, (D,), g1, b1)
+    qkv = F.linear(h, wq, bq).view(B, S, 3, num_heads, D // num_heads).permute(2, 0, 3, 1, 4)
+    att = torch.matmul(qkv[0], qkv[1].transpose(-2, -1)) * scale
+    if mask is not None:
+        att = torch.where(mask[:, None, None, :].expand(att.shape) > 0, torch.tensor(-1e7, device=x.device), att)
+    att = F.softmax(att, dim=-1)
+    h = torch.matmul(att, qkv[2]).permute(0, 2, 1, 3).reshape(B, S, D)
+    x = x + F.linear(h, wo, bo)
+    h = F.layer_norm(x, (D,), g2, b2)
+    return x + F.linear(F.gelu(F.linear(h, w1, c1)), w2, c2)
+
+
 def m3ae_representation(sd, prefix, image, text, text_padding_mask, num_heads):
     """MaskedMultimodalAutoencoder.forward_representation (m3ae.py:337-370) + Transformer/Block/Attention/TransformerMLP
     (m3ae.py:65-179), functional over a state dict. DropPath is the identity (as published it returns None and
@@ -396,22 +417,13 @@ def m3ae_representation(sd, prefix, image, text, text_padding_mask, num_heads):
         masks.append(text_padding_mask)
     x = torch.cat(xs, dim=1)
     mask = torch.cat(masks, dim=1)
-    S = x.shape[1]
     depth = 1 + max(int(k[len(prefix) + 15:].split(".")[0]) for k in sd if k.startswith(prefix + "encoder.blocks."))
-    scale = (D // num_heads) ** -0.5
     for i in range(depth):
         p = "%sencoder.blocks.%d." % (prefix, i)
-        h = F.layer_norm(x, (D,), sd[p + "layer_norm1.weight"], sd[p + "layer_norm1.bias"])
-        qkv = F.linear(h, sd[p + "attention.qkv_linear.weight"], sd[p + "attention.qkv_linear.bias"])
-        qkv = qkv.view(B, S, 3, num_heads, D // num_heads).permute(2, 0, 3, 1, 4)
-        att = torch.matmul(qkv[0], qkv[1].transpose(-2, -1)) * scale
-        att = torch.where(mask[:, None, None, :].expand(att.shape) > 0, torch.tensor(-1e7, device=dev), att)
-        att = F.softmax(att, dim=-1)
-        h = torch.matmul(att, qkv[2]).permute(0, 2, 1, 3).reshape(B, S, D)
-        x = x + F.linear(h, sd[p + "attention.fc.weight"], sd[p + "attention.fc.bias"])
-        h = F.layer_norm(x, (D,), sd[p + "layer_norm2.weight"], sd[p + "layer_norm2.bias"])
-        h = F.gelu(F.linear(h, sd[p + "transformer_mlp.fc1.weight"], sd[p + "transformer_mlp.fc1.bias"]))
-        x = x + F.linear(h, sd[p + "transformer_mlp.fc2.weight"], sd[p + "transformer_mlp.fc2.bias"])
+        x = preln_block(x, mask, num_heads, *[sd[p + k] for k in (
+            "layer_norm1.weight", "layer_norm1.bias", "attention.qkv_linear.weight", "attention.qkv_linear.bias",
+            "attention.fc.weight", "attention.fc.bias", "layer_norm2.weight", "layer_norm2.bias",
+            "transformer_mlp.fc1.weight", "transformer_mlp.fc1.bias", "transformer_mlp.fc2.weight", "transformer_mlp.fc2.bias")])
     return F.layer_norm(x, (D,), sd[prefix + "encoder.layer_norm.weight"], sd[prefix + "encoder.layer_norm.bias"])
 
 
@@ -468,6 +480,84 @@ class M3AEOracle(AVOracle):
             hits += r["hits"]
         tot = float(num.sum())
         return hits[0].sum() / tot, hits[1].sum() / tot, hits[2].sum() / tot
+
+
+# --------------------------------------------------------------------------------------------
+# CAV-MAE audio encoder / Modal3Classifier — models/cav_mae.py:69-113,116-151,337-351, basic_model.py:252-275.
+# The block's Attention / Mlp classes come from timm==0.4.5 (requirements.txt:55), which is NOT in /root/reference and not
+# installed: PARITY OF THOSE TWO CLASSES IS UNPINNED. Their published algorithm (qkv Linear with bias -> heads ->
+# softmax(q k^T * head_dim^-0.5) v -> proj Linear; fc1 -> exact GELU -> fc2) is what preln_block computes with mask=None;
+# everything around them (patch embedding, embeddings, block wiring, norms, the classifier, the step) is pinned to the
+# reference's own code executed with those two classes restated (tests/golden/make_golden.py).
+# --------------------------------------------------------------------------------------------
+def cav_audio_features(sd, prefix, audio, num_heads):
+    """CAVMAEFT.forward_feat(a, None, 'a') (cav_mae.py:337-351): [B, T, 128] -> [B, T*128/256, D]."""
+    import torch.nn.functional as F
+    a = audio.unsqueeze(1).transpose(2, 3)
+    a = F.conv2d(a, sd[prefix + "patch_embed_a.proj.weight"], sd[prefix + "patch_embed_a.proj.bias"], stride=16)
+    a = a.flatten(2).transpose(1, 2) + sd[prefix + "pos_embed_a"] + sd[prefix + "modality_a"]
+    D = a.shape[-1]
+
+    def run(group, n1, n2, x):
+        depth = 1 + max([int(k[len(prefix) + len(group) + 1:].split(".")[0]) for k in sd if k.startswith(prefix + group + ".")],
+                        default=-1)
+        for i in range(depth):
+            p = "%s%s.%d." % (prefix, group, i)
+            x = preln_block(x, None, num_heads, *[sd[p + k] for k in (
+                n1 + ".weight", n1 + ".bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+                n2 + ".weight", n2 + ".bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias")])
+        return x
+    a = run("blocks_a", "norm1", "norm2", a)
+    a = run("blocks_u", "norm1_a", "norm2_a", a)
+    return F.layer_norm(a, (D,), sd[prefix + "norm_a.weight"], sd[prefix + "norm_a.bias"])
+
+
+def modal3_forward(sd, token, padding_mask, visual, audio, num_heads):
+    """Modal3Classifier.forward (basic_model.py:252-275) -> (a, v, t)."""
+    B, C, H, W = visual.shape
+    patches = visual.reshape(B, C, H // 16, 16, W // 16, 16).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // 16) * (W // 16), C * 256)
+    a = cav_audio_features(sd, "mae_a.", audio, num_heads)
+    t = m3ae_representation(sd, "mae_t.", None, token.squeeze(1), padding_mask.squeeze(1), num_heads)
+    v = m3ae_representation(sd, "mae_v.", patches, None, None, num_heads)
+    return a.mean(dim=1), v.mean(dim=1), t.mean(dim=1)
+
+
+class Modal3Oracle(AVOracle):
+    """The alternating step over THREE encoders (main.py:419-466, modal3): a -> v -> t turns on the shared head."""
+
+    def __init__(self, state, num_heads, **kw):
+        super().__init__(state, **kw)
+        self.num_heads = num_heads
+
+    def train_step(self, token, padding_mask, image, spec, label, batch_step=0, len_dl=1):
+        self.opt.zero_grad()
+        a, v, t = modal3_forward(self.sd, token, padding_mask, image, spec, self.num_heads)   # main.py:426
+        return (self._turn(a, label, batch_step, len_dl, "mae_a."), self._turn(v, label, batch_step, len_dl, "mae_v."),
+                self._turn(t, label, batch_step, len_dl, "mae_t."))
+
+    def train_epoch(self, batches, av_alpha=0.5):
+        tot = np.zeros(4)
+        for step, b in enumerate(batches):
+            la, lv, lt = self.train_step(b[0], b[1], b[2], b[3], b[4], step, len(batches))
+            mix = float(np.float32(np.float32(la) * np.float32(av_alpha)) + np.float32(np.float32(lv) * np.float32(1 - av_alpha)))
+            tot += (mix, la, lv, lt)                       # main.py:472-476: the mixed loss ignores the third modality
+        return tuple(tot / len(batches))
+
+    def valid(self, batches, n_classes=4, dynamic=True, alphas=(0.35, 0.25, 0.4)):
+        torch = self.torch
+        import torch.nn.functional as F
+        num = np.zeros(n_classes, np.int64)
+        hits = np.zeros((4, n_classes), np.int64)
+        W, b = self.sd["fusion_module.fc_out.weight"], self.sd["fusion_module.fc_out.bias"]
+        for bt in batches:
+            with torch.no_grad():
+                feats = modal3_forward(self.sd, bt[0], bt[1], bt[2], bt[3], self.num_heads)
+                outs = [F.linear(f, W, b).cpu().numpy() for f in feats]
+            r = fuse_eval(outs, bt[4].cpu().numpy(), n_classes, dynamic=dynamic, fixed_w=alphas)
+            num += r["num"]
+            hits += r["hits"]
+        tot = float(num.sum())
+        return tuple(hits[i].sum() / tot for i in range(4))
 
 
 def synthetic_m3ae_batch(batch, seed, text_len=256, image_hw=(256, 256), n_classes=101, vocab=30522):

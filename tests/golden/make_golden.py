@@ -7,7 +7,8 @@ oracle/mla_oracle.py and, through it, for the CUDA kernels. Nothing here runs on
 (the reference does not travel); only the small .npz outputs are committed.
 
 Shims (no reference source is edited or copied):
-  * stub modules `ml_collections` and `timm` (not installed; not on the CREMA-D path)
+  * stub modules `ml_collections` and `timm` (not installed); timm 0.4.5's Attention / Mlp, which the CAV-MAE block of the
+    three-modality path calls, are restated in import_reference()
   * GSPlugin built via __new__ + a CPU `Pl` (its __init__ needs torch.cuda.FloatTensor)
   * nn.DataParallel(model, device_ids=[]) keeps the `.module` indirection on CPU
 """
@@ -55,7 +56,40 @@ def import_reference():
     lay.trunc_normal_ = nn.init.trunc_normal_
     lay.DropPath = nn.Identity
     vt = sys.modules["timm.models.vision_transformer"]
-    vt.Attention = vt.Mlp = vt.PatchEmbed = vt.Block = nn.Identity
+    vt.PatchEmbed = vt.Block = nn.Identity              # models/cav_mae.py defines its own and overwrites these
+    timm.models.vision_transformer = vt
+
+    # timm==0.4.5 (requirements.txt:55) is not installed and not part of /root/reference: its two classes the CAV-MAE block
+    # uses (cav_mae.py:15-16,93-94,101) are RESTATED here from the published 0.4.5 vision_transformer module. Everything
+    # else on the modal3 path is the reference's own code. Parity of these two classes is therefore unpinned.
+    class Attention(nn.Module):
+        def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0.):
+            super().__init__()
+            self.num_heads = num_heads
+            self.scale = qk_scale or (dim // num_heads) ** -0.5
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+            self.attn_drop = nn.Dropout(attn_drop)
+            self.proj = nn.Linear(dim, dim)
+            self.proj_drop = nn.Dropout(proj_drop)
+
+        def forward(self, x):
+            B, N, C = x.shape
+            qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+            attn = ((qkv[0] @ qkv[1].transpose(-2, -1)) * self.scale).softmax(dim=-1)
+            x = (self.attn_drop(attn) @ qkv[2]).transpose(1, 2).reshape(B, N, C)
+            return self.proj_drop(self.proj(x))
+
+    class Mlp(nn.Module):
+        def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+            super().__init__()
+            self.fc1 = nn.Linear(in_features, hidden_features or in_features)
+            self.act = act_layer()
+            self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
+            self.drop = nn.Dropout(drop)
+
+        def forward(self, x):
+            return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+    vt.Attention, vt.Mlp = Attention, Mlp
     sys.modules["timm.data"].create_transform = lambda *a, **k: None
 
     import main as ref_main
@@ -412,16 +446,117 @@ def make_m3ae(ref_main, ref_utils):
                         abs_sums=np.array([float(v.double().abs().sum()) for v in sd.values()]))
 
 
+CAV_TINY = dict(img_size=32, audio_length=64, embed_dim=64, modality_specific_depth=1, num_heads=2)
+
+
+def modal3_batches(n, B, seed, L=12, img=32, T=64, n_classes=4, vocab=M3AE_VOCAB):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    res = []
+    for _ in range(n):
+        token = torch.randint(0, vocab, (B, 1, L), generator=g)
+        n_valid = torch.randint(3, L + 1, (B,), generator=g)
+        pm = (torch.arange(L)[None, :] >= n_valid[:, None]).long()[:, None, :]
+        image = torch.randn(B, 3, img, img, generator=g)
+        spec = torch.randn(B, T, 128, generator=g)
+        label = torch.randint(0, n_classes, (B,), generator=g)
+        res.append((token, pm, image, spec, label, torch.zeros(B, 1, dtype=torch.long)))
+    return res
+
+
+def make_modal3(ref_main, ref_utils):
+    """--lorb m3ae --modal3 --gs_flag (BASELINE.json configs[3]) on tiny encoders: the reference's own CAVMAEFT (PatchEmbed,
+    Block wiring, embeddings, initialisation, forward_feat), Modal3Classifier.forward, train_epoch and valid; timm's
+    Attention / Mlp restated (import_reference). Same generator-side shims as make_m3ae."""
+    import torch
+    import torch.nn as nn
+    from torch.optim import SGD
+    from torch.optim.lr_scheduler import StepLR
+    from models import m3ae as ref_m3ae
+    from models import cav_mae as ref_cav
+    from models import basic_model as ref_bm
+    from models.fusion_modules import ConcatFusion3
+    ref_m3ae.DropPath.forward = lambda self, input, deterministic=False: input
+    real_to = torch.Tensor.to
+
+    def cpu_to(self, *a, **k):
+        a = tuple(torch.device("cpu") if isinstance(x, torch.device) and x.type == "cuda" else x for x in a)
+        return real_to(self, *a, **k)
+    torch.Tensor.to = cpu_to
+    out = {}
+    args = ref_main.get_arguments()
+    args.dataset, args.lorb, args.gs_flag, args.dynamic, args.modal3 = "IEMOCAP", "m3ae", True, True, True
+    args.fusion_method, args.modulation, args.clip = "concat", "Normal", False
+    cfg = sys.modules["ml_collections"].ConfigDict(M3AE_TINY)
+
+    def build():
+        ref_utils.setup_seed(0)
+        model = ref_bm.Modal3Classifier.__new__(ref_bm.Modal3Classifier)
+        nn.Module.__init__(model)
+        model.fusion_module = ConcatFusion3(input_dim=M3AE_TINY["emb_dim"], output_dim=4)        # basic_model.py:218
+        model.mae_a = ref_cav.CAVMAEFT(4, **CAV_TINY)
+        model.mae_v = ref_m3ae.MaskedMultimodalAutoencoder(text_vocab_size=M3AE_VOCAB, config_updates=cfg)
+        model.mae_t = ref_m3ae.MaskedMultimodalAutoencoder(text_vocab_size=M3AE_VOCAB, config_updates=cfg)
+        model.args = args
+        return model
+
+    model = build()
+    for k, v in model.state_dict().items():
+        out["state/" + k] = v.numpy().copy()
+    out["pos_embed_a_8x64_768"] = ref_cav.get_2d_sincos_pos_embed(768, 8, 64)[::7, ::5].astype(np.float32)
+    (token, pm, image, spec, label, _), = modal3_batches(1, 4, 41)
+    a, v, t = model(token, pm, image, spec)
+    out["fwd_a"], out["fwd_v"], out["fwd_t"] = a.detach().numpy(), v.detach().numpy(), t.detach().numpy()
+    a.square().sum().backward()
+    named = dict(model.named_parameters())
+    for k in ("mae_a.patch_embed_a.proj.weight", "mae_a.pos_embed_a", "mae_a.modality_a", "mae_a.blocks_a.0.attn.qkv.weight",
+              "mae_a.blocks_u.0.norm1_a.weight", "mae_a.blocks_u.0.mlp.fc2.weight", "mae_a.norm_a.bias"):
+        out["grad/" + k] = named[k].grad.numpy().copy()
+    out["grad_none"] = np.array([k for k, p_ in named.items() if k.startswith("mae_a.") and p_.grad is None])
+
+    def run_epoch(bl):
+        model = build()
+        dp = nn.DataParallel(model, device_ids=[])
+        opt = SGD(dp.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+        sch = StepLR(opt, 70, 0.1)
+        gs = ref_utils.GSPlugin.__new__(ref_utils.GSPlugin)
+        gs.Pl = torch.eye(M3AE_TINY["emb_dim"])
+        gs.exp_count = 0
+        losses = ref_main.train_epoch(args, 0, dp, torch.device("cpu"), bl, opt, sch, gs_plugin=gs, gs_flag=True,
+                                      av_alpha=0.55)
+        accs_dyn = ref_main.valid(args, dp, torch.device("cpu"), bl, gs_flag=True, av_alpha=0.55)
+        args.dynamic = False
+        accs_fix = ref_main.valid(args, dp, torch.device("cpu"), bl, gs_flag=True, av_alpha=0.55)
+        args.dynamic = True
+        fin = model.state_dict()
+        return dict(losses=np.array(losses), accs_dyn=np.array(accs_dyn), accs_fix=np.array(accs_fix),
+                    exp_count=np.array(gs.exp_count), fc_w=fin["fusion_module.fc_out.weight"].numpy().copy(),
+                    qkv_a=fin["mae_a.blocks_a.0.attn.qkv.weight"].numpy().copy(),
+                    patch_a=fin["mae_a.patch_embed_a.proj.weight"].numpy().copy(),
+                    unused_v=fin["mae_a.blocks_v.0.attn.qkv.weight"].numpy().copy(),
+                    fc2_t=fin["mae_t.encoder.blocks.1.transformer_mlp.fc2.weight"].numpy().copy())
+
+    bl = modal3_batches(3, 8, 9)
+    for k, v in run_epoch(bl[:1]).items():
+        out["step1_" + k] = v
+    for k, v in run_epoch(bl).items():
+        out["step3_" + k] = v
+    torch.Tensor.to = real_to
+    np.savez_compressed(os.path.join(OUT, "modal3.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_main, ref_utils = import_reference()
     import torch
     torch.set_num_threads(8)
-    if "--only-m3ae" not in sys.argv[1:] and not os.environ.get("MLA_GOLDEN_ONLY_M3AE"):
+    if not os.environ.get("MLA_GOLDEN_ONLY_M3AE") and not os.environ.get("MLA_GOLDEN_ONLY_MODAL3"):
         make_gs(ref_utils)
         make_fusion(ref_main)
         make_head()
         make_av(ref_main, ref_utils)
-    make_m3ae(ref_main, ref_utils)
+    if not os.environ.get("MLA_GOLDEN_ONLY_MODAL3"):
+        make_m3ae(ref_main, ref_utils)
+    make_modal3(ref_main, ref_utils)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

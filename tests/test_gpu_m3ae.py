@@ -163,7 +163,7 @@ def test_step_with_projection_vs_oracle(built_lib, golden):
 
 
 def test_base_encoder_full_size_vs_oracle(built_lib):
-    """The 'base' encoders (768 wide, 12 blocks, 12 heads) at the Food-101 shapes (512 tokens, 256x256 image, B=2): features
+    """The 'base' encoders (768 wide, 12 blocks, 12 heads) at the Food-101 shapes (256 tokens, 256x256 image, B=2): features
     and one training step against the oracle's restatement run in fp32 on this GPU (TF32 off)."""
     import mla_b200
     mla_b200.setup_seed(0)

@@ -275,3 +275,86 @@ def test_m3ae_tiny_state_loads_into_host_mirror(golden):
     assert not missing and not unexpected
     with pytest.raises(RuntimeError):                                                  # no CPU fallback
         net(*_m3ae_batches(1, 2, 3)[0][:3])
+
+
+# ------------------------------------------------------------------------------------------------
+# --lorb m3ae --modal3 (BASELINE.json configs[3]): fixtures from the reference's CAVMAEFT / Modal3Classifier.forward /
+# train_epoch / valid on tiny encoders, with timm 0.4.5's Attention / Mlp restated (unpinned; make_golden.make_modal3)
+# ------------------------------------------------------------------------------------------------
+CAV_TINY = dict(img_size=32, audio_length=64, embed_dim=64, modality_specific_depth=1, num_heads=2)
+
+
+def _modal3_batches(n, B, seed, L=12, img=32, T=64, n_classes=4, vocab=512):
+    gen = torch.Generator().manual_seed(seed)
+    res = []
+    for _ in range(n):
+        token = torch.randint(0, vocab, (B, 1, L), generator=gen)
+        n_valid = torch.randint(3, L + 1, (B,), generator=gen)
+        pm = (torch.arange(L)[None, :] >= n_valid[:, None]).long()[:, None, :]
+        image = torch.randn(B, 3, img, img, generator=gen)
+        spec = torch.randn(B, T, 128, generator=gen)
+        label = torch.randint(0, n_classes, (B,), generator=gen)
+        res.append((token, pm, image, spec, label))
+    return res
+
+
+def _modal3_args():
+    import argparse
+    return argparse.Namespace(dataset="IEMOCAP", fusion_method="concat", modulation="Normal", gs_flag=True, dynamic=True,
+                              lorb="m3ae", modal3=True, clip=False)
+
+
+def test_modal3_oracle_forward_and_gradients_match_reference(golden):
+    g = golden("modal3")
+    o = orc.Modal3Oracle(_m3ae_state(g), num_heads=2)
+    (token, pm, image, spec, _), = _modal3_batches(1, 4, 41)
+    a, v, t = orc.modal3_forward(o.sd, token, pm, image, spec, 2)
+    for x, k in ((a, "fwd_a"), (v, "fwd_v"), (t, "fwd_t")):
+        assert np.allclose(x.detach().numpy(), g[k], rtol=1e-5, atol=1e-6), k
+    a.square().sum().backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert relf(o.sd[k[5:]].grad.numpy(), g[k]) < 1e-5, k
+    # the visual branch of CAVMAEFT is never touched in audio mode
+    none = sorted(k for k in o.sd if k.startswith("mae_a.") and o.sd[k].requires_grad and o.sd[k].grad is None)
+    assert none == sorted(g["grad_none"])
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+def test_modal3_oracle_train_epoch_and_valid_match_reference(golden, steps):
+    g = golden("modal3")
+    tag = "step%d_" % steps
+    o = orc.Modal3Oracle(_m3ae_state(g), num_heads=2)
+    batches = _modal3_batches(3, 8, 9)[:steps]
+    losses = o.train_epoch(batches, av_alpha=0.55)
+    assert len(losses) == 4 and np.allclose(losses, g[tag + "losses"], rtol=1e-5), (losses, g[tag + "losses"])
+    assert o.exp_count == int(g[tag + "exp_count"]) == 3 * steps
+    for name, key in (("fusion_module.fc_out.weight", "fc_w"), ("mae_a.blocks_a.0.attn.qkv.weight", "qkv_a"),
+                      ("mae_a.patch_embed_a.proj.weight", "patch_a"), ("mae_a.blocks_v.0.attn.qkv.weight", "unused_v"),
+                      ("mae_t.encoder.blocks.1.transformer_mlp.fc2.weight", "fc2_t")):
+        assert relf(o.sd[name].detach().numpy(), g[tag + key]) < 1e-5, name
+    assert np.array_equal(g[tag + "unused_v"], g["state/mae_a.blocks_v.0.attn.qkv.weight"])      # skipped by SGD (grad None)
+    assert np.allclose(o.valid(batches, dynamic=True), g[tag + "accs_dyn"], atol=1e-9)
+    assert np.allclose(o.valid(batches, dynamic=False), g[tag + "accs_fix"], atol=1e-9)
+
+
+def test_modal3_host_mirror_seeded_init_is_bit_identical_to_reference(golden):
+    """Modal3Classifier built under the reference's seed draws the reference's random numbers in its order: every tensor
+    of the tiny configuration equals the reference's (incl. CAVMAEFT's sin-cos tables and its unused visual branch)."""
+    import mla_b200
+    from mla_b200 import cav_mae
+    g = golden("modal3")
+    mla_b200.setup_seed(0)
+    net = cav_mae.Modal3Classifier(_modal3_args(), model_config=dict(model_type=None, emb_dim=64, depth=2, num_heads=2),
+                                   text_vocab_size=512, audio_kwargs=CAV_TINY)
+    sd = net.state_dict()
+    ref = _m3ae_state(g)
+    assert list(sd.keys()) == list(ref.keys())
+    bad = [k for k in sd if not torch.equal(sd[k], ref[k])]
+    assert not bad, bad[:5]
+    assert np.array_equal(cav_mae.sincos_2d_rect(768, 8, 64)[::7, ::5].astype(np.float32), g["pos_embed_a_8x64_768"])
+    hot = {id(p) for p in net.mae_a.hot_parameters()}
+    cold = sorted(k for k, p in net.named_parameters() if k.startswith("mae_a.") and id(p) not in hot)
+    assert cold == sorted(g["grad_none"])
+    with pytest.raises(RuntimeError):                                                  # no CPU fallback
+        net(*_modal3_batches(1, 2, 3)[0][:4])
