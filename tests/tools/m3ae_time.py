@@ -1,7 +1,7 @@
 """Step time of the --lorb m3ae --gs_flag path ('base' encoders, Food-101 shapes) through train_epoch, next to the oracle's
 torch restatement on the same GPU (what the reference's own code would cost), plus a per-kernel breakdown.
 
-    python tests/tools/m3ae_time.py [B=32] [steps=4] [profile=0|1] [eager=0|1]
+    python tests/tools/m3ae_time.py [B=32] [steps=4] [profile=0|1] [eager=0|1] [modal3=0|1]
 """
 import argparse
 import os
@@ -21,10 +21,14 @@ def main():
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     profile = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     eager = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-    args = argparse.Namespace(dataset="Food101", fusion_method="concat", modulation="Normal", gs_flag=True, dynamic=True,
-                              lorb="m3ae", modal3=False, clip=False)
+    modal3 = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False
+    args = argparse.Namespace(dataset="IEMOCAP" if modal3 else "Food101", fusion_method="concat", modulation="Normal",
+                              gs_flag=True, dynamic=True, lorb="m3ae", modal3=modal3, clip=False)
     mla_b200.setup_seed(0)
-    net = mla_b200.M3AEClassifier(args)
+    net = mla_b200.Modal3Classifier(args) if modal3 else mla_b200.M3AEClassifier(args)
+
+    def Loader(b, n, seed):
+        return SyntheticTextImageLoader(b, n, seed, n_classes=4 if modal3 else 101, audio_len=1024 if modal3 else 0)
     state = {k: v.detach().clone() for k, v in net.state_dict().items()}
     model = mla_b200.ModuleHolder(net.cuda())
     dev = torch.device("cuda")
@@ -33,7 +37,7 @@ def main():
     gs = mla_b200.GSPlugin()
 
     def run(n):
-        loader = SyntheticTextImageLoader(B, n, seed=1)
+        loader = Loader(B, n, 1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -42,17 +46,17 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n, losses
 
-    for bf16 in (False, True):
-        m3ae.BACKWARD_BF16 = bf16
+    for fused, bf16 in ((True, False), (False, False), (False, True)):
+        m3ae.FUSED_BLOCK, m3ae.BACKWARD_BF16 = fused, bf16
         run(2)
         ms, losses = run(steps)
-        print("m3ae base B=%d backward=%s: %.2f ms/step, %.1f samples/s, peak mem %.1f GB, losses %s" % (
-            B, "bf16" if bf16 else "tf32", ms, B * 1000.0 / ms, torch.cuda.max_memory_allocated() / 2**30,
-            tuple(round(x, 4) for x in losses)), flush=True)
-    m3ae.BACKWARD_BF16 = False
+        print("%s base B=%d %s backward=%s: %.2f ms/step, %.1f samples/s, peak mem %.1f GB, losses %s" % (
+            "modal3" if modal3 else "m3ae", B, "fused blocks" if fused else "per-module", "bf16" if bf16 else "tf32", ms,
+            B * 1000.0 / ms, torch.cuda.max_memory_allocated() / 2**30, tuple(round(x, 4) for x in losses)), flush=True)
+    m3ae.FUSED_BLOCK, m3ae.BACKWARD_BF16 = True, False
     if profile:
         from torch.profiler import profile as tprof, ProfilerActivity
-        loader = SyntheticTextImageLoader(B, 2, seed=1)
+        loader = Loader(B, 2, 1)
         with tprof(activities=[ProfilerActivity.CUDA]) as prof:
             mla_b200.train_epoch(args, 0, model, dev, loader, opt, sch, gs_plugin=gs, gs_flag=True, av_alpha=0.55)
             torch.cuda.synchronize()
@@ -61,11 +65,13 @@ def main():
         from oracle import mla_oracle as orc
         del model, net, opt
         torch.cuda.empty_cache()
-        o = orc.M3AEOracle({k: v.cuda() for k, v in state.items()}, num_heads=12)
-        loader = SyntheticTextImageLoader(B, steps, seed=1)
-        bl = [tuple(t.cuda() for t in b[:4]) for b in loader.batches]
+        O = orc.Modal3Oracle if modal3 else orc.M3AEOracle
+        o = O({k: v.cuda() for k, v in state.items()}, num_heads=12)
+        loader = Loader(B, steps, 1)
+        bl = [tuple(t.cuda() for t in b[:-1]) for b in loader.batches]
         for tf32 in (False, True):
             torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
             o.train_epoch(bl[:1])
             torch.cuda.synchronize()
             t0 = time.perf_counter()
