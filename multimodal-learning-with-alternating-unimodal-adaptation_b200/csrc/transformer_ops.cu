@@ -212,9 +212,9 @@ __global__ void ew_colsum_kernel(const float* __restrict__ dy, const float* __re
   *reinterpret_cast<float4*>(part + (long long)blockIdx.y * N + c) = acc;
 }
 
-int ln_blocks(long long M) {
+int ln_blocks(long long M, int per_sm = 2) {
   const mla::DeviceInfo& di = mla::device_info();
-  return (int)std::min<long long>((M + 7) / 8, (long long)di.sm_count * 2);
+  return (int)std::min<long long>((M + 7) / 8, (long long)di.sm_count * per_sm);
 }
 
 int colsum_chunks(long long M, int N) {
@@ -241,7 +241,7 @@ extern "C" int mla_layernorm_forward(const float* x, const float* gamma, const f
   const mla::DeviceInfo& di = mla::device_info();
   if (di.ok != 1) return di.ok;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nb = ln_blocks(M), nv = (D + 127) / 128;
+  const int nb = ln_blocks(M, 8), nv = (D + 127) / 128;     // 64 registers: rows in flight, not occupancy, bound this pass
   uint2* h = static_cast<uint2*>(y16);
 #define LN_FWD(NV) ln_fwd_kernel<NV><<<nb, 256, 0, st>>>(x, gamma, beta, eps, M, D, y, h, y_r, mean, rstd)
   if (nv <= 1) LN_FWD(1); else if (nv <= 3) LN_FWD(3); else if (nv <= 6) LN_FWD(6); else if (nv <= 8) LN_FWD(8); else LN_FWD(10);
