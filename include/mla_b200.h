@@ -172,6 +172,11 @@ MLA_API int    mla_attention_backward(const void* qkv16, const float* key_mask, 
  * (bias / resid may be NULL; the adds happen in the GEMM epilogue). K, N % 64 == 0. nn.Linear of m3ae.py:72-73,98-99. */
 MLA_API int    mla_linear_forward16(const void* x16, const void* w16, const float* bias, const float* resid, float* y,
                         int M, int K, int N, void* stream);
+/* dx [M, K] = dy [M, N] * w [N, K], both fp32 already rounded to TF32 (mla_round_colsum / mla_round_tf32): the data
+ * gradient of the same Linear. K, N % 64 == 0. (The weight gradient is mla_conv2d_wgrad with N=1, H=M, W=1, R=S=1.)
+ * The two Linear entry points use tcgen05 CTA pairs (256-row MMAs); they must not run concurrently with OTHER pair
+ * kernels on a second stream (MLA_LINEAR_PAIR=0 selects single-CTA tiles). */
+MLA_API int    mla_linear_dgrad(const float* dy, const float* w, float* dx, int M, int K, int N, void* stream);
 /* nn.LayerNorm over the last dimension D (D % 4 == 0, D <= 1280), biased variance, as torch. Outputs (each may be NULL):
  * y fp32, y16 fp16 (the operand of the next GEMM), y_r fp32 rounded to TF32 (the operand of that GEMM's weight
  * gradient); mean / rstd [M] are kept for the backward pass. */

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   static_assert(CL == 1 || (MODE != 2 && IM2COL && NT == 1), "weight multicast exists for the im2col fprop / dgrad only");
   static_assert(CL == 1 || MODE == 0 || (BN / 32) % CL == 0, "dgrad splits whole 32-column weight panels");
   static_assert(!PAIR || (CL == 1 && NT == 1 && IM2COL && MODE != 2), "CTA pairs exist for the im2col fprop / dgrad only");
-  static_assert(ET == 0 || (MODE != 1 && IM2COL && CL == 1 && !PAIR), "2-byte operands: im2col fprop-type and wgrad only");
+  static_assert(ET == 0 || (MODE != 1 && IM2COL && CL == 1), "2-byte operands: im2col fprop-type and wgrad only");
+  static_assert(ET == 0 || !PAIR || MODE == 0, "2-byte CTA pairs: fprop-type only");
   static_assert(ET == 0 || MODE == 0 || ET == 2, "the 2-byte wgrad takes bf16 x bf16");
   // MN-major panels (wgrad): [K rows = pixels][128 B along M/N]; 32 tf32 or 64 2-byte elements wide, 32 / 64 pixels deep
   constexpr int PW = ET == 0 ? 32 : 64;
@@ -341,15 +342,15 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
           if (IM2COL) {
             const int ti = tap / p.ns, tj = tap - ti * p.ns;
             if (PAIR)
-              tc::tma_load_im2col_4d_2sm(stage, &tmap_g, bar, cb * 32, gw, gh, gn, (uint16_t)p.off_s[tj],
+              tc::tma_load_im2col_4d_2sm(stage, &tmap_g, bar, cb * KE, gw, gh, gn, (uint16_t)p.off_s[tj],
                                          (uint16_t)p.off_r[ti]);
             else
               tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * KE, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
             tap = p.tap_r[ti] * p.S + p.tap_s[tj];   // filter position whose weights this k-block multiplies
           }
           if (MODE == 0) {
-            if (PAIR) {   // box {32 k, BN / 2 rows}: this CTA's half of the weight tile
-              tc::tma_load_2d_2sm(stage + kABytes, &tmap, bar, tap * p.CinW + cb * 32, n0 + (int)cl_rank * (BN / 2));
+            if (PAIR) {   // box {KE k, BN / 2 rows}: this CTA's half of the weight tile
+              tc::tma_load_2d_2sm(stage + kABytes, &tmap, bar, tap * p.CinW + cb * KE, n0 + (int)cl_rank * (BN / 2));
             } else if (CL == 1) {
               tc::tma_load_2d(stage + kABytes, &tmap, bar, tap * p.CinW + cb * KE, n0);  // box {KE k, BN rows}
             } else {   // box {32 k, BN / CL rows}: this CTA's slice of the weight tile, delivered to the whole cluster
@@ -404,8 +405,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     // ===================== MMA issuer =====================
     if (lane == 0 && KB > 0 && (!PAIR || cl_rank == 0)) {
       constexpr uint32_t idesc = ET == 0 ? tc::make_idesc_tf32(PAIR ? 256 : 128, NTOT, MODE == 2 ? 1 : 0, MODE != 0 ? 1 : 0)
-                                         : tc::make_idesc_f16(128, NTOT, ET >= 2 ? 1 : 0, ET == 2 ? 1 : 0, MODE == 2 ? 1 : 0,
-                                                              MODE == 2 ? 1 : 0);
+                                         : tc::make_idesc_f16(PAIR ? 256 : 128, NTOT, ET >= 2 ? 1 : 0, ET == 2 ? 1 : 0,
+                                                              MODE == 2 ? 1 : 0, MODE == 2 ? 1 : 0);
       constexpr bool a_mn = (MODE == 2), b_mn = (MODE != 0);
       // MN-major operands: tf32 -> SWIZZLE_128B_BASE32B panels (4-row atoms); 2-byte -> plain SWIZZLE_128B panels (8-row
       // atoms, LBO = panel stride, SBO = 1024, 16 K rows per instruction; profiles/r1_umma_mn16_probe.txt)
@@ -425,7 +426,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = tc::make_smem_desc(stage + k * a_kstep, a_lbo, a_sbo, a_lay);
           const uint64_t bd = tc::make_smem_desc(stage + kABytes + k * b_kstep, b_lbo, b_sbo, b_lay);
-          if (PAIR) tc::umma_tf32_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (PAIR && ET != 0) tc::umma_f16_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          else if (PAIR) tc::umma_tf32_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           else if (ET != 0) tc::umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           else tc::umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
@@ -572,6 +574,15 @@ int conv_pair_env() {
   return v;
 }
 // tile width for `nch` output columns of the GEMM, or 0 = no pairing
+// MLA_LINEAR_PAIR=0 disables CTA pairs in the Linear-layer entry points (default on: they run on a single stream).
+bool linear_pair() {
+  static const bool v = [] {
+    const char* e = getenv("MLA_LINEAR_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  return v && !force_gather();
+}
+
 int conv_pair_bn(int nch) {
   const int e = conv_pair_env();
   if (e == 0 || force_gather()) return 0;
@@ -882,14 +893,54 @@ extern "C" int mla_linear_forward16(const void* x16, const void* w16, const floa
   full_taps(p, 1, 1, false);
   const int BN = (N % 128 == 0) ? 128 : 64;
   CUtensorMap map, gmap;
-  int rc = make_map_2d16(&map, w16, false, N, K, BN);
+  int rc = make_map_im2col16(&gmap, x16, false, 1, M, 1, K, 0, 0, 0, 0, 1, 128);
   if (rc) return rc;
-  rc = make_map_im2col16(&gmap, x16, false, 1, M, 1, K, 0, 0, 0, 0, 1, 128);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // CTA pairs (one 256 x N MMA per k-step over two SMs): the Linear layers run on ONE stream, where pair kernels are
+  // safe (see conv_pair_env); 256-column tiles where N allows. MLA_LINEAR_PAIR=0 falls back to single-CTA tiles.
+  if (linear_pair() && N % 128 == 0 && M > 128) {
+    const int BNp = (N % 256 == 0) ? 256 : 128;
+    rc = make_map_2d16(&map, w16, false, N, K, BNp / 2);
+    if (rc) return rc;
+    dim3 gp((M + 127) / 128, N / BNp);
+    return BNp == 256 ? launch<0, 256, 3, true, 1, 1, true, 1>(map, gmap, p, gp, st)
+                      : launch<0, 128, 4, true, 1, 1, true, 1>(map, gmap, p, gp, st);
+  }
+  rc = make_map_2d16(&map, w16, false, N, K, BN);
   if (rc) return rc;
   dim3 grid((M + 127) / 128, N / BN);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 1>(map, gmap, p, grid, st)
                   : launch<0, 128, 3, true, 1, 1, false, 1>(map, gmap, p, grid, st);
+}
+
+// dx [M, K] = dy [M, N] (fp32, TF32-rounded) * w [N, K] (fp32, TF32-rounded): the 1x1 case of mla_conv2d_dgrad, with CTA
+// pairs (single-stream Linear layers). K % 64 == 0, N % 64 == 0.
+extern "C" int mla_linear_dgrad(const float* dy, const float* w, float* dx, int M, int K, int N, void* stream) {
+  if (!dy || !w || !dx || !mla::aligned16(dy) || !mla::aligned16(w) || !mla::aligned16(dx)) return MLA_E_BADARG;
+  if (!conv_shape_ok(1, M, 1, K, N, 1, 1, 1, 0)) return MLA_E_SHAPE;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  ConvGemmParams p{};
+  p.src = dy; p.Hs = M; p.Ws = 1; p.Cs = N; p.OH = M; p.OW = 1; p.M = M; p.R = 1; p.S = 1;
+  p.mul = 1; p.sgn = -1; p.off = 0; p.div = 1; p.kcb = N / 32; p.KB = p.kcb; p.CinW = K;
+  p.out = dx; p.ldo = K; p.accumulate = 0; p.Cout = N;
+  full_taps(p, 1, 1, true);
+  CUtensorMap map, gmap;
+  int rc = make_map_2d(&map, w, N, K, 32, true);
+  if (rc) return rc;
+  rc = make_map_im2col(&gmap, dy, 1, M, 1, N, 0, 0, 0, 0, 1, 128, false);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int BN = (K % 128 == 0) ? 128 : 64;
+  dim3 grid((M + 127) / 128, K / BN);
+  if (linear_pair() && K % 128 == 0 && M > 128) {
+    if (K % 256 == 0) {
+      grid.y = K / 256;
+      return launch<1, 256, 3, true, 1, 1, true>(map, gmap, p, grid, st);
+    }
+    return launch<1, 128, 4, true, 1, 1, true>(map, gmap, p, grid, st);
+  }
+  return BN == 64 ? launch<1, 64, 4, true>(map, gmap, p, grid, st) : launch<1, 128, 3, true>(map, gmap, p, grid, st);
 }
 
 extern "C" int mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx, int N, int H, int W, int Cin, int Cout,

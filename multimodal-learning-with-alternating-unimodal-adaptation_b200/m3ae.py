@@ -239,8 +239,7 @@ def _linear_grads(x_r, dy_r, w, M, K, N):
     st = _lib.stream_ptr()
     w_r = _round_tf32(w)
     dx = torch.empty(M, K, dtype=torch.float32, device=dev)
-    _lib.check(L.mla_conv2d_dgrad(dy_r.data_ptr(), w_r.data_ptr(), dx.data_ptr(), 1, M, 1, K, N, 1, 1, 1, 0, 0, st),
-               "mla_conv2d_dgrad")
+    _lib.check(L.mla_linear_dgrad(dy_r.data_ptr(), w_r.data_ptr(), dx.data_ptr(), M, K, N, st), "mla_linear_dgrad")
     dw = torch.empty(N, K, dtype=torch.float32, device=dev)
     ws = _scratch(L.mla_conv2d_wgrad_workspace_bytes(1, M, 1, K, N, 1, 1, 1, 0), dev)
     _lib.check(L.mla_conv2d_wgrad(x_r.data_ptr(), dy_r.data_ptr(), dw.data_ptr(), 1, M, 1, K, N, 1, 1, 1, 0, ws.data_ptr(),
