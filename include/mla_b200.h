@@ -177,6 +177,20 @@ MLA_API int    mla_linear_forward16(const void* x16, const void* w16, const floa
  * The two Linear entry points use tcgen05 CTA pairs (256-row MMAs); they must not run concurrently with OTHER pair
  * kernels on a second stream (MLA_LINEAR_PAIR=0 selects single-CTA tiles). */
 MLA_API int    mla_linear_dgrad(const float* dy, const float* w, float* dx, int M, int K, int N, void* stream);
+/* fp16 backward of a Linear (default of the transformer paths): the gradient operand is cast to fp16 after multiplying by a
+ * power of two F chosen from its largest element (exact; fp16 then carries TF32's 10-bit mantissa at twice TF32's
+ * tensor-core rate), and the GEMM epilogues multiply by 1/F.
+ *   mla_grad_operand16: out16 [M, N] = fp16(F * v), v = dy (u == NULL) or dy * gelu'(u); colsum [N] = column sums of v (the
+ *     bias gradient); scale_io = 2 floats, [1] receives 1/F. ws from mla_round_colsum_workspace_bytes(M, N).
+ *   mla_linear_dgrad16: dx [M, K] = *out_scale * dy16 [M, N] * wt16 [K, N]^T, wt16 = mla_filter_transpose16(w, ., N, 1, K, 0).
+ *   mla_linear_wgrad16: dw [N, K] = *out_scale * dy16^T x16, x16 [M, K] fp16; ws from
+ *     mla_conv2d_wgrad16_workspace_bytes(1, M, 1, K, N, 1, 1, 1, 0). */
+MLA_API int    mla_grad_operand16(const float* dy, const float* u, void* out16, float* colsum, float* scale_io, long long M,
+                        int N, void* ws, size_t ws_bytes, void* stream);
+MLA_API int    mla_linear_dgrad16(const void* dy16, const void* wt16, const float* out_scale, float* dx, int M, int K, int N,
+                        void* stream);
+MLA_API int    mla_linear_wgrad16(const void* x16, const void* dy16, const float* out_scale, float* dw, int M, int K, int N,
+                        void* ws, size_t ws_bytes, void* stream);
 /* nn.LayerNorm over the last dimension D (D % 4 == 0, D <= 1280), biased variance, as torch. Outputs (each may be NULL):
  * y fp32, y16 fp16 (the operand of the next GEMM), y_r fp32 rounded to TF32 (the operand of that GEMM's weight
  * gradient); mean / rstd [M] are kept for the backward pass. */

@@ -53,6 +53,9 @@ _SIGNATURES = {
     "mla_attention_backward": (_c_int, [_c_void_p] * 6 + [_c_int] * 4 + [_c_float, _c_void_p, _c_size_t, _c_void_p]),
     "mla_linear_forward16": (_c_int, [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p]),
     "mla_linear_dgrad": (_c_int, [_c_void_p] * 3 + [_c_int] * 3 + [_c_void_p]),
+    "mla_grad_operand16": (_c_int, [_c_void_p] * 5 + [_c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "mla_linear_dgrad16": (_c_int, [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p]),
+    "mla_linear_wgrad16": (_c_int, [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p, _c_size_t, _c_void_p]),
     "mla_layernorm_forward": (_c_int, [_c_void_p] * 3 + [_c_float, _c_ll, _c_int] + [_c_void_p] * 6),
     "mla_layernorm_backward_workspace_bytes": (_c_size_t, [_c_ll, _c_int]),
     "mla_layernorm_backward": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 4 + [_c_size_t, _c_void_p]),

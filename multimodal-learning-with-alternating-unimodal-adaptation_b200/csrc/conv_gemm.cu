@@ -67,6 +67,9 @@ struct ConvGemmParams {
   // fprop-type launches only (Linear layers): out = acc + bias[column] + resid[row][column] (either may be NULL)
   const float* bias;
   const float* resid;
+  // every mode: the accumulator is multiplied by *out_scale (a device scalar, NULL = 1) before anything is added —
+  // undoes the power-of-two scale of fp16 gradient operands
+  const float* out_scale;
 };
 
 template <bool MN_MAJOR>
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   static_assert(!PAIR || (CL == 1 && NT == 1 && IM2COL && MODE != 2), "CTA pairs exist for the im2col fprop / dgrad only");
   static_assert(ET == 0 || (MODE != 1 && IM2COL && CL == 1), "2-byte operands: im2col fprop-type and wgrad only");
   static_assert(ET == 0 || !PAIR || MODE == 0, "2-byte CTA pairs: fprop-type only");
-  static_assert(ET == 0 || MODE == 0 || ET == 2, "the 2-byte wgrad takes bf16 x bf16");
+  static_assert(ET == 0 || MODE == 0 || ET == 2 || ET == 1, "the 2-byte wgrad takes bf16 x bf16 or fp16 x fp16");
   // MN-major panels (wgrad): [K rows = pixels][128 B along M/N]; 32 tf32 or 64 2-byte elements wide, 32 / 64 pixels deep
   constexpr int PW = ET == 0 ? 32 : 64;
   constexpr uint32_t kPanel = ET == 0 ? 4096u : 8192u;
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       }
     }
     const float* rrow = (MODE == 0 && p.resid != nullptr && orow != nullptr) ? p.resid + (long long)(m0 + row) * p.ldo + n0 : nullptr;
+    const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;
 #pragma unroll 1
     for (int c = 0; c < NTOT; c += 32) {
       if (MODE == 2 && NT == 1 && n0 + c >= p.CinW) break;   // partial last ci tile (Cin % BN == 32)
@@ -261,25 +265,41 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
       if (orow != nullptr) {
+        // every optional addend is loaded for the whole 32-column chunk BEFORE the first store, so the loads are in flight
+        // together (interleaving load / add / store per float4 serialises eight global round trips per chunk)
         float4* dst = reinterpret_cast<float4*>(orow + c);
+        float4 o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                 __uint_as_float(v[4 * j + 3]));
-          if (p.accumulate) {
-            const float4 old = dst[j];
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          if (MODE == 0 && p.bias != nullptr) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j);
-            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-          }
-          if (MODE == 0 && rrow != nullptr) {
-            const float4 rv = reinterpret_cast<const float4*>(rrow + c)[j];
-            o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-          }
-          dst[j] = o;
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3]));
+        if (p.out_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o[j].x *= oscale; o[j].y *= oscale; o[j].z *= oscale; o[j].w *= oscale; }
         }
+        if (p.accumulate) {
+          float4 old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) old[j] = dst[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o[j].x += old[j].x; o[j].y += old[j].y; o[j].z += old[j].z; o[j].w += old[j].w; }
+        }
+        if (MODE == 0 && rrow != nullptr) {
+          float4 rv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rv[j] = reinterpret_cast<const float4*>(rrow + c)[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o[j].x += rv[j].x; o[j].y += rv[j].y; o[j].z += rv[j].z; o[j].w += rv[j].w; }
+        }
+        if (MODE == 0 && p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j);
+            o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = o[j];
       }
       if (MODE == 0 && p.stat_part != nullptr) {
         // column sums over this warp's 32 rows (rows past M are exact zeros): butterfly transpose-reduce, lane j
@@ -878,8 +898,24 @@ extern "C" int mla_conv2d_fprop16(const void* x16, const void* w16, float* y, in
 
 // y [M, N] = x16 [M, K] (fp16) w16 [N, K]^T (fp16) + bias [N] + resid [M, N]: a Linear layer = the 1x1 case of fprop16
 // over an N=1 image of M x 1 pixels, with the bias / residual adds in the epilogue. K, N % 64 == 0.
+static int linear_gemm16(const void* x16, const void* w16, const float* bias, const float* resid, const float* out_scale,
+                         float* y, int M, int K, int N, void* stream);
+
 extern "C" int mla_linear_forward16(const void* x16, const void* w16, const float* bias, const float* resid, float* y, int M,
                                     int K, int N, void* stream) {
+  return linear_gemm16(x16, w16, bias, resid, nullptr, y, M, K, N, stream);
+}
+
+// dx [M, K] = *out_scale * dy16 [M, N] (fp16, scaled by a power of two) * wt16 [K, N]^T (fp16: the TRANSPOSED weight,
+// mla_filter_transpose16(w, wt16, N, 1, K, 0)): the data gradient of a Linear as the same K-major GEMM as its forward.
+extern "C" int mla_linear_dgrad16(const void* dy16, const void* wt16, const float* out_scale, float* dx, int M, int K, int N,
+                                  void* stream) {
+  if (!out_scale) return MLA_E_BADARG;
+  return linear_gemm16(dy16, wt16, nullptr, nullptr, out_scale, dx, M, N, K, stream);
+}
+
+static int linear_gemm16(const void* x16, const void* w16, const float* bias, const float* resid, const float* out_scale,
+                         float* y, int M, int K, int N, void* stream) {
   if (!x16 || !w16 || !y || !mla::aligned16(x16) || !mla::aligned16(w16) || !mla::aligned16(y) || !mla::aligned16(bias) ||
       !mla::aligned16(resid))
     return MLA_E_BADARG;
@@ -889,7 +925,7 @@ extern "C" int mla_linear_forward16(const void* x16, const void* w16, const floa
   ConvGemmParams p{};
   p.OH = M; p.OW = 1; p.M = M; p.R = 1; p.S = 1; p.mul = 1;
   p.kcb = K / 64; p.KB = p.kcb; p.CinW = K;
-  p.out = y; p.ldo = N; p.accumulate = 0; p.Cout = N; p.bias = bias; p.resid = resid;
+  p.out = y; p.ldo = N; p.accumulate = 0; p.Cout = N; p.bias = bias; p.resid = resid; p.out_scale = out_scale;
   full_taps(p, 1, 1, false);
   const int BN = (N % 128 == 0) ? 128 : 64;
   CUtensorMap map, gmap;
@@ -1105,8 +1141,24 @@ extern "C" size_t mla_conv2d_wgrad16_workspace_bytes(int N, int H, int W, int Ci
   return pl.ws_bytes + 256;
 }
 
+static int wgrad16_impl(const void* x16, const void* dy16, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
+                        int stride, int pad, void* ws, size_t ws_bytes, void* stream, bool bf16, const float* out_scale);
+
 extern "C" int mla_conv2d_wgrad16(const void* x16, const void* dy16, float* dw, int N, int H, int W, int Cin, int Cout,
                                   int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream) {
+  return wgrad16_impl(x16, dy16, dw, N, H, W, Cin, Cout, R, S, stride, pad, ws, ws_bytes, stream, true, nullptr);
+}
+
+// dw [N, K] = *out_scale * dy16 [M, N]^T (fp16, scaled by a power of two) * x16 [M, K] (fp16): the weight gradient of a
+// Linear; workspace from mla_conv2d_wgrad16_workspace_bytes(1, M, 1, K, N, 1, 1, 1, 0).
+extern "C" int mla_linear_wgrad16(const void* x16, const void* dy16, const float* out_scale, float* dw, int M, int K, int N,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  if (!out_scale) return MLA_E_BADARG;
+  return wgrad16_impl(x16, dy16, dw, 1, M, 1, K, N, 1, 1, 1, 0, ws, ws_bytes, stream, false, out_scale);
+}
+
+static int wgrad16_impl(const void* x16, const void* dy16, float* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
+                        int stride, int pad, void* ws, size_t ws_bytes, void* stream, bool bf16, const float* out_scale) {
   if (!x16 || !dy16 || !dw || !mla::aligned16(x16) || !mla::aligned16(dy16) || !mla::aligned16(dw) || !mla::aligned16(ws))
     return MLA_E_BADARG;
   WgradPlan pl;
@@ -1122,15 +1174,21 @@ extern "C" int mla_conv2d_wgrad16(const void* x16, const void* dy16, float* dw, 
   p.g_base_w = p.g_base_h = -pad;
   full_taps(p, R, S, false);
   CUtensorMap map, gmap;
-  rc = make_map_2d16(&map, dy16, true, pl.M, Cout, 64);                       // box {64 co, 64 pixel rows}
+  p.out_scale = out_scale;
+  rc = make_map_2d16(&map, dy16, bf16, pl.M, Cout, 64);                       // box {64 co, 64 pixel rows}
   if (rc) return rc;
-  rc = make_map_im2col16(&gmap, x16, true, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 64);
+  rc = make_map_im2col16(&gmap, x16, bf16, N, H, W, Cin, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, 64);
   if (rc) return rc;
   dim3 grid(Cin / pl.BN, (Cout + 127) / 128, (R * S / pl.NT) * pl.splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = pl.NT == 3 ? launch<2, 64, 2, true, 3, 1, false, 2>(map, gmap, p, grid, st)
-       : pl.BN == 64 ? launch<2, 64, 4, true, 1, 1, false, 2>(map, gmap, p, grid, st)
-                     : launch<2, 128, 3, true, 1, 1, false, 2>(map, gmap, p, grid, st);
+  if (bf16)
+    rc = pl.NT == 3 ? launch<2, 64, 2, true, 3, 1, false, 2>(map, gmap, p, grid, st)
+         : pl.BN == 64 ? launch<2, 64, 4, true, 1, 1, false, 2>(map, gmap, p, grid, st)
+                       : launch<2, 128, 3, true, 1, 1, false, 2>(map, gmap, p, grid, st);
+  else
+    rc = pl.NT == 3 ? MLA_E_SHAPE
+         : pl.BN == 64 ? launch<2, 64, 4, true, 1, 1, false, 1>(map, gmap, p, grid, st)
+                       : launch<2, 128, 3, true, 1, 1, false, 1>(map, gmap, p, grid, st);
   if (rc) return rc;
   if (pl.splits > 1) {
     const long long n4 = p.split_stride / 4;

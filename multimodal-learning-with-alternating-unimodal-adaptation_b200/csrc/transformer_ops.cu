@@ -212,6 +212,56 @@ __global__ void ew_colsum_kernel(const float* __restrict__ dy, const float* __re
   *reinterpret_cast<float4*>(part + (long long)blockIdx.y * N + c) = acc;
 }
 
+// power of two F with F * amax in [2^11, 2^12): fp16 then carries TF32's mantissa over 2^-26..1 of the largest element
+__device__ __forceinline__ float operand_scale(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);
+  return ldexpf(1.f, max(-100, min(100, 12 - e)));
+}
+
+// pass 1 of the fp16 gradient operand: part[row chunk][N] = column sums of v = dy (KIND 0) or dy * gelu'(u) (KIND 1),
+// *amax = max |v| (the caller zeroes it)
+template <int KIND>
+__global__ void colsum_amax_kernel(const float* __restrict__ dy, const float* __restrict__ u, float* __restrict__ part,
+                                   float* __restrict__ amax, long long M, int N, int rows_per_chunk) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  float mx = 0.f;
+  if (c < N) {
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+      float4 v = *reinterpret_cast<const float4*>(dy + r * N + c);
+      if (KIND == 1) {
+        const float4 uu = *reinterpret_cast<const float4*>(u + r * N + c);
+        v.x *= gelu_d(uu.x); v.y *= gelu_d(uu.y); v.z *= gelu_d(uu.z); v.w *= gelu_d(uu.w);
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    *reinterpret_cast<float4*>(part + (long long)blockIdx.y * N + c) = acc;
+  }
+  mx = mla::warp_max(mx);
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(mx));
+}
+
+// pass 2: out16 = fp16(F * v), F = operand_scale(*amax); scale_io[1] = 1 / F for the GEMM epilogues
+template <int KIND>
+__global__ void cast_scaled16_kernel(const float* __restrict__ dy, const float* __restrict__ u, uint2* __restrict__ out16,
+                                     float* __restrict__ scale_io, long long n4) {
+  const float F = operand_scale(scale_io[0]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale_io[1] = 1.f / F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = *reinterpret_cast<const float4*>(dy + 4 * i);
+    if (KIND == 1) {
+      const float4 uu = *reinterpret_cast<const float4*>(u + 4 * i);
+      v.x *= gelu_d(uu.x); v.y *= gelu_d(uu.y); v.z *= gelu_d(uu.z); v.w *= gelu_d(uu.w);
+    }
+    out16[i] = make_uint2(h2(v.x * F, v.y * F), h2(v.z * F, v.w * F));
+  }
+}
+
 int ln_blocks(long long M, int per_sm = 2) {
   const mla::DeviceInfo& di = mla::device_info();
   return (int)std::min<long long>((M + 7) / 8, (long long)di.sm_count * per_sm);
@@ -331,6 +381,36 @@ extern "C" int mla_round_colsum(const float* dy, const float* u, float* out_r, f
   else ew_colsum_kernel<0><<<grid, 256, 0, st>>>(dy, nullptr, out_r, part, M, N, rows);
   MLA_LAUNCH_OK();
   partial_reduce_kernel<<<(N + 31) / 32, 1024, 0, st>>>(part, nchunks, N, N, colsum);
+  MLA_LAUNCH_OK();
+  return 0;
+}
+
+// The dy operand of a Linear's gradient GEMMs in fp16: out16 [M, N] = fp16(F * v), v = dy or dy * gelu'(u), F the power of
+// two that puts max|v| in [2^11, 2^12); scale_io = 2 floats: [0] max|v| (scratch), [1] 1 / F (what mla_linear_dgrad16 /
+// mla_linear_wgrad16 take as out_scale); colsum [N] = column sums of v (the bias gradient). Two passes over v.
+extern "C" int mla_grad_operand16(const float* dy, const float* u, void* out16, float* colsum, float* scale_io, long long M,
+                                  int N, void* ws, size_t ws_bytes, void* stream) {
+  if (!dy || !out16 || !colsum || !scale_io || !ws || M < 1 || N < 4 || (N & 3) || !mla::aligned16(dy) || !mla::aligned16(u) ||
+      (reinterpret_cast<uintptr_t>(out16) & 7u) || !mla::aligned16(ws))
+    return MLA_E_BADARG;
+  const mla::DeviceInfo& di = mla::device_info();
+  if (di.ok != 1) return di.ok;
+  if (ws_bytes < mla_round_colsum_workspace_bytes(M, N)) return MLA_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunks = colsum_chunks(M, N);
+  const int rows = (int)((M + chunks - 1) / chunks);
+  const int nchunks = (int)((M + rows - 1) / rows);
+  float* part = static_cast<float*>(ws);
+  MLA_CUDA_TRY(cudaMemsetAsync(scale_io, 0, sizeof(float), st));
+  dim3 grid((N + 1023) / 1024, nchunks);
+  if (u != nullptr) colsum_amax_kernel<1><<<grid, 256, 0, st>>>(dy, u, part, scale_io, M, N, rows);
+  else colsum_amax_kernel<0><<<grid, 256, 0, st>>>(dy, nullptr, part, scale_io, M, N, rows);
+  MLA_LAUNCH_OK();
+  partial_reduce_kernel<<<(N + 31) / 32, 1024, 0, st>>>(part, nchunks, N, N, colsum);
+  MLA_LAUNCH_OK();
+  const long long n4 = M * N / 4;
+  if (u != nullptr) cast_scaled16_kernel<1><<<ew_grid(n4), 256, 0, st>>>(dy, u, static_cast<uint2*>(out16), scale_io, n4);
+  else cast_scaled16_kernel<0><<<ew_grid(n4), 256, 0, st>>>(dy, nullptr, static_cast<uint2*>(out16), scale_io, n4);
   MLA_LAUNCH_OK();
   return 0;
 }

@@ -166,24 +166,28 @@ class _AttentionFn(torch.autograd.Function):
 # (csrc/transformer_ops.cu). False: the per-module path above (same arithmetic up to summation order), which also offers
 # BACKWARD_BF16.
 FUSED_BLOCK = True
+# Backward GEMM operands of the fused block. "fp16": x in fp16 (the copy the forward GEMM already consumed) and dy in fp16
+# after an exact power-of-two scale taken from max|dy| (mla_grad_operand16) — TF32's 10-bit mantissa at the full fp16
+# tensor-core rate, nothing kept in fp32 for the backward GEMMs. "tf32": TF32-rounded fp32 operands (half the rate).
+BLOCK_BACKWARD = "fp16"
 
 
 def _scratch(nbytes, dev):
     return _Workspace.get(nbytes, dev)
 
 
-def _ln_fwd(x2, w, b, eps, want_y=False):
+def _ln_fwd(x2, w, b, eps, want_y=False, want_r=True):
     L = _lib.lib()
     M, D = x2.shape
     dev = x2.device
     y = torch.empty(M, D, dtype=torch.float32, device=dev) if want_y else None
     y16 = None if want_y else torch.empty(M, D, dtype=torch.float16, device=dev)
-    y_r = None if want_y else torch.empty(M, D, dtype=torch.float32, device=dev)
+    y_r = None if (want_y or not want_r) else torch.empty(M, D, dtype=torch.float32, device=dev)
     mean = torch.empty(M, dtype=torch.float32, device=dev)
     rstd = torch.empty(M, dtype=torch.float32, device=dev)
     _lib.check(L.mla_layernorm_forward(x2.data_ptr(), w.data_ptr(), b.data_ptr(), eps, M, D,
                                        y.data_ptr() if want_y else None, None if want_y else y16.data_ptr(),
-                                       None if want_y else y_r.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                       y_r.data_ptr() if y_r is not None else None, mean.data_ptr(), rstd.data_ptr(),
                                        _lib.stream_ptr()), "mla_layernorm_forward")
     return y, y16, y_r, mean, rstd
 
@@ -212,12 +216,43 @@ def _linear16(x16, w, bias, resid, M, K, N):
     return y
 
 
-def _cast_round(x2, gelu):
+def _cast_round(x2, gelu, want_r=True):
     x16 = torch.empty(x2.shape, dtype=torch.float16, device=x2.device)
-    x_r = torch.empty_like(x2)
-    _lib.check(_lib.lib().mla_cast_round(x2.data_ptr(), x16.data_ptr(), x_r.data_ptr(), x2.numel(), 1 if gelu else 0,
-                                         _lib.stream_ptr()), "mla_cast_round")
+    x_r = torch.empty_like(x2) if want_r else None
+    _lib.check(_lib.lib().mla_cast_round(x2.data_ptr(), x16.data_ptr(), x_r.data_ptr() if want_r else None, x2.numel(),
+                                         1 if gelu else 0, _lib.stream_ptr()), "mla_cast_round")
     return x16, x_r
+
+
+def _grad_operand16(dy2, u):
+    """fp16(F * dy [* gelu'(u)]) with F a power of two from max|.|, the bias gradient, and the device scalar 1/F."""
+    L = _lib.lib()
+    M, N = dy2.shape
+    dev = dy2.device
+    out = torch.empty(M, N, dtype=torch.float16, device=dev)
+    col = torch.empty(N, dtype=torch.float32, device=dev)
+    sc = torch.empty(4, dtype=torch.float32, device=dev)
+    ws = _scratch(L.mla_round_colsum_workspace_bytes(M, N), dev)
+    _lib.check(L.mla_grad_operand16(dy2.data_ptr(), u.data_ptr() if u is not None else None, out.data_ptr(), col.data_ptr(),
+                                    sc.data_ptr(), M, N, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mla_grad_operand16")
+    return out, col, sc[1:]
+
+
+def _linear_grads16(x16, dy16, inv_scale, w, M, K, N):
+    """dx [M, K] = dy w, dw [N, K] = dy^T x from fp16 operands (dy16 = F * dy, results multiplied by 1/F in the epilogues)."""
+    L = _lib.lib()
+    dev = dy16.device
+    st = _lib.stream_ptr()
+    wt16 = torch.empty(K, N, dtype=torch.float16, device=dev)
+    _lib.check(L.mla_filter_transpose16(w.data_ptr(), wt16.data_ptr(), N, 1, K, 0, st), "mla_filter_transpose16")
+    dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+    _lib.check(L.mla_linear_dgrad16(dy16.data_ptr(), wt16.data_ptr(), inv_scale.data_ptr(), dx.data_ptr(), M, K, N, st),
+               "mla_linear_dgrad16")
+    dw = torch.empty(N, K, dtype=torch.float32, device=dev)
+    ws = _scratch(L.mla_conv2d_wgrad16_workspace_bytes(1, M, 1, K, N, 1, 1, 1, 0), dev)
+    _lib.check(L.mla_linear_wgrad16(x16.data_ptr(), dy16.data_ptr(), inv_scale.data_ptr(), dw.data_ptr(), M, K, N,
+                                    ws.data_ptr(), ws.numel(), st), "mla_linear_wgrad16")
+    return dx, dw
 
 
 def _round_colsum(dy2, u):
@@ -259,9 +294,9 @@ class _BlockFn(torch.autograd.Function):
         x2 = x.reshape(M, D)
         if x2.dtype != torch.float32 or not x2.is_contiguous():
             x2 = x2.float().contiguous()
-        _, h16, h_r, mu1, rs1 = _ln_fwd(x2, g1, b1, eps1)
+        f16 = BLOCK_BACKWARD == "fp16"
+        _, h16, h_r, mu1, rs1 = _ln_fwd(x2, g1, b1, eps1, want_r=not f16)
         qkv = _linear16(h16, wq, bq, None, M, D, 3 * D)
-        del h16
         ao = torch.empty(M, D, dtype=torch.float32, device=dev)
         stats = torch.empty(B, H, S, 2, dtype=torch.float32, device=dev)
         qkv16 = torch.empty(M, 3 * D, dtype=torch.float16, device=dev)
@@ -269,16 +304,17 @@ class _BlockFn(torch.autograd.Function):
                                            stats.data_ptr(), qkv16.data_ptr(), B, S, H, Dh, scale, _lib.stream_ptr()),
                    "mla_attention_forward")
         del qkv
-        ao16, ao_r = _cast_round(ao, False)
+        ao16, ao_r = _cast_round(ao, False, want_r=not f16)
         x1 = _linear16(ao16, wo, bo, x2, M, D, D)
-        del ao16
-        _, h2_16, h2_r, mu2, rs2 = _ln_fwd(x1, g2, b2, eps2)
+        _, h2_16, h2_r, mu2, rs2 = _ln_fwd(x1, g2, b2, eps2, want_r=not f16)
         u = _linear16(h2_16, w1, c1, None, M, D, 4 * D)
-        del h2_16
-        g16, g_r = _cast_round(u, True)
+        g16, g_r = _cast_round(u, True, want_r=not f16)
         y = _linear16(g16, w2, c2, x1, M, 4 * D, D)
-        ctx.save_for_backward(x2, mask, mu1, rs1, h_r, qkv16, stats, ao, ao_r, x1, mu2, rs2, h2_r, u, g_r,
+        # the x operands of the four weight gradients: the fp16 copies the forward GEMMs consumed, or TF32-rounded fp32
+        ops = (h16, ao16, h2_16, g16) if f16 else (h_r, ao_r, h2_r, g_r)
+        ctx.save_for_backward(x2, mask, mu1, rs1, ops[0], qkv16, stats, ao, ops[1], x1, mu2, rs2, ops[2], u, ops[3],
                               g1, wq, wo, g2, w1, w2)
+        ctx.f16 = f16
         ctx.cfg = (B, S, D, H, scale)
         return y.view(B, S, D)
 
@@ -292,25 +328,38 @@ class _BlockFn(torch.autograd.Function):
         dy2 = dy.reshape(M, D)
         if dy2.dtype != torch.float32 or not dy2.is_contiguous():
             dy2 = dy2.float().contiguous()
+        if ctx.f16:
+            def operand(t, uu):                       # -> (fp16 operand, 1/F), bias gradient
+                o16, col, inv = _grad_operand16(t, uu)
+                return (o16, inv), col
+
+            def grads(x_op, d_op, w, K, N):
+                return _linear_grads16(x_op, d_op[0], d_op[1], w, M, K, N)
+        else:
+            def operand(t, uu):                       # -> (TF32-rounded operand, None), bias gradient
+                r, col = _round_colsum(t, uu)
+                return (r, None), col
+
+            def grads(x_op, d_op, w, K, N):
+                return _linear_grads(x_op, d_op[0], w, M, K, N)
         # MLP: y = x1 + fc2(gelu(fc1(LN2(x1))))
-        dy_r, dc2 = _round_colsum(dy2, None)
-        dg, dw2 = _linear_grads(g_r, dy_r, w2, M, 4 * D, D)
-        du_r, dc1 = _round_colsum(dg, u)
+        d_op, dc2 = operand(dy2, None)
+        dg, dw2 = grads(g_r, d_op, w2, 4 * D, D)
+        d_op, dc1 = operand(dg, u)
         del dg
-        dh2, dw1 = _linear_grads(h2_r, du_r, w1, M, D, 4 * D)
-        del du_r
+        dh2, dw1 = grads(h2_r, d_op, w1, D, 4 * D)
         dx1, dg2, db2 = _ln_bwd(dh2, x1, mu2, rs2, g2, dy2)
         # attention: x1 = x + fc(attn(qkv(LN1(x))))
-        d_r, dbo = _round_colsum(dx1, None)
-        dao, dwo = _linear_grads(ao_r, d_r, wo, M, D, D)
+        d_op, dbo = operand(dx1, None)
+        dao, dwo = grads(ao_r, d_op, wo, D, D)
         dqkv = torch.empty(M, 3 * D, dtype=torch.float32, device=dev)
         ws = torch.empty(L.mla_attention_backward_workspace_bytes(B, S, H, Dh), dtype=torch.uint8, device=dev)
         _lib.check(L.mla_attention_backward(qkv16.data_ptr(), mask.data_ptr() if mask is not None else None, ao.data_ptr(),
                                             dao.data_ptr(), stats.data_ptr(), dqkv.data_ptr(), B, S, H, Dh, scale,
                                             ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mla_attention_backward")
-        dq_r, dbq = _round_colsum(dqkv, None)
+        d_op, dbq = operand(dqkv, None)
         del dqkv
-        dh1, dwq = _linear_grads(h_r, dq_r, wq, M, D, 3 * D)
+        dh1, dwq = grads(h_r, d_op, wq, D, 3 * D)
         dx, dg1, db1 = _ln_bwd(dh1, x2, mu1, rs1, g1, dx1)
         return (dx.view(B, S, D), None, None, None, None, None, dg1, db1, dwq, dbq, dwo, dbo, dg2, db2, dw1, dc1, dw2, dc2)
 

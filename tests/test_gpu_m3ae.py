@@ -319,8 +319,39 @@ def test_linear_epilogue_bias_and_residual(built_lib, M, K, N):
     assert relf(y2.cpu(), (ref + bias.double() + resid.double()).cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("M,K,N,scale", [(771, 768, 2304, 3e-6), (1026, 3072, 768, 40.0), (48, 64, 192, 1e-9), (130, 768, 64, 1.0)])
+def test_fp16_scaled_linear_backward(built_lib, M, K, N, scale):
+    """mla_grad_operand16 + mla_linear_dgrad16 / mla_linear_wgrad16: gradients of any magnitude (here 1e-9 .. 40, with
+    three decades of spread inside the tensor) through fp16 operands and an exact power-of-two scale, against fp64."""
+    from mla_b200 import m3ae
+    gen = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=gen).cuda()
+    w = (torch.randn(N, K, generator=gen) * 0.05).cuda()
+    dy = (torch.randn(M, N, generator=gen) * scale * torch.logspace(-3, 0, M, dtype=torch.float32)[:, None]).cuda()
+    u = (torch.randn(M, N, generator=gen) * 1.5).cuda()
+    x16 = x.half()
+    for uu in (None, u):
+        d16, col, inv = m3ae._grad_operand16(dy, uu)
+        dx, dw = m3ae._linear_grads16(x16, d16, inv, w, M, K, N)
+        torch.cuda.synchronize()
+        v = dy.double()
+        if uu is not None:
+            u64 = uu.double().requires_grad_(True)
+            torch.nn.functional.gelu(u64).backward(dy.double())
+            v = u64.grad
+        F = 1.0 / float(inv[0])
+        amax = float(v.abs().max())
+        assert 2048 <= F * amax < 4096.001 and F == 2.0 ** round(np.log2(F))
+        e = (relf(d16.float().cpu() / F, v.cpu()), relf(col.cpu(), v.sum(0).cpu()), relf(dx.cpu(), (v @ w.double()).cpu()),
+             relf(dw.cpu(), (v.t() @ x16.double()).cpu()))
+        print("fp16-scaled backward M=%d K=%d N=%d |dy|~%.0e gelu=%s: operand %.2e colsum %.2e dx %.2e dW %.2e" % (
+            (M, K, N, scale, uu is not None) + e))
+        assert e[0] < 4e-4 and e[1] < 1e-5 and e[2] < 1e-3 and e[3] < 1e-3
+
+
+@pytest.mark.parametrize("bwd", ["fp16", "tf32"])
 @pytest.mark.parametrize("B,S,D,H,masked", [(2, 513, 768, 12, True), (3, 17, 64, 2, False)])
-def test_fused_block_matches_per_module_path(built_lib, B, S, D, H, masked):
+def test_fused_block_matches_per_module_path(built_lib, B, S, D, H, masked, bwd):
     """_BlockFn (one node, hand-written backward) against the per-module autograd path of the same Block and against the
     oracle's fp32 restatement of the block on this GPU: output, input gradient and every parameter gradient."""
     from mla_b200 import m3ae
@@ -337,8 +368,8 @@ def test_fused_block_matches_per_module_path(built_lib, B, S, D, H, masked):
         mask = (torch.arange(S)[None, :] >= n_valid[:, None]).float().cuda()
 
     def run(fused):
-        prev = m3ae.FUSED_BLOCK
-        m3ae.FUSED_BLOCK = fused
+        prev = m3ae.FUSED_BLOCK, m3ae.BLOCK_BACKWARD
+        m3ae.FUSED_BLOCK, m3ae.BLOCK_BACKWARD = fused, bwd
         try:
             blk.zero_grad()
             xi = x.clone().requires_grad_(True)
@@ -347,7 +378,7 @@ def test_fused_block_matches_per_module_path(built_lib, B, S, D, H, masked):
             torch.cuda.synchronize()
             return y.detach(), xi.grad.clone(), {k: v.grad.clone() for k, v in blk.named_parameters()}
         finally:
-            m3ae.FUSED_BLOCK = prev
+            m3ae.FUSED_BLOCK, m3ae.BLOCK_BACKWARD = prev
 
     yf, dxf, gf = run(True)
     ym, dxm, gm = run(False)

@@ -46,14 +46,15 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n, losses
 
-    for fused, bf16 in ((True, False), (False, False), (False, True)):
-        m3ae.FUSED_BLOCK, m3ae.BACKWARD_BF16 = fused, bf16
+    for fused, bwd in ((True, "fp16"), (True, "tf32"), (False, "tf32"), (False, "bf16")):
+        m3ae.FUSED_BLOCK, m3ae.BLOCK_BACKWARD, m3ae.BACKWARD_BF16 = fused, bwd if fused else "fp16", bwd == "bf16"
         run(2)
+        torch.cuda.reset_peak_memory_stats()
         ms, losses = run(steps)
         print("%s base B=%d %s backward=%s: %.2f ms/step, %.1f samples/s, peak mem %.1f GB, losses %s" % (
-            "modal3" if modal3 else "m3ae", B, "fused blocks" if fused else "per-module", "bf16" if bf16 else "tf32", ms,
+            "modal3" if modal3 else "m3ae", B, "fused blocks" if fused else "per-module", bwd, ms,
             B * 1000.0 / ms, torch.cuda.max_memory_allocated() / 2**30, tuple(round(x, 4) for x in losses)), flush=True)
-    m3ae.FUSED_BLOCK, m3ae.BACKWARD_BF16 = True, False
+    m3ae.FUSED_BLOCK, m3ae.BLOCK_BACKWARD, m3ae.BACKWARD_BF16 = True, "fp16", False
     if profile:
         from torch.profiler import profile as tprof, ProfilerActivity
         loader = Loader(B, 2, 1)
