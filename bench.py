@@ -35,6 +35,7 @@ def parse():
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-sweep", action="store_true")
+    p.add_argument("--no-extra", action="store_true", help="skip the informational transformer-path timings (N=1 only)")
     return p.parse_args()
 
 
@@ -356,7 +357,53 @@ def run_native(a, rank, world):
         out["gs_sweep"] = pts
     if not a.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline()
+    if not a.no_extra and world == 1:
+        out["other_workloads"] = other_workloads(torch)
     print(json.dumps(out), flush=True)
+
+
+def other_workloads(torch, steps=3):
+    """Informational, N = 1 only, outside the timed region of the headline metric: step time of the other parity
+    configurations of BASELINE.json through the same public API (train_epoch), device-resident synthetic inputs.
+    configs[2] = m3ae 'base' image-text pair, configs[3] = three-modality model; B = 64, S = 257 (+512 audio tokens)."""
+    import argparse
+    import contextlib
+    import io
+    import mla_b200
+    from mla_b200.main import SyntheticTextImageLoader
+    res = {}
+    for name, modal3 in (("configs[2] m3ae image-text", False), ("configs[3] three-modality", True)):
+        try:
+            args = argparse.Namespace(dataset="IEMOCAP" if modal3 else "Food101", fusion_method="concat", modulation="Normal",
+                                      gs_flag=True, dynamic=True, lorb="m3ae", modal3=modal3, clip=False)
+            mla_b200.setup_seed(0)
+            net = mla_b200.Modal3Classifier(args) if modal3 else mla_b200.M3AEClassifier(args)
+            model = mla_b200.ModuleHolder(net.cuda())
+            opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+            sch = torch.optim.lr_scheduler.StepLR(opt, 70, 0.1)
+            gs = mla_b200.GSPlugin()
+            dev = torch.device("cuda")
+
+            def run(n):
+                loader = SyntheticTextImageLoader(BATCH, n, 1, n_classes=4 if modal3 else 101, audio_len=1024 if modal3 else 0)
+                loader.batches = [tuple(t.cuda() if torch.is_tensor(t) else t for t in b) for b in loader.batches]
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    mla_b200.train_epoch(args, 0, model, dev, loader, opt, sch, gs_plugin=gs, gs_flag=True, av_alpha=0.55)
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / n
+            run(2)
+            ms = run(steps)
+            res[name] = {"ms_per_step": ms, "samples_per_s": BATCH * 1e3 / ms, "batch": BATCH, "steps": steps,
+                         "encoders": "m3ae base x2" + (" + CAV-MAE audio" if modal3 else "")}
+            del model, net, opt
+            torch.cuda.empty_cache()
+        except Exception as exc:                                      # informational only: never lose the headline line
+            res[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    return res
 
 
 def start_watchdog(limit_s):

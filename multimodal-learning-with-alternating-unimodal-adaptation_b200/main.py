@@ -173,7 +173,8 @@ def main(av_alpha=0.5):
                          a_alpha=args.a_alpha, v_alpha=args.v_alpha, t_alpha=args.t_alpha)
             if rank == 0:
                 print("Loss: {:.4f}, Acc: {:.4f}, Acc_a: {:.4f}, Acc_v: {:.4f}".format(losses[0], accs[0], accs[1],
-                                                                                       accs[2]))
+                                                                                       accs[2])
+                      + (", Acc_t: {:.4f}".format(accs[3]) if len(accs) > 3 else ""))
                 if accs[0] > best_acc:
                     best_acc = float(accs[0])
                     os.makedirs(args.ckpt_path, exist_ok=True)
