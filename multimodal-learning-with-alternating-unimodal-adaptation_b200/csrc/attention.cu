@@ -192,15 +192,15 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(AttnParams p) {
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
-    const float c0 = expf(m0 - n0), c1 = expf(m1 - n1);
+    const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);
     m0 = n0; m1 = n1;
     l0 *= c0; l1 *= c1;
 #pragma unroll
     for (int j = 0; j < NT; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j][0] = expf(s[j][0] - n0); s[j][1] = expf(s[j][1] - n0);
-      s[j][2] = expf(s[j][2] - n1); s[j][3] = expf(s[j][3] - n1);
+      s[j][0] = __expf(s[j][0] - n0); s[j][1] = __expf(s[j][1] - n0);
+      s[j][2] = __expf(s[j][2] - n1); s[j][3] = __expf(s[j][3] - n1);
       l0 += s[j][0] + s[j][1]; l1 += s[j][2] + s[j][3];
     }
 #pragma unroll
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(AttnParams p) {
         const float st = Kstc[j * 8 + 2 * t + (e & 1)];
         const float M = e < 2 ? M0 : M1, I = e < 2 ? I0 : I1, D = e < 2 ? D0 : D1;
         // padded keys hold the CONSTANT -1e7 (torch.where): no gradient flows to their scores
-        const float pr = st == 0.f ? expf(s[j][e] * p.scale - M) * I : 0.f;
+        const float pr = st == 0.f ? __expf(s[j][e] * p.scale - M) * I : 0.f;
         s[j][e] = pr * (dp[j][e] - D) * p.scale;
       }
     }
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(AttnParams p) {
         const int q = j * 8 + 2 * t + (e & 1);
         const float st = e < 2 ? st0 : st1;
         float pr = 0.f;
-        if (st != 2.f) pr = expf((st == 0.f ? s[j][e] * p.scale : -1e7f) - Mc[q]) * Mc[kTile + q];
+        if (st != 2.f) pr = __expf((st == 0.f ? s[j][e] * p.scale : -1e7f) - Mc[q]) * Mc[kTile + q];
         s[j][e] = pr;
         dp[j][e] = st == 0.f ? pr * (dp[j][e] - Mc[2 * kTile + q]) * p.scale : 0.f;
       }
