@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(AttnParams p) {
 // (rows = keys): S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
 // --------------------------------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(AttnParams p) {
+__global__ void __launch_bounds__(kThreads, 3) attn_bwd_dkv_kernel(AttnParams p) {
   constexpr int LD = DH + 8, NK = DH / 16, NT = DH / 8, TS = kTile * LD;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __half* Ks = reinterpret_cast<__half*>(sm_raw);
