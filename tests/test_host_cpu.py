@@ -34,6 +34,37 @@ def test_argument_errors_do_not_need_a_gpu(built_lib):
     assert L.mla_gs_project(None, None, None, 1.0, 0.1, None, 4, 64, 6, 0, None, 0, None) == -1
     assert L.mla_head_ce(None, None, None, None, 4, 64, 6, None, None, None, None, None, None, 1.0, None, 0, None) == -1
     assert L.mla_head_ce_workspace_bytes(0, 64, 6) == 0
+    # transformer entry points: NULL / misaligned pointers and bad shapes are rejected before any CUDA call
+    assert L.mla_attention_forward(None, None, None, None, None, 2, 16, 2, 64, 0.125, None) == -1
+    assert L.mla_attention_backward(None, None, None, None, None, None, 2, 16, 2, 64, 0.125, None, 0, None) == -1
+    assert L.mla_attention_backward_workspace_bytes(2, 16, 2, 48) == 0            # head width must be 32 or 64
+    assert L.mla_attention_backward_workspace_bytes(2, 16, 2, 64) >= (2 * 2 * 16 + 4) * 4 + 2 * 16 * 2 * 64 * 2
+    assert L.mla_linear_forward16(None, None, None, None, None, 128, 64, 64, None) == -1
+    assert L.mla_linear_dgrad16(None, None, None, None, 128, 64, 64, None) == -1
+    assert L.mla_linear_wgrad16(None, None, None, None, 128, 64, 64, None, 0, None) == -1
+    assert L.mla_linear_dgrad(None, None, None, 128, 64, 64, None) == -1
+    assert L.mla_layernorm_forward(None, None, None, 1e-5, 8, 64, None, None, None, None, None, None) == -1
+    assert L.mla_layernorm_backward(None, None, None, None, None, None, 8, 64, None, None, None, None, 0, None) == -1
+    assert L.mla_cast_round(None, None, None, 64, 0, None) == -1
+    assert L.mla_round_colsum(None, None, None, None, 8, 64, None, 0, None) == -1
+    assert L.mla_grad_operand16(None, None, None, None, None, 8, 64, None, 0, None) == -1
+
+
+def test_transformer_host_mirrors_refuse_out_of_scope_configurations():
+    import argparse
+    import mla_b200
+    from mla_b200.main import build_model
+    ok = dict(dataset="Food101", fusion_method="concat", modulation="Normal", gs_flag=True, dynamic=True, lorb="m3ae",
+              modal3=False, clip=False)
+    for bad in (dict(fusion_method="sum"), dict(gs_flag=False), dict(modulation="QMF"), dict(dataset="AVE")):
+        with pytest.raises(NotImplementedError):
+            mla_b200.M3AEClassifier(argparse.Namespace(**{**ok, **bad}), model_config=dict(model_type=None, emb_dim=64, depth=1,
+                                                                                           num_heads=2), text_vocab_size=16)
+    with pytest.raises(NotImplementedError):                                       # Modal3Classifier knows IEMOCAP only
+        mla_b200.Modal3Classifier(argparse.Namespace(**{**ok, "modal3": True}))
+    for bad in (dict(lorb="large"), dict(clip=True)):                               # CAVClassifier / CLIPClassifier
+        with pytest.raises(NotImplementedError):
+            build_model(argparse.Namespace(**{**ok, **bad, "ckpt_load_path_train": None}), "cpu")
 
 
 def test_no_cpu_fallback(built_lib):
