@@ -311,7 +311,7 @@ def run_native(a, rank, world):
     out = {"metric": "MLA train samples/sec (CREMA-D AV, ResNet-18)", "value": value, "unit": "samples/s",
            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f16+tf32" if encoder_engine.USE_F16 else "tf32", "data": "synthetic",
+           "dtype": ("f16" if encoder_engine.STEM_F16 else "f16+tf32") if encoder_engine.USE_F16 else "tf32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                       "encoder_backend": encoder_engine.BACKEND, "gs_projection": "fires (force_projection)",
                       "streams": ("audio / visual encoders on two CUDA streams" if overlap else "single stream") +
@@ -335,7 +335,7 @@ def run_native(a, rank, world):
                       for k, v in conv["by_kind"].items())
         peak = conv["flops"] / t_ideal / 1e12
         ach = conv["flops"] / conv["seconds"] / 1e12
-        out["roofline"] = {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, im2col-TMA fed; kind::f16 fprop/dgrad, kind::tf32 wgrad/stem)",
+        out["roofline"] = {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, im2col-TMA fed; kind::f16: fp16 fprop, bf16 dgrad/wgrad, stem included)",
                            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                            "traffic": prof.get("conv_traffic"),
                            "peak_source": "FLOP-weighted blend of bf16_tflops_sustained (f16 launches) and 0.5x (tf32 launches), "

@@ -237,6 +237,10 @@ MLA_API int    mla_round_colsum(const float* dy, const float* u, float* out_r, f
 MLA_API int    mla_stem_im2col(const float* in, float* col, int N, int T, long long sB, long long sT,
                         long long sC, int Cin, int H, int W, int R, int S, int stride, int pad, int Kp,
                         void* stream);
+/* The same matrix as 2-byte copies: col16 fp16 (the fprop16 operand) and col16b bf16 (the wgrad16 operand; may be NULL,
+ * e.g. in evaluation). Kp % 64 == 0. */
+MLA_API int    mla_stem_im2col16(const float* in, void* col16, void* col16b, int N, int T, long long sB, long long sT,
+                        long long sC, int Cin, int H, int W, int R, int S, int stride, int pad, int Kp, void* stream);
 /* dst = round-to-nearest-TF32(src), n % 4 == 0 (weights before they feed the tensor cores). */
 MLA_API int    mla_round_tf32(const float* src, float* dst, long long n, void* stream);
 MLA_API int    mla_pad_rows(const float* src, float* dst, int rows, int k, int kp, int unpad, void* stream);

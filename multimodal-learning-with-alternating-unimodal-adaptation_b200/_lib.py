@@ -63,6 +63,7 @@ _SIGNATURES = {
     "mla_round_colsum_workspace_bytes": (_c_size_t, [_c_ll, _c_int]),
     "mla_round_colsum": (_c_int, [_c_void_p] * 4 + [_c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "mla_stem_im2col": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_ll, _c_ll] + [_c_int] * 8 + [_c_void_p]),
+    "mla_stem_im2col16": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_ll, _c_ll] + [_c_int] * 8 + [_c_void_p]),
     "mla_round_tf32": (_c_int, [_c_void_p, _c_void_p, _c_ll, _c_void_p]),
     "mla_pad_rows": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "mla_bn_workspace_bytes": (_c_size_t, [_c_ll, _c_int]),

@@ -88,7 +88,11 @@ __global__ void filter_transpose16_kernel(const float* __restrict__ w, unsigned 
 // One block per output row (n, oh): the R input rows of every channel are staged in shared memory
 // (coalesced, zero-padded left/right/top/bottom), a k -> offset table replaces the per-element
 // div/mod, and the row's OW x Kp outputs leave as coalesced float4 stores. HBM-bound by the col write.
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ in, float* __restrict__ col, int T,
+// OUT16: the matrix leaves as an fp16 copy (fprop16 operand) and, when col16b != NULL, a bf16 copy (wgrad16 operand)
+// instead of TF32-rounded fp32.
+template <bool OUT16>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ in, float* __restrict__ col,
+                                                          uint2* __restrict__ col16, uint2* __restrict__ col16b, int T,
                                                           long long sB, long long sT, long long sC, int Cin, int H, int W,
                                                           int OH, int OW, int R, int S, int stride, int pad, int K, int Kp) {
   extern __shared__ __align__(16) float sm[];
@@ -111,11 +115,12 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     const int h = oh * stride + r - pad, w = wp - pad;
     float v = 0.f;
     if (h >= 0 && h < H && w >= 0 && w < W) v = src[(long long)ci * sC + (long long)h * W + w];
-    sm[i] = tf32r(v);
+    sm[i] = OUT16 ? v : tf32r(v);
   }
   __syncthreads();
   const int K4 = Kp >> 2;
-  float* dst = col + (long long)blockIdx.x * OW * Kp;
+  float* dst = OUT16 ? nullptr : col + (long long)blockIdx.x * OW * Kp;
+  const long long base4 = (long long)blockIdx.x * OW * K4;
   for (int i = threadIdx.x; i < OW * K4; i += blockDim.x) {
     const int ow = i / K4, k = (i - ow * K4) * 4;
     const int base = ow * stride;
@@ -125,7 +130,12 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     v.y = o.y >= 0 ? sm[o.y + base] : 0.f;
     v.z = o.z >= 0 ? sm[o.z + base] : 0.f;
     v.w = o.w >= 0 ? sm[o.w + base] : 0.f;
-    st4(dst + 4 * (long long)i, v);
+    if (OUT16) {
+      col16[base4 + i] = pack_h4(v);
+      if (col16b != nullptr) col16b[base4 + i] = pack_b4(v);
+    } else {
+      st4(dst + 4 * (long long)i, v);
+    }
   }
 }
 
@@ -535,22 +545,41 @@ int red_plan(long long M, int C, RedPlan* pl) {
   MLA_CUDA_TRY(cudaGetLastError());   \
   mla::count_launch()
 
-extern "C" int mla_stem_im2col(const float* in, float* col, int N, int T, long long sB, long long sT, long long sC, int Cin,
-                               int H, int W, int R, int S, int stride, int pad, int Kp, void* stream) {
-  if (!in || !col || N < 1 || T < 1 || Cin < 1 || Kp < R * S * Cin || (Kp & 3) || !mla::aligned16(col)) return MLA_E_BADARG;
+static int stem_im2col_impl(const float* in, float* col, void* col16, void* col16b, int N, int T, long long sB, long long sT,
+                            long long sC, int Cin, int H, int W, int R, int S, int stride, int pad, int Kp, void* stream) {
+  if (!in || N < 1 || T < 1 || Cin < 1 || Kp < R * S * Cin || (Kp & 3)) return MLA_E_BADARG;
   const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
   if (OH < 1 || OW < 1) return MLA_E_SHAPE;
   const size_t smem = ((((size_t)Cin * R * (W + 2 * pad + 2) + 3) & ~(size_t)3) + (size_t)Kp) * sizeof(float);
   if (smem > 200 * 1024) return MLA_E_SHAPE;
   static std::atomic<int> cfg{0};
   if (!cfg.load()) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MLA_CUDA_TRY(cudaFuncSetAttribute(stem_im2col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MLA_CUDA_TRY(cudaFuncSetAttribute(stem_im2col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cfg.store(1);
   }
-  stem_im2col_kernel<<<N * OH, 256, smem, static_cast<cudaStream_t>(stream)>>>(in, col, T, sB, sT, sC, Cin, H, W, OH, OW, R, S,
-                                                                              stride, pad, R * S * Cin, Kp);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (col16 != nullptr)
+    stem_im2col_kernel<true><<<N * OH, 256, smem, st>>>(in, nullptr, static_cast<uint2*>(col16), static_cast<uint2*>(col16b), T,
+                                                       sB, sT, sC, Cin, H, W, OH, OW, R, S, stride, pad, R * S * Cin, Kp);
+  else
+    stem_im2col_kernel<false><<<N * OH, 256, smem, st>>>(in, col, nullptr, nullptr, T, sB, sT, sC, Cin, H, W, OH, OW, R, S,
+                                                        stride, pad, R * S * Cin, Kp);
   MLA_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mla_stem_im2col(const float* in, float* col, int N, int T, long long sB, long long sT, long long sC, int Cin,
+                               int H, int W, int R, int S, int stride, int pad, int Kp, void* stream) {
+  if (!col || !mla::aligned16(col)) return MLA_E_BADARG;
+  return stem_im2col_impl(in, col, nullptr, nullptr, N, T, sB, sT, sC, Cin, H, W, R, S, stride, pad, Kp, stream);
+}
+
+extern "C" int mla_stem_im2col16(const float* in, void* col16, void* col16b, int N, int T, long long sB, long long sT,
+                                 long long sC, int Cin, int H, int W, int R, int S, int stride, int pad, int Kp, void* stream) {
+  if (!col16 || (reinterpret_cast<uintptr_t>(col16) & 7u) || (reinterpret_cast<uintptr_t>(col16b) & 7u) || (Kp & 63))
+    return MLA_E_BADARG;
+  return stem_im2col_impl(in, nullptr, col16, col16b, N, T, sB, sT, sC, Cin, H, W, R, S, stride, pad, Kp, stream);
 }
 
 extern "C" int mla_round_tf32(const float* src, float* dst, long long n, void* stream) {

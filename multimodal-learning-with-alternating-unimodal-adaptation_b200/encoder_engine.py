@@ -28,6 +28,10 @@ USE_GRAPHS = os.environ.get("MLA_GRAPHS", "1") != "0"               # replay the
 _OVERLAP_WGRAD = os.environ.get("MLA_OVERLAP_WGRAD", "1") != "0"    # wgrad kernels on a side stream of the plan
 _USE_RELU_MASK = os.environ.get("MLA_RELU_MASK", "1") != "0"      # A/B switch (bitmask vs reading the activation)
 _STEM_KP = {1: 64, 3: 160}     # K = 49*Cin padded to a multiple of 32 (tcgen05 k-blocks of 32 tf32)
+_STEM_KP16 = {1: 64, 3: 192}   # ... to a multiple of 64 (k-blocks of 64 2-byte elements)
+# 2-byte stem: the im2col matrix leaves as fp16 (fprop16) + bf16 (wgrad16) copies instead of TF32 fp32, the stem GEMMs
+# run at the kind::f16 rate, and BN backward writes dy in bf16 only. Needs USE_F16.
+STEM_F16 = True
 
 
 def _p(t):
@@ -140,19 +144,25 @@ class ResNetPlan:
         self.flat, self.wr, self.woff = net._mla_flat, net._mla_wr, net._mla_off
         self._params = list(net.parameters())
         # ---- stem
-        self.Kp = _STEM_KP[Cin]
+        self.f16 = USE_F16
+        self.stem16 = bool(USE_F16 and STEM_F16)
+        self.Kp = (_STEM_KP16 if self.stem16 else _STEM_KP)[Cin]
         self.OH0, self.OW0 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         self.PH, self.PW = (self.OH0 + 2 - 3) // 2 + 1, (self.OW0 + 2 - 3) // 2 + 1
         self.M0 = N * self.OH0 * self.OW0
         e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)   # noqa: E731
-        self.col = e(self.M0, self.Kp)
+        half = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)          # noqa: E731
+        bhalf = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)        # noqa: E731
+        if self.stem16:
+            self.col = None
+            self.col16, self.col16b = half(self.M0, self.Kp), bhalf(self.M0, self.Kp)
+            self.wpad16 = half(64, self.Kp)
+        else:
+            self.col = e(self.M0, self.Kp)
         self.wpad = e(64, self.Kp)
         self.dwpad = e(64, self.Kp)
         self.y0 = e(N, self.OH0, self.OW0, 64)
         self.p0 = e(N, self.PH, self.PW, 64)
-        self.f16 = USE_F16
-        half = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)          # noqa: E731
-        bhalf = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)        # noqa: E731
         self.p0_16 = half(N, self.PH, self.PW, 64) if self.f16 else None
         self.p0_b = bhalf(N, self.PH, self.PW, 64) if self.f16 else None            # bf16 copy: wgrad16 x operand
         self.w16 = torch.empty(self.flat.numel(), dtype=torch.float16, device=dev) if self.f16 else None     # fp16 weights
@@ -194,7 +204,8 @@ class ResNetPlan:
                                           for b in self.blocks]),
                                      dtype=torch.float32, device=dev)          # per-tile BN partial sums (fprop epilogue)
         self.bn_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)      # ticket counters start at 0 (mla_b200.h)
-        nw = self.L.mla_conv2d_wgrad_workspace_bytes(N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
+        nw = (self.L.mla_conv2d_wgrad16_workspace_bytes if self.stem16 else self.L.mla_conv2d_wgrad_workspace_bytes)(
+            N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
         for b in self.blocks:
             nw = max(nw, self.L.mla_conv2d_wgrad_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3,
                                                                   b["stride"], 1),
@@ -297,7 +308,7 @@ class ResNetPlan:
         t = _conv_timer_begin()
         _chk(self.L.mla_conv2d_wgrad16(_p(x16b), _p(dy16), _p(dw), N, H, W, Cin, Cout, R, R, stride, pad, _p(self.wg_ws),
                                        self.wg_ws.numel(), st), "mla_conv2d_wgrad16")
-        _conv_timer_end(t, "wgrad16", N, H, W, Cin, Cout, R, stride, pad)
+        _conv_timer_end(t, "wgrad16", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
 
     def _bn_coeffs(self, y, M, b, training, st):
         bn = b.bn
@@ -369,8 +380,12 @@ class ResNetPlan:
         else:                              # [B,1,H,W]
             sB, sT, sC = self.Cin * HW, 0, HW
         # the only launch that reads the caller's buffer (its address changes from batch to batch): outside the graph
-        _chk(L.mla_stem_im2col(_p(x), _p(self.col), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp,
-                               st), "mla_stem_im2col")
+        if self.stem16:
+            _chk(L.mla_stem_im2col16(_p(x), _p(self.col16), _p(self.col16b) if training else None, N, self.T, sB, sT, sC,
+                                     self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp, st), "mla_stem_im2col16")
+        else:
+            _chk(L.mla_stem_im2col(_p(x), _p(self.col), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp,
+                                   st), "mla_stem_im2col")
         self._run(("fwd", bool(training)), lambda: self._forward_body(training))
         self.trained_forward = training
         return self.feat_static.clone()
@@ -380,9 +395,27 @@ class ResNetPlan:
         net = self.net
         K = 49 * self.Cin
         _chk(L.mla_round_tf32(_p(self.flat), _p(self.wr), self.flat.numel(), st), "mla_round_tf32")
-        _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
-        self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
-                      k_alg=K)
+        if self.stem16:
+            # the stem as an fp16 GEMM over the fp16 im2col matrix (same 10-bit operand mantissa as the TF32 path)
+            _chk(L.mla_pad_rows(_p(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
+            _chk(L.mla_cast16(_p(self.wpad), _p(self.wpad16), self.wpad.numel(), 0, st), "mla_cast16")
+            t = _conv_timer_begin()
+            _chk(L.mla_conv2d_fprop16(_p(self.col16), _p(self.wpad16), _p(self.y0), N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0,
+                                      _p(self.stat_part) if training else None, st), "mla_conv2d_fprop16")
+            _conv_timer_end(t, "fprop16", N, self.OH0, self.OW0, K, 64, 1, 1, 0)
+            if training:
+                bn = self.bn0.bn
+                _chk(L.mla_bn_stats_from_partials(_p(self.stat_part), (self.M0 + 127) // 128, self.M0, 64, _p(bn.weight),
+                                                  _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.momentum),
+                                                  float(bn.eps), _p(self.bn0.mean), _p(self.bn0.invstd), _p(self.bn0.scale),
+                                                  _p(self.bn0.shift), _p(self.bn_ws), self.bn_ws.numel(), st),
+                     "mla_bn_stats_from_partials")
+            else:
+                self._bn_coeffs(self.y0, 0, self.bn0, False, st)
+        else:
+            _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
+            self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
+                          k_alg=K)
         _chk(L.mla_bn_relu_maxpool_ex(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.p0_16),
                                       _p(self.p0_b) if training else None, _p(self.idx0), N, self.OH0, self.OW0, 64, st),
              "mla_bn_relu_maxpool")
@@ -480,7 +513,7 @@ class ResNetPlan:
                 wsm.wait_event(ready)
             with torch.cuda.stream(wsm):
                 if two_byte:
-                    self._wgrad16(x, dy, dw, *geom, wst)
+                    self._wgrad16(x, dy, dw, *geom, wst, k_alg=k_alg)
                 else:
                     self._wgrad(x, dy, dw, *geom, wst, k_alg=k_alg)
             if wsm is not cur:
@@ -555,9 +588,15 @@ class ResNetPlan:
         g0 = self.tmp("g0", self.y0.shape)
         _chk(L.mla_maxpool_relu_backward(_p(dout), _p(self.p0), _p(self.idx0), _p(g0), N, self.OH0, self.OW0, 64, st),
              "mla_maxpool_relu_backward")
-        dy0 = buf("dy0", self.y0.shape)
-        self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, dy0, None, st)
-        wgrad_async(self.col, dy0, "dy0", self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, k_alg=49 * self.Cin)
+        if self.stem16:
+            dy0 = buf16("dy0", self.y0.shape)            # bf16 only: nothing reads the stem's dy in fp32
+            self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, None, None, st, dy16=dy0)
+            wgrad_async(self.col16b, dy0, "dy0", self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, k_alg=49 * self.Cin,
+                        two_byte=True)
+        else:
+            dy0 = buf("dy0", self.y0.shape)
+            self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, dy0, None, st)
+            wgrad_async(self.col, dy0, "dy0", self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, k_alg=49 * self.Cin)
         with torch.cuda.stream(wsm):
             _chk(L.mla_pad_rows(_p(self.dwpad), _p(_grad_buffer(net.conv1.weight)), 64, 49 * self.Cin, self.Kp, 1, wst),
                  "mla_pad_rows")
