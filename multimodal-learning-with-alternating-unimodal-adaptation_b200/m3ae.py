@@ -36,13 +36,18 @@ _SIZES = {  # emb_dim, depth, heads (m3ae.py:226-270)
 
 
 class _Workspace:
-    buf = None
+    """Grow-only device scratch, one buffer per (device, CUDA stream): the kernels that use it are ordered on their stream,
+    and two streams never share a buffer."""
+    bufs = {}
 
     @classmethod
     def get(cls, nbytes, device):
-        if cls.buf is None or cls.buf.numel() < nbytes or cls.buf.device != device:
-            cls.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        return cls.buf
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        buf = cls.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            cls.bufs[key] = buf
+        return buf
 
 
 def _cast16(x, bf16):

@@ -1,9 +1,14 @@
+#!/bin/bash
+# ncu launch list of ONE alternating step in single-stream mode (per-launch durations must not include a co-running
+# kernel; graphs off so that every launch is listed). Run on the GPU box:   bash tests/tools/ncu_step.sh
+# Then:  python tests/tools/launch_summary.py gpurun_out/step_launches.csv   (or the per-step slicing in DESIGN.md section 6)
+# Keep the launch count bounded (-c): bench.py also runs e2e / eval / instrumented passes, and an unbounded ncu run of all of
+# them takes >10 minutes.
 set -e
 export MLA_OVERLAP=0 MLA_OVERLAP_WGRAD=0 MLA_GRAPHS=0
-timeout 200 python bench.py --steps 2 --warmup 3 --no-sweep --no-cpu-baseline --no-extra > gpurun_out/f7_plain_ss.json 2> gpurun_out/f7_plain_ss.err
+timeout 200 python bench.py --steps 1 --warmup 3 --no-sweep --no-cpu-baseline --no-extra > gpurun_out/step_plain_ss.json 2> gpurun_out/step_plain_ss.err
 echo plain rc=$?
-python -c "
-import json; d=json.load(open('gpurun_out/f7_plain_ss.json')); print('single-stream plain', d['ms_per_step'], d['gpu_launches'])"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/f7_launches.csv python bench.py --steps 2 --warmup 3 --no-sweep --no-cpu-baseline --no-extra > gpurun_out/f7_ncu.log 2>&1
-echo ncu rc=$?
-wc -l gpurun_out/f7_launches.csv
+# 3 warm-up steps + 1 timed step ~ 2100 launches including model set-up: -c 2400 stops right after them
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 2400 --csv --log-file gpurun_out/step_launches.csv \
+  python bench.py --steps 1 --warmup 3 --no-sweep --no-cpu-baseline --no-extra > gpurun_out/step_ncu.log 2>&1 || true
+wc -l gpurun_out/step_launches.csv
