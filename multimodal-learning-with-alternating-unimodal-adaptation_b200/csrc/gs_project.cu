@@ -18,7 +18,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kGT = 8;        // grad rows staged per tile in phase C
 constexpr int kChunk = 1024;  // columns held in registers per pass of phase C (8 float4/lane)
