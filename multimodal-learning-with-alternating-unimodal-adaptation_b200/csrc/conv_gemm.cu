@@ -898,6 +898,370 @@ extern "C" int mla_conv2d_fprop16(const void* x16, const void* w16, float* y, in
 
 // y [M, N] = x16 [M, K] (fp16) w16 [N, K]^T (fp16) + bias [N] + resid [M, N]: a Linear layer = the 1x1 case of fprop16
 // over an N=1 image of M x 1 pixels, with the bias / residual adds in the epilogue. K, N % 64 == 0.
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent Linear GEMM (fp16 x fp16 -> fp32): y [M, N] = *out_scale * x16 [M, K] w16 [N, K]^T + bias + resid.
+// One CTA per SM walks 128 x 256 output tiles (m fastest, so the CTAs of a wave share the weight tile in L2). The
+// accumulator is double-buffered in TMEM (2 x 256 of the 512 columns): the four epilogue warps drain tile i (tcgen05.ld ->
+// scale / bias / residual -> fp32 stores) while the MMA warp already accumulates tile i + 1 — at K = 768 the epilogue of a
+// tile costs as much as its main loop, and in the one-tile-per-CTA kernel above the two never overlap inside a CTA.
+// warp 4 = TMA producer (2-D tiled maps, SWIZZLE_128B, 4 stages of 16 + 32 KB), warp 5 = MMA issuer, warps 0-3 = epilogue.
+namespace {
+constexpr int kLinStages = 4;
+constexpr int kLinBN = 256;
+constexpr uint32_t kLinABytes = 128 * 128, kLinBBytes = kLinBN * 128, kLinStageBytes = kLinABytes + kLinBBytes;
+
+struct LinearParams {
+  float* out;
+  const float* bias;
+  const float* resid;
+  const float* out_scale;
+  int M, N, KB, tiles_m, tiles;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) linear_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                             const __grid_constant__ CUtensorMap tmap_b,
+                                                                             LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kLinStages];
+  __shared__ __align__(8) uint64_t empty_bar[kLinStages];
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLinStages; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&acc_full_bar[b]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty_bar[b]), 4);     // one arrive per epilogue warp
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap_a);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 5) {
+    tc::tmem_alloc(tc::smem_u32(&tmem_slot), 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int KB = p.KB;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;                                           // k-blocks issued so far (ring position)
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.tiles_m) * 128, n0 = (tile / p.tiles_m) * kLinBN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % kLinStages;
+          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((it / kLinStages) & 1) ^ 1);
+          const uint32_t stage = tiles + s * kLinStageBytes;
+          const uint32_t bar = tc::smem_u32(&full_bar[s]);
+          tc::mbar_arrive_expect_tx(bar, kLinStageBytes);
+          tc::tma_load_2d(stage, &tmap_a, bar, kb * 64, m0);                 // box {64 k, 128 rows}
+          tc::tma_load_2d(stage + kLinABytes, &tmap_b, bar, kb * 64, n0);    // box {64 k, 256 rows}
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_f16(128, kLinBN, 0, 0, 0, 0);
+      int it = 0, nt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++nt) {
+        const int buf = nt & 1;
+        tc::mbar_wait(tc::smem_u32(&acc_empty_bar[buf]), ((nt >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
+        tc::tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)buf * kLinBN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % kLinStages;
+          tc::mbar_wait(tc::smem_u32(&full_bar[s]), (it / kLinStages) & 1);
+          tc::tc_fence_after();
+          const uint32_t stage = tiles + s * kLinStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = tc::make_smem_desc(stage + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            const uint64_t bd = tc::make_smem_desc(stage + kLinABytes + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            tc::umma_f16(acc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+        }
+        tc::umma_commit(tc::smem_u32(&acc_full_bar[buf]));
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0-3: TMEM lanes warp * 32 .. + 31 = rows of the tile =====================
+    const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;
+    int nt = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++nt) {
+      const int buf = nt & 1;
+      const int m0 = (tile % p.tiles_m) * 128, n0 = (tile / p.tiles_m) * kLinBN;
+      tc::mbar_wait(tc::smem_u32(&acc_full_bar[buf]), (nt >> 1) & 1);
+      tc::tc_fence_after();
+      const int row = m0 + warp * 32 + lane;
+      float* orow = row < p.M ? p.out + (long long)row * p.N + n0 : nullptr;
+      const float* rrow = (p.resid != nullptr && row < p.M) ? p.resid + (long long)row * p.N + n0 : nullptr;
+      const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * kLinBN;
+#pragma unroll 1
+      for (int c = 0; c < kLinBN; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(acc + c, v);
+        tc::tmem_ld_wait();
+        if (orow != nullptr) {
+          float4 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+          if (p.out_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x *= oscale; o[j].y *= oscale; o[j].z *= oscale; o[j].w *= oscale; }
+          }
+          if (rrow != nullptr) {
+            float4 rv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = reinterpret_cast<const float4*>(rrow + c)[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x += rv[j].x; o[j].y += rv[j].y; o[j].z += rv[j].z; o[j].w += rv[j].w; }
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j);
+              o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
+            }
+          }
+          float4* dst = reinterpret_cast<float4*>(orow + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = o[j];
+        }
+      }
+      // every tcgen05.ld of this buffer has completed (wait::ld above): hand it back to the MMA warp
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty_bar[buf]));
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// The same persistent scheme on CTA PAIRS (cta_group::2): a pair walks 256 x 256 tiles; each CTA stages its own 128 rows
+// of x and HALF of the weight tile (32 KB per k-block instead of 48 for the same MMA work: the operand stream from L2 is
+// what bounds these GEMMs), the leader issues one 256 x 256 x 16 MMA per k-step, both CTAs drain their 128 accumulator
+// rows. Accumulator hand-back: all 8 epilogue warps of the pair arrive on the LEADER's barrier.
+constexpr int kPairStages = 6;
+constexpr uint32_t kPairStageBytes = 128 * 128 + 128 * 128;   // 128 rows of x + 128 rows of w
+
+__global__ void __launch_bounds__(kThreads, 1) linear_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                       const __grid_constant__ CUtensorMap tmap_b,
+                                                                       LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kPairStages];
+  __shared__ __align__(8) uint64_t empty_bar[kPairStages];
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t rank = tc::cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPairStages; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&acc_full_bar[b]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty_bar[b]), 8);     // 4 epilogue warps of each CTA of the pair
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap_a);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 5) {
+    tc::tmem_alloc2(tc::smem_u32(&tmem_slot), 512);
+    tc::tmem_relinquish2();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int KB = p.KB;
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = cluster; tile < p.tiles; tile += nclusters) {
+        const int m0 = (tile % p.tiles_m) * 256 + (int)rank * 128, n0 = (tile / p.tiles_m) * kLinBN + (int)rank * 128;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % kPairStages;
+          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((it / kPairStages) & 1) ^ 1);
+          const uint32_t stage = tiles + s * kPairStageBytes;
+          const uint32_t bar = tc::smem_u32(&full_bar[s]);
+          if (rank == 0) tc::mbar_arrive_expect_tx(bar, 2u * kPairStageBytes);       // both CTAs' bytes land on the leader
+          tc::tma_load_2d_2sm(stage, &tmap_a, bar, kb * 64, m0);                     // box {64 k, 128 rows}
+          tc::tma_load_2d_2sm(stage + 128 * 128, &tmap_b, bar, kb * 64, n0);         // box {64 k, 128 rows}: half tile
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_f16(256, kLinBN, 0, 0, 0, 0);
+      int it = 0, nt = 0;
+      for (int tile = cluster; tile < p.tiles; tile += nclusters, ++nt) {
+        const int buf = nt & 1;
+        tc::mbar_wait(tc::smem_u32(&acc_empty_bar[buf]), ((nt >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)buf * kLinBN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % kPairStages;
+          tc::mbar_wait(tc::smem_u32(&full_bar[s]), (it / kPairStages) & 1);
+          tc::tc_fence_after();
+          const uint32_t stage = tiles + s * kPairStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = tc::make_smem_desc(stage + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            const uint64_t bd = tc::make_smem_desc(stage + 128 * 128 + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            tc::umma_f16_2sm(acc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit_2sm(tc::smem_u32(&empty_bar[s]), (uint16_t)3);
+        }
+        tc::umma_commit_2sm(tc::smem_u32(&acc_full_bar[buf]), (uint16_t)3);
+      }
+    }
+  } else {
+    const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;
+    int nt = 0;
+    for (int tile = cluster; tile < p.tiles; tile += nclusters, ++nt) {
+      const int buf = nt & 1;
+      const int m0 = (tile % p.tiles_m) * 256 + (int)rank * 128, n0 = (tile / p.tiles_m) * kLinBN;
+      tc::mbar_wait(tc::smem_u32(&acc_full_bar[buf]), (nt >> 1) & 1);
+      tc::tc_fence_after();
+      const int row = m0 + warp * 32 + lane;
+      float* orow = row < p.M ? p.out + (long long)row * p.N + n0 : nullptr;
+      const float* rrow = (p.resid != nullptr && row < p.M) ? p.resid + (long long)row * p.N + n0 : nullptr;
+      const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * kLinBN;
+#pragma unroll 1
+      for (int c = 0; c < kLinBN; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(acc + c, v);
+        tc::tmem_ld_wait();
+        if (orow != nullptr) {
+          float4 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+          if (p.out_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x *= oscale; o[j].y *= oscale; o[j].z *= oscale; o[j].w *= oscale; }
+          }
+          if (rrow != nullptr) {
+            float4 rv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = reinterpret_cast<const float4*>(rrow + c)[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x += rv[j].x; o[j].y += rv[j].y; o[j].z += rv[j].z; o[j].w += rv[j].w; }
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + j);
+              o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
+            }
+          }
+          float4* dst = reinterpret_cast<float4*>(orow + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = o[j];
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_leader(tc::smem_u32(&acc_empty_bar[buf]));
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();                       // no CTA exits while its peer can still signal its barriers / read its smem
+  if (warp == 5) tc::tmem_dealloc2(tmem_base, 512);
+}
+
+int launch_linear_pair(const void* x16, const void* w16, const float* bias, const float* resid, const float* out_scale,
+                       float* y, int M, int K, int N, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc = make_map_2d16(&ma, x16, false, M, K, 128);
+  if (rc) return rc;
+  rc = make_map_2d16(&mb, w16, false, N, K, 128);
+  if (rc) return rc;
+  constexpr size_t smem = (size_t)kPairStages * kPairStageBytes + 1024;
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_acquire)) {
+    MLA_CUDA_TRY(cudaFuncSetAttribute(linear_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured.store(1, std::memory_order_release);
+  }
+  LinearParams p{};
+  p.out = y; p.bias = bias; p.resid = resid; p.out_scale = out_scale; p.M = M; p.N = N; p.KB = K / 64;
+  p.tiles_m = (M + 255) / 256;
+  p.tiles = p.tiles_m * (N / kLinBN);
+  const int nclusters = std::max(1, std::min(p.tiles, mla::device_info().sm_count / 2));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, linear_gemm_pair_kernel, ma, mb, p));
+  mla::count_launch();
+  return 0;
+}
+
+// MLA_LINEAR_PERSISTENT: 1 (default) = persistent single-CTA kernel (no clusters: safe next to any other stream),
+// 2 = persistent CTA pairs (same speed on B200: 62.3 vs 62.2 ms per m3ae step at B = 64), 0 = the one-tile-per-CTA kernels
+// (67.6 ms).
+int linear_persistent() {
+  static const int v = [] {
+    const char* e = getenv("MLA_LINEAR_PERSISTENT");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+int launch_linear_persistent(const void* x16, const void* w16, const float* bias, const float* resid, const float* out_scale,
+                             float* y, int M, int K, int N, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc = make_map_2d16(&ma, x16, false, M, K, 128);
+  if (rc) return rc;
+  rc = make_map_2d16(&mb, w16, false, N, K, kLinBN);
+  if (rc) return rc;
+  constexpr size_t smem = (size_t)kLinStages * kLinStageBytes + 1024;
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_acquire)) {
+    MLA_CUDA_TRY(cudaFuncSetAttribute(linear_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured.store(1, std::memory_order_release);
+  }
+  LinearParams p{};
+  p.out = y; p.bias = bias; p.resid = resid; p.out_scale = out_scale; p.M = M; p.N = N; p.KB = K / 64;
+  p.tiles_m = (M + 127) / 128;
+  p.tiles = p.tiles_m * (N / kLinBN);
+  const int grid = std::min(p.tiles, mla::device_info().sm_count);
+  linear_gemm_persistent_kernel<<<grid, kThreads, smem, st>>>(ma, mb, p);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  return 0;
+}
+}  // namespace
+
 static int linear_gemm16(const void* x16, const void* w16, const float* bias, const float* resid, const float* out_scale,
                          float* y, int M, int K, int N, void* stream);
 
@@ -927,11 +1291,15 @@ static int linear_gemm16(const void* x16, const void* w16, const float* bias, co
   p.kcb = K / 64; p.KB = p.kcb; p.CinW = K;
   p.out = y; p.ldo = N; p.accumulate = 0; p.Cout = N; p.bias = bias; p.resid = resid; p.out_scale = out_scale;
   full_taps(p, 1, 1, false);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (linear_persistent() == 2 && N % kLinBN == 0 && M > 128 && !force_gather())
+    return launch_linear_pair(x16, w16, bias, resid, out_scale, y, M, K, N, st);
+  if (linear_persistent() == 1 && N % kLinBN == 0 && M >= 128)
+    return launch_linear_persistent(x16, w16, bias, resid, out_scale, y, M, K, N, st);
   const int BN = (N % 128 == 0) ? 128 : 64;
   CUtensorMap map, gmap;
   int rc = make_map_im2col16(&gmap, x16, false, 1, M, 1, K, 0, 0, 0, 0, 1, 128);
   if (rc) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   // CTA pairs (one 256 x N MMA per k-step over two SMs): the Linear layers run on ONE stream, where pair kernels are
   // safe (see conv_pair_env); 256-column tiles where N allows. MLA_LINEAR_PAIR=0 falls back to single-CTA tiles.
   if (linear_pair() && N % 128 == 0 && M > 128) {

@@ -1,7 +1,7 @@
 """Step time of the --lorb m3ae --gs_flag path ('base' encoders, Food-101 shapes) through train_epoch, next to the oracle's
 torch restatement on the same GPU (what the reference's own code would cost), plus a per-kernel breakdown.
 
-    python tests/tools/m3ae_time.py [B=32] [steps=4] [profile=0|1] [eager=0|1] [modal3=0|1]
+    python tests/tools/m3ae_time.py [B=32] [steps=4] [profile=0|1] [eager=0|1] [modal3=0|1] [only_default=0|1]
 """
 import argparse
 import os
@@ -46,7 +46,8 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n, losses
 
-    for fused, bwd in ((True, "fp16"), (True, "tf32"), (False, "tf32"), (False, "bf16")):
+    only_default = bool(int(sys.argv[6])) if len(sys.argv) > 6 else False
+    for fused, bwd in ((True, "fp16"), (True, "tf32"), (False, "tf32"), (False, "bf16"))[:1 if only_default else 4]:
         m3ae.FUSED_BLOCK, m3ae.BLOCK_BACKWARD, m3ae.BACKWARD_BF16 = fused, bwd if fused else "fp16", bwd == "bf16"
         run(2)
         torch.cuda.reset_peak_memory_stats()
