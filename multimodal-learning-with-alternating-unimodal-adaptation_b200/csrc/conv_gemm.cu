@@ -865,6 +865,209 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Persistent 2-byte implicit-GEMM convolution (the fprop-type launches: fprop16 and dgrad16): the same producer / MMA /
+// epilogue roles as conv_gemm_kernel<0, BN, STAGES, true, 1, 1, false, ET>, but a CTA walks several 128 x BN output tiles and
+// the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (fp32 stores, the accumulating read
+// of dgrad, the BatchNorm partial sums of fprop) overlaps the im2col TMA + MMA main loop of tile i + 1. KB > 0 required.
+namespace {
+template <int BN, int STAGES, int ET>
+__global__ void __launch_bounds__(kThreads) conv16_persistent_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                     const __grid_constant__ CUtensorMap tmap_g, ConvGemmParams p,
+                                                                     int tiles_m, int tiles) {
+  constexpr uint32_t kBBytes = BN * 128, kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_stat[4 * 2 * BN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_tiles = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&acc_full_bar[b]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty_bar[b]), 4);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap);
+    tc::tma_prefetch_desc(&tmap_g);
+  }
+  if (warp == 5) {
+    tc::tmem_alloc(tc::smem_u32(&tmem_slot), 2 * BN);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int KB = p.KB;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * 128, n0 = (tile / tiles_m) * BN;
+        const int ow = m0 % p.OW, t = m0 / p.OW;
+        const int gw = ow * p.mul + p.g_base_w, gh = (t % p.OH) * p.mul + p.g_base_h, gn = t / p.OH;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((it / STAGES) & 1) ^ 1);
+          const uint32_t stage = smem_tiles + s * kStageBytes;
+          const uint32_t bar = tc::smem_u32(&full_bar[s]);
+          const int tap = kb / p.kcb, cb = kb - tap * p.kcb;
+          const int ti = tap / p.ns, tj = tap - ti * p.ns;
+          tc::mbar_arrive_expect_tx(bar, kStageBytes);
+          tc::tma_load_im2col_4d(stage, &tmap_g, bar, cb * 64, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
+          tc::tma_load_2d(stage + kABytes, &tmap, bar, (p.tap_r[ti] * p.S + p.tap_s[tj]) * p.CinW + cb * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_f16(128, BN, ET >= 2 ? 1 : 0, ET == 2 ? 1 : 0, 0, 0);
+      int it = 0, nt = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++nt) {
+        const int buf = nt & 1;
+        tc::mbar_wait(tc::smem_u32(&acc_empty_bar[buf]), ((nt >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)buf * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(tc::smem_u32(&full_bar[s]), (it / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint32_t stage = smem_tiles + s * kStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = tc::make_smem_desc(stage + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            const uint64_t bd = tc::make_smem_desc(stage + kABytes + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            tc::umma_f16(acc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+        }
+        tc::umma_commit(tc::smem_u32(&acc_full_bar[buf]));
+      }
+    }
+  } else {
+    int nt = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++nt) {
+      const int buf = nt & 1;
+      const int bx = tile % tiles_m;
+      const int m0 = bx * 128, n0 = (tile / tiles_m) * BN;
+      tc::mbar_wait(tc::smem_u32(&acc_full_bar[buf]), (nt >> 1) & 1);
+      tc::tc_fence_after();
+      const int m = m0 + warp * 32 + lane;
+      float* orow = nullptr;
+      if (m < p.M) {
+        long long orow_idx = m;
+        if (p.o_mul > 1) {
+          const int j = m % p.OW;
+          const int t = m / p.OW;
+          orow_idx = ((long long)(t / p.OH) * p.o_H + (t % p.OH) * p.o_mul + p.o_ph) * p.o_W + j * p.o_mul + p.o_pw;
+        }
+        orow = p.out + orow_idx * p.ldo + n0;
+      }
+      const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(acc + c, v);
+        tc::tmem_ld_wait();
+        if (orow != nullptr) {
+          float4* dst = reinterpret_cast<float4*>(orow + c);
+          float4 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+          if (p.accumulate) {
+            float4 old[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) old[j] = dst[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x += old[j].x; o[j].y += old[j].y; o[j].z += old[j].z; o[j].w += old[j].w; }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = o[j];
+        }
+        if (p.stat_part != nullptr) {      // BatchNorm partial sums of this warp's 32 rows (see conv_gemm_kernel)
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(v[j]); b[j] = a[j] * a[j]; }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float sa = up ? a[i] : a[i + off], ka = up ? a[i + off] : a[i];
+              const float sb = up ? b[i] : b[i + off], kb2 = up ? b[i + off] : b[i];
+              a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+              b[i] = kb2 + __shfl_xor_sync(0xffffffffu, sb, off);
+            }
+          }
+          s_stat[(warp * 2 + 0) * BN + c + lane] = a[0];
+          s_stat[(warp * 2 + 1) * BN + c + lane] = b[0];
+        }
+      }
+      // the accumulator buffer has been read completely: hand it back before the (slower) statistics write-out
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty_bar[buf]));
+      if (p.stat_part != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+        for (int t = threadIdx.x; t < BN; t += 128) {
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { sa += s_stat[(w * 2 + 0) * BN + t]; sb += s_stat[(w * 2 + 1) * BN + t]; }
+          float* dstp = p.stat_part + (size_t)bx * 2 * p.Cout + n0 + t;
+          dstp[0] = sa;
+          dstp[p.Cout] = sb;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_stat is rewritten by the next tile
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// MLA_CONV_PERSIST=0 goes back to one tile per CTA for fprop16 / dgrad16. Default on: fprop16 301 -> 381 TF/s, dgrad16
+// 316 -> 378 TF/s, ResNet step 9.6 -> 8.8 ms (gpurun_out/f8_bench_*.json).
+bool conv_persist() {
+  static const bool v = [] {
+    const char* e = getenv("MLA_CONV_PERSIST");
+    return e != nullptr ? e[0] == '1' : true;
+  }();
+  return v && !force_gather();
+}
+
+template <int BN, int STAGES, int ET>
+int launch_conv16_persistent(const CUtensorMap& map, const CUtensorMap& gmap, const ConvGemmParams& p, int n_tiles_n,
+                             cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (kABytes + BN * 128) + 1024;
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_acquire)) {
+    MLA_CUDA_TRY(cudaFuncSetAttribute(conv16_persistent_kernel<BN, STAGES, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    configured.store(1, std::memory_order_release);
+  }
+  const int tiles_m = (p.M + 127) / 128, tiles = tiles_m * n_tiles_n;
+  const int grid = std::min(tiles, 2 * mla::device_info().sm_count);       // two CTAs per SM (96 KB of stages each)
+  conv16_persistent_kernel<BN, STAGES, ET><<<grid, kThreads, smem, st>>>(map, gmap, p, tiles_m, tiles);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  return 0;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
 // 2-byte operand convolutions (kind::f16, fp32 accumulate). fprop16: x fp16, w fp16 [Cout][R][S][Cin]. dgrad16: dy bf16,
 // wt bf16 = the TRANSPOSED filter [Cin][R][S][Cout], which makes dgrad the same K-major GEMM as fprop (flipped taps,
 // stride-2 by output parity classes) — no MN-major operand. fp16 has TF32's 10-bit mantissa, so fprop16 multiplies
@@ -892,6 +1095,9 @@ extern "C" int mla_conv2d_fprop16(const void* x16, const void* w16, float* y, in
   if (rc) return rc;
   dim3 grid((p.M + 127) / 128, Cout / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (conv_persist() && p.KB > 0)
+    return BN == 64 ? launch_conv16_persistent<64, 4, 1>(map, gmap, p, Cout / BN, st)
+                    : launch_conv16_persistent<128, 3, 1>(map, gmap, p, Cout / BN, st);
   return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 1>(map, gmap, p, grid, st)
                   : launch<0, 128, 3, true, 1, 1, false, 1>(map, gmap, p, grid, st);
 }
@@ -1365,6 +1571,9 @@ extern "C" int mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx,
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto go = [&](const ConvGemmParams& q, dim3 g) {
+    if (conv_persist() && q.KB > 0)
+      return BN == 64 ? launch_conv16_persistent<64, 4, 2>(map, gmap, q, (int)g.y, st)
+                      : launch_conv16_persistent<128, 3, 2>(map, gmap, q, (int)g.y, st);
     return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 2>(map, gmap, q, g, st)
                     : launch<0, 128, 3, true, 1, 1, false, 2>(map, gmap, q, g, st);
   };
