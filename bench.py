@@ -335,7 +335,7 @@ def run_native(a, rank, world):
                       for k, v in conv["by_kind"].items())
         peak = conv["flops"] / t_ideal / 1e12
         ach = conv["flops"] / conv["seconds"] / 1e12
-        out["roofline"] = {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, im2col-TMA fed; kind::f16: fp16 fprop, bf16 dgrad/wgrad, stem included)",
+        out["roofline"] = {"kernel": "conv16_persistent_kernel (fprop16 / dgrad16) + conv_gemm_kernel (wgrad16): tcgen05 implicit GEMM, im2col-TMA fed, kind::f16 (fp16 fprop, bf16 dgrad/wgrad, stem included)",
                            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                            "traffic": prof.get("conv_traffic"),
                            "peak_source": "FLOP-weighted blend of bf16_tflops_sustained (f16 launches) and 0.5x (tf32 launches), "
