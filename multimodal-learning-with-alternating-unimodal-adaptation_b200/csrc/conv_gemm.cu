@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads) conv16_persistent_kernel(const __gri
 }
 
 // MLA_CONV_PERSIST=0 goes back to one tile per CTA for fprop16 / dgrad16. Default on: fprop16 301 -> 381 TF/s, dgrad16
-// 316 -> 378 TF/s, ResNet step 9.6 -> 8.8 ms (gpurun_out/f8_bench_*.json).
+// 316 -> 378 TF/s, ResNet step 9.6 -> 8.8 ms (profiles/runs/f8_bench_*.json).
 bool conv_persist() {
   static const bool v = [] {
     const char* e = getenv("MLA_CONV_PERSIST");
