@@ -238,10 +238,8 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                 st.flat[m].attach()
             optimizer.step()
             optimizer.zero_grad()
-        if n_mod == 2:                                                     # main.py:472 (fp32, like the reference)
-            mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
-        else:
-            mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
+        # main.py:472 (fp32, like the reference; with three modalities the mixed loss still ignores the third)
+        mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
         step_vec = torch.cat([mix] + losses).double()                      # (_loss, _loss_a, _loss_v[, _loss_t]) of this step
         acc += step_vec
         if step_log is not None:                                           # per-step device->host read, asynchronous
