@@ -1059,7 +1059,8 @@ int launch_conv16_persistent(const CUtensorMap& map, const CUtensorMap& gmap, co
     configured.store(1, std::memory_order_release);
   }
   const int tiles_m = (p.M + 127) / 128, tiles = tiles_m * n_tiles_n;
-  const int grid = std::min(tiles, 2 * mla::device_info().sm_count);       // two CTAs per SM (96 KB of stages each)
+  static const int per_sm = [] { const char* e = getenv("MLA_CONV_PERSIST_CTAS"); return e ? std::max(1, atoi(e)) : 2; }();
+  const int grid = std::min(tiles, per_sm * mla::device_info().sm_count);  // two CTAs per SM fit (96 KB of stages each)
   conv16_persistent_kernel<BN, STAGES, ET><<<grid, kThreads, smem, st>>>(map, gmap, p, tiles_m, tiles);
   MLA_CUDA_TRY(cudaGetLastError());
   mla::count_launch();
