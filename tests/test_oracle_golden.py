@@ -262,6 +262,7 @@ def test_m3ae_seeded_init_is_bit_identical_to_reference(golden):
     assert np.array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["sums"])
     assert np.array_equal(np.array([float(v.double().abs().sum()) for v in sd.values()]), g["abs_sums"])
     assert (enc.emb_dim, enc.depth, enc.num_heads) == (768, 12, 12)
+    assert sum(p.numel() for p in enc.parameters()) == 109089792                      # SURVEY KAT-5
 
 
 def test_m3ae_tiny_state_loads_into_host_mirror(golden):
