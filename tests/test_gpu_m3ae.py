@@ -1,9 +1,10 @@
 """--lorb m3ae --gs_flag (BASELINE.json configs[2]) through the public API against the
 reference fixtures (tests/golden/m3ae.npz, produced by executing the reference) and the oracle.
 
-Tolerance: the encoder GEMMs multiply operands with a 10-bit mantissa (fp16 forward, TF32 backward; fp32 accumulate)
-where the reference multiplies in fp32: north_star's fp32/TF32 tolerance, rel 1e-3 (Frobenius), on features, losses and
-weights after a step; gradients of a single Linear 1e-3 as well. The optional bf16 backward gets 4e-3 on gradients."""
+Tolerance: the encoder GEMMs multiply operands with a 10-bit mantissa (fp16 forward; fp16 backward with an exact
+power-of-two gradient scale in the fused blocks, TF32 on the per-module path; fp32 accumulate) where the reference
+multiplies in fp32: north_star's fp32/TF32 tolerance, rel 1e-3 (Frobenius), on features, losses and weights after a step;
+gradients of a single Linear 1e-3 as well. The optional bf16 backward gets 4e-3 on gradients."""
 import argparse
 
 import numpy as np
