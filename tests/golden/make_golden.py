@@ -446,6 +446,42 @@ def make_m3ae(ref_main, ref_utils):
                         abs_sums=np.array([float(v.double().abs().sum()) for v in sd.values()]))
 
 
+def make_m3ae_dh64(ref_main, ref_utils):
+    """A second encoder geometry for the oracle: head width 64 (the 'base' head width; the tiny configuration above has 32),
+    emb 128, 2 heads, 1 block, vocabulary 64: text and image representations of the reference's encoder + their gradients."""
+    import torch
+    from models import m3ae as ref_m3ae
+    ref_m3ae.DropPath.forward = lambda self, input, deterministic=False: input
+    real_to = torch.Tensor.to
+
+    def cpu_to(self, *a, **k):
+        a = tuple(torch.device("cpu") if isinstance(x, torch.device) and x.type == "cuda" else x for x in a)
+        return real_to(self, *a, **k)
+    torch.Tensor.to = cpu_to
+    try:
+        ref_utils.setup_seed(3)
+        cfg = sys.modules["ml_collections"].ConfigDict(dict(model_type=None, emb_dim=128, depth=1, num_heads=2))
+        enc = ref_m3ae.MaskedMultimodalAutoencoder(text_vocab_size=64, config_updates=cfg)
+        out = {"state/" + k: v.numpy().copy() for k, v in enc.state_dict().items()}
+        g = torch.Generator().manual_seed(17)
+        text = torch.randint(0, 64, (3, 70), generator=g)                # 71 tokens with CLS: two 64-key tiles
+        pm = (torch.arange(70)[None, :] >= torch.tensor([70, 33, 1])[:, None]).long()
+        image = torch.randn(3, 9, 768, generator=g)
+        t = enc.forward_representation(None, text, pm)
+        v = enc.forward_representation(image, None, None)
+        out["rep_text"], out["rep_image"] = t.detach().numpy(), v.detach().numpy()
+        # a fixed random linear functional of the outputs (NOT a function of the LayerNorm-ed rows' norms, whose gradient
+        # cancels to rounding noise)
+        wt, wv = torch.randn(t.shape, generator=g), torch.randn(v.shape, generator=g)
+        ((t * wt).sum() + (v * wv).sum()).backward()
+        for k in ("encoder.blocks.0.attention.qkv_linear.weight", "encoder.blocks.0.attention.fc.bias", "cls_token",
+                  "image_embedding.weight", "encoder.blocks.0.layer_norm2.weight"):
+            out["grad/" + k] = dict(enc.named_parameters())[k].grad.numpy().copy()
+    finally:
+        torch.Tensor.to = real_to
+    np.savez_compressed(os.path.join(OUT, "m3ae_dh64.npz"), **out)
+
+
 CAV_TINY = dict(img_size=32, audio_length=64, embed_dim=64, modality_specific_depth=1, num_heads=2)
 
 
@@ -549,14 +585,18 @@ if __name__ == "__main__":
     ref_main, ref_utils = import_reference()
     import torch
     torch.set_num_threads(8)
-    if not os.environ.get("MLA_GOLDEN_ONLY_M3AE") and not os.environ.get("MLA_GOLDEN_ONLY_MODAL3"):
+    if not any(os.environ.get(k) for k in ("MLA_GOLDEN_ONLY_M3AE", "MLA_GOLDEN_ONLY_MODAL3", "MLA_GOLDEN_ONLY_DH64")):
         make_gs(ref_utils)
         make_fusion(ref_main)
         make_head()
         make_av(ref_main, ref_utils)
-    if not os.environ.get("MLA_GOLDEN_ONLY_MODAL3"):
-        make_m3ae(ref_main, ref_utils)
-    make_modal3(ref_main, ref_utils)
+    if os.environ.get("MLA_GOLDEN_ONLY_DH64"):
+        make_m3ae_dh64(ref_main, ref_utils)
+    else:
+        if not os.environ.get("MLA_GOLDEN_ONLY_MODAL3"):
+            make_m3ae(ref_main, ref_utils)
+            make_m3ae_dh64(ref_main, ref_utils)
+        make_modal3(ref_main, ref_utils)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -407,3 +407,31 @@ def test_fused_block_matches_per_module_path(built_lib, B, S, D, H, masked, bwd)
     for k, (a_, b_) in e.items():
         print("  %-32s fused %.2e  per-module %.2e" % (k, a_, b_))
     assert max(v[0] for v in e.values()) < 1e-3 and max(v[1] for v in e.values()) < 1e-3
+
+
+def test_encoder_head_width_64_matches_reference_fixture(built_lib, golden):
+    """tests/golden/m3ae_dh64.npz: the reference's own encoder at head width 64 (emb 128, 2 heads, 71 text tokens = two key
+    tiles, a sample with one unpadded key besides CLS; 10 image tokens). Exercises every Linear dispatch: persistent
+    (N = 512), CTA-pair 128-column tiles (N = 384, 128) and the plain kernel (M = 30 < 128 rows)."""
+    from mla_b200 import m3ae
+    g = golden("m3ae_dh64")
+    enc = m3ae.MaskedMultimodalAutoencoder(64, dict(model_type=None, emb_dim=128, depth=1, num_heads=2))
+    enc.load_state_dict({k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}, strict=True)
+    enc = enc.cuda()
+    gen = torch.Generator().manual_seed(17)
+    text = torch.randint(0, 64, (3, 70), generator=gen)
+    pm = (torch.arange(70)[None, :] >= torch.tensor([70, 33, 1])[:, None]).long()
+    image = torch.randn(3, 9, 768, generator=gen)
+    t = enc.forward_representation(None, text.cuda(), pm.cuda())
+    v = enc.forward_representation(image.cuda(), None, None)
+    et, ev = relf(t.detach().cpu(), g["rep_text"]), relf(v.detach().cpu(), g["rep_image"])
+    print("head-width-64 encoder rel-F error vs the reference fixture: text %.2e image %.2e" % (et, ev))
+    assert t.shape == (3, 71, 128) and et < 1e-3 and ev < 1e-3
+    wt, wv = torch.randn(t.shape, generator=gen), torch.randn(v.shape, generator=gen)
+    ((t * wt.cuda()).sum() + (v * wv.cuda()).sum()).backward()
+    params = dict(enc.named_parameters())
+    for k in g.files:
+        if k.startswith("grad/"):
+            e = relf(params[k[5:]].grad.cpu(), g[k])
+            print("  grad %-50s rel-F %.2e" % (k[5:], e))
+            assert e < 2e-3, k

@@ -359,3 +359,25 @@ def test_modal3_host_mirror_seeded_init_is_bit_identical_to_reference(golden):
     assert cold == sorted(g["grad_none"])
     with pytest.raises(RuntimeError):                                                  # no CPU fallback
         net(*_modal3_batches(1, 2, 3)[0][:4])
+
+
+def test_m3ae_oracle_head_width_64_matches_reference(golden):
+    """A second geometry (emb 128, 2 heads of width 64 — the 'base' head width, 71 text tokens = two 64-key tiles, a row with
+    a single unpadded key besides CLS) against the reference's own encoder."""
+    g = golden("m3ae_dh64")
+    sd = {k[6:]: torch.from_numpy(g[k]).requires_grad_(torch.from_numpy(g[k]).is_floating_point()) for k in g.files
+          if k.startswith("state/")}
+    gen = torch.Generator().manual_seed(17)
+    text = torch.randint(0, 64, (3, 70), generator=gen)
+    pm = (torch.arange(70)[None, :] >= torch.tensor([70, 33, 1])[:, None]).long()
+    image = torch.randn(3, 9, 768, generator=gen)
+    t = orc.m3ae_representation(sd, "", None, text, pm, 2)
+    v = orc.m3ae_representation(sd, "", image, None, None, 2)
+    assert t.shape == (3, 71, 128) and v.shape == (3, 10, 128)
+    assert np.allclose(t.detach().numpy(), g["rep_text"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(v.detach().numpy(), g["rep_image"], rtol=1e-5, atol=1e-6)
+    wt, wv = torch.randn(t.shape, generator=gen), torch.randn(v.shape, generator=gen)
+    ((t * wt).sum() + (v * wv).sum()).backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert relf(sd[k[5:]].grad.numpy(), g[k]) < 1e-5, k
