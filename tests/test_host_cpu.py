@@ -184,3 +184,44 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_flat_gradient_buckets_with_autograd_encoders():
+    """The transformer encoders are autograd graphs: gradients ACCUMULATE into the flat per-encoder bucket, which is therefore
+    zero-filled when attached; p.grad stays a view of the bucket (the all-reduce and the optimiser read the same memory)."""
+    from mla_b200 import dist as mdist
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
+    fg = mdist.FlatGrads(ps)
+    for _ in range(2):                                   # a second step must not see the first step's gradients
+        fg.flat.fill_(7.0)
+        fg.attach(zero=True)
+        (ps[0].sum() * 2 + ps[1].sum() * 3).backward()
+        assert torch.equal(fg.flat, torch.tensor([2.0] * 12 + [3.0] * 5))
+        assert ps[0].grad.data_ptr() == fg.flat.data_ptr() and ps[1].grad.data_ptr() == fg.flat[12:].data_ptr()
+    fg.detach()
+    assert ps[0].grad is None and ps[1].grad is None
+
+
+def test_encoder_param_groups_follow_the_turn_order_and_hot_parameters():
+    from mla_b200.engine import encoder_param_groups
+
+    class Enc(torch.nn.Module):
+        def __init__(self, hot_only):
+            super().__init__()
+            self.used, self.unused = torch.nn.Linear(2, 2), torch.nn.Linear(2, 2)
+            if hot_only:
+                self.hot_parameters = lambda: list(self.used.parameters())
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mae_t, self.mae_a, self.mae_v = Enc(False), Enc(True), Enc(False)      # creation order != turn order
+
+    net = Net()
+    groups = encoder_param_groups(net)
+    assert len(groups) == 3                                                            # a -> v -> t (main.py:432-466)
+    assert [id(p) for p in groups[0]] == [id(p) for p in net.mae_a.used.parameters()]   # only what the forward reads
+    assert len(groups[1]) == 4 and groups[1][0] is net.mae_v.used.weight
+    assert groups[2][0] is net.mae_t.used.weight
+    with pytest.raises(RuntimeError):
+        encoder_param_groups(torch.nn.Linear(2, 2))
