@@ -292,6 +292,24 @@ MLA_API int    mla_maxpool_relu_backward(const float* dp, const float* p, const 
 MLA_API int    mla_avgpool_forward(const float* fm, float* feat, int B, int rows, int C, void* stream);
 MLA_API int    mla_avgpool_backward(const float* dfeat, float* dfm, int B, int rows, int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * OGM / OGM-GE gradient modulation of the joint-training step — main.py:312-410.
+ *   mla_ogm_scores   score[m] = sum_b softmax(logits[m])[b][label[b]], b added in index order   main.py:315-317, 373-374
+ *                    `logits` is a HOST array of M (2 or 3) device pointers to B x C matrices; ws >= M * B floats.
+ *   mla_ogm_coeff    coeff[m] from the (global-batch) scores: M = 2 -> main.py:376-384, M = 3 -> main.py:319-334;
+ *                    score / coeff are device arrays, the branch runs on the device (no host read).
+ *   mla_ogm_modulate grad[seg_off[i] .. + seg_len[i]) = grad * *coeff (+ noise * seg_std[i])    main.py:393-408
+ *                    over `nseg` segments of one flat gradient buffer (the 4-D parameters of one encoder); seg_off /
+ *                    seg_len are DEVICE arrays (elements), max_len = the longest segment; noise (same layout as grad,
+ *                    N(0,1) draws) and seg_std (std(grad) + 1e-8 per segment) are both NULL for plain OGM.
+ */
+MLA_API size_t mla_ogm_scores_workspace_bytes(int M, int B);
+MLA_API int    mla_ogm_scores(const float* const* logits, int M, const int64_t* label, int B, int C, float* score,
+                        void* ws, size_t ws_bytes, void* stream);
+MLA_API int    mla_ogm_coeff(const float* score, int M, float alpha, float* coeff, void* stream);
+MLA_API int    mla_ogm_modulate(float* grad, const long long* seg_off, const long long* seg_len, int nseg,
+                        long long max_len, const float* coeff, const float* noise, const float* seg_std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

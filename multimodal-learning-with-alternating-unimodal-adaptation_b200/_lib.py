@@ -83,6 +83,12 @@ _SIGNATURES = {
     "mla_maxpool_relu_backward": (_c_int, [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p]),
     "mla_avgpool_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "mla_avgpool_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "mla_ogm_scores_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "mla_ogm_scores": (_c_int, [ctypes.POINTER(_c_void_p), _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
+                                _c_size_t, _c_void_p]),
+    "mla_ogm_coeff": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
+    "mla_ogm_modulate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_ll, _c_void_p, _c_void_p, _c_void_p,
+                                  _c_void_p]),
 }
 
 _lib = None

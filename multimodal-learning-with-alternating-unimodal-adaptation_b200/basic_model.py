@@ -1,10 +1,10 @@
-"""AVClassifier (reference models/basic_model.py:14-77), gs_flag path.
+"""AVClassifier (reference models/basic_model.py:14-77).
 
-forward(audio [B,1,H,W], visual [B,3,T,H,W]) -> (a, v), each [B,512]; features require grad
-in training. Sub-module names (`fusion_module.fc_out`, `audio_net`, `visual_net`) and their
-creation order follow the reference so state dicts and seeded initialisation are identical.
-Only the concat head under --gs_flag is in scope (QMF / film / gated / sum are
-out of scope and raise).
+forward(audio [B,1,H,W], visual [B,3,T,H,W]) -> (a, v), each [B,512], under --gs_flag (512-wide shared head), or
+(a, v, out) with the 1024-wide concatenated head without it (joint training, basic_model.py:73-75); features require
+grad in training. Sub-module names (`fusion_module.fc_out`, `audio_net`, `visual_net`) and their creation order follow
+the reference so state dicts and seeded initialisation are identical. Only the concat head is in scope (SURVEY.md §2:
+QMF / film / gated / sum are out of scope and raise).
 """
 import os
 
@@ -56,7 +56,17 @@ class AVClassifier(nn.Module):
             a = self.audio_net.pooled(audio)        # backbone + adaptive_avg_pool2d + flatten
         return [(a, sa), (v, sv)]
 
+    def features(self, audio, visual):
+        """(a, v) without the head (what train_epoch / valid consume in both modes)."""
+        return self._features(audio, visual)
+
     def forward(self, audio, visual):
+        a, v = self._features(audio, visual)
+        if not self.args.gs_flag:
+            return self.fusion_module(a, v)          # basic_model.py:73-75: (a, v, out)
+        return a, v
+
+    def _features(self, audio, visual):
         if audio.is_cuda and OVERLAP_ENCODERS:
             cur = torch.cuda.current_stream(audio.device)
             (a, sa), (v, sv) = self.forward_streams(audio, visual)
@@ -66,6 +76,4 @@ class AVClassifier(nn.Module):
         else:
             a = self.audio_net.pooled(audio)
             v = self.visual_net.pooled(visual)
-        if not self.args.gs_flag:
-            return self.fusion_module(a, v)
         return a, v

@@ -162,15 +162,15 @@ class Modal3Classifier(nn.Module):
         super().__init__()
         if args.dataset != "IEMOCAP":
             raise NotImplementedError("Incorrect dataset name {}".format(args.dataset))
-        if args.fusion_method != "concat" or not args.gs_flag:
-            raise NotImplementedError("mla_b200 implements the concat head of the --gs_flag path only")
+        if args.fusion_method != "concat":
+            raise NotImplementedError("mla_b200 implements the concat head only")
         if getattr(args, "modulation", "Normal") == "QMF":
-            raise NotImplementedError("QMF is outside the MLA --gs_flag path (SURVEY.md section 2)")
+            raise NotImplementedError("QMF is outside the MLA hot path (SURVEY.md section 2)")
         n_classes = 4
         model_config = dict(model_config or {"model_type": "base"})
         audio_kwargs = dict(audio_kwargs or {})
         emb = m3ae._SIZES[model_config["model_type"]][0] if model_config.get("model_type") else model_config["emb_dim"]
-        self.fusion_module = ConcatFusion3(input_dim=emb, output_dim=n_classes)          # basic_model.py:218
+        self.fusion_module = ConcatFusion3(input_dim=emb if args.gs_flag else 3 * emb, output_dim=n_classes)   # basic_model.py:218 / 221
         self.mae_a = CAVMAEFT(n_classes, **audio_kwargs)                                 # basic_model.py:231
         self.mae_v = MaskedMultimodalAutoencoder(text_vocab_size, model_config)
         self.mae_t = MaskedMultimodalAutoencoder(text_vocab_size, model_config)

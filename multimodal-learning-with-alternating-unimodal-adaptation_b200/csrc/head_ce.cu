@@ -56,16 +56,20 @@ __global__ void __launch_bounds__(kFwdThreads) head_fwd_kernel(
     for (int c = lane; c < C; c += 32) s += expf(s_l[c] - m);
     s = mla::warp_sum(s);
     const float lse = logf(s);
-    const int lab = (int)label[b];
+    // an out-of-range label (nn.CrossEntropyLoss raises a device assert for it) poisons this row's loss and gradient
+    // with NaN instead of reading shared memory out of bounds: the error surfaces in the step's loss
+    const long long lab64 = label[b];
+    const bool lab_ok = lab64 >= 0 && lab64 < (long long)C;
+    const int lab = lab_ok ? (int)lab64 : 0;
     for (int c = lane; c < C; c += 32) {
       const float l = s_l[c];
       if (logits) logits[(size_t)b * C + c] = l;
       if (dlogits) {
         const float pr = expf(l - m - lse);
-        dlogits[(size_t)b * C + c] = (pr - (c == lab ? 1.f : 0.f)) * grad_scale;
+        dlogits[(size_t)b * C + c] = lab_ok ? (pr - (c == lab ? 1.f : 0.f)) * grad_scale : __int_as_float(0x7fc00000);
       }
     }
-    if (lane == 0) rowloss[b] = -(s_l[lab] - m - lse);
+    if (lane == 0) rowloss[b] = lab_ok ? -(s_l[lab] - m - lse) : __int_as_float(0x7fc00000);
     __syncwarp();
   }
 }

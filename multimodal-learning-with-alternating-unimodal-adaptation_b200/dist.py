@@ -87,13 +87,35 @@ def allreduce_sum_(t):
     return t
 
 
-def all_gather_rows(t):
-    """Concatenate equally sized [B_local, ...] tensors from all ranks in rank order."""
+def all_gather_rows(t, sizes=None):
+    """Concatenate [B_local, ...] tensors from all ranks in rank order. The local batch sizes may differ (the last batch
+    of a sharded loader without drop_last): they are exchanged first, shards are padded to the largest one for the
+    collective and trimmed afterwards. `sizes` (the list returned by `gather_sizes`) skips the exchange when several
+    tensors of the same batch are gathered."""
     if not is_dist():
         return t
+    if sizes is None:
+        sizes = gather_sizes(t.shape[0], t.device)
+    big = max(sizes)
+    t = t.contiguous()
+    if t.shape[0] < big:
+        pad = torch.zeros((big - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        t = torch.cat([t, pad], dim=0)
     out = [torch.empty_like(t) for _ in range(world_size())]
-    dist.all_gather(out, t.contiguous())
-    return torch.cat(out, dim=0)
+    dist.all_gather(out, t)
+    if all(n == big for n in sizes):
+        return torch.cat(out, dim=0)
+    return torch.cat([o[:n] for o, n in zip(out, sizes)], dim=0)
+
+
+def gather_sizes(n, device):
+    """Local batch sizes of all ranks, in rank order (one tiny all-gather; a host read)."""
+    if not is_dist():
+        return [int(n)]
+    mine = torch.tensor([int(n)], dtype=torch.int64, device=device)
+    out = [torch.empty_like(mine) for _ in range(world_size())]
+    dist.all_gather(out, mine)
+    return [int(o.item()) for o in out]
 
 
 def broadcast_buffers_(module, src=0):

@@ -217,6 +217,8 @@ class ResNetPlan:
                          self.L.mla_conv2d_wgrad16_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 1, 1, b["stride"], 0))
         self.wg_ws = torch.empty(max(nw, 256), dtype=torch.uint8, device=dev)
         self.trained_forward = False
+        self.serial = 0                 # number of the last training forward (activations are single-buffered)
+        self._param_ptrs = [p.data_ptr() for p in self._params]
         self.feat_static = torch.empty(self.B, self.C_out, dtype=torch.float32, device=dev)    # pooled feature (graph output)
         self.dfeat_static = torch.empty(self.B, self.C_out, dtype=torch.float32, device=dev)   # its gradient (graph input)
         self._graphs, self._warm = {}, {}
@@ -388,6 +390,8 @@ class ResNetPlan:
                                    st), "mla_stem_im2col")
         self._run(("fwd", bool(training)), lambda: self._forward_body(training))
         self.trained_forward = training
+        if training:
+            self.serial += 1
         return self.feat_static.clone()
 
     def _forward_body(self, training):
@@ -461,9 +465,14 @@ class ResNetPlan:
             torch._foreach_add_(self.nbt, 1)
 
     # ----------------------------------------------------------------------- backward
-    def backward(self, dfeat):
+    def backward(self, dfeat, serial=None):
         if not self.trained_forward:
             raise RuntimeError("encoder backward needs a training-mode forward on the same plan")
+        if serial is not None and serial != self.serial:
+            # a plan owns ONE set of activation buffers per input shape: a later forward of the same shape overwrote the
+            # ones this backward pass would differentiate through
+            raise RuntimeError("encoder backward for forward #%d, but forward #%d of the same input shape has overwritten "
+                               "its activations: run backward before the next forward" % (serial, self.serial))
         self.dfeat_static.copy_(dfeat)
         params = self._params
         if params[0].grad is not None and params[-1].grad is not None:
@@ -610,11 +619,19 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, x, anchor):
         ctx.plan = plan
-        return plan.forward(x, True)
+        out = plan.forward(x, True)
+        ctx.serial = plan.serial
+        return out
 
     @staticmethod
     def backward(ctx, dfeat):
-        ctx.plan.backward(dfeat)
+        # the native backward OVERWRITES its gradient buffers; autograd semantics are accumulation, so gradients that were
+        # already there (a second backward without zero_grad, another loss term) are added back afterwards
+        plan = ctx.plan
+        old = [(p, p.grad.clone()) for p in plan._params if p.grad is not None]
+        plan.backward(dfeat, ctx.serial)
+        for p, g in old:
+            p.grad.add_(g)
         return None, None, None
 
 
@@ -622,8 +639,15 @@ def _plan(net, x):
     plans = net.__dict__.setdefault("_mla_plans", {})
     key = (tuple(x.shape), x.device)
     p = plans.get(key)
+    if p is not None and p._param_ptrs != [q.data_ptr() for q in p._params]:
+        # a parameter was re-homed after the plan captured its address (p.data = ..., load_state_dict(assign=True), a
+        # dtype / device round trip): the plan's flat buffer, offsets and CUDA graphs point at stale memory
+        torch.cuda.synchronize(x.device)
+        plans.clear()
+        p = None
     if p is None:
         if len(plans) >= 4:
+            torch.cuda.synchronize(x.device)     # buffers of the dropped plans may still be in use on side streams
             plans.clear()
         p = ResNetPlan(net, x)
         plans[key] = p
@@ -638,6 +662,7 @@ def resnet_pooled(net, x):
     if net.training and torch.is_grad_enabled():
         out = _EncoderFn.apply(plan, x, net.conv1.weight)
         out._mla_plan = plan          # lets train_epoch run the native backward directly, on a stream of its choice
+        out._mla_serial = plan.serial
         return out
     with torch.no_grad():
         return plan.forward(x, net.training)

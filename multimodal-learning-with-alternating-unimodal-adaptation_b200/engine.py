@@ -7,7 +7,9 @@
   * evaluation does fusion, argmax and per-class counters in one kernel per batch — the
     reference's per-sample numpy loop (~8 D2H syncs per sample, main.py:659-676) is gone;
   * multi-GPU is one process per GPU with two NCCL all-reduces per turn (dist.py).
-Out of scope (raises): the joint-training branch without --gs_flag (main.py:165-418).
+Without --gs_flag the same kernels run the reference's JOINT-training step (main.py:165-168, 269-310, 412-418: one
+concatenated head, one backward through every encoder, one optimiser step) with its OGM / OGM-GE gradient modulation
+(main.py:312-410) — the "MLA vs joint" comparison line. Out of scope (raises): QMF, --lorb large, --clip, sum/film/gated.
 """
 import torch
 import torch.nn as nn
@@ -155,8 +157,7 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                 txt_history=None, img_history=None, audio_history=None):
     """main.py:127-484. Returns (loss, loss_a, loss_v[, loss_t]) as Python floats."""
     if not gs_flag:
-        raise NotImplementedError("mla_b200 implements MLA's alternating step (--gs_flag) only; the joint-training "
-                                  "branch (main.py:165-418) is out of scope")
+        return _train_epoch_joint(args, epoch, model, device, dataloader, optimizer, scheduler)
     net = _unwrap(model)
     model.train()
     print("Start training ... ")
@@ -210,7 +211,7 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                     stream.wait_stream(torch.cuda.current_stream())        # dfeat is ready
                 with torch.cuda.stream(stream):
                     st.flat[m].attach()
-                    plan.backward(o["dfeat"])
+                    plan.backward(o["dfeat"], getattr(feat, "_mla_serial", None))
                     if world > 1 and not deferred:                         # encoder-gradient all-reduce
                         mdist.allreduce_sum_(st.flat[m].flat)
                 if deferred:
@@ -254,6 +255,221 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
     return tuple(vals)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Joint training (no --gs_flag): main.py:165-168, 269-310 (forward + per-modality logit slices), 312-410 (OGM / OGM-GE),
+# 412-418 (step, loss accumulation). SURVEY section 8 f1 / f2.
+# ------------------------------------------------------------------------------------------------------------------
+def _check_joint_scope(args):
+    if getattr(args, "modulation", "Normal") == "QMF":
+        raise NotImplementedError("QMF (main.py:171-225) is outside the hot path (SURVEY.md section 2)")
+    if getattr(args, "fusion_method", "concat") != "concat":
+        raise NotImplementedError("only the concat head is implemented (got fusion_method={})".format(args.fusion_method))
+    if getattr(args, "lorb", "base") == "large" or getattr(args, "clip", False):
+        raise NotImplementedError("--lorb large / --clip are out of scope (SURVEY.md section 2)")
+    if getattr(args, "modulation", "Normal") not in ("Normal", "OGM", "OGM_GE"):
+        raise NotImplementedError("unknown modulation {}".format(args.modulation))
+
+
+def _encoder_names(net):
+    for cand in (("audio_net", "visual_net"), ("mae_a", "mae_v", "mae_t")):
+        if all(hasattr(net, n) for n in cand[:2]):
+            return [n for n in cand if hasattr(net, n)]
+    raise RuntimeError("model has no known encoders (audio_net/visual_net or mae_a/mae_v[/mae_t])")
+
+
+def ogm_coeff_index(name, modal3):
+    """Which coefficient the reference's name test applies to the parameters of encoder `name`: main.py:350,357,362 for
+    three modalities ('mae_a' / 'mae_v' / 'mae_t' in layer), main.py:396,403 otherwise ('audio' / 'visual' in layer — which
+    the two-modality m3ae encoders `mae_a` / `mae_v` never match: as published, OGM is a no-op for them). None = untouched."""
+    if modal3:
+        return {"mae_a": 0, "mae_v": 1, "mae_t": 2}.get(name)
+    if "audio" in name:
+        return 0
+    if "visual" in name:
+        return 1
+    return None
+
+
+class _JointState:
+    """Per-model buffers of the joint step: packed [dW | db] of the concatenated head, flat per-encoder gradient buckets,
+    and for OGM the segment tables of every encoder's 4-D parameters inside its bucket."""
+
+    def __init__(self, net, modal3):
+        fc = net.fusion_module.fc_out
+        C, Dcat = fc.weight.shape
+        dev = fc.weight.device
+        o_db = (C * Dcat + 3) // 4 * 4
+        self.packed = torch.zeros(o_db + (C + 3) // 4 * 4, dtype=torch.float32, device=dev)
+        self.head_out = {"dW": self.packed[:C * Dcat].view(C, Dcat), "db": self.packed[o_db:o_db + C]}
+        self.names = _encoder_names(net)
+        self.encoders = encoder_param_groups(net)
+        self.flat = [mdist.FlatGrads(g) for g in self.encoders]
+        self.score = torch.zeros(len(self.names), dtype=torch.float32, device=dev)
+        self.coeff = torch.ones(len(self.names), dtype=torch.float32, device=dev)
+        self.slice_out = [dict() for _ in self.names]
+        self.seg = []
+        for name, fg in zip(self.names, self.flat):
+            ci = ogm_coeff_index(name, modal3)
+            offs, lens, views, off = [], [], [], 0
+            for p, v in zip(fg.params, fg.views):
+                if p.dim() == 4 and ci is not None:                       # len(parms.grad.size()) == 4: conv weights only
+                    offs.append(off); lens.append(p.numel()); views.append(v)
+                off += p.numel()
+            if offs:
+                self.seg.append(dict(ci=ci, off=torch.tensor(offs, dtype=torch.int64, device=dev),
+                                     len=torch.tensor(lens, dtype=torch.int64, device=dev), max_len=max(lens), views=views,
+                                     params=[p for p in fg.params if p.dim() == 4], noise=None))
+            else:
+                self.seg.append(None)
+        self._side = {}
+
+    def side_stream(self, m):
+        s = self._side.get(m)
+        if s is None:
+            s = torch.cuda.Stream()
+            self._side[m] = s
+        return s
+
+
+def _modality_logits(fc, feats, label, outs):
+    """out_m = feat_m W[:, m-th slice]^T + b / M (main.py:276-308) with its mean CE, through the head kernel (forward only)."""
+    M = len(feats)
+    D = fc.weight.shape[1] // M
+    b = fc.bias.detach() / M
+    res = []
+    for m, f in enumerate(feats):
+        w = fc.weight.detach()[:, m * D:(m + 1) * D].contiguous()
+        res.append(ops.head_ce(f.detach().contiguous(), w, b, label, need_grad=False, out=outs[m]))
+    return res
+
+
+def _train_epoch_joint(args, epoch, model, device, dataloader, optimizer, scheduler):
+    """main.py:127-168, 269-418 for --modulation Normal / OGM / OGM_GE. Returns (loss, loss_a, loss_v[, loss_t])."""
+    _check_joint_scope(args)
+    net = _unwrap(model)
+    model.train()
+    print("Start training ... ")
+    fc = net.fusion_module.fc_out
+    world = mdist.world_size()
+    modal3 = bool(getattr(args, "modal3", False))
+    names = _encoder_names(net)
+    n_mod = len(names)
+    if fc.weight.shape[1] % n_mod:
+        raise RuntimeError("joint training needs the concatenated head (width = %d x feature width); build the model "
+                           "without --gs_flag" % n_mod)
+    modulate = args.modulation in ("OGM", "OGM_GE")
+    acc = torch.zeros(1 + n_mod, dtype=torch.float64, device=device)
+    len_dataloader = len(dataloader)
+    for batch_step, (inputs, label) in enumerate(_batches_on_device(args, dataloader, device)):
+        optimizer.zero_grad()                                              # main.py:164
+        if basic_model.OVERLAP_ENCODERS and hasattr(net, "forward_streams") and inputs[0].is_cuda:
+            pairs = net.forward_streams(*inputs)                           # main.py:166 / 227-232 / 265-268
+            feats = []
+            for f, s in pairs:
+                torch.cuda.current_stream().wait_stream(s)
+                f.record_stream(torch.cuda.current_stream())
+                feats.append(f)
+        else:
+            feats = list(net.features(*inputs)) if hasattr(net, "features") else list(model(*inputs))[:n_mod]
+        st = getattr(net, "_mla_joint_state", None)
+        if st is None:
+            st = _JointState(net, modal3)
+            net._mla_joint_state = st
+        B = feats[0].shape[0]
+        D = feats[0].shape[1]
+        inv_global = 1.0 / (B * world)
+        cat = torch.cat([f.detach() for f in feats], dim=1)                # fusion_modules.py:22 / 32
+        o = head_turn(fc, cat, label, grad_scale=inv_global, out=st.head_out)     # main.py:309 + head part of :313
+        if world > 1:
+            mdist.allreduce_sum_(st.packed)
+        per_mod = _modality_logits(fc, feats, label, st.slice_out)         # main.py:276-308, 310-312 (logging, OGM scores)
+        # main.py:313 (encoder part): every encoder's backward from its slice of d(loss)/d(cat)
+        native = [getattr(f, "_mla_plan", None) for f in feats]
+        pending = []
+        for m, (f, plan) in enumerate(zip(feats, native)):
+            dslice = o["dfeat"][:, m * D:(m + 1) * D]
+            if plan is not None:
+                side = basic_model.OVERLAP_ENCODERS and m < n_mod - 1
+                stream = st.side_stream(m) if side else torch.cuda.current_stream()
+                if side:
+                    stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(stream):
+                    st.flat[m].attach()
+                    plan.backward(dslice, getattr(f, "_mla_serial", None))
+                if side:
+                    pending.append(stream)
+            else:
+                st.flat[m].attach(zero=True)
+                f.backward(dslice.contiguous())
+        for stream in pending:
+            torch.cuda.current_stream().wait_stream(stream)
+        if world > 1:
+            for fg in st.flat:
+                mdist.allreduce_sum_(fg.flat)
+        if modulate:                                                       # main.py:315-410
+            ops.ogm_scores([r["logits"] for r in per_mod], label, out=st.score)
+            if world > 1:
+                mdist.allreduce_sum_(st.score)                             # the scores are sums over the GLOBAL batch
+            ops.ogm_coeff(st.score, args.alpha, out=st.coeff)
+            if args.modulation_starts <= epoch <= args.modulation_ends:    # main.py:343 / 393
+                for m, seg in enumerate(st.seg):
+                    if seg is not None:
+                        _ogm_apply(st, m, seg, args.modulation == "OGM_GE")
+            train_epoch.last_ogm = (st.score, st.coeff)
+        optimizer.step()                                                   # main.py:412
+        step_vec = torch.cat([o["loss"]] + [r["loss"] for r in per_mod]).double()     # main.py:414-418
+        acc += step_vec
+    scheduler.step()                                                       # main.py:481
+    if world > 1:
+        mdist.allreduce_sum_(acc)
+        acc /= world
+    return tuple((acc / len_dataloader).tolist())
+
+
+def _ogm_apply(st, m, seg, ge):
+    """main.py:393-408 for one encoder: grad = grad * coeff [+ N(0, std(grad) + 1e-8)] over its 4-D parameters."""
+    flat = st.flat[m].flat
+    coeff = st.coeff[seg["ci"]:seg["ci"] + 1]
+    if not ge:
+        ops.ogm_modulate(flat, seg["off"], seg["len"], seg["max_len"], coeff)
+        return
+    if seg["noise"] is None:
+        seg["noise"] = torch.empty_like(flat)
+        seg["nviews"] = [torch.as_strided(seg["noise"], v.shape, v.stride(), storage_offset=int(o))
+                         for v, o in zip(seg["views"], seg["off"].tolist())]
+    stds = []
+    for v, nv in zip(seg["views"], seg["nviews"]):
+        # the reference draws zeros_like(grad).normal_(0, std) parameter by parameter in named_parameters() order from the
+        # default CUDA generator: the same draws, in the same logical element order, scaled inside the kernel
+        stds.append(v.std().double() + 1e-8)
+        nv.copy_(torch.empty(v.shape, dtype=torch.float32, device=v.device).normal_())
+    seg_std = torch.stack(stds).float()
+    ops.ogm_modulate(flat, seg["off"], seg["len"], seg["max_len"], coeff, noise=seg["noise"], seg_std=seg_std)
+
+
+@torch.no_grad()
+def _valid_joint(args, model, net, fc, n_mod, n_classes, device, dataloader):
+    """main.py:538-620, 653-679: the joint head's prediction plus the per-modality slices (bias / M)."""
+    num = torch.zeros(n_classes, dtype=torch.int64, device=device)
+    hits = torch.zeros(n_mod + 2, n_classes, dtype=torch.int64, device=device)
+    outs = [dict() for _ in range(n_mod)]
+    for inputs, label in _batches_on_device(args, dataloader, device):
+        feats = list(net.features(*inputs)) if hasattr(net, "features") else list(model(*inputs))[:n_mod]
+        feats = [f.contiguous() for f in feats]
+        out = fc(torch.cat(feats, dim=1))                                  # main.py:543 / 575-579 / 598
+        logits = [out] + [r["logits"] for r in _modality_logits(fc, feats, label, outs)]
+        if mdist.is_dist():
+            sizes = mdist.gather_sizes(label.shape[0], label.device)
+            logits = [mdist.all_gather_rows(x, sizes) for x in logits]
+            label = mdist.all_gather_rows(label, sizes)
+        # fused = 1 * out + 0 * out_a + ... = out exactly: rows of `hits` are [out, out, out_a, out_v(, out_t)]
+        ops.fuse_eval(logits, label, dynamic=False, fixed_w=(1.0,) + (0.0,) * n_mod, hits=hits, num=num,
+                      want_fused=False, want_argmax=False)
+    h = hits.sum(dim=1).tolist()
+    n = float(num.sum().item())
+    return tuple(h[i] / n for i in [0] + list(range(2, n_mod + 2)))
+
+
 @torch.no_grad()
 def valid(args, model, device, dataloader, gs_flag=False, av_alpha=0.5,
           a_alpha=0.35, v_alpha=0.25, t_alpha=0.4):
@@ -261,13 +477,15 @@ def valid(args, model, device, dataloader, gs_flag=False, av_alpha=0.5,
     if args.dataset not in N_CLASSES:
         raise NotImplementedError("Incorrect dataset name {}".format(args.dataset))
     if not gs_flag:
-        raise NotImplementedError("mla_b200 implements the --gs_flag evaluation branch only (main.py:622-679)")
+        _check_joint_scope(args)
     n_classes = N_CLASSES[args.dataset]
     net = _unwrap(model)
     model.eval()
     mdist.broadcast_buffers_(net)                                          # DataParallel keeps replica 0's BN statistics
     fc = net.fusion_module.fc_out
     n_mod = 3 if getattr(args, "modal3", False) else 2
+    if not gs_flag:
+        return _valid_joint(args, model, net, fc, n_mod, n_classes, device, dataloader)
     num = torch.zeros(n_classes, dtype=torch.int64, device=device)
     hits = torch.zeros(n_mod + 1, n_classes, dtype=torch.int64, device=device)
     if args.dynamic:
@@ -281,8 +499,11 @@ def valid(args, model, device, dataloader, gs_flag=False, av_alpha=0.5,
         logits = [fc(f.contiguous()) for f in feats]                       # main.py:636-639
         if mdist.is_dist():
             # the entropy weights are a GLOBAL-batch quantity: gather the tiny logits
-            logits = [mdist.all_gather_rows(x) for x in logits]
-            label = mdist.all_gather_rows(label)
+            # (every rank then counts the same gathered batch: the counters are identical on all ranks by construction).
+            # Shards may differ in size on the last batch: sizes are exchanged once per batch
+            sizes = mdist.gather_sizes(label.shape[0], label.device)
+            logits = [mdist.all_gather_rows(x, sizes) for x in logits]
+            label = mdist.all_gather_rows(label, sizes)
         ops.fuse_eval(logits, label, dynamic=bool(args.dynamic), fixed_w=fixed, hits=hits, num=num,
                       want_fused=False, want_argmax=False)                 # main.py:640-676
     h = hits.sum(dim=1).tolist()

@@ -506,6 +506,22 @@ class MaskedMultimodalAutoencoder(nn.Module):
         self.cls_token = nn.Parameter(torch.empty(1, 1, D).normal_(0.02))
         self.encoder = Transformer(D, self.depth, self.num_heads)
         self._pos = {}
+        self._used = None            # which inputs the last forward_representation read: (image?, text?)
+
+    def hot_parameters(self):
+        """The parameters the last forward_representation read, i.e. the ones that receive gradients. The unused input
+        branch (text embedding table of an image encoder, image projection of a text encoder, their type embeddings)
+        keeps grad None and is skipped by SGD — no weight decay, no momentum — as in the reference, where autograd
+        never touches it (main.py:435-440)."""
+        if self._used is None:
+            return list(self.parameters())
+        image, text = self._used
+        ps = [self.cls_token] + list(self.encoder.parameters())
+        if image:
+            ps += list(self.image_embedding.parameters()) + [self.encoder_image_type_embedding]
+        if text:
+            ps += list(self.text_embedding.parameters()) + [self.encoder_text_type_embedding]
+        return ps
 
     def _pos_embed(self, kind, length, device):
         key = (kind, length, device)
@@ -519,6 +535,7 @@ class MaskedMultimodalAutoencoder(nn.Module):
     def forward_representation(self, image, text, text_padding_mask, deterministic=False):
         B = image.shape[0] if image is not None else text.shape[0]
         dev = image.device if image is not None else text.device
+        self._used = (image is not None, text is not None)
         parts = [self.cls_token.expand(B, 1, self.emb_dim)]
         masks = [torch.zeros(B, 1, dtype=torch.float32, device=dev)]
         if image is not None:
@@ -543,15 +560,15 @@ class M3AEClassifier(nn.Module):
         super().__init__()
         if args.dataset not in _N_CLASSES:
             raise NotImplementedError("Incorrect dataset name {}".format(args.dataset))
-        if args.fusion_method != "concat" or not args.gs_flag:
-            raise NotImplementedError("mla_b200 implements the concat head of the --gs_flag path only")
+        if args.fusion_method != "concat":
+            raise NotImplementedError("mla_b200 implements the concat head only")
         if getattr(args, "modulation", "Normal") == "QMF":
-            raise NotImplementedError("QMF is outside the MLA --gs_flag path (SURVEY.md section 2)")
+            raise NotImplementedError("QMF is outside the MLA hot path (SURVEY.md section 2)")
         model_config = dict(model_config or {"model_type": "base"})               # basic_model.py:163
-        # the reference hard-codes a 768-wide head next to its 'base' encoders (basic_model.py:150); sized from the
-        # encoder here so other model sizes work too
+        # the reference hard-codes a 768-wide head next to its 'base' encoders under --gs_flag (basic_model.py:150) and a
+        # 1536-wide concatenated one without it (:153); sized from the encoder here so other model sizes work too
         emb = _SIZES[model_config["model_type"]][0] if model_config.get("model_type") else model_config["emb_dim"]
-        self.fusion_module = ConcatFusion(input_dim=emb, output_dim=_N_CLASSES[args.dataset])
+        self.fusion_module = ConcatFusion(input_dim=emb if args.gs_flag else 2 * emb, output_dim=_N_CLASSES[args.dataset])
         self.mae_a = MaskedMultimodalAutoencoder(text_vocab_size, model_config)
         self.mae_v = MaskedMultimodalAutoencoder(text_vocab_size, model_config)
         # basic_model.py:167-174 loads pretrained encoders from hard-coded placeholder paths ("/path/to/..."); here they

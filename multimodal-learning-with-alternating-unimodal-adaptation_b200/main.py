@@ -144,6 +144,36 @@ def build_model(args, device):
     return ModuleHolder(model.to(device))
 
 
+def checkpoint_name(args, epoch, acc):
+    """main.py:900-909."""
+    return ("best_model_of_dataset_{}_{}_alpha_{}_optimizer_{}_modulate_starts_{}_ends_{}_epoch_{}_acc_{}.pth".format(
+        args.dataset, args.modulation, args.alpha, args.optimizer, args.modulation_starts, args.modulation_ends, epoch, acc))
+
+
+def save_checkpoint(path, args, epoch, acc, model, optimizer, scheduler, gs_plugin=None):
+    """The reference's checkpoint dictionary (main.py:911-921: saved_epoch, modulation, alpha, fusion, acc, model with the
+    DataParallel 'module.' prefix, optimizer, scheduler) plus one extension the reference lacks: the GSPlugin state
+    (`Pl`, `exp_count`), without which a resumed --gs_flag run restarts the projection from the identity."""
+    torch.save({"saved_epoch": epoch, "modulation": args.modulation, "alpha": args.alpha, "fusion": args.fusion_method,
+                "acc": acc, "model": model.state_dict(), "optimizer": optimizer.state_dict(),
+                "scheduler": scheduler.state_dict(),
+                "gs_plugin": gs_plugin.state_dict() if gs_plugin is not None else None}, path)
+
+
+def load_checkpoint(path, model, optimizer=None, scheduler=None, gs_plugin=None, map_location="cpu"):
+    """main.py:946-953 (evaluation: strict load of loaded['model'] into the wrapped model) and, when optimizer / scheduler /
+    gs_plugin are given, a full training resume. Returns the loaded dictionary."""
+    loaded = torch.load(path, map_location=map_location)
+    model.load_state_dict(loaded["model"])                           # strict, 'module.'-prefixed keys (main.py:952)
+    if optimizer is not None and loaded.get("optimizer") is not None:
+        optimizer.load_state_dict(loaded["optimizer"])
+    if scheduler is not None and loaded.get("scheduler") is not None:
+        scheduler.load_state_dict(loaded["scheduler"])
+    if gs_plugin is not None and loaded.get("gs_plugin") is not None:
+        gs_plugin.load_state_dict(loaded["gs_plugin"])
+    return loaded
+
+
 def main(av_alpha=0.5):
     args = get_arguments()
     if args.dataset == "CREMA-D":
@@ -178,14 +208,13 @@ def main(av_alpha=0.5):
                 if accs[0] > best_acc:
                     best_acc = float(accs[0])
                     os.makedirs(args.ckpt_path, exist_ok=True)
-                    torch.save({"saved_epoch": epoch, "modulation": args.modulation, "alpha": args.alpha,
-                                "fusion": args.fusion_method, "acc": accs[0], "model": model.state_dict(),
-                                "optimizer": optimizer.state_dict(), "scheduler": scheduler.state_dict(),
-                                "gs_plugin": gs.state_dict() if gs is not None else None},
-                               os.path.join(args.ckpt_path, "best_model_of_dataset_{}_gs_epoch_{}.pth".format(
-                                   args.dataset, epoch)))
+                    save_checkpoint(os.path.join(args.ckpt_path, checkpoint_name(args, epoch, accs[0])), args, epoch,
+                                    accs[0], model, optimizer, scheduler, gs)
     else:
-        accs = valid(args, model, device, test_loader, gs_flag=args.gs_flag, av_alpha=av_alpha)
+        load_checkpoint(args.ckpt_path, model)                                                         # main.py:946-953
+        print("Trained model loaded!")
+        accs = valid(args, model, device, test_loader, gs_flag=args.gs_flag, av_alpha=args.av_alpha,
+                     a_alpha=args.a_alpha, v_alpha=args.v_alpha, t_alpha=args.t_alpha)
         if rank == 0:
             print("Acc: {:.4f}, Acc_a: {:.4f}, Acc_v: {:.4f}".format(*accs[:3]))
 

@@ -75,6 +75,12 @@ def head_ce(feat, weight, bias, label, grad_scale=None, need_grad=True, need_log
         raise RuntimeError("head_ce: weight is %s, features are %d wide" % (tuple(weight.shape), D))
     if label.dtype != torch.int64:
         raise RuntimeError("head_ce: label must be int64")
+    if label.numel() != B:
+        raise RuntimeError("head_ce: %d labels for a batch of %d" % (label.numel(), B))
+    if not label.is_contiguous():
+        label = label.contiguous()
+    if not (feat.is_contiguous() and weight.is_contiguous()):
+        raise RuntimeError("head_ce: feat and weight must be contiguous")
     dev = feat.device
     o = out if out is not None else {}
 
@@ -147,6 +153,53 @@ def fuse_eval(logits, label=None, dynamic=True, fixed_w=None, hits=None, num=Non
     if want_entropy:
         return fused, w, argmax, ent
     return fused, w, argmax
+
+
+# ----------------------------------------------------------------------------------------------
+# OGM / OGM-GE (main.py:312-410)
+# ----------------------------------------------------------------------------------------------
+def ogm_scores(logits, label, out=None):
+    """score[m] = sum_b softmax(logits[m])[b][label[b]] (main.py:315-317 / 373-374) as a device tensor of M floats."""
+    L = _lib.lib()
+    _need_cuda(*logits, label)
+    M = len(logits)
+    B, C = logits[0].shape
+    for t in logits:
+        if tuple(t.shape) != (B, C):
+            raise RuntimeError("ogm_scores: all logit matrices must have the same shape")
+        _f32(t, "logits")
+    if label.dtype != torch.int64 or label.numel() != B:
+        raise RuntimeError("ogm_scores: label must be int64 with one entry per sample")
+    score = out if out is not None else torch.empty(M, dtype=torch.float32, device=label.device)
+    ptrs = (ctypes.c_void_p * M)(*[_lib.ptr(t) for t in logits])
+    ws = _workspace("ogm", L.mla_ogm_scores_workspace_bytes(M, B), label.device)
+    rc = L.mla_ogm_scores(ptrs, M, _lib.ptr(label.contiguous()), B, C, _lib.ptr(score), ws.data_ptr(), ws.numel(),
+                          _lib.stream_ptr())
+    _lib.check(rc, "mla_ogm_scores")
+    return score
+
+
+def ogm_coeff(score, alpha, out=None):
+    """Per-modality gradient coefficients from the (global-batch) scores, on the device (main.py:319-334 / 376-384)."""
+    L = _lib.lib()
+    _need_cuda(score)
+    M = score.numel()
+    coeff = out if out is not None else torch.empty(M, dtype=torch.float32, device=score.device)
+    rc = L.mla_ogm_coeff(_lib.ptr(_f32(score, "score")), M, float(alpha), _lib.ptr(coeff), _lib.stream_ptr())
+    _lib.check(rc, "mla_ogm_coeff")
+    return coeff
+
+
+def ogm_modulate(flat_grad, seg_off, seg_len, max_len, coeff, noise=None, seg_std=None):
+    """flat_grad[segments] = flat_grad * coeff (+ noise * seg_std) in one launch (main.py:393-408)."""
+    L = _lib.lib()
+    _need_cuda(flat_grad, seg_off, seg_len, coeff, noise, seg_std)
+    if seg_off.dtype != torch.int64 or seg_len.dtype != torch.int64 or seg_off.numel() != seg_len.numel():
+        raise RuntimeError("ogm_modulate: seg_off / seg_len must be int64 device arrays of equal length")
+    rc = L.mla_ogm_modulate(_lib.ptr(_f32(flat_grad, "grad")), _lib.ptr(seg_off), _lib.ptr(seg_len), seg_off.numel(),
+                            int(max_len), _lib.ptr(_f32(coeff, "coeff")), _lib.ptr(_f32(noise, "noise")),
+                            _lib.ptr(_f32(seg_std, "seg_std")), _lib.stream_ptr())
+    _lib.check(rc, "mla_ogm_modulate")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ It restates, on the CPU, what the reference computes on the path named by BASELI
   * ResNet-18 encoders / AVClassifier models/backbone.py:142-160, basic_model.py:52-77 (torch CPU fp32)
   * the alternating gs train step     main.py:419-476               (torch CPU fp32 + autograd + SGD)
   * valid() gs branch                 main.py:622-679
+  * joint training step + OGM / OGM-GE main.py:165-168,269-418; valid() without gs_flag main.py:538-620  (torch CPU fp32)
   * m3ae encoders / M3AEClassifier    models/m3ae.py:65-224,337-370, basic_model.py:184-200 (torch CPU fp32)
   * CAV-MAE audio / Modal3Classifier  models/cav_mae.py:69-151,337-351, basic_model.py:252-275 (torch CPU fp32; the
                                       block's Attention / Mlp come from un-vendored timm==0.4.5: those two UNPINNED)
@@ -154,6 +155,46 @@ def head_ce(feat, W, b, label, grad_scale=None, dtype=np.float64):
     dl[np.arange(B), lab] -= 1.0
     dl *= gs
     return dict(logits=logits, loss=loss, dW=dl.T @ feat, db=dl.sum(0), dfeat=dl @ W, feat_sum=feat.sum(0))
+
+
+# --------------------------------------------------------------------------------------------
+# OGM / OGM-GE coefficients — main.py:315-334 (three modalities), 373-384 (two)
+# --------------------------------------------------------------------------------------------
+def ogm_coefficients(outs, label, alpha):
+    """scores = sum_b softmax(out_m)[b][label_b] added in index order in fp32 (the reference's Python sum of 0-dim
+    tensors); coefficients 1 - tanh(alpha * relu(ratio)) of the dominant modality. Returns (scores, coeffs) as fp32
+    arrays; modality order a, v(, t)."""
+    lab = np.asarray(label)
+    scores = []
+    for o in outs:
+        o = np.asarray(o, np.float32)
+        e = np.exp(o - o.max(axis=1, keepdims=True), dtype=np.float32)
+        p = (e / e.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
+        acc = np.float32(0)
+        for i in range(o.shape[0]):
+            acc = np.float32(acc + p[i, lab[i]])
+        scores.append(acc)
+    alpha = np.float32(alpha)
+    f = lambda r: np.float32(1) - np.tanh(alpha * np.maximum(r, np.float32(0)), dtype=np.float32)   # noqa: E731
+    coeff = [np.float32(1)] * len(outs)
+    if len(outs) == 2:
+        ratio_v = np.float32(scores[1] / scores[0])
+        ratio_a = np.float32(np.float32(1) / ratio_v)
+        if ratio_v > 1:
+            coeff[1] = f(ratio_v)
+        else:
+            coeff[0] = f(ratio_a)
+    else:
+        ratio_v = np.float32(scores[1] / np.float32(scores[0] + scores[2]))
+        ratio_a = np.float32(scores[0] / np.float32(scores[1] + scores[2]))
+        ratio_t = np.float32(scores[2] / np.float32(scores[1] + scores[0]))
+        if ratio_v > 1:
+            coeff[1] = f(ratio_v)
+        elif ratio_t > 1:
+            coeff[2] = f(ratio_t)
+        else:
+            coeff[0] = f(ratio_a)
+    return np.array(scores, np.float32), np.array(coeff, np.float32)
 
 
 # --------------------------------------------------------------------------------------------
@@ -332,6 +373,69 @@ class AVOracle:
             tot_v += lv
         n = len(batches)
         return tot / n, tot_a / n, tot_v / n
+
+    # ---- joint training without --gs_flag: main.py:165-168, 269-310, 312-410, 412-418 ----
+    def joint_step(self, spec, image, label, modulation="Normal", alpha=0.3, in_window=True):
+        """One iteration of the non-gs loop body for AVClassifier with the concatenated head. Returns
+        (loss, loss_a, loss_v); self.last_ogm = (scores, coeffs) when a modulation is active."""
+        torch = self.torch
+        import torch.nn.functional as F
+        self.opt.zero_grad()                                           # main.py:164
+        a, v = av_forward(self.sd, spec.unsqueeze(1).float(), image.float(), training=True)
+        _bump_num_batches(self.sd, "audio_net.")
+        _bump_num_batches(self.sd, "visual_net.")
+        W, b = self.sd["fusion_module.fc_out.weight"], self.sd["fusion_module.fc_out.bias"]
+        out = F.linear(torch.cat((a, v), dim=1), W, b)                 # fusion_modules.py:21-24
+        D = W.shape[1] // 2
+        out_v = torch.mm(v, W[:, D:].t()) + b / 2                      # main.py:304-305
+        out_a = torch.mm(a, W[:, :D].t()) + b / 2                      # main.py:307-308
+        loss = F.cross_entropy(out, label)                             # main.py:309
+        loss_a, loss_v = F.cross_entropy(out_a, label), F.cross_entropy(out_v, label)
+        loss.backward()                                                # main.py:313
+        if modulation in ("OGM", "OGM_GE"):
+            scores, coeff = ogm_coefficients([out_a.detach().cpu().numpy(), out_v.detach().cpu().numpy()],
+                                             label.cpu().numpy(), alpha)
+            self.last_ogm = (scores, coeff)
+            if in_window:                                              # main.py:393
+                for k in self.param_names:                             # named_parameters() order
+                    p = self.sd[k]
+                    if p.grad is None or p.grad.dim() != 4:
+                        continue
+                    for key, c in (("audio", coeff[0]), ("visual", coeff[1])):
+                        if key in k.split(".")[0]:
+                            if modulation == "OGM_GE":                 # main.py:398-399
+                                p.grad = p.grad * float(c) + torch.zeros_like(p.grad).normal_(0, p.grad.std().item() + 1e-8)
+                            else:
+                                p.grad *= float(c)                     # main.py:401
+        self.opt.step()                                                # main.py:412
+        return float(loss.detach()), float(loss_a.detach()), float(loss_v.detach())
+
+    def joint_epoch(self, batches, modulation="Normal", alpha=0.3, epoch=0, starts=0, ends=50):
+        tot = np.zeros(3)
+        for spec, image, label in batches:
+            tot += np.array(self.joint_step(spec, image, label, modulation, alpha, starts <= epoch <= ends))
+        return tuple(tot / len(batches))
+
+    def joint_valid(self, batches, n_classes=6):
+        """main.py:538-620, 653-679 for the concatenated head. Returns (acc, acc_a, acc_v)."""
+        torch = self.torch
+        import torch.nn.functional as F
+        num = np.zeros(n_classes, np.int64)
+        hits = np.zeros((3, n_classes), np.int64)
+        with torch.no_grad():
+            for spec, image, label in batches:
+                a, v = av_forward(self.sd, spec.unsqueeze(1).float(), image.float(), training=False)
+                W, b = self.sd["fusion_module.fc_out.weight"], self.sd["fusion_module.fc_out.bias"]
+                D = W.shape[1] // 2
+                outs = [F.linear(torch.cat((a, v), dim=1), W, b), torch.mm(a, W[:, :D].t()) + b / 2,
+                        torch.mm(v, W[:, D:].t()) + b / 2]
+                lab = label.cpu().numpy()
+                for i, o in enumerate(outs):
+                    pred = np.argmax(F.softmax(o, dim=1).cpu().numpy(), axis=1)     # main.py:653-663
+                    np.add.at(hits[i], lab[pred == lab], 1)
+                np.add.at(num, lab, 1)
+        tot = float(num.sum())
+        return hits[0].sum() / tot, hits[1].sum() / tot, hits[2].sum() / tot
 
     def eval_logits(self, spec, image):
         torch = self.torch

@@ -334,6 +334,95 @@ def make_av(ref_main, ref_utils):
     np.savez_compressed(os.path.join(OUT, "av_classifier.npz"), **out)
 
 
+def make_av_joint(ref_main, ref_utils):
+    """Joint training without --gs_flag (main.py:165-168, 269-310, 412-418) and its OGM / OGM-GE modulation
+    (main.py:312-410), executed by the reference's own train_epoch / valid on small CREMA-D-shaped batches (SURVEY
+    section 8 f1 / f2). OGM_GE draws its noise from torch's default CPU generator, re-seeded before the epoch."""
+    import torch
+    import torch.nn as nn
+    from torch.optim import SGD
+    from torch.optim.lr_scheduler import StepLR
+    out = {}
+    args = ref_main.get_arguments()
+    args.dataset, args.lorb, args.gs_flag, args.dynamic = "CREMAD", "base", False, False
+    args.fusion_method, args.modal3, args.clip, args.use_tensorboard = "concat", False, False, False
+    args.alpha, args.modulation_starts, args.modulation_ends = 0.8, 0, 50
+
+    def batches(n, B, seed, hw, img):
+        g = torch.Generator().manual_seed(seed)
+        res = []
+        for _ in range(n):
+            spec = torch.randn(B, *hw, generator=g)
+            image = torch.randn(B, 3, 2, img, img, generator=g)
+            label = torch.randint(0, 6, (B,), generator=g)
+            res.append((spec, image, label, torch.zeros(B, 1, dtype=torch.long)))
+        return res
+
+    bl = batches(3, 4, 3, (65, 48), 64)
+    for modulation, epoch in (("Normal", 0), ("OGM", 0), ("OGM", 51), ("OGM_GE", 0)):
+        args.modulation = modulation
+        ref_utils.setup_seed(0)
+        model = ref_main.AVClassifier(args)
+        model.apply(ref_utils.weight_init)
+        if modulation == "Normal":
+            out["head_shape"] = np.array(model.fusion_module.fc_out.weight.shape)
+        dp = nn.DataParallel(model, device_ids=[])
+        opt = SGD(dp.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+        sch = StepLR(opt, 70, 0.1)
+        torch.manual_seed(1234)                      # the OGM_GE noise stream
+        losses = ref_main.train_epoch(args, epoch, dp, torch.device("cpu"), bl, opt, sch)
+        accs = ref_main.valid(args, dp, torch.device("cpu"), bl)
+        tag = "%s_e%d_" % (modulation, epoch)
+        out[tag + "losses"] = np.array(losses)
+        out[tag + "accs"] = np.array(accs)
+        sd = model.state_dict()
+        out[tag + "fc_w"] = sd["fusion_module.fc_out.weight"].numpy().copy()
+        # row / column subsets keep the fixture small; the initial values regenerate from the seed
+        out[tag + "a_l4_conv"] = sd["audio_net.layer4.1.conv2.weight"].numpy()[::64, ::8].copy()
+        out[tag + "v_l1_conv"] = sd["visual_net.layer1.0.conv1.weight"].numpy()[::4].copy()
+        out[tag + "a_bn1_w"] = sd["audio_net.bn1.weight"].numpy().copy()
+    # the coefficient rule alone, two and three modalities (main.py:373-384, 315-334), from seeded logits
+    tanh, relu, softmax = nn.Tanh(), nn.ReLU(inplace=True), nn.Softmax(dim=1)
+    for name, B, C, M in (("c2", 16, 6, 2), ("c3", 12, 4, 3), ("c3t", 12, 4, 3), ("c2a", 16, 6, 2), ("c2v", 16, 6, 2),
+                           ("c3v", 12, 4, 3)):
+        g = torch.Generator().manual_seed(sum(map(ord, name)))
+        outs = [torch.randn(B, C, generator=g) for _ in range(M)]
+        label = torch.randint(0, C, (B,), generator=g)
+        if name == "c3t":
+            outs[2][torch.arange(B), label] += 4.0     # text dominates
+        if name == "c2a":
+            outs[0][torch.arange(B), label] += 3.0     # audio dominates
+        if name in ("c2v", "c3v"):
+            outs[1][torch.arange(B), label] += 3.5     # visual dominates
+        score = [sum([softmax(o)[i][label[i]] for i in range(B)]) for o in outs]
+        if M == 2:
+            ratio_v = score[1] / score[0]
+            ratio_a = 1 / ratio_v
+            coeff = [1.0, 1.0]
+            if ratio_v > 1:
+                coeff[1] = float(1 - tanh(args.alpha * relu(ratio_v)))
+            else:
+                coeff[0] = float(1 - tanh(args.alpha * relu(ratio_a)))
+        else:
+            ratio_v = score[1] / (score[0] + score[2])
+            ratio_a = score[0] / (score[1] + score[2])
+            ratio_t = score[2] / (score[1] + score[0])
+            coeff = [1.0, 1.0, 1.0]
+            if ratio_v > 1:
+                coeff[1] = float(1 - tanh(args.alpha * relu(ratio_v)))
+            elif ratio_t > 1:
+                coeff[2] = float(1 - tanh(args.alpha * relu(ratio_t)))
+            else:
+                coeff[0] = float(1 - tanh(args.alpha * relu(ratio_a)))
+        for m in range(M):
+            out["%s_out%d" % (name, m)] = outs[m].numpy()
+        out[name + "_label"] = label.numpy()
+        out[name + "_score"] = np.array([float(x) for x in score], np.float32)
+        out[name + "_coeff"] = np.array(coeff, np.float32)
+    out["alpha"] = np.array(args.alpha)
+    np.savez_compressed(os.path.join(OUT, "av_joint.npz"), **out)
+
+
 M3AE_TINY = dict(model_type=None, emb_dim=64, depth=2, num_heads=2)
 M3AE_VOCAB = 512
 
@@ -585,11 +674,15 @@ if __name__ == "__main__":
     ref_main, ref_utils = import_reference()
     import torch
     torch.set_num_threads(8)
+    if os.environ.get("MLA_GOLDEN_ONLY_JOINT"):
+        make_av_joint(ref_main, ref_utils)
+        sys.exit(0)
     if not any(os.environ.get(k) for k in ("MLA_GOLDEN_ONLY_M3AE", "MLA_GOLDEN_ONLY_MODAL3", "MLA_GOLDEN_ONLY_DH64")):
         make_gs(ref_utils)
         make_fusion(ref_main)
         make_head()
         make_av(ref_main, ref_utils)
+        make_av_joint(ref_main, ref_utils)
     if os.environ.get("MLA_GOLDEN_ONLY_DH64"):
         make_m3ae_dh64(ref_main, ref_utils)
     else:

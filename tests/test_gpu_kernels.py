@@ -166,6 +166,23 @@ def test_head_vs_oracle_seeded(ops, B, D, C):
     assert torch.equal(fwd["logits"], o["logits"]) and fwd["dW"] is None
 
 
+def test_head_out_of_range_label_poisons_the_loss(ops):
+    """nn.CrossEntropyLoss raises for a label outside [0, C); the kernel must not read out of bounds and must
+    not return a plausible number: the row's loss and gradient become NaN."""
+    rng = np.random.default_rng(5)
+    feat = rng.standard_normal((8, 64)).astype(np.float32)
+    W = (rng.standard_normal((6, 64)) * 0.05).astype(np.float32)
+    b = np.zeros(6, np.float32)
+    for bad in (6, -1, 1 << 40):
+        lab = rng.integers(0, 6, 8)
+        lab[3] = bad
+        o = ops.head_ce(dev(feat), dev(W), dev(b), dev(lab, torch.int64))
+        assert np.isnan(float(o["loss"]))
+        assert torch.isnan(o["dfeat"][3]).all() and not torch.isnan(o["dfeat"][2]).any()
+    with pytest.raises(RuntimeError):
+        ops.head_ce(dev(feat), dev(W), dev(b), dev(np.zeros(7, np.int64), torch.int64))
+
+
 # -------------------------------------------------------------------------------- fusion
 @pytest.mark.parametrize("name", ["b64c6m2", "b32c101m3", "b7c4m3", "b256c6m2"])
 @pytest.mark.parametrize("x", [3, 10, 30])

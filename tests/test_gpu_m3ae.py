@@ -129,6 +129,10 @@ def test_train_epoch_and_valid_match_reference_fixture(built_lib, golden, steps)
         print("  %-55s rel-F %.2e, update cosine %.5f, |update| ratio %.4f" % (name, e, cos,
                                                                                np.linalg.norm(upd) / np.linalg.norm(ref)))
         assert e < 1e-3 and cos > 0.999
+    # parameters the forward never reads get no gradient, so SGD (weight decay, momentum) must leave them bit-unchanged
+    for name in ("mae_v.text_embedding.weight", "mae_v.encoder_text_type_embedding", "mae_a.image_embedding.weight",
+                 "mae_a.image_embedding.bias", "mae_a.encoder_image_type_embedding"):
+        assert np.array_equal(sd[name].cpu().numpy(), g["state/" + name]), name
     accs = mla_b200.valid(_args(True), model, dev, batches, gs_flag=True, av_alpha=0.55)
     accs_fix = mla_b200.valid(_args(False), model, dev, batches, gs_flag=True, av_alpha=0.55)
     n = 8.0 * steps

@@ -56,7 +56,7 @@ def test_transformer_host_mirrors_refuse_out_of_scope_configurations():
     from mla_b200.main import build_model
     ok = dict(dataset="Food101", fusion_method="concat", modulation="Normal", gs_flag=True, dynamic=True, lorb="m3ae",
               modal3=False, clip=False)
-    for bad in (dict(fusion_method="sum"), dict(gs_flag=False), dict(modulation="QMF"), dict(dataset="AVE")):
+    for bad in (dict(fusion_method="sum"), dict(modulation="QMF"), dict(dataset="AVE")):
         with pytest.raises(NotImplementedError):
             mla_b200.M3AEClassifier(argparse.Namespace(**{**ok, **bad}), model_config=dict(model_type=None, emb_dim=64, depth=1,
                                                                                            num_heads=2), text_vocab_size=16)
@@ -127,11 +127,31 @@ def test_out_of_scope_paths_raise():
     import mla_b200
     args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modulation="Normal", gs_flag=True,
                               dynamic=True, lorb="base", modal3=False, clip=False)
-    with pytest.raises(NotImplementedError):
-        mla_b200.train_epoch(args, 0, None, "cpu", [], None, None, gs_flag=False)
+    for bad in (dict(modulation="QMF"), dict(lorb="large"), dict(clip=True), dict(fusion_method="sum")):
+        with pytest.raises(NotImplementedError):                  # joint training: QMF / large / clip / sum stay out of scope
+            mla_b200.train_epoch(argparse.Namespace(**{**vars(args), **bad}), 0, None, "cpu", [], None, None, gs_flag=False)
     args.fusion_method = "film"
     with pytest.raises(NotImplementedError):
         mla_b200.AVClassifier(args)
+
+
+def test_joint_mode_head_widths_and_ogm_name_gate():
+    """Without --gs_flag the head is the concatenated one (basic_model.py:34,153,221); the OGM name test of main.py:350-362 /
+    396-403 selects encoders by the substrings the reference uses (so it never fires for the 2-modality m3ae encoders)."""
+    import argparse
+    import mla_b200
+    from mla_b200.engine import ogm_coeff_index
+    a = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modulation="OGM", gs_flag=False, dynamic=False,
+                           lorb="base", modal3=False, clip=False)
+    assert mla_b200.AVClassifier(a).fusion_module.fc_out.weight.shape == (6, 1024)
+    a.gs_flag = True
+    assert mla_b200.AVClassifier(a).fusion_module.fc_out.weight.shape == (6, 512)
+    tiny = dict(model_type=None, emb_dim=64, depth=1, num_heads=2)
+    m = argparse.Namespace(dataset="Food101", fusion_method="concat", modulation="Normal", gs_flag=False, dynamic=False,
+                           lorb="m3ae", modal3=False, clip=False)
+    assert mla_b200.M3AEClassifier(m, model_config=tiny, text_vocab_size=16).fusion_module.fc_out.weight.shape == (101, 128)
+    assert [ogm_coeff_index(n, False) for n in ("audio_net", "visual_net", "mae_a", "mae_v")] == [0, 1, None, None]
+    assert [ogm_coeff_index(n, True) for n in ("mae_a", "mae_v", "mae_t", "audio_net")] == [0, 1, 2, None]
 
 
 _WORKER = r"""
@@ -168,6 +188,10 @@ mdist.allreduce_sum_(fg.flat)
 assert torch.all(ps[0].grad == 3) and torch.all(ps[1].grad == 30)
 g = mdist.all_gather_rows(torch.full((2, 3), float(rank)))
 assert g.shape == (4, 3) and g[0, 0] == 0 and g[3, 0] == 1
+# ragged shards (last batch of a sharded loader without drop_last): rank 0 holds 3 rows, rank 1 holds 1
+g = mdist.all_gather_rows(torch.full((3 - 2 * rank, 2), float(rank + 5)))
+assert g.shape == (4, 2) and g[:3].eq(5).all() and g[3].eq(6).all()
+assert mdist.gather_sizes(3 - 2 * rank, "cpu") == [3, 1]
 # loss mean over ranks == global mean
 l = torch.tensor([loc["loss"]], dtype=torch.float64); mdist.allreduce_sum_(l)
 assert abs(l.item() / world - full["loss"]) < 1e-12
@@ -225,3 +249,21 @@ def test_encoder_param_groups_follow_the_turn_order_and_hot_parameters():
     assert groups[2][0] is net.mae_t.used.weight
     with pytest.raises(RuntimeError):
         encoder_param_groups(torch.nn.Linear(2, 2))
+
+
+def test_m3ae_encoder_names_only_the_parameters_its_forward_reads():
+    """an image encoder never reads its text embedding table (and vice versa); those parameters must keep grad
+    None so that SGD skips them (no weight decay / momentum drift), as in the reference where autograd never touches them."""
+    from mla_b200.m3ae import MaskedMultimodalAutoencoder
+    enc = MaskedMultimodalAutoencoder(32, dict(model_type=None, emb_dim=64, depth=1, num_heads=2))
+    everything = {id(p) for p in enc.parameters()}
+    assert {id(p) for p in enc.hot_parameters()} == everything          # before any forward: nothing is known
+    enc._used = (True, False)                                           # what forward_representation(image, None, None) records
+    hot = {id(p) for p in enc.hot_parameters()}
+    cold = everything - hot
+    assert cold == {id(enc.text_embedding.weight), id(enc.encoder_text_type_embedding)}
+    enc._used = (False, True)
+    hot = {id(p) for p in enc.hot_parameters()}
+    assert everything - hot == {id(enc.image_embedding.weight), id(enc.image_embedding.bias),
+                                id(enc.encoder_image_type_embedding)}
+    assert len(hot) == len(enc.hot_parameters())                        # no duplicates

@@ -183,6 +183,64 @@ def test_kat6_full_size_losses_are_recorded(golden):
 
 
 # ------------------------------------------------------------------------------------------------
+# joint training without --gs_flag + OGM / OGM-GE: make_golden.make_av_joint
+# ------------------------------------------------------------------------------------------------
+def _joint_state(seed=0):
+    import argparse
+    import mla_b200
+    args = argparse.Namespace(dataset="CREMAD", fusion_method="concat", modulation="Normal", gs_flag=False,
+                              dynamic=False, lorb="base", modal3=False, clip=False)
+    mla_b200.setup_seed(seed)
+    model = mla_b200.AVClassifier(args)
+    model.apply(mla_b200.weight_init)
+    return model
+
+
+def _joint_batches():
+    gen = torch.Generator().manual_seed(3)
+    res = []
+    for _ in range(3):
+        spec = torch.randn(4, 65, 48, generator=gen)
+        image = torch.randn(4, 3, 2, 64, 64, generator=gen)
+        label = torch.randint(0, 6, (4,), generator=gen)
+        res.append((spec, image, label))
+    return res
+
+
+@pytest.mark.parametrize("name", ["c2", "c2a", "c2v", "c3", "c3t", "c3v"])
+def test_ogm_coefficients_match_reference(golden, name):
+    g = golden("av_joint")
+    M = 3 if name.startswith("c3") else 2
+    scores, coeff = orc.ogm_coefficients([g["%s_out%d" % (name, m)] for m in range(M)], g[name + "_label"], float(g["alpha"]))
+    assert np.allclose(scores, g[name + "_score"], rtol=2e-6)
+    assert np.allclose(coeff, g[name + "_coeff"], rtol=1e-5, atol=1e-7)
+    assert (coeff == 1).sum() == M - 1                                   # exactly one modality is damped
+
+
+@pytest.mark.parametrize("modulation,epoch", [("Normal", 0), ("OGM", 0), ("OGM", 51), ("OGM_GE", 0)])
+def test_oracle_joint_epoch_matches_reference(golden, modulation, epoch):
+    g = golden("av_joint")
+    model = _joint_state()
+    assert tuple(model.fusion_module.fc_out.weight.shape) == tuple(g["head_shape"]) == (6, 1024)
+    o = orc.AVOracle(model.state_dict())
+    tag = "%s_e%d_" % (modulation, epoch)
+    torch.manual_seed(1234)                                              # the OGM_GE noise stream of the fixture
+    batches = _joint_batches()
+    losses = o.joint_epoch(batches, modulation, float(g["alpha"]), epoch)
+    assert np.allclose(losses, g[tag + "losses"], rtol=1e-5), (losses, g[tag + "losses"])
+    sd = o.sd
+    assert np.allclose(sd["fusion_module.fc_out.weight"].detach().numpy(), g[tag + "fc_w"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(sd["audio_net.layer4.1.conv2.weight"].detach().numpy()[::64, ::8], g[tag + "a_l4_conv"], rtol=1e-4,
+                       atol=1e-6)
+    assert np.allclose(sd["visual_net.layer1.0.conv1.weight"].detach().numpy()[::4], g[tag + "v_l1_conv"], rtol=1e-4,
+                       atol=1e-6)
+    assert np.allclose(sd["audio_net.bn1.weight"].detach().numpy(), g[tag + "a_bn1_w"], rtol=1e-5)
+    assert np.allclose(o.joint_valid(batches), g[tag + "accs"], atol=1e-9)
+    if modulation == "OGM" and epoch == 51:                              # outside the modulation window == Normal
+        assert np.array_equal(g[tag + "fc_w"], g["Normal_e0_fc_w"])
+
+
+# ------------------------------------------------------------------------------------------------
 # --lorb m3ae (BASELINE.json configs[2]): fixtures from the reference's own M3AEClassifier.forward /
 # MaskedMultimodalAutoencoder / train_epoch / valid on a tiny encoder configuration (make_golden.make_m3ae)
 # ------------------------------------------------------------------------------------------------
