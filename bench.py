@@ -36,6 +36,9 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-sweep", action="store_true")
     p.add_argument("--no-extra", action="store_true", help="skip the informational transformer-path timings (N=1 only)")
+    p.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager legs (N=1 only)")
+    p.add_argument("--no-tf32-leg", action="store_true", help="skip the TF32-operand re-run of the step (N=1 only)")
+    p.add_argument("--tf32-leg", action="store_true", help=argparse.SUPPRESS)     # internal: child process of the TF32 leg
     return p.parse_args()
 
 
@@ -124,10 +127,11 @@ def run_reference(a, rank):
     mla_b200.setup_seed(0)
     net = mla_b200.AVClassifier(make_args()).apply(mla_b200.weight_init)      # parameter container only (CPU init)
     o = orc.AVOracle(net.state_dict(), force_projection=True)
-    # calibrate a bounded sample: whole run <= ~150 s
+    # the full B = 64 batch of the metric's configuration whenever the whole run stays within ~4 minutes (2.4 s per step
+    # on 16 cores: 25 steps = 60 s); otherwise a bounded sample of it
     spec, image, label = orc.synthetic_av_batch(4, 7)
     t0 = time.perf_counter(); o.train_step(spec, image, label, 0, 1); per_sample = (time.perf_counter() - t0) / 4
-    budget = 150.0 / max(1, a.steps + a.warmup)
+    budget = 240.0 / max(1, a.steps + a.warmup)
     bs = int(max(2, min(BATCH, budget / per_sample)))
     spec, image, label = orc.synthetic_av_batch(bs, 1)
     for i in range(a.warmup):
@@ -141,7 +145,8 @@ def run_reference(a, rank):
            "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "sample_batch": bs, "device": "host CPU"},
+           "config": {"workload": WORKLOAD, "global_batch": bs, "sample_batch": bs, "device": "host CPU",
+                      "same_batch_as_native_arm": bs == BATCH},
            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                             "sample": "%d timed steps of the oracle's alternating step on %d-sample batches" % (a.steps, bs)},
            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -156,12 +161,12 @@ def cpu_baseline():
     mla_b200.setup_seed(0)
     net = mla_b200.AVClassifier(make_args()).apply(mla_b200.weight_init)
     o = orc.AVOracle(net.state_dict(), force_projection=True)
-    bs = 16
+    bs = BATCH                                     # the metric's own batch: ~2.4 s per step on 16 host cores
     spec, image, label = orc.synthetic_av_batch(bs, 1)
     o.train_step(spec, image, label, 0, 3)
     t0 = time.perf_counter()
     n = 0
-    while n < 2 or (time.perf_counter() - t0 < 10 and n < 6):
+    while n < 2 or (time.perf_counter() - t0 < 10 and n < 4):
         o.train_step(spec, image, label, n + 1, 8)
         n += 1
     dt = time.perf_counter() - t0
@@ -170,32 +175,194 @@ def cpu_baseline():
 
 
 # --------------------------------------------------------------------------------- native arm
+SWEEP_D, SWEEP_B, SWEEP_C = (512, 768, 1024, 2048), (64, 256, 1024, 4096), (6, 101)     # BASELINE.json configs[4]
+
+
+def _time_launch(torch, fn, flush, reps=10, warm=3):
+    """Median CUDA-event time of fn() on the current stream, the L2 flushed (256 MB written) before every timed launch."""
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return statistics.median(ts)
+
+
+def _point(pk, t, nbytes, **kw):
+    # a launch whose algorithmic bytes would take < 3 us at the HBM peak cannot be HBM-bound: launch latency, grid-wide
+    # synchronisation and L2 residency decide its time (SURVEY F12); such points are labelled, not hidden
+    d = dict(kw, us=t * 1e6, bytes=nbytes, gbs=nbytes / t / 1e9, frac=nbytes / t / 1e9 / pk["hbm"])
+    d["regime"] = "latency" if nbytes / (pk["hbm"] * 1e9) < 3e-6 else "bandwidth"
+    return d
+
+
 def gs_sweep(torch, ops, pk):
-    """GSPlugin HBM GB/s (second half of BASELINE.json's metric): algorithmic bytes
+    """GSPlugin HBM GB/s (second half of BASELINE.json's metric) over the full configs[4] grid: algorithmic bytes
     4*(B*D + 2*D*D + 2*C*D) / CUDA-event time, L2 flushed between launches."""
     from mla_b200.gs_plugin import GSPlugin
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    alpha = GSPlugin.alpha(1, 10)
     pts = []
-    for (B, D, C) in [(64, 512, 6), (64, 768, 101), (4096, 2048, 6), (4096, 2048, 101)]:
-        feat = torch.randn(B, D, device=dev).relu()
-        grad = torch.randn(C, D, device=dev)
-        P = torch.eye(D, device=dev)
-        alpha = GSPlugin.alpha(1, 10)
-        for _ in range(3):
-            ops.gs_project(P, grad, alpha, feat=feat)
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); ops.gs_project(P, grad, alpha, feat=feat); e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e-3)
-        t = statistics.median(ts)
-        nbytes = 4 * (B * D + 2 * D * D + 2 * C * D)
-        pts.append({"B": B, "D": D, "C": C, "us": t * 1e6, "bytes": nbytes, "gbs": nbytes / t / 1e9,
-                    "frac": nbytes / t / 1e9 / pk["hbm"]})
+    for D in SWEEP_D:
+        for B in SWEEP_B:
+            for C in SWEEP_C:
+                feat = torch.randn(B, D, device=dev).relu()
+                grad = torch.randn(C, D, device=dev)
+                P = torch.eye(D, device=dev)
+                t = _time_launch(torch, lambda: ops.gs_project(P, grad, alpha, feat=feat), flush)
+                pts.append(_point(pk, t, 4 * (B * D + 2 * D * D + 2 * C * D), B=B, D=D, C=C))
     return pts
+
+
+def head_sweep(torch, ops, pk):
+    """Shared head forward + backward (main.py:432-435): algorithmic bytes 4*(2*B*D + 3*C*D + 2*B*C)."""
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pts = []
+    for D in SWEEP_D:
+        for B in SWEEP_B:
+            for C in SWEEP_C:
+                feat = torch.randn(B, D, device=dev).relu()
+                W = torch.randn(C, D, device=dev) * 0.05
+                b = torch.zeros(C, device=dev)
+                label = torch.randint(0, C, (B,), device=dev)
+                out = {}
+                t = _time_launch(torch, lambda: ops.head_ce(feat, W, b, label, out=out), flush)
+                pts.append(_point(pk, t, 4 * (2 * B * D + 3 * C * D + 2 * B * C), B=B, D=D, C=C))
+    return pts
+
+
+def fusion_sweep(torch, ops, pk):
+    """Test-time entropy fusion + argmax + counters (main.py:65-106, 640-676): bytes 4*(M+1)*B*C + 8*B."""
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pts = []
+    for M in (2, 3):
+        for B in SWEEP_B:
+            for C in SWEEP_C:
+                outs = [torch.randn(B, C, device=dev) for _ in range(M)]
+                label = torch.randint(0, C, (B,), device=dev)
+                hits = torch.zeros(M + 1, C, dtype=torch.int64, device=dev)
+                num = torch.zeros(C, dtype=torch.int64, device=dev)
+                t = _time_launch(torch, lambda: ops.fuse_eval(outs, label, hits=hits, num=num), flush)
+                pts.append(_point(pk, t, 4 * (M + 1) * B * C + 8 * B, M=M, B=B, C=C))
+    return pts
+
+
+# ----------------------------------------------------------------------------- PyTorch-eager legs
+def eager_baseline(torch, steps=5, warm=2):
+    """The reference's step (main.py:127-164, 419-476) executed by PyTorch eager on this GPU — cuDNN / cuBLAS / ATen, the
+    reference's per-turn optimizer.step() and per-step .item() reads — in three arithmetic modes: torch's defaults (cuDNN
+    TF32: what the reference runs as published), strict fp32, and autocast-bf16 with channels_last tensors (the usual
+    2-byte eager configuration; narrower than the reference, listed for context next to the 2-byte kernels)."""
+    import torch.nn.functional as F
+    import mla_b200
+    dev = torch.device("cuda")
+    res = {}
+    layers = ((64, 1), (128, 2), (256, 2), (512, 2))
+
+    def bn(x, sd, p):
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], True, 0.1,
+                            1e-5)
+
+    def resnet(sd, p, x, visual):                       # models/backbone.py:142-160, 36-52
+        if visual:
+            B, C, T, H, W = x.shape
+            x = x.permute(0, 2, 1, 3, 4).contiguous().view(B * T, C, H, W)
+        x = F.max_pool2d(F.relu(bn(F.conv2d(x, sd[p + "conv1.weight"], None, 2, 3), sd, p + "bn1")), 3, 2, 1)
+        inpl = 64
+        for li, (planes, stride) in enumerate(layers, start=1):
+            for bi in range(2):
+                st = stride if bi == 0 else 1
+                q = "%slayer%d.%d." % (p, li, bi)
+                idn = x
+                o = F.relu(bn(F.conv2d(x, sd[q + "conv1.weight"], None, st, 1), sd, q + "bn1"))
+                o = bn(F.conv2d(o, sd[q + "conv2.weight"], None, 1, 1), sd, q + "bn2")
+                if bi == 0 and (st != 1 or inpl != planes):
+                    idn = bn(F.conv2d(x, sd[q + "downsample.0.weight"], None, st), sd, q + "downsample.1")
+                x = F.relu(o + idn)
+                inpl = planes
+        return x
+
+    gen = torch.Generator().manual_seed(1)
+    spec = torch.randn(BATCH, 257, 188, generator=gen).to(dev)
+    image = torch.randn(BATCH, 3, 2, 224, 224, generator=gen).to(dev)
+    label = torch.randint(0, 6, (BATCH,), generator=gen).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    for mode in ("tf32", "fp32", "amp_bf16_channels_last"):
+        try:
+            torch.backends.cudnn.allow_tf32 = mode != "fp32"
+            mla_b200.setup_seed(0)
+            net = mla_b200.AVClassifier(make_args()).apply(mla_b200.weight_init)      # parameter container (same init)
+            sd = {k: v.detach().to(dev) for k, v in net.state_dict().items()}
+            cl = mode.startswith("amp")
+            for k in sd:
+                if cl and sd[k].dim() == 4:
+                    sd[k] = sd[k].contiguous(memory_format=torch.channels_last)
+            names = [k for k in sd if sd[k].dtype.is_floating_point and not k.endswith(("running_mean", "running_var"))]
+            for k in names:
+                sd[k].requires_grad_(True)
+            opt = torch.optim.SGD([sd[k] for k in names], lr=1e-3, momentum=0.9, weight_decay=1e-4)
+            W, b = sd["fusion_module.fc_out.weight"], sd["fusion_module.fc_out.bias"]
+
+            def step():
+                opt.zero_grad()
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cl):
+                    a_in = spec.unsqueeze(1)
+                    v_in = image
+                    if cl:
+                        a_in = a_in.contiguous(memory_format=torch.channels_last)
+                    fa = torch.flatten(F.adaptive_avg_pool2d(resnet(sd, "audio_net.", a_in, False), 1), 1)
+                    fv = resnet(sd, "visual_net.", v_in, True)
+                    _, C, H, Wd = fv.shape
+                    fv = torch.flatten(F.adaptive_avg_pool3d(fv.view(BATCH, -1, C, H, Wd).permute(0, 2, 1, 3, 4), 1), 1)
+                tot = []
+                for feat in (fa, fv):                                             # main.py:432-442 / 444-454
+                    loss = F.cross_entropy(F.linear(feat.float(), W, b), label)
+                    loss.backward()
+                    opt.step()
+                    opt.zero_grad()
+                    tot.append(loss)
+                return (tot[0] * 0.55 + tot[1] * 0.45).item(), tot[0].item(), tot[1].item()   # main.py:472-475
+
+            for _ in range(warm):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[mode] = {"ms_per_step": ms, "samples_per_s": BATCH * 1e3 / ms}
+            del sd, opt, net
+            torch.cuda.empty_cache()
+        except Exception as exc:                                                  # informational: never lose the headline
+            res[mode] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    torch.backends.cudnn.allow_tf32 = prev
+    res["what"] = ("the reference's alternating step under PyTorch eager on this GPU (cuDNN / ATen; B = 64, %d timed "
+                   "steps after %d warm-up, CUDA events); GS hook as published = no-op" % (steps, warm))
+    return res
+
+
+def tf32_leg(a):
+    """The same K timed steps with TF32 operands (kind::tf32 tensor-core instructions, MLA_F16=0) in a child process:
+    the operand format is fixed when the package is imported. Returns {value, ms_per_step} or {error}."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--tf32-leg", "--steps", str(a.steps), "--warmup", str(a.warmup)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, MLA_F16="0"))
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as exc:
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
 
 
 def run_native(a, rank, world):
@@ -244,6 +411,22 @@ def run_native(a, rank, world):
     with quiet:
         t_dev = timed(lambda: epoch(resident, a.steps))
     launches = _lib.launch_count() + encoder_engine.GRAPH_LAUNCHES - l0     # eager launches + graph-replayed kernel nodes
+    if a.tf32_leg:                          # child process of tf32_leg(): the device-resident timed region only
+        print(json.dumps({"value": BATCH * world * a.steps / t_dev, "ms_per_step": 1e3 * t_dev / a.steps, "unit": "samples/s",
+                          "dtype": "tf32" if not encoder_engine.USE_F16 else "f16"}), flush=True)
+        return
+    # data-parallel invariant: P, the head and both encoders are bit-identical on every rank
+    dp_identical = None
+    if world > 1:
+        net_ = model.module
+        cs = torch.tensor([mdist.params_checksum(gs.Pl), mdist.params_checksum(net_.fusion_module.fc_out.weight),
+                           mdist.params_checksum(net_.audio_net._mla_flat), mdist.params_checksum(net_.visual_net._mla_flat),
+                           gs.exp_count], dtype=torch.int64, device=dev)
+        allc = [torch.zeros_like(cs) for _ in range(world)]
+        torch.distributed.all_gather(allc, cs)
+        dp_identical = all(torch.equal(allc[0], c) for c in allc)
+        if not dp_identical:
+            raise SystemExit("bench.py: data-parallel state differs across ranks: %s" % [c.tolist() for c in allc])
     # end to end: host (pinned) buffers in, H2D every step, losses read back to the host every step
     with quiet:
         epoch(host, min(2, a.warmup))
@@ -311,7 +494,14 @@ def run_native(a, rank, world):
     out = {"metric": "MLA train samples/sec (CREMA-D AV, ResNet-18)", "value": value, "unit": "samples/s",
            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": ("f16" if encoder_engine.STEM_F16 else "f16+tf32") if encoder_engine.USE_F16 else "tf32", "data": "synthetic",
+           "dtype": ("f16" if encoder_engine.STEM_F16 else "f16+tf32") if encoder_engine.USE_F16 else "tf32",
+           "dtype_note": ("tensor-core operands fp16 = TF32's 10-bit mantissa (forward: activations / weights; backward: "
+                          "gradients multiplied by an exact power of two chosen per layer on the device, activations, "
+                          "transposed filters), fp32 accumulation, fp32 conv outputs / BatchNorm / residual stream / SGD: "
+                          "the arithmetic class of the reference under torch's default cudnn.allow_tf32=True "
+                          "(tests/test_gpu_encoder_grad.py); value_tf32 = the same step on kind::tf32 instructions")
+                         if encoder_engine.USE_F16 else "TF32 operands (kind::tf32), fp32 accumulation",
+           "data": "synthetic",
            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                       "encoder_backend": encoder_engine.BACKEND, "gs_projection": "fires (force_projection)",
                       "streams": ("audio / visual encoders on two CUDA streams" if overlap else "single stream") +
@@ -322,6 +512,7 @@ def run_native(a, rank, world):
            "e2e": {"value": samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * t_e2e / a.steps},
            "eval_samples_per_s": samples / t_eval, "host_enqueue_ms_per_step": host_ms,
+           "dp_state_identical": dp_identical,
            "encoder_tflops": FLOP_PER_SAMPLE_STEP * samples / t_dev / 1e12}
     prof = profile_summary()
     if conv is not None and conv["seconds"] > 0:
@@ -335,9 +526,10 @@ def run_native(a, rank, world):
                       for k, v in conv["by_kind"].items())
         peak = conv["flops"] / t_ideal / 1e12
         ach = conv["flops"] / conv["seconds"] / 1e12
-        out["roofline"] = {"kernel": "conv16_persistent_kernel (fprop16 / dgrad16) + conv_gemm_kernel (wgrad16): tcgen05 implicit GEMM, im2col-TMA fed, kind::f16 (fp16 fprop, bf16 dgrad/wgrad, stem included)",
+        out["roofline"] = {"kernel": "conv16_persistent_kernel (fprop16 / dgrad16) + conv_gemm_kernel (wgrad16): tcgen05 implicit GEMM, im2col-TMA fed, kind::f16 (fp16 operands, scaled fp16 gradients, stem included)",
                            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                            "traffic": prof.get("conv_traffic"),
+                           "traffic_source": "ncu --set full capture of one 56x56x64 fprop16 launch (profiles/), not this run",
                            "peak_source": "FLOP-weighted blend of bf16_tflops_sustained (f16 launches) and 0.5x (tf32 launches), "
                                           + pk["source"],
                            "launches_per_step": conv["launches"] / a.steps,
@@ -347,14 +539,24 @@ def run_native(a, rank, world):
                                                                            if conv["instrumented_ms_per_step"] else t_dev / a.steps),
                            "by_kind": {k: {kk: vv for kk, vv in v.items() if kk != "flops"} for k, v in conv["by_kind"].items()},
                            "instrumented_ms_per_step": conv["instrumented_ms_per_step"]}
-    if not a.no_sweep:
-        pts = gs_sweep(torch, ops, pk)
-        top = max(pts, key=lambda p: p["gbs"])
-        out["roofline_gs"] = {"kernel": "gs_project_kernel", "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"],
-                              "unit": "GB/s", "frac": top["frac"], "traffic": prof.get("gs_traffic"),
-                              "peak_source": pk["source"],
-                              "point": {k: top[k] for k in ("B", "D", "C", "us", "bytes")}}
-        out["gs_sweep"] = pts
+    if not a.no_sweep and world == 1:
+        # BASELINE.json configs[4]: D {512..2048} x B {64..4096} x C {6, 101} (x M {2, 3} for the fusion kernel). The headline
+        # point of each kernel is its best bandwidth-regime point; every point (latency-bound ones labelled) is listed
+        for key, fn, kern in (("gs", gs_sweep, "gs_project_kernel"), ("head", head_sweep, "head_fwd_kernel + head_bwd_kernel"),
+                              ("fusion", fusion_sweep, "fuse_eval_kernel")):
+            pts = fn(torch, ops, pk)
+            top = max(pts, key=lambda p: p["gbs"])
+            out["roofline_" + key] = {"kernel": kern, "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"],
+                                      "unit": "GB/s", "frac": top["frac"],
+                                      "traffic": prof.get("gs_traffic") if key == "gs" else None, "peak_source": pk["source"],
+                                      "point": {k: v for k, v in top.items() if k not in ("gbs", "frac")},
+                                      "latency_bound_points": sum(1 for p in pts if p["regime"] == "latency"),
+                                      "points": len(pts)}
+            out[key + "_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()} for p in pts]
+    if not a.no_tf32_leg and world == 1 and encoder_engine.USE_F16:
+        out["value_tf32"] = tf32_leg(a)
+    if not a.no_eager and world == 1:
+        out["eager_baseline"] = eager_baseline(torch)
     if not a.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline()
     if not a.no_extra and world == 1:

@@ -293,6 +293,28 @@ MLA_API int    mla_avgpool_forward(const float* fm, float* feat, int B, int rows
 MLA_API int    mla_avgpool_backward(const float* dfeat, float* dfm, int B, int rows, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * fp16 gradient operands with an exact power-of-two scale (the backward convolutions of backbone.py:39-50 under autograd,
+ * main.py:435): TF32's 10-bit operand mantissa at the kind::f16 tensor-core rate.
+ *   mla_bn_backward_f16     BatchNorm backward whose dy leaves as fp16(dy * F); F = 2^k is chosen on the device from
+ *                           max |dz * relu mask| * |gamma| * invstd (found by the reduction pass) so that the bound lands in
+ *                           [2^8, 2^9); conversions saturate. gscale[0] = F, gscale[1] = 1 / F (device floats).
+ *   mla_conv2d_dgrad16_f16  dx (+)= *out_scale * (dy16 (*) wt16)   dy16 fp16 scaled, wt16 fp16 transposed filter [Cin][R][S][Cout]
+ *   mla_conv2d_wgrad16_f16  dw = *out_scale * (dy16^T (*) x16)     x16 = the forward's fp16 activation; workspace as
+ *                           mla_conv2d_wgrad16_workspace_bytes
+ *   mla_filter_transpose16_batch  every filter of an encoder transposed / cast in one launch; seg_table = device array of
+ *                           {int64 element offset, int32 Cout, RS, Cin, first tile} (24 bytes each), ntiles = all 32x32 tiles
+ */
+MLA_API int    mla_bn_backward_f16(const float* dz, const unsigned int* relu_mask, const float* y, const float* mean,
+                        const float* invstd, const float* gamma, long long M, int C, float* dgamma, float* dbeta,
+                        void* dy16, float* g_out, float* gscale, void* ws, size_t ws_bytes, void* stream);
+MLA_API int    mla_conv2d_dgrad16_f16(const void* dy16, const void* wt16, const float* out_scale, float* dx, int N, int H,
+                        int W, int Cin, int Cout, int R, int S, int stride, int pad, int accumulate, void* stream);
+MLA_API int    mla_conv2d_wgrad16_f16(const void* x16, const void* dy16, const float* out_scale, float* dw, int N, int H,
+                        int W, int Cin, int Cout, int R, int S, int stride, int pad, void* ws, size_t ws_bytes, void* stream);
+MLA_API int    mla_filter_transpose16_batch(const float* flat, void* flat_t16, const void* seg_table, int nseg, int ntiles,
+                        int bf16, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * OGM / OGM-GE gradient modulation of the joint-training step — main.py:312-410.
  *   mla_ogm_scores   score[m] = sum_b softmax(logits[m])[b][label[b]], b added in index order   main.py:315-317, 373-374
  *                    `logits` is a HOST array of M (2 or 3) device pointers to B x C matrices; ws >= M * B floats.

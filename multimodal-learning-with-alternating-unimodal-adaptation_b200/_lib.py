@@ -83,6 +83,10 @@ _SIGNATURES = {
     "mla_maxpool_relu_backward": (_c_int, [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p]),
     "mla_avgpool_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "mla_avgpool_backward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "mla_bn_backward_f16": (_c_int, [_c_void_p] * 6 + [_c_ll, _c_int] + [_c_void_p] * 6 + [_c_size_t, _c_void_p]),
+    "mla_conv2d_dgrad16_f16": (_c_int, [_c_void_p] * 4 + [_c_int] * 10 + [_c_void_p]),
+    "mla_conv2d_wgrad16_f16": (_c_int, [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),
+    "mla_filter_transpose16_batch": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "mla_ogm_scores_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "mla_ogm_scores": (_c_int, [ctypes.POINTER(_c_void_p), _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
                                 _c_size_t, _c_void_p]),

@@ -955,6 +955,7 @@ __global__ void __launch_bounds__(kThreads) conv16_persistent_kernel(const __gri
       }
     }
   } else {
+    const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;   // undoes the power-of-two scale of fp16 gradients
     int nt = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++nt) {
       const int buf = nt & 1;
@@ -986,6 +987,10 @@ __global__ void __launch_bounds__(kThreads) conv16_persistent_kernel(const __gri
           for (int j = 0; j < 8; ++j)
             o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                __uint_as_float(v[4 * j + 3]));
+          if (p.out_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x *= oscale; o[j].y *= oscale; o[j].z *= oscale; o[j].w *= oscale; }
+          }
           if (p.accumulate) {
             float4 old[8];
 #pragma unroll
@@ -1554,8 +1559,24 @@ extern "C" int mla_linear_dgrad(const float* dy, const float* w, float* dx, int 
   return BN == 64 ? launch<1, 64, 4, true>(map, gmap, p, grid, st) : launch<1, 128, 3, true>(map, gmap, p, grid, st);
 }
 
+static int dgrad16_impl(const void* dy16, const void* wt16, float* dx, int N, int H, int W, int Cin, int Cout, int R, int S,
+                        int stride, int pad, int accumulate, void* stream, bool bf16, const float* out_scale);
+
 extern "C" int mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx, int N, int H, int W, int Cin, int Cout,
                                   int R, int S, int stride, int pad, int accumulate, void* stream) {
+  return dgrad16_impl(dy16, wt16, dx, N, H, W, Cin, Cout, R, S, stride, pad, accumulate, stream, true, nullptr);
+}
+
+// fp16 operands: dy16 = fp16(dy * F) with F a power of two (mla_bn_backward_f16), wt16 = the transposed fp16 filter;
+// dx (+)= *out_scale * (dy16 (*) wt16), out_scale = 1 / F (device scalar). TF32's 10-bit operand mantissa at the kind::f16 rate.
+extern "C" int mla_conv2d_dgrad16_f16(const void* dy16, const void* wt16, const float* out_scale, float* dx, int N, int H, int W,
+                                      int Cin, int Cout, int R, int S, int stride, int pad, int accumulate, void* stream) {
+  if (!out_scale) return MLA_E_BADARG;
+  return dgrad16_impl(dy16, wt16, dx, N, H, W, Cin, Cout, R, S, stride, pad, accumulate, stream, false, out_scale);
+}
+
+static int dgrad16_impl(const void* dy16, const void* wt16, float* dx, int N, int H, int W, int Cin, int Cout, int R, int S,
+                        int stride, int pad, int accumulate, void* stream, bool bf16, const float* out_scale) {
   if (!dy16 || !wt16 || !dx || !mla::aligned16(dy16) || !mla::aligned16(wt16) || !mla::aligned16(dx)) return MLA_E_BADARG;
   if (!conv_shape_ok(N, H, W, Cin, Cout, R, S, stride, pad)) return MLA_E_SHAPE;
   const mla::DeviceInfo& di = mla::device_info();
@@ -1565,24 +1586,31 @@ extern "C" int mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx,
   ConvGemmParams p{};
   p.OH = H; p.OW = W; p.M = N * H * W; p.R = R; p.S = S; p.mul = 1;
   p.kcb = Cout / 64; p.CinW = Cout;      // GEMM K = dy channels; a filter tap spans Cout columns of the transposed filter
-  p.out = dx; p.ldo = Cin; p.accumulate = accumulate ? 1 : 0; p.Cout = Cin;
+  p.out = dx; p.ldo = Cin; p.accumulate = accumulate ? 1 : 0; p.Cout = Cin; p.out_scale = out_scale;
   const int BN = (Cin % 128 == 0) ? 128 : 64;
   CUtensorMap map, gmap;
-  int rc = make_map_2d16(&map, wt16, true, Cin, (long long)R * S * Cout, BN);
+  int rc = make_map_2d16(&map, wt16, bf16, Cin, (long long)R * S * Cout, BN);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto go = [&](const ConvGemmParams& q, dim3 g) {
-    if (conv_persist() && q.KB > 0)
-      return BN == 64 ? launch_conv16_persistent<64, 4, 2>(map, gmap, q, (int)g.y, st)
-                      : launch_conv16_persistent<128, 3, 2>(map, gmap, q, (int)g.y, st);
-    return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 2>(map, gmap, q, g, st)
-                    : launch<0, 128, 3, true, 1, 1, false, 2>(map, gmap, q, g, st);
+    if (conv_persist() && q.KB > 0) {
+      if (bf16)
+        return BN == 64 ? launch_conv16_persistent<64, 4, 2>(map, gmap, q, (int)g.y, st)
+                        : launch_conv16_persistent<128, 3, 2>(map, gmap, q, (int)g.y, st);
+      return BN == 64 ? launch_conv16_persistent<64, 4, 1>(map, gmap, q, (int)g.y, st)
+                      : launch_conv16_persistent<128, 3, 1>(map, gmap, q, (int)g.y, st);
+    }
+    if (bf16)
+      return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 2>(map, gmap, q, g, st)
+                      : launch<0, 128, 3, true, 1, 1, false, 2>(map, gmap, q, g, st);
+    return BN == 64 ? launch<0, 64, 4, true, 1, 1, false, 1>(map, gmap, q, g, st)
+                    : launch<0, 128, 3, true, 1, 1, false, 1>(map, gmap, q, g, st);
   };
   if (stride == 1) {
     p.KB = R * S * p.kcb;
     p.g_base_w = pad - (S - 1); p.g_base_h = pad - (R - 1);
     full_taps(p, R, S, true);
-    rc = make_map_im2col16(&gmap, dy16, true, N, OH, OW, Cout, p.g_base_w, p.g_base_h, p.g_base_w + (W - OW),
+    rc = make_map_im2col16(&gmap, dy16, bf16, N, OH, OW, Cout, p.g_base_w, p.g_base_h, p.g_base_w + (W - OW),
                            p.g_base_h + (H - OH), 1, 128);
     if (rc) return rc;
     return go(p, dim3((p.M + 127) / 128, Cin / BN));
@@ -1620,7 +1648,7 @@ extern "C" int mla_conv2d_dgrad16(const void* dy16, const void* wt16, float* dx,
       for (int i = 0; i < q.nr; ++i) q.off_r[i] = (signed char)(qr[i] - lo_h);
       for (int j = 0; j < q.ns; ++j) q.off_s[j] = (signed char)(qs[j] - lo_w);
       q.g_base_w = lo_w; q.g_base_h = lo_h;
-      rc = make_map_im2col16(&gmap, dy16, true, N, OH, OW, Cout, lo_w, lo_h, lo_w + Ws - OW, lo_h + Hs - OH, 1, 128);
+      rc = make_map_im2col16(&gmap, dy16, bf16, N, OH, OW, Cout, lo_w, lo_h, lo_w + Ws - OW, lo_h + Hs - OH, 1, 128);
       if (rc) return rc;
       rc = go(q, dim3((q.M + 127) / 128, Cin / BN));
       if (rc) return rc;
@@ -1727,6 +1755,15 @@ extern "C" int mla_conv2d_wgrad16(const void* x16, const void* dy16, float* dw, 
   return wgrad16_impl(x16, dy16, dw, N, H, W, Cin, Cout, R, S, stride, pad, ws, ws_bytes, stream, true, nullptr);
 }
 
+// fp16 operands: x16 = the fp16 activation the forward convolution already read, dy16 = fp16(dy * F) (mla_bn_backward_f16);
+// dw = *out_scale * (dy16^T (*) x16), out_scale = 1 / F (device scalar).
+extern "C" int mla_conv2d_wgrad16_f16(const void* x16, const void* dy16, const float* out_scale, float* dw, int N, int H, int W,
+                                      int Cin, int Cout, int R, int S, int stride, int pad, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  if (!out_scale) return MLA_E_BADARG;
+  return wgrad16_impl(x16, dy16, dw, N, H, W, Cin, Cout, R, S, stride, pad, ws, ws_bytes, stream, false, out_scale);
+}
+
 // dw [N, K] = *out_scale * dy16 [M, N]^T (fp16, scaled by a power of two) * x16 [M, K] (fp16): the weight gradient of a
 // Linear; workspace from mla_conv2d_wgrad16_workspace_bytes(1, M, 1, K, N, 1, 1, 1, 0).
 extern "C" int mla_linear_wgrad16(const void* x16, const void* dy16, const float* out_scale, float* dw, int M, int K, int N,
@@ -1764,7 +1801,7 @@ static int wgrad16_impl(const void* x16, const void* dy16, float* dw, int N, int
          : pl.BN == 64 ? launch<2, 64, 4, true, 1, 1, false, 2>(map, gmap, p, grid, st)
                        : launch<2, 128, 3, true, 1, 1, false, 2>(map, gmap, p, grid, st);
   else
-    rc = pl.NT == 3 ? MLA_E_SHAPE
+    rc = pl.NT == 3 ? launch<2, 64, 2, true, 3, 1, false, 1>(map, gmap, p, grid, st)
          : pl.BN == 64 ? launch<2, 64, 4, true, 1, 1, false, 1>(map, gmap, p, grid, st)
                        : launch<2, 128, 3, true, 1, 1, false, 1>(map, gmap, p, grid, st);
   if (rc) return rc;

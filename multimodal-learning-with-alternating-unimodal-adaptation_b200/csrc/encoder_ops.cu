@@ -46,6 +46,14 @@ __device__ __forceinline__ uint2 pack_h4(float4 v) {
   const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
   return make_uint2(*reinterpret_cast<const unsigned int*>(&a), *reinterpret_cast<const unsigned int*>(&b));
 }
+// fp16 pack with saturation to +-65504 (an overflow of the power-of-two-scaled gradients becomes the largest finite value,
+// never inf)
+__device__ __forceinline__ uint2 pack_h4_sat(float4 v) {
+  uint2 r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(v.y), "f"(v.x));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(v.w), "f"(v.z));
+  return r;
+}
 __device__ __forceinline__ uint2 pack_b4(float4 v) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   return make_uint2(*reinterpret_cast<const unsigned int*>(&a), *reinterpret_cast<const unsigned int*>(&b));
@@ -77,6 +85,39 @@ __global__ void filter_transpose16_kernel(const float* __restrict__ w, unsigned 
       if (bf16) { const __nv_bfloat16 h = __float2bfloat16_rn(v); bits = *reinterpret_cast<const unsigned short*>(&h); }
       else { const __half h = __float2half_rn(v); bits = *reinterpret_cast<const unsigned short*>(&h); }
       wt[((long long)ci * RS + rs) * Cout + co] = bits;
+    }
+  }
+}
+
+// All filters of an encoder in ONE launch: seg[i] = {element offset of filter i in the flat parameter buffer (= in the 2-byte
+// buffer), Cout, RS, Cin, first tile}; a block finds its filter by a linear scan over the (<= 64) segments.
+struct TransposeSeg { long long off; int Cout, RS, Cin, tile0; };
+__global__ void filter_transpose16_batch_kernel(const float* __restrict__ flat, unsigned short* __restrict__ flat_t,
+                                                const TransposeSeg* __restrict__ seg, int nseg, int bf16) {
+  __shared__ float tile[32][33];
+  int i = 0;
+  while (i + 1 < nseg && (int)blockIdx.x >= seg[i + 1].tile0) ++i;
+  const TransposeSeg sg = seg[i];
+  const int t = blockIdx.x - sg.tile0;
+  const int tci = (sg.Cin + 31) / 32, tco = (sg.Cout + 31) / 32;
+  const int rs = t / (tci * tco), rem = t - rs * (tci * tco);
+  const int co0 = (rem / tci) * 32, ci0 = (rem % tci) * 32;
+  const float* w = flat + sg.off;
+  unsigned short* wt = flat_t + sg.off;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int co = co0 + j, ci = ci0 + tx;
+    tile[j][tx] = (co < sg.Cout && ci < sg.Cin) ? w[((long long)co * sg.RS + rs) * sg.Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int ci = ci0 + j, co = co0 + tx;
+    if (ci < sg.Cin && co < sg.Cout) {
+      const float v = tile[tx][j];
+      unsigned short bits;
+      if (bf16) { const __nv_bfloat16 h = __float2bfloat16_rn(v); bits = *reinterpret_cast<const unsigned short*>(&h); }
+      else { const __half h = __float2half_rn(v); bits = *reinterpret_cast<const unsigned short*>(&h); }
+      wt[((long long)ci * sg.RS + rs) * sg.Cout + co] = bits;
     }
   }
 }
@@ -171,6 +212,10 @@ struct BnFinal {
   float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
   // MODE 1
   float* dgamma; float* dbeta; float* sums;   // sums [2][C]: dbeta, dgamma (read by the apply pass)
+  // MODE 1, scaled-fp16 gradients: bound_bits[chunk] accumulates (atomicMax on the bit pattern of non-negative floats:
+  // order-independent, hence deterministic) max over the chunk of |g| * |gamma| * invstd; the last block of the chunk
+  // publishes it to cbound[chunk] and clears the accumulator. NULL = off.
+  unsigned int* bound_bits; float* cbound;
 };
 
 template <int MODE>
@@ -201,6 +246,7 @@ __global__ void __launch_bounds__(kRedThreads, 4) channel_reduce_kernel(const fl
     const float* dzp = (MODE == 1) ? dz + (r0 + ty) * rs + c0 : nullptr;
     const float* zp = (MODE == 1 && z != nullptr) ? z + (r0 + ty) * rs + c0 : nullptr;
     float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
+    float gmx[4] = {0, 0, 0, 0};                                     // MODE 1: max |g| per channel of this thread
     auto flush = [&]() {
 #pragma unroll
       for (int q = 0; q < 4; ++q) { a[q] += (double)fa[q]; b[q] += (double)fb[q]; fa[q] = 0.f; fb[q] = 0.f; }
@@ -219,6 +265,8 @@ __global__ void __launch_bounds__(kRedThreads, 4) channel_reduce_kernel(const fl
         fa[0] += gx; fa[1] += gy; fa[2] += gz; fa[3] += gw;
         fb[0] = fmaf(gx, (v.x - mu.x) * is.x, fb[0]); fb[1] = fmaf(gy, (v.y - mu.y) * is.y, fb[1]);
         fb[2] = fmaf(gz, (v.z - mu.z) * is.z, fb[2]); fb[3] = fmaf(gw, (v.w - mu.w) * is.w, fb[3]);
+        gmx[0] = fmaxf(gmx[0], fabsf(gx)); gmx[1] = fmaxf(gmx[1], fabsf(gy));
+        gmx[2] = fmaxf(gmx[2], fabsf(gz)); gmx[3] = fmaxf(gmx[3], fabsf(gw));
       }
     };
     auto bits = [&](long long o, long long rowidx) -> unsigned {   // ReLU pass bits of the float4 at row offset o
@@ -260,6 +308,14 @@ __global__ void __launch_bounds__(kRedThreads, 4) channel_reduce_kernel(const fl
       s_acc[ty][0][4 * tx + q] = a[q];
       s_acc[ty][1][4 * tx + q] = b[q];
     }
+    if (MODE == 1 && f.bound_bits != nullptr) {
+      const float4 ga = ld4(f.gamma + c0);
+      float m = fmaxf(fmaxf(gmx[0] * fabsf(ga.x) * is.x, gmx[1] * fabsf(ga.y) * is.y),
+                      fmaxf(gmx[2] * fabsf(ga.z) * is.z, gmx[3] * fabsf(ga.w) * is.w));
+      m = mla::warp_max(m);
+      if (!(m == m)) m = __int_as_float(0x7f800000);                   // NaN gradients: the bound becomes +inf
+      if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&f.bound_bits[chunk], __float_as_uint(m));
+    }
   }
   __syncthreads();
   if (threadIdx.x < 128) {
@@ -289,7 +345,12 @@ __global__ void __launch_bounds__(kRedThreads, 4) channel_reduce_kernel(const fl
     if (half == 0) s_fin[col >> 6][col & 63] = sum + s_half[col];
   }
   __syncthreads();
-  if (threadIdx.x == 0) counters[chunk] = 0;   // leave the workspace reusable
+  if (threadIdx.x == 0) {
+    counters[chunk] = 0;   // leave the workspace reusable
+    if (MODE == 1 && f.bound_bits != nullptr) {
+      f.cbound[chunk] = __uint_as_float(atomicExch(&f.bound_bits[chunk], 0u));
+    }
+  }
   if (threadIdx.x >= 64) return;
   const int c = chunk * 64 + threadIdx.x;
   const double sa = s_fin[0][threadIdx.x], sb = s_fin[1][threadIdx.x];
@@ -388,8 +449,24 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums, float inv_m,
                                     float* __restrict__ dy, float* __restrict__ g_out, long long n4, int C4,
-                                    const unsigned int* __restrict__ mask, uint2* __restrict__ dy16) {
+                                    const unsigned int* __restrict__ mask, uint2* __restrict__ dy16,
+                                    const float* __restrict__ cbound, int chunks, float* __restrict__ gscale) {
   const int C = C4 * 4;
+  // scaled-fp16 gradients: F = the power of two that puts the bound of |dy| (from the reduction pass) into [2^8, 2^9):
+  // 2^7 of headroom below fp16's largest finite value (the bound ignores the mean terms; conversions saturate), fp16's
+  // full 10-bit mantissa down to 2^-22 of the bound. Every thread derives the same F; block 0 publishes F and 1 / F.
+  float F = 1.f;
+  if (cbound != nullptr) {
+    float bound = 0.f;
+    for (int k = 0; k < chunks; ++k) bound = fmaxf(bound, cbound[k]);
+    if (bound > 0.f && bound < __int_as_float(0x7f800000)) {
+      int e;
+      frexpf(bound, &e);                        // bound = m * 2^e, m in [0.5, 1)
+      e = max(-100, min(100, 9 - e));
+      F = ldexpf(1.f, e);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { gscale[0] = F; gscale[1] = 1.f / F; }
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     float4 g = ld4(dz + 4 * i);
@@ -411,7 +488,10 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
     o.z = ga.z * is.z * (g.z - db.z * inv_m - (v.z - mu.z) * is.z * dg.z * inv_m);
     o.w = ga.w * is.w * (g.w - db.w * inv_m - (v.w - mu.w) * is.w * dg.w * inv_m);
     if (dy != nullptr) st4(dy + 4 * i, tf32r4(o));    // dy only feeds dgrad / wgrad
-    if (dy16 != nullptr) dy16[i] = pack_b4(o);    // bf16 copy: the operand of the kind::f16 dgrad
+    if (dy16 != nullptr) {
+      if (cbound != nullptr) dy16[i] = pack_h4_sat(make_float4(o.x * F, o.y * F, o.z * F, o.w * F));   // fp16, scaled
+      else dy16[i] = pack_b4(o);                  // bf16 copy: the operand of the bf16 kind::f16 dgrad
+    }
   }
 }
 
@@ -521,7 +601,10 @@ int ew_grid(long long n, int threads) {
 struct RedPlan {
   int nrb, chunks;          // row blocks x 64-channel chunks
   long long rows_per_block;
-  size_t off_sums, off_part, bytes;   // workspace layout: [counters | sums 2C floats | partials]
+  // workspace: [ticket counters | bound bits | cbound | sums 2C floats | partials]. The first three regions hold state that
+  // persists between calls (self-clearing counters / accumulators) and therefore sit at FIXED offsets (64 chunks max),
+  // whatever (M, C) the call has: one workspace serves every BatchNorm layer of an encoder.
+  size_t off_sums, off_part, off_bound, bytes;
 };
 int red_plan(long long M, int C, RedPlan* pl) {
   if (M < 1 || C < 64 || (C & 63) || C > 4096) return MLA_E_SHAPE;
@@ -533,7 +616,8 @@ int red_plan(long long M, int C, RedPlan* pl) {
   if (nrb > cap) nrb = cap;
   pl->rows_per_block = (M + nrb - 1) / nrb;
   pl->nrb = (int)((M + pl->rows_per_block - 1) / pl->rows_per_block);
-  pl->off_sums = mla::align_up((size_t)pl->chunks * sizeof(unsigned int), 256);
+  pl->off_bound = 256;                      // 64 x uint bound bits, then 64 x float published bounds
+  pl->off_sums = 768;
   pl->off_part = pl->off_sums + mla::align_up(2 * (size_t)C * sizeof(float), 256);
   pl->bytes = pl->off_part + (size_t)pl->chunks * pl->nrb * 128 * sizeof(double);
   return 0;
@@ -601,6 +685,15 @@ extern "C" int mla_filter_transpose16(const float* w, void* wt16, int Cout, int 
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, RS);
   filter_transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<unsigned short*>(wt16), Cout, RS,
                                                                               Cin, bf16);
+  MLA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mla_filter_transpose16_batch(const float* flat, void* flat_t16, const void* seg_table, int nseg, int ntiles,
+                                            int bf16, void* stream) {
+  if (!flat || !flat_t16 || !seg_table || nseg < 1 || ntiles < 1) return MLA_E_BADARG;
+  filter_transpose16_batch_kernel<<<ntiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      flat, static_cast<unsigned short*>(flat_t16), static_cast<const TransposeSeg*>(seg_table), nseg, bf16);
   MLA_LAUNCH_CHECK();
   return 0;
 }
@@ -700,8 +793,10 @@ extern "C" int mla_bn_apply(const float* y, const float* scale, const float* shi
 
 static int bn_backward_impl(const float* dz, const float* z, const unsigned int* mask, const float* y, const float* mean,
                             const float* invstd, const float* gamma, long long M, int C, float* dgamma, float* dbeta,
-                            float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream, void* dy16 = nullptr) {
+                            float* dy, float* g_out, void* ws, size_t ws_bytes, void* stream, void* dy16 = nullptr,
+                            float* gscale = nullptr) {
   if (!dz || !y || !mean || !invstd || !gamma || (!dy && !dy16)) return MLA_E_BADARG;
+  if (gscale != nullptr && !dy16) return MLA_E_BADARG;
   RedPlan pl;
   int rc = red_plan(M, C, &pl);
   if (rc) return rc;
@@ -711,13 +806,20 @@ static int bn_backward_impl(const float* dz, const float* z, const unsigned int*
   float* sums = reinterpret_cast<float*>(base + pl.off_sums);
   BnFinal f{};
   f.M = M; f.dgamma = dgamma; f.dbeta = dbeta; f.sums = sums;
+  float* cbound = nullptr;
+  if (gscale != nullptr) {           // the bound accumulators live in the (zero-initialised, self-clearing) workspace
+    f.gamma = gamma;
+    f.bound_bits = reinterpret_cast<unsigned int*>(base + pl.off_bound);
+    cbound = reinterpret_cast<float*>(base + pl.off_bound) + 64;
+    f.cbound = cbound;
+  }
   channel_reduce_kernel<1><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, st>>>(
       y, dz, z, mean, invstd, M, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
       reinterpret_cast<unsigned int*>(base), f, mask);
   MLA_LAUNCH_CHECK();
   const long long n4 = M * (C / 4);
   bn_bwd_apply_kernel<<<ew_grid(n4, 256), 256, 0, st>>>(dz, z, y, mean, invstd, gamma, sums, 1.f / (float)M, dy, g_out, n4,
-                                                       C / 4, mask, static_cast<uint2*>(dy16));
+                                                       C / 4, mask, static_cast<uint2*>(dy16), cbound, pl.chunks, gscale);
   MLA_LAUNCH_CHECK();
   return 0;
 }
@@ -734,6 +836,16 @@ extern "C" int mla_bn_backward_ex(const float* dz, const float* z, const unsigne
                                   size_t ws_bytes, void* stream) {
   return bn_backward_impl(dz, z, relu_mask, y, mean, invstd, gamma, M, C, dgamma, dbeta, dy, g_out, ws, ws_bytes, stream,
                           dy16);
+}
+
+// BN backward whose dy leaves as fp16 multiplied by a power of two F chosen from the data (gscale[0] = F, gscale[1] = 1 / F,
+// device scalars the consuming dgrad / wgrad multiply their accumulators by): the operand keeps TF32's 10-bit mantissa.
+extern "C" int mla_bn_backward_f16(const float* dz, const unsigned int* relu_mask, const float* y, const float* mean,
+                                   const float* invstd, const float* gamma, long long M, int C, float* dgamma, float* dbeta,
+                                   void* dy16, float* g_out, float* gscale, void* ws, size_t ws_bytes, void* stream) {
+  if (!dy16 || !gscale) return MLA_E_BADARG;
+  return bn_backward_impl(dz, nullptr, relu_mask, y, mean, invstd, gamma, M, C, dgamma, dbeta, nullptr, g_out, ws, ws_bytes,
+                          stream, dy16, gscale);
 }
 
 extern "C" int mla_bn_backward_mask(const float* dz, const unsigned int* relu_mask, const float* y, const float* mean,

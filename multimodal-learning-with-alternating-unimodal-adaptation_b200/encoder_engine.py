@@ -23,14 +23,14 @@ from . import _lib
 import os
 
 BACKEND = "native-tcgen05"
-USE_F16 = os.environ.get("MLA_F16", "1") != "0"                     # 2-byte conv operands: fp16 fprop, bf16 dgrad (kind::f16)
+USE_F16 = os.environ.get("MLA_F16", "1") != "0"     # 2-byte conv operands (kind::f16): fp16 forward, power-of-two-scaled fp16 backward
 USE_GRAPHS = os.environ.get("MLA_GRAPHS", "1") != "0"               # replay the plans' launch sequences as CUDA graphs
 _OVERLAP_WGRAD = os.environ.get("MLA_OVERLAP_WGRAD", "1") != "0"    # wgrad kernels on a side stream of the plan
 _USE_RELU_MASK = os.environ.get("MLA_RELU_MASK", "1") != "0"      # A/B switch (bitmask vs reading the activation)
 _STEM_KP = {1: 64, 3: 160}     # K = 49*Cin padded to a multiple of 32 (tcgen05 k-blocks of 32 tf32)
 _STEM_KP16 = {1: 64, 3: 192}   # ... to a multiple of 64 (k-blocks of 64 2-byte elements)
-# 2-byte stem: the im2col matrix leaves as fp16 (fprop16) + bf16 (wgrad16) copies instead of TF32 fp32, the stem GEMMs
-# run at the kind::f16 rate, and BN backward writes dy in bf16 only. Needs USE_F16.
+# 2-byte stem: the im2col matrix leaves as ONE fp16 copy (operand of fprop16 and of wgrad16) instead of TF32 fp32, the stem
+# GEMMs run at the kind::f16 rate, and BN backward writes dy as scaled fp16 only. Needs USE_F16.
 STEM_F16 = True
 
 
@@ -122,6 +122,8 @@ class _BN:
         self.invstd = torch.empty(C, device=dev)
         self.scale = torch.empty(C, device=dev)
         self.shift = torch.empty(C, device=dev)
+        # [F, 1 / F]: the power-of-two scale of this layer's fp16 dy (written by the BN backward, read by dgrad / wgrad)
+        self.gscale = torch.ones(2, device=dev)
 
 
 class ResNetPlan:
@@ -152,10 +154,9 @@ class ResNetPlan:
         self.M0 = N * self.OH0 * self.OW0
         e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)   # noqa: E731
         half = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)          # noqa: E731
-        bhalf = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)        # noqa: E731
         if self.stem16:
             self.col = None
-            self.col16, self.col16b = half(self.M0, self.Kp), bhalf(self.M0, self.Kp)
+            self.col16 = half(self.M0, self.Kp)
             self.wpad16 = half(64, self.Kp)
         else:
             self.col = e(self.M0, self.Kp)
@@ -164,9 +165,8 @@ class ResNetPlan:
         self.y0 = e(N, self.OH0, self.OW0, 64)
         self.p0 = e(N, self.PH, self.PW, 64)
         self.p0_16 = half(N, self.PH, self.PW, 64) if self.f16 else None
-        self.p0_b = bhalf(N, self.PH, self.PW, 64) if self.f16 else None            # bf16 copy: wgrad16 x operand
         self.w16 = torch.empty(self.flat.numel(), dtype=torch.float16, device=dev) if self.f16 else None     # fp16 weights
-        self.wt16 = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=dev) if self.f16 else None   # transposed, bf16
+        self.wt16 = torch.empty(self.flat.numel(), dtype=torch.float16, device=dev) if self.f16 else None    # transposed, fp16
         self.idx0 = e(N, self.PH, self.PW, 64, dt=torch.uint8)
         self.bn0 = _BN(net.bn1, dev)
         # ---- residual blocks
@@ -181,10 +181,8 @@ class ResNetPlan:
                          y1=e(N, ho, wo, cout), a1=e(N, ho, wo, cout), y2=e(N, ho, wo, cout), out=e(N, ho, wo, cout),
                          # ReLU sign bitmasks of a1 / out (1 bit per element): what BN backward reads instead of them
                          m1=e(N * ho * wo * cout // 32, dt=torch.int32), m2=e(N * ho * wo * cout // 32, dt=torch.int32),
-                         # fp16 copies of a1 / out: the operands of the kind::f16 forward convolutions
+                         # fp16 copies of a1 / out: the operands of the kind::f16 forward convolutions AND weight gradients
                          a1_16=half(N, ho, wo, cout) if self.f16 else None, out_16=half(N, ho, wo, cout) if self.f16 else None,
-                         # bf16 copies: the x operands of the kind::f16 weight gradients
-                         a1_b=bhalf(N, ho, wo, cout) if self.f16 else None, out_b=bhalf(N, ho, wo, cout) if self.f16 else None,
                          bn1=_BN(blk.bn1, dev), bn2=_BN(blk.bn2, dev), yd=None, bnd=None)
                 if blk.downsample is not None:
                     d["yd"] = e(N, ho, wo, cout)
@@ -216,6 +214,20 @@ class ResNetPlan:
                          self.L.mla_conv2d_wgrad16_workspace_bytes(N, b["ho"], b["wo"], b["cout"], b["cout"], 3, 3, 1, 1),
                          self.L.mla_conv2d_wgrad16_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 1, 1, b["stride"], 0))
         self.wg_ws = torch.empty(max(nw, 256), dtype=torch.uint8, device=dev)
+        if self.f16:      # one launch transposes every BasicBlock filter into its fp16 [Cin][R][S][Cout] copy (dgrad16 operand)
+            import numpy as np
+            seg, tile0 = [], 0
+            for b in self.blocks:
+                blk = b["blk"]
+                ws_ = [(blk.conv1.weight, b["cout"], 9, b["cin"]), (blk.conv2.weight, b["cout"], 9, b["cout"])]
+                if b["yd"] is not None:
+                    ws_.append((blk.downsample[0].weight, b["cout"], 1, b["cin"]))
+                for w, co, rs, ci in ws_:
+                    seg.append((self.woff[id(w)], co, rs, ci, tile0))
+                    tile0 += rs * ((co + 31) // 32) * ((ci + 31) // 32)
+            tab = np.array(seg, dtype=np.dtype([("off", "<i8"), ("co", "<i4"), ("rs", "<i4"), ("ci", "<i4"), ("t0", "<i4")]))
+            self.tr_table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+            self.tr_nseg, self.tr_tiles = len(seg), tile0
         self.trained_forward = False
         self.serial = 0                 # number of the last training forward (activations are single-buffered)
         self._param_ptrs = [p.data_ptr() for p in self._params]
@@ -262,10 +274,11 @@ class ResNetPlan:
                                                _p(b.mean), _p(b.invstd), _p(b.scale), _p(b.shift), _p(self.bn_ws),
                                                self.bn_ws.numel(), st), "mla_bn_stats_from_partials")
 
-    def _dgrad16(self, dy16, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
+    def _dgrad16(self, dy16, gscale, w, dx, N, H, W, Cin, Cout, R, stride, pad, acc, st):
+        """dx (+)= (1 / F) * dgrad(fp16 dy * F, fp16 transposed filter); gscale = the producing BN's [F, 1 / F]."""
         t = _conv_timer_begin()
-        _chk(self.L.mla_conv2d_dgrad16(_p(dy16), self._wt16ptr(w), _p(dx), N, H, W, Cin, Cout, R, R, stride, pad,
-                                       1 if acc else 0, st), "mla_conv2d_dgrad16")
+        _chk(self.L.mla_conv2d_dgrad16_f16(_p(dy16), self._wt16ptr(w), gscale.data_ptr() + 4, _p(dx), N, H, W, Cin, Cout, R, R,
+                                           stride, pad, 1 if acc else 0, st), "mla_conv2d_dgrad16_f16")
         _conv_timer_end(t, "dgrad16", N, H, W, Cin, Cout, R, stride, pad)
 
     def _conv(self, x, w, y, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
@@ -306,10 +319,10 @@ class ResNetPlan:
                                      self.wg_ws.numel(), st), "mla_conv2d_wgrad")
         _conv_timer_end(t, "wgrad", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
 
-    def _wgrad16(self, x16b, dy16, dw, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
+    def _wgrad16(self, x16, dy16, gscale, dw, N, H, W, Cin, Cout, R, stride, pad, st, k_alg=None):
         t = _conv_timer_begin()
-        _chk(self.L.mla_conv2d_wgrad16(_p(x16b), _p(dy16), _p(dw), N, H, W, Cin, Cout, R, R, stride, pad, _p(self.wg_ws),
-                                       self.wg_ws.numel(), st), "mla_conv2d_wgrad16")
+        _chk(self.L.mla_conv2d_wgrad16_f16(_p(x16), _p(dy16), gscale.data_ptr() + 4, _p(dw), N, H, W, Cin, Cout, R, R, stride,
+                                           pad, _p(self.wg_ws), self.wg_ws.numel(), st), "mla_conv2d_wgrad16_f16")
         _conv_timer_end(t, "wgrad16", N, H, W, Cin if k_alg is None else k_alg, Cout, R, stride, pad)
 
     def _bn_coeffs(self, y, M, b, training, st):
@@ -326,15 +339,20 @@ class ResNetPlan:
     def _bn_bwd(self, dz, z, y, b, M, dy, g_out, st, mask=None, dy16=None):
         bn = b.bn
         dg, db = _grad_buffer(bn.weight), _grad_buffer(bn.bias)
+        if dy16 is not None:           # 2-byte path: dy leaves as fp16 * F (power of two from the data), F -> b.gscale
+            _chk(self.L.mla_bn_backward_f16(_p(dz), _p(mask), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C, _p(dg),
+                                            _p(db), _p(dy16), _p(g_out), _p(b.gscale), _p(self.bn_ws), self.bn_ws.numel(), st),
+                 "mla_bn_backward_f16")
+            return
         _chk(self.L.mla_bn_backward_ex(_p(dz), _p(z), _p(mask), _p(y), _p(b.mean), _p(b.invstd), _p(bn.weight), M, b.C,
                                        _p(dg), _p(db), _p(dy), _p(dy16), _p(g_out), _p(self.bn_ws), self.bn_ws.numel(), st),
              "mla_bn_backward")
 
     def tmp16(self, slot, shape):
-        k = (slot, tuple(shape), "bf16")
+        k = (slot, tuple(shape), "f16")
         t = self._pool.get(k)
         if t is None:
-            t = torch.empty(shape, dtype=torch.bfloat16, device=self.dev)
+            t = torch.empty(shape, dtype=torch.float16, device=self.dev)
             self._pool[k] = t
         return t
 
@@ -383,7 +401,7 @@ class ResNetPlan:
             sB, sT, sC = self.Cin * HW, 0, HW
         # the only launch that reads the caller's buffer (its address changes from batch to batch): outside the graph
         if self.stem16:
-            _chk(L.mla_stem_im2col16(_p(x), _p(self.col16), _p(self.col16b) if training else None, N, self.T, sB, sT, sC,
+            _chk(L.mla_stem_im2col16(_p(x), _p(self.col16), None, N, self.T, sB, sT, sC,
                                      self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp, st), "mla_stem_im2col16")
         else:
             _chk(L.mla_stem_im2col(_p(x), _p(self.col), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp,
@@ -421,7 +439,7 @@ class ResNetPlan:
             self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
                           k_alg=K)
         _chk(L.mla_bn_relu_maxpool_ex(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.p0_16),
-                                      _p(self.p0_b) if training else None, _p(self.idx0), N, self.OH0, self.OW0, 64, st),
+                                      None, _p(self.idx0), N, self.OH0, self.OW0, 64, st),
              "mla_bn_relu_maxpool")
         f16 = self.f16
         if f16:      # fp16 copy of every parameter (same offsets as the flat buffer): the B operand of fprop16
@@ -438,7 +456,7 @@ class ResNetPlan:
             # a1 in fp32 is only read by the TF32 wgrad / the unmasked BN backward: not written on the 2-byte path
             a1_32 = None if (f16 and _USE_RELU_MASK) else b["a1"]
             _chk(L.mla_bn_apply_ex(_p(b["y1"]), _p(b["bn1"].scale), _p(b["bn1"].shift), None, None, None, 1, _p(a1_32),
-                                   mk1, _p(b["a1_16"]), _p(b["a1_b"]) if training else None, M, cout, st), "mla_bn_apply")
+                                   mk1, _p(b["a1_16"]), None, M, cout, st), "mla_bn_apply")
             if f16:
                 self._conv_bn16(b["a1_16"], blk.conv2.weight, b["y2"], N, b["ho"], b["wo"], cout, cout, 3, 1, 1, b["bn2"],
                                 training, st)
@@ -454,10 +472,10 @@ class ResNetPlan:
                                   training, st)
                 _chk(L.mla_bn_apply_ex(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(b["yd"]),
                                        _p(b["bnd"].scale), _p(b["bnd"].shift), 1, _p(b["out"]), mk2, _p(b["out_16"]),
-                                       _p(b["out_b"]) if training else None, M, cout, st), "mla_bn_apply")
+                                       None, M, cout, st), "mla_bn_apply")
             else:
                 _chk(L.mla_bn_apply_ex(_p(b["y2"]), _p(b["bn2"].scale), _p(b["bn2"].shift), _p(xin), None, None, 1,
-                                       _p(b["out"]), mk2, _p(b["out_16"]), _p(b["out_b"]) if training else None, M, cout, st),
+                                       _p(b["out"]), mk2, _p(b["out_16"]), None, M, cout, st),
                      "mla_bn_apply")
             xin, xin16 = b["out"], b["out_16"]
         _chk(L.mla_avgpool_forward(_p(xin), _p(self.feat_static), self.B, self.rows, self.C_out, st), "mla_avgpool_forward")
@@ -509,20 +527,20 @@ class ResNetPlan:
                 cur.wait_event(ev)
             return self.tmp(slot, shape)
 
-        def buf16(slot, shape):                     # same for the bf16 gradient buffers (dgrad16 / wgrad16 operands)
+        def buf16(slot, shape):                     # same for the fp16 gradient buffers (dgrad16 / wgrad16 operands)
             ev = events.pop((slot, tuple(shape)), None)
             if ev is not None:
                 cur.wait_event(ev)
             return self.tmp16(slot, shape)
 
-        def wgrad_async(x, dy, slot, dw, *geom, k_alg=None, two_byte=False):
+        def wgrad_async(x, dy, slot, dw, *geom, k_alg=None, two_byte=False, gscale=None):
             if wsm is not cur:
                 ready = torch.cuda.Event()
                 ready.record(cur)
                 wsm.wait_event(ready)
             with torch.cuda.stream(wsm):
                 if two_byte:
-                    self._wgrad16(x, dy, dw, *geom, wst, k_alg=k_alg)
+                    self._wgrad16(x, dy, gscale, dw, *geom, wst, k_alg=k_alg)
                 else:
                     self._wgrad(x, dy, dw, *geom, wst, k_alg=k_alg)
             if wsm is not cur:
@@ -531,14 +549,9 @@ class ResNetPlan:
                 events[(slot, tuple(dy.shape))] = done
 
         f16 = self.f16
-        if f16:      # transposed bf16 filters: the K-major B operand of dgrad16 (weights are those of this step's forward)
-            for b in self.blocks:
-                blk = b["blk"]
-                ws_ = [(blk.conv1.weight, b["cout"], 9, b["cin"]), (blk.conv2.weight, b["cout"], 9, b["cout"])]
-                if b["yd"] is not None:
-                    ws_.append((blk.downsample[0].weight, b["cout"], 1, b["cin"]))
-                for w, co, rs, ci in ws_:
-                    _chk(L.mla_filter_transpose16(_p(w), self._wt16ptr(w), co, rs, ci, 1, st), "mla_filter_transpose16")
+        if f16:      # transposed fp16 filters: the K-major B operand of dgrad16 (weights are those of this step's forward)
+            _chk(L.mla_filter_transpose16_batch(_p(self.flat), _p(self.wt16), _p(self.tr_table), self.tr_nseg, self.tr_tiles,
+                                                0, st), "mla_filter_transpose16_batch")
         last = self.blocks[-1]
         dout = self.tmp("dXa", last["out"].shape)
         _chk(L.mla_avgpool_backward(_p(dfeat), _p(dout), self.B, self.rows, self.C_out, st), "mla_avgpool_backward")
@@ -550,21 +563,21 @@ class ResNetPlan:
             shp = b["out"].shape
             par = i & 1
             g = self.tmp("g%d" % par, shp)
-            xin_b = (self.blocks[i - 1]["out_b"] if i > 0 else self.p0_b) if f16 else None
+            xin_h = (self.blocks[i - 1]["out_16"] if i > 0 else self.p0_16) if f16 else None
             z2, mk2 = (None, b["m2"]) if _USE_RELU_MASK else (b["out"], None)
             z1, mk1 = (None, b["m1"]) if _USE_RELU_MASK else (b["a1"], None)
             da1 = self.tmp("da", shp)
             if f16:
-                # 2-byte path: the gradients exist in bf16 only; wgrad16 reads (x bf16, dy bf16), dgrad16 (dy bf16, w^T bf16)
+                # 2-byte path: the gradients exist as scaled fp16 only; wgrad16 reads (x fp16, dy fp16), dgrad16 (dy fp16, w^T fp16)
                 dy2 = buf16("dy2h_%d" % par, shp)
                 self._bn_bwd(dout, z2, b["y2"], b["bn2"], M, None, g, st, mask=mk2, dy16=dy2)
-                wgrad_async(b["a1_b"], dy2, "dy2h_%d" % par, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3,
-                            1, 1, two_byte=True)
-                self._dgrad16(dy2, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
+                wgrad_async(b["a1_16"], dy2, "dy2h_%d" % par, _grad_buffer(blk.conv2.weight), N, b["ho"], b["wo"], cout, cout, 3,
+                            1, 1, two_byte=True, gscale=b["bn2"].gscale)
+                self._dgrad16(dy2, b["bn2"].gscale, blk.conv2.weight, da1, N, b["ho"], b["wo"], cout, cout, 3, 1, 1, False, st)
                 dy1 = buf16("dy1h_%d" % par, shp)
                 self._bn_bwd(da1, z1, b["y1"], b["bn1"], M, None, None, st, mask=mk1, dy16=dy1)
-                wgrad_async(xin_b, dy1, "dy1h_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1,
-                            two_byte=True)
+                wgrad_async(xin_h, dy1, "dy1h_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1,
+                            two_byte=True, gscale=b["bn1"].gscale)
             else:
                 dy2 = buf("dy2_%d" % par, shp)
                 self._bn_bwd(dout, z2, b["y2"], b["bn2"], M, dy2, g, st, mask=mk2)
@@ -573,13 +586,18 @@ class ResNetPlan:
                 dy1 = buf("dy1_%d" % par, shp)
                 self._bn_bwd(da1, z1, b["y1"], b["bn1"], M, dy1, None, st, mask=mk1)
                 wgrad_async(xin, dy1, "dy1_%d" % par, _grad_buffer(blk.conv1.weight), N, b["h"], b["w"], cin, cout, 3, s, 1)
-            dg = self._dgrad16 if f16 else self._dgrad
+            if f16:
+                def dg(dy, w, dx, *geom_acc, gs=None):
+                    self._dgrad16(dy, gs, w, dx, *geom_acc)
+            else:
+                def dg(dy, w, dx, *geom_acc, gs=None):
+                    self._dgrad(dy, w, dx, *geom_acc)
             if b["yd"] is not None:
                 if f16:
                     dyd = buf16("dydh", shp)
                     self._bn_bwd(g, None, b["yd"], b["bnd"], M, None, None, st, dy16=dyd)
-                    wgrad_async(xin_b, dyd, "dydh", _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0,
-                                two_byte=True)
+                    wgrad_async(xin_h, dyd, "dydh", _grad_buffer(blk.downsample[0].weight), N, b["h"], b["w"], cin, cout, 1, s, 0,
+                                two_byte=True, gscale=b["bnd"].gscale)
                 else:
                     dyd = buf("dyd", shp)
                     self._bn_bwd(g, None, b["yd"], b["bnd"], M, dyd, None, st)
@@ -587,21 +605,21 @@ class ResNetPlan:
                 dx = self.tmp("dXa", xin.shape)         # xin.shape != out.shape here, so never aliases dout
                 # the 3x3 dgrad touches every pixel of dx and goes first; the 1x1/2 shortcut then ADDS into the
                 # one output parity class it reaches (its other classes are skipped, not zero-filled)
-                dg(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, False, st)
-                dg(dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, True, st)
+                dg(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, False, st, gs=b["bn1"].gscale)
+                dg(dyd, blk.downsample[0].weight, dx, N, b["h"], b["w"], cin, cout, 1, s, 0, True, st, gs=b["bnd"].gscale)
             else:
                 dx = g                                  # identity shortcut: dX starts as the masked gradient
-                dg(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st)
+                dg(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st, gs=b["bn1"].gscale)
             dout = dx
         # stem: maxpool+relu backward, BN backward, weight gradient (no dgrad: the input needs none)
         g0 = self.tmp("g0", self.y0.shape)
         _chk(L.mla_maxpool_relu_backward(_p(dout), _p(self.p0), _p(self.idx0), _p(g0), N, self.OH0, self.OW0, 64, st),
              "mla_maxpool_relu_backward")
         if self.stem16:
-            dy0 = buf16("dy0", self.y0.shape)            # bf16 only: nothing reads the stem's dy in fp32
+            dy0 = buf16("dy0", self.y0.shape)            # scaled fp16 only: nothing reads the stem's dy in fp32
             self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, None, None, st, dy16=dy0)
-            wgrad_async(self.col16b, dy0, "dy0", self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, k_alg=49 * self.Cin,
-                        two_byte=True)
+            wgrad_async(self.col16, dy0, "dy0", self.dwpad, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, k_alg=49 * self.Cin,
+                        two_byte=True, gscale=self.bn0.gscale)
         else:
             dy0 = buf("dy0", self.y0.shape)
             self._bn_bwd(g0, None, self.y0, self.bn0, self.M0, dy0, None, st)

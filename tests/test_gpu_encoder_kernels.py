@@ -9,6 +9,7 @@ Tolerances (Frobenius-relative):
   BatchNorm / pooling          1e-5  (fp32 arithmetic, fp64 reductions); outputs that feed convolutions are rounded to
                                TF32 on store, so they are compared at 1e-3
 """
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -117,6 +118,91 @@ def test_conv_2byte_operands(L, case):
     dwr = torch.nn.grad.conv2d_weight(xb.float().permute(0, 3, 1, 2), (Cout, Cin, R, R), dy16.float().permute(0, 3, 1, 2),
                                       stride, pad)
     assert relf(dw.permute(0, 3, 1, 2), dwr) < 2e-5
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("mag", [3e-7, 1.0, 5e3])
+def test_conv_backward_scaled_fp16_operands(L, case, mag):
+    """The default backward: BN backward emits dy as fp16 * F (F = a power of two chosen on the device from the data),
+    dgrad16_f16 / wgrad16_f16 multiply fp16 x fp16 and undo the scale in the epilogue. Gradients of any magnitude (3e-7 ..
+    5e3, three decades of spread inside the tensor) must come out with TF32-class error against fp64, and EXACTLY equal to
+    fp32 math on the rounded operands (2e-5)."""
+    N, H, W, Cin, Cout, R, stride = case
+    pad, x, w, dy, OH, OW = _conv_data(*case)
+    gen = torch.Generator(device="cuda").manual_seed(N + H + Cin)
+    dy = dy * mag * torch.pow(10.0, -3 * torch.rand(dy.shape, device="cuda", generator=gen))
+    M, C = N * OH * OW, Cout
+    # a BatchNorm in front of the conv output: dz -> dy through mla_bn_backward_f16
+    y = torch.randn(M, C, device="cuda", generator=gen) * 1.5 + 0.2
+    gamma = torch.rand(C, device="cuda", generator=gen) + 0.5
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-5)
+    dz = dy.permute(0, 2, 3, 1).reshape(M, C).contiguous()
+    xhat = (y - mean) * invstd
+    dy_ref = (gamma * invstd * (dz.double() - dz.double().mean(0) - xhat.double() * (dz.double() * xhat.double()).mean(0)))
+    ws = torch.zeros(L.mla_bn_workspace_bytes(M, C), dtype=torch.uint8, device="cuda")
+    dy16 = torch.empty(M, C, dtype=torch.float16, device="cuda")
+    gs = torch.zeros(2, device="cuda")
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    for _ in range(2):                                       # twice: the self-clearing accumulators must leave no state
+        assert L.mla_bn_backward_f16(P(dz), None, P(y), P(mean), P(invstd), P(gamma), M, C, P(dg), P(db), P(dy16), None, P(gs),
+                                     P(ws), ws.numel(), st()) == 0
+    torch.cuda.synchronize()
+    Fs, inv = float(gs[0]), float(gs[1])
+    assert Fs > 0 and np.log2(Fs) == round(np.log2(Fs)) and Fs * inv == 1.0          # an exact power of two
+    amax = float((dy16.float().abs().max()))
+    assert 16.0 <= amax <= 65504.0 and not torch.isinf(dy16.float()).any()           # well inside fp16, never saturated here
+    assert relf(dy16.double() * inv, dy_ref) < 6e-4                                   # 10-bit mantissa
+    assert relf(dg, (dz.double() * xhat.double()).sum(0)) < 1e-4 and relf(db, dz.double().sum(0)) < 1e-4
+    # dgrad / wgrad on the scaled operand
+    wk = w.permute(0, 2, 3, 1).contiguous()
+    wt16 = torch.empty(Cin, R, R, Cout, dtype=torch.float16, device="cuda")
+    assert L.mla_filter_transpose16(P(wk), P(wt16), Cout, R * R, Cin, 0, st()) == 0
+    x16 = x.permute(0, 2, 3, 1).contiguous().half()
+    base = 1.0 if mag == 1.0 else 0.0                     # accumulating form: dx = base + ... (exactly representable sums only)
+    dx = torch.full((N, H, W, Cin), base, device="cuda")
+    assert L.mla_conv2d_dgrad16_f16(P(dy16), P(wt16), gs.data_ptr() + 4, P(dx), N, H, W, Cin, Cout, R, R, stride, pad, 1,
+                                    st()) == 0
+    dw = torch.empty(Cout, R, R, Cin, device="cuda")
+    nb = L.mla_conv2d_wgrad16_workspace_bytes(N, H, W, Cin, Cout, R, R, stride, pad)
+    wsw = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    assert L.mla_conv2d_wgrad16_f16(P(x16), P(dy16), gs.data_ptr() + 4, P(dw), N, H, W, Cin, Cout, R, R, stride, pad, P(wsw),
+                                    nb, st()) == 0
+    torch.cuda.synchronize()
+    dyq = (dy16.float() * inv).view(N, OH, OW, Cout).permute(0, 3, 1, 2)             # what the tensor cores multiplied
+    dxr = torch.nn.grad.conv2d_input((N, Cin, H, W), wt16.float().permute(3, 0, 1, 2), dyq, stride, pad)
+    dwr = torch.nn.grad.conv2d_weight(x16.float().permute(0, 3, 1, 2), (Cout, Cin, R, R), dyq, stride, pad)
+    assert relf((dx.double() - base).float().permute(0, 3, 1, 2), dxr) < (2e-5 if base == 0.0 else 2e-4)
+    assert relf(dw.permute(0, 3, 1, 2), dwr) < 2e-5
+    # against exact math on the unrounded operands: the TF32-class bound
+    d64 = dy_ref.view(N, OH, OW, Cout).permute(0, 3, 1, 2)
+    dx64 = torch.nn.grad.conv2d_input((N, Cin, H, W), w.double(), d64, stride, pad)
+    dw64 = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, R, R), d64, stride, pad)
+    assert relf(dw.permute(0, 3, 1, 2), dw64) < 1e-3
+    assert relf((dx.double() - base).permute(0, 3, 1, 2), dx64) < 1e-3
+
+
+def test_filter_transpose_batch(L):
+    """Every filter of an encoder transposed to fp16 [Cin][R][S][Cout] by one launch over a segment table."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    shapes = [(64, 9, 64), (128, 9, 64), (128, 1, 64), (256, 9, 128), (96, 9, 40)]
+    offs, off = [], 8
+    for co, rs, ci in shapes:
+        offs.append(off)
+        off += (co * rs * ci + 3) // 4 * 4 + 4
+    flat = torch.randn(off, device="cuda", generator=gen)
+    seg, t0 = [], 0
+    for (co, rs, ci), o in zip(shapes, offs):
+        seg.append((o, co, rs, ci, t0))
+        t0 += rs * ((co + 31) // 32) * ((ci + 31) // 32)
+    tab = np.array(seg, dtype=np.dtype([("off", "<i8"), ("co", "<i4"), ("rs", "<i4"), ("ci", "<i4"), ("t0", "<i4")]))
+    table = torch.from_numpy(tab.view(np.uint8).copy()).cuda()
+    out = torch.zeros(off, dtype=torch.float16, device="cuda")
+    assert L.mla_filter_transpose16_batch(P(flat), P(out), P(table), len(seg), t0, 0, st()) == 0
+    torch.cuda.synchronize()
+    for (co, rs, ci), o in zip(shapes, offs):
+        w = flat[o:o + co * rs * ci].view(co, rs, ci)
+        assert torch.equal(out[o:o + co * rs * ci].view(ci, rs, co), w.permute(2, 1, 0).contiguous().half())
 
 
 @pytest.mark.parametrize("N,H,W,C,relu,res", [(2, 5, 3, 64, True, True), (4, 9, 6, 512, True, True),

@@ -64,7 +64,9 @@ def main():
         w0 = state["fusion_module.fc_out.weight"].to(dev)
         num = float((fc_after1 - w_ref).norm() / (w_ref - w0).norm())
         print("head UPDATE after step 1 (audio + visual turn, projection fired): rel-F error vs oracle %.3e" % num)
-        assert num < 2e-2
+        # relative error of the UPDATE w1 - w0 (|update| ~ 1e-3 |w|): two TF32-class feature errors (<= 1e-3 each) pushed through
+        # the ill-conditioned GS projection; the weights themselves agree to ~3e-6
+        assert num < 3e-3
         print("dp_check ok: world %d, P / head / encoders bit-identical on all ranks, accs %s" % (world, accs))
     dist.barrier()
     dist.destroy_process_group()
