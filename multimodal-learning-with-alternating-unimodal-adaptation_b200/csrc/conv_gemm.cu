@@ -1678,7 +1678,8 @@ int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
   pl->NT = (Cin == 64 && S == 3 && !force_gather()) ? 3 : 1;
   const int tiles = (R * S / pl->NT) * ((Cin + pl->BN - 1) / pl->BN) * ((Cout + 127) / 128);
   static const int waves3 = [] { const char* e = getenv("MLA_WGRAD_WAVES"); return e ? atoi(e) : 2; }();
-  const int target = (pl->NT == 3 ? waves3 : 4) * di.sm_count;   // CTAs in total (2 are resident per SM)
+  static const int waves1 = [] { const char* e = getenv("MLA_WGRAD_TARGET"); return e ? std::max(1, atoi(e)) : 4; }();
+  const int target = (pl->NT == 3 ? waves3 : waves1) * di.sm_count;   // CTAs in total (2 are resident per SM)
   int splits = (target + tiles - 1) / tiles;
   const int min_kb = kp == 32 ? 8 : 4;                                    // >= 256 pixels per split
   splits = max(1, min(splits, pl->KBtot / min_kb > 0 ? pl->KBtot / min_kb : 1));

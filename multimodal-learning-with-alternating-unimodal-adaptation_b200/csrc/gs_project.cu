@@ -1,18 +1,21 @@
 // Fused GSPlugin projection — replaces the body of GSPlugin.before_update
 // (reference utils/utils.py:34-41). One cooperative launch:
 //
-//   phase 0  copy grad_w -> workspace (so the in-place projection can't race);
-//            raw-feature path only: 2-stage deterministic batch-sum of feat -> r
-//   phase A  k = P r^T          each CTA streams its row slice of P from HBM ONCE, keeps it
-//                               in shared memory for the remaining phases
+//   phase 0  one thread issues bulk async copies (cp.async.bulk, completing on an mbarrier) of the CTA's row slice of P
+//            into shared memory: P leaves HBM ONCE, with zero register cost, while every warp of the CTA streams
+//            its share of feat (raw-feature path: CTA-blocked rows, up to 16 independent 512-byte loads in flight per
+//            warp, fixed-order partial sums) and grad_w is copied to the workspace (the in-place projection can't race)
+//   phase 1  r = inv_batch * sum of the per-CTA partials (fixed order), one column slice per thread of the grid
+//   phase A  k = P r^T          from the shared-memory rows
 //   phase B  P' = P - (k k^T) ./ (alpha + k r)   in shared memory, + sum(P'^2) partials
-//   phase C  P = P' / ||P'||_F  written to HBM once; grad_w = grad_w @ P^T from the
-//                               smem-resident rows (register-blocked dot products)
+//   phase C  P = P' / ||P'||_F  written to HBM once; grad_w = grad_w @ P^T from the smem-resident rows: every warp owns a
+//            (4-row group, 512-column chunk) block held in registers, staged gradient rows are read once per 16 FMAs
 //
-// HBM traffic is the algorithmic minimum 4*(B*D + 2*D*D + 2*C*D) bytes: P is read once and
+// HBM traffic is the algorithmic minimum 4*(B*D + 2*D*D + 2*C*D) bytes: feat is read once, P is read once and
 // written once. All reductions have a fixed order, so every rank of a data-parallel job
 // that feeds identical (P, feat_sum, grad_w) computes bit-identical results.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -21,7 +24,9 @@ namespace {
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kGT = 8;        // grad rows staged per tile in phase C
-constexpr int kChunk = 1024;  // columns held in registers per pass of phase C (8 float4/lane)
+constexpr int kRB = 4;        // P rows per register block in phase C
+constexpr int kCB = 512;      // columns per register block in phase C (4 float4 per lane and row)
+constexpr int kMaxCB = 4;     // D <= kMaxCB * kCB
 
 struct GsParams {
   float* P;
@@ -32,112 +37,149 @@ struct GsParams {
   float* grad_w;
   int B, D, C, mode;
   int rows_per_cta;
-  int nb;           // batch chunks of the raw-feature reduction
-  int rows_per_nb;  // rows per batch chunk
+  int nb;           // CTAs that hold a batch slice in the raw-feature reduction
+  int rows_per_nb;  // batch rows per such CTA
   float* ws_r;      // [D]
   float* ws_k;      // [D]
   float* ws_part;   // [nb][D]
   double* ws_norm;  // [grid]
   float* ws_g;      // [C][D]
+  unsigned long long* ws_ts;   // [8] %globaltimer at the phase boundaries of CTA 0 (profiling aid)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float smem[];
+  __shared__ __align__(8) uint64_t s_bar;
   const int D = p.D, D4 = p.D >> 2;
   float* s_r = smem;                      // [D]
   float* s_k = s_r + D;                   // [D]
   float* s_P = s_k + D;                   // [rows_per_cta][D]
-  float* s_G = s_P + (size_t)p.rows_per_cta * D;  // [kGT][D]
-  float* s_red = s_G + (size_t)kGT * D;   // [32]
+  float* s_G = s_P + (size_t)p.rows_per_cta * D;  // [kGT][D]   (phase 0: scratch of the feature reduction)
+  float* s_red = s_G + (size_t)kGT * D;   // [kWarps * kGT * kRB]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gtid = blockIdx.x * kThreads + tid;
   const int gthreads = gridDim.x * kThreads;
   const int row0 = blockIdx.x * p.rows_per_cta;
   const int nrows = max(0, min(p.rows_per_cta, D - row0));
+  const bool stamp = (blockIdx.x == 0 && tid == 0);
+  if (stamp) p.ws_ts[0] = tc::globaltimer_ns();
 
-  // ---------------- phase 0
+  // ---------------- phase 0: P rows -> smem (async), feat partial sums, grad copy
+  if (tid == 0) {
+    tc::mbar_init(tc::smem_u32(&s_bar), 1);
+    tc::fence_mbar_init();
+    if (nrows > 0) {
+      tc::mbar_arrive_expect_tx(tc::smem_u32(&s_bar), (uint32_t)nrows * (uint32_t)D * 4u);
+      for (int lr = 0; lr < nrows; ++lr)
+        bulk_g2s(tc::smem_u32(s_P + (size_t)lr * D), p.P + (size_t)(row0 + lr) * D, (uint32_t)D * 4u, tc::smem_u32(&s_bar));
+    }
+  }
   if (p.grad_w != nullptr) {
     const int n4 = p.C * D4;
     for (int i = gtid; i < n4; i += gthreads) st4(p.ws_g + 4 * (size_t)i, ld4(p.grad_w + 4 * (size_t)i));
   }
   if (p.feat != nullptr) {
-    // stage 1: unit = (128-column chunk, batch chunk); one warp per unit, float4 per lane.
-    const int cchunks = (D + 127) / 128;
-    const int units = cchunks * p.nb;
-    const int gwarp = blockIdx.x * kWarps + warp, gwarps = gridDim.x * kWarps;
-    for (int u = gwarp; u < units; u += gwarps) {
-      const int cc = u % cchunks, bc = u / cchunks;
-      const int col = cc * 128 + lane * 4;
-      const int b0 = bc * p.rows_per_nb, b1 = min(p.B, b0 + p.rows_per_nb);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col < D) {
-        const float* src = p.feat + col;
-        int b = b0;
-        for (; b + 8 <= b1; b += 8) {
-          float4 v[8];
+    // CTA c < nb sums batch rows [c * rows_per_nb, ...). Inside the CTA a unit = (128-column chunk, row split): with few
+    // column chunks (small D) the rows are split over the warps as well; the row-split partials are combined through
+    // shared memory in split order (fixed -> deterministic).
+    if ((int)blockIdx.x < p.nb) {
+      const int cchunks = (D + 127) / 128;
+      const int rsplit = min(kGT, max(1, kWarps / cchunks));     // the scratch holds kGT rows of D
+      const int b0 = blockIdx.x * p.rows_per_nb, b1 = min(p.B, b0 + p.rows_per_nb);
+      float* scratch = s_G;                                     // [rsplit][D]  (rsplit * D <= kGT * D)
+      for (int u = warp; u < cchunks * rsplit; u += kWarps) {
+        const int cc = u % cchunks, rs = u / cchunks;
+        const int col = cc * 128 + lane * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < D) {
+          const float* src = p.feat + col;
+          int b = b0 + rs;
+          for (; b + 15 * rsplit < b1; b += 16 * rsplit) {      // 16 independent row segments in flight
+            float4 v[16];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = ld4(src + (size_t)(b + q) * D);
+            for (int q = 0; q < 16; ++q) v[q] = ldcs4(src + (size_t)(b + q * rsplit) * D);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+            for (int q = 0; q < 16; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+          }
+          {                                                     // tail: the remaining (< 16) rows, all loads first
+            float4 v[16];
+            int n = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (b + q * rsplit < b1) { v[q] = ldcs4(src + (size_t)(b + q * rsplit) * D); n = q + 1; }
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (q < n) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+          }
+          st4(scratch + (size_t)rs * D + col, acc);
         }
-        for (; b < b1; ++b) {
-          float4 v = ld4(src + (size_t)b * D);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      __syncthreads();
+      for (int j4 = tid; j4 < D4; j4 += kThreads) {
+        float4 s = ld4(scratch + 4 * j4);
+        for (int rs = 1; rs < rsplit; ++rs) {
+          const float4 v = ld4(scratch + (size_t)rs * D + 4 * j4);
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
-        st4(p.ws_part + (size_t)bc * D + col, acc);
+        st4(p.ws_part + (size_t)blockIdx.x * D + 4 * j4, s);
       }
     }
+    if (stamp) p.ws_ts[1] = tc::globaltimer_ns();
     grid.sync();
-    // stage 2: r[j] = inv_batch * sum_bc part[bc][j]  (fixed order over bc)
+    if (stamp) p.ws_ts[2] = tc::globaltimer_ns();
+    // r[j] = inv_batch * sum_c part[c][j]  (fixed order over c; 8 partials in flight)
     for (int j = gtid; j < D; j += gthreads) {
       float s = 0.f;
-      for (int bc = 0; bc < p.nb; ++bc) s += p.ws_part[(size_t)bc * D + j];
+      int c = 0;
+      for (; c + 8 <= p.nb; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(p.ws_part + (size_t)(c + q) * D + j);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += v[q];
+      }
+      for (; c < p.nb; ++c) s += __ldcg(p.ws_part + (size_t)c * D + j);
       p.ws_r[j] = s * p.inv_batch;
     }
     grid.sync();
-    for (int j = tid; j < D; j += kThreads) s_r[j] = p.ws_r[j];
+    for (int j = tid; j < D; j += kThreads) s_r[j] = __ldcg(p.ws_r + j);
   } else {
     for (int j = tid; j < D; j += kThreads) s_r[j] = p.feat_sum[j] * p.inv_batch;
   }
   __syncthreads();
+  if (stamp) p.ws_ts[3] = tc::globaltimer_ns();
 
-  // ---------------- phase A: k_i = sum_j P_ij r_j ; P rows -> smem
+  // ---------------- phase A: k_i = sum_j P_ij r_j from the smem-resident rows
+  if (nrows > 0) tc::mbar_wait(tc::smem_u32(&s_bar), 0);
   for (int lr = warp; lr < nrows; lr += kWarps) {
-    const float* src = p.P + (size_t)(row0 + lr) * D;
-    float* dst = s_P + (size_t)lr * D;
+    const float* src = s_P + (size_t)lr * D;
     float acc = 0.f;
-    int j4 = lane;
-    for (; j4 + 7 * 32 < D4; j4 += 8 * 32) {      // 8 independent 512-byte row segments in flight per warp
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = ld4(src + 4 * (j4 + 32 * u));
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 r = ld4(s_r + 4 * (j4 + 32 * u));
-        st4(dst + 4 * (j4 + 32 * u), v[u]);
-        acc = fmaf(v[u].x, r.x, acc); acc = fmaf(v[u].y, r.y, acc);
-        acc = fmaf(v[u].z, r.z, acc); acc = fmaf(v[u].w, r.w, acc);
-      }
-    }
-    for (; j4 < D4; j4 += 32) {
-      float4 v = ld4(src + 4 * j4);
-      float4 r = ld4(s_r + 4 * j4);
-      st4(dst + 4 * j4, v);
+    for (int j4 = lane; j4 < D4; j4 += 32) {
+      const float4 v = ld4(src + 4 * j4);
+      const float4 r = ld4(s_r + 4 * j4);
       acc = fmaf(v.x, r.x, acc); acc = fmaf(v.y, r.y, acc);
       acc = fmaf(v.z, r.z, acc); acc = fmaf(v.w, r.w, acc);
     }
     acc = mla::warp_sum(acc);
     if (lane == 0) p.ws_k[row0 + lr] = acc;
   }
+  if (stamp) p.ws_ts[4] = tc::globaltimer_ns();
   grid.sync();
 
   // ---------------- phase B: elementwise update in smem + sum of squares
-  for (int j = tid; j < D; j += kThreads) s_k[j] = p.ws_k[j];
+  for (int j = tid; j < D; j += kThreads) s_k[j] = __ldcg(p.ws_k + j);
   __syncthreads();
   float scal_den = 0.f;
   if (p.mode == 1) {  // canonical OWM: scalar denominator alpha + r.k (same order in every CTA)
@@ -171,11 +213,24 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     const float bs = mla::block_sum(sq, s_red);
     if (tid == 0) p.ws_norm[blockIdx.x] = (double)bs;
   }
+  if (stamp) p.ws_ts[5] = tc::globaltimer_ns();
   grid.sync();
 
   // ---------------- phase C: normalise, write P, project the gradient
   double tot = 0.0;
-  for (int c = 0; c < (int)gridDim.x; ++c) tot += p.ws_norm[c];  // fixed order, identical everywhere
+  {
+    // fixed order, identical in every CTA; 8 loads in flight
+    int c = 0;
+    const int G = (int)gridDim.x;
+    for (; c + 8 <= G; c += 8) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldcg(p.ws_norm + c + q);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot += v[q];
+    }
+    for (; c < G; ++c) tot += __ldcg(p.ws_norm + c);
+  }
   const float nrm = (float)sqrt(tot);
   {
     const int n4 = nrows * D4;
@@ -185,76 +240,87 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
       pv.x = __fdiv_rn(pv.x, nrm); pv.y = __fdiv_rn(pv.y, nrm);
       pv.z = __fdiv_rn(pv.z, nrm); pv.w = __fdiv_rn(pv.w, nrm);
       st4(s_P + (size_t)lr * D + 4 * j4, pv);
-      st4(p.P + (size_t)(row0 + lr) * D + 4 * j4, pv);
+      __stcs(reinterpret_cast<float4*>(p.P + (size_t)(row0 + lr) * D) + j4, pv);
     }
   }
+  if (stamp) p.ws_ts[6] = tc::globaltimer_ns();
   if (p.grad_w == nullptr) return;
   __syncthreads();
 
-  // grad_w[c][i] = sum_j G[c][j] * P[i][j].  Warp owns a pair of rows; per 1024-column
-  // chunk the two P rows sit in registers and each staged G row is read once from smem.
-  const int npairs = (nrows + 1) >> 1;
+  // grad_w[c][i] = sum_j G[c][j] * P[i][j]. Work unit = (group of kRB rows, kCB-column chunk): the unit's P block sits in
+  // registers (kRB x 4 float4 per lane) and every staged G value is loaded once per kRB * 4 FMAs. A pass covers whole row
+  // groups (all their column chunks); when a pass has fewer units than warps, several warps share a unit and split the
+  // staged gradient rows. The column-chunk partials of one (c, row) are combined through shared memory in chunk order.
+  const int ngroups = (nrows + kRB - 1) / kRB;
+  const int nchunks = (D + kCB - 1) / kCB;
+  const int gpp = max(1, kWarps / nchunks);                     // row groups per pass
   for (int c0 = 0; c0 < p.C; c0 += kGT) {
     const int ct = min(kGT, p.C - c0);
     __syncthreads();
-    for (int i = tid; i < ct * D4; i += kThreads) st4(s_G + 4 * (size_t)i, ld4(p.ws_g + (size_t)c0 * D + 4 * (size_t)i));
+    for (int i = tid; i < ct * D4; i += kThreads)
+      st4(s_G + 4 * (size_t)i, __ldcg(reinterpret_cast<const float4*>(p.ws_g + (size_t)c0 * D) + i));
     __syncthreads();
-    for (int pr = warp; pr < npairs; pr += kWarps) {
-      const int lr0 = 2 * pr, lr1 = min(2 * pr + 1, nrows - 1);
-      float acc0[kGT], acc1[kGT];
+    for (int g0 = 0; g0 < ngroups; g0 += gpp) {
+      const int gn = min(gpp, ngroups - g0);                    // groups in this pass
+      const int units = gn * nchunks;                           // <= kWarps
+      const int csplit = max(1, kWarps / units);
+      const int ul = warp % units, csub = warp / units;
+      if (csub < csplit) {
+        const int g = g0 + ul / nchunks, ch = ul % nchunks;
+        const int jb = ch * kCB;
+        float4 a[kRB][4];
 #pragma unroll
-      for (int c = 0; c < kGT; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
-      for (int jb = 0; jb < D; jb += kChunk) {
-        float4 a0[8], a1[8];
+        for (int rr = 0; rr < kRB; ++rr) {
+          const int lr = min(g * kRB + rr, nrows - 1);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int j = jb + (q * 32 + lane) * 4;
-          if (j < D) {
-            a0[q] = ld4(s_P + (size_t)lr0 * D + j);
-            a1[q] = ld4(s_P + (size_t)lr1 * D + j);
-          } else {
-            a0[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            a1[q] = a0[q];
+          for (int q = 0; q < 4; ++q) {
+            const int j = jb + (q * 32 + lane) * 4;
+            a[rr][q] = (j < D) ? ld4(s_P + (size_t)lr * D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        for (int c = csub; c < ct; c += csplit) {
+          float sacc[kRB];
 #pragma unroll
-        for (int c = 0; c < kGT; ++c) {
-          if (c < ct) {
-            float s0 = acc0[c], s1 = acc1[c];
+          for (int rr = 0; rr < kRB; ++rr) sacc[rr] = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int j = jb + (q * 32 + lane) * 4;
-              if (j < D) {
-                const float4 g = ld4(s_G + (size_t)c * D + j);
-                s0 = fmaf(g.x, a0[q].x, s0); s0 = fmaf(g.y, a0[q].y, s0);
-                s0 = fmaf(g.z, a0[q].z, s0); s0 = fmaf(g.w, a0[q].w, s0);
-                s1 = fmaf(g.x, a1[q].x, s1); s1 = fmaf(g.y, a1[q].y, s1);
-                s1 = fmaf(g.z, a1[q].z, s1); s1 = fmaf(g.w, a1[q].w, s1);
+          for (int q = 0; q < 4; ++q) {
+            const int j = jb + (q * 32 + lane) * 4;
+            if (j < D) {
+              const float4 gv = ld4(s_G + (size_t)c * D + j);
+#pragma unroll
+              for (int rr = 0; rr < kRB; ++rr) {
+                sacc[rr] = fmaf(gv.x, a[rr][q].x, sacc[rr]); sacc[rr] = fmaf(gv.y, a[rr][q].y, sacc[rr]);
+                sacc[rr] = fmaf(gv.z, a[rr][q].z, sacc[rr]); sacc[rr] = fmaf(gv.w, a[rr][q].w, sacc[rr]);
               }
             }
-            acc0[c] = s0; acc1[c] = s1;
           }
-        }
-      }
 #pragma unroll
-      for (int c = 0; c < kGT; ++c) {
-        if (c < ct) {
-          const float s0 = mla::warp_sum(acc0[c]);
-          const float s1 = mla::warp_sum(acc1[c]);
-          if (lane == 0) {
-            p.grad_w[(size_t)(c0 + c) * D + row0 + lr0] = s0;
-            if (lr1 != lr0) p.grad_w[(size_t)(c0 + c) * D + row0 + lr1] = s1;
+          for (int rr = 0; rr < kRB; ++rr) {
+            const float t = mla::warp_sum(sacc[rr]);
+            if (lane == 0) s_red[(ul * kGT + c) * kRB + rr] = t;
           }
         }
       }
+      __syncthreads();
+      for (int t = tid; t < gn * ct * kRB; t += kThreads) {      // (group, c, row): chunks added in chunk order
+        const int rr = t % kRB, c = (t / kRB) % ct, gl = t / (kRB * ct);
+        const int lr = (g0 + gl) * kRB + rr;
+        if (lr < nrows) {
+          float acc = 0.f;
+          for (int ch = 0; ch < nchunks; ++ch) acc += s_red[((gl * nchunks + ch) * kGT + c) * kRB + rr];
+          p.grad_w[(size_t)(c0 + c) * D + row0 + lr] = acc;
+        }
+      }
+      __syncthreads();
     }
   }
+  if (stamp) p.ws_ts[7] = tc::globaltimer_ns();
 }
 
 struct GsPlan {
   int grid, rows_per_cta, nb, rows_per_nb;
   size_t smem;
-  size_t off_r, off_k, off_part, off_norm, off_g, total;
+  size_t off_r, off_k, off_part, off_norm, off_g, off_ts, total;
 };
 
 int make_plan(int B, int D, int C, GsPlan* pl) {
@@ -265,14 +331,13 @@ int make_plan(int B, int D, int C, GsPlan* pl) {
   int rpc = (D + sms - 1) / sms;
   if (rpc < 4) rpc = min(4, D);          // tiny D: fewer, fuller CTAs
   int grid = (D + rpc - 1) / rpc;
-  size_t smem = ((size_t)2 * D + (size_t)rpc * D + (size_t)kGT * D + 32) * sizeof(float);
+  if (D > kMaxCB * kCB) return MLA_E_SHAPE;
+  size_t smem = ((size_t)2 * D + (size_t)rpc * D + (size_t)kGT * D + (size_t)kWarps * kGT * kRB + 32) * sizeof(float);
   if (smem > (size_t)di.smem_optin) return MLA_E_SHAPE;
-  // raw-feature reduction: >= 8 rows per unit, about one unit per warp of the grid
-  const int cchunks = (D + 127) / 128;
-  int nb = (grid * kWarps) / cchunks;
-  nb = max(1, min(nb, (B + 7) / 8));
-  int rows_per_nb = (B + nb - 1) / nb;
-  nb = (B + rows_per_nb - 1) / rows_per_nb;
+  // raw-feature reduction: the batch rows are dealt to the CTAs in contiguous slices (>= 1 row each); inside a CTA the
+  // warps split columns (and rows, when D has fewer than kWarps 128-column chunks)
+  int rows_per_nb = (B + grid - 1) / grid;
+  int nb = (B + rows_per_nb - 1) / rows_per_nb;
   pl->grid = grid; pl->rows_per_cta = rpc; pl->nb = nb; pl->rows_per_nb = rows_per_nb; pl->smem = smem;
   size_t off = 0;
   pl->off_r = off;    off += mla::align_up((size_t)D * 4, 256);
@@ -280,6 +345,7 @@ int make_plan(int B, int D, int C, GsPlan* pl) {
   pl->off_part = off; off += mla::align_up((size_t)nb * D * 4, 256);
   pl->off_norm = off; off += mla::align_up((size_t)grid * 8, 256);
   pl->off_g = off;    off += mla::align_up((size_t)max(C, 1) * D * 4, 256);
+  pl->off_ts = off;   off += 256;
   pl->total = off;
   return 0;
 }
@@ -324,6 +390,7 @@ extern "C" int mla_gs_project(float* P, const float* feat, const float* feat_sum
   prm.ws_part = reinterpret_cast<float*>(w + pl.off_part);
   prm.ws_norm = reinterpret_cast<double*>(w + pl.off_norm);
   prm.ws_g = reinterpret_cast<float*>(w + pl.off_g);
+  prm.ws_ts = reinterpret_cast<unsigned long long*>(w + pl.off_ts);
   void* args[] = {&prm};
   MLA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)gs_project_kernel, dim3(pl.grid), dim3(kThreads), args,
                                            pl.smem, static_cast<cudaStream_t>(stream)));

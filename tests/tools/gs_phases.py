@@ -1,0 +1,50 @@
+"""Phase timing of gs_project_kernel (CTA 0's %globaltimer stamps, written to the tail of the workspace) + CUDA-event time.
+
+    python tests/tools/gs_phases.py            # the corners of the BASELINE.json configs[4] sweep
+"""
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import mla_b200  # noqa: E402
+from mla_b200 import _lib, ops  # noqa: E402
+
+NAMES = ["feat partials + grad copy (P rows in flight)", "grid.sync", "r = sum of partials + grid.sync + smem",
+         "k = P r (smem)", "grid.sync + update + sum sq", "grid.sync + normalise + write P", "projection"]
+
+
+def main():
+    dev = torch.device("cuda")
+    L = _lib.lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for (B, D, C) in [(64, 512, 6), (64, 768, 101), (4096, 512, 6), (64, 2048, 6), (4096, 2048, 6), (4096, 2048, 101),
+                      (1024, 1024, 101)]:
+        feat = torch.randn(B, D, device=dev).relu()
+        grad = torch.randn(C, D, device=dev)
+        P = torch.eye(D, device=dev)
+        for _ in range(3):
+            ops.gs_project(P, grad, 0.05, feat=feat)
+        ts, phases = [], []
+        nbytes = L.mla_gs_project_workspace_bytes(B, D, C)
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.gs_project(P, grad, 0.05, feat=feat); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+            ws = ops._ws[("gs", P.device)].buf
+            st = ws[nbytes - 256:nbytes - 256 + 64].view(torch.int64).tolist()
+            phases.append([(st[i + 1] - st[i]) / 1e3 for i in range(7)])
+        med = [statistics.median(p[i] for p in phases) for i in range(7)]
+        nb = 4 * (B * D + 2 * D * D + 2 * C * D)
+        t = statistics.median(ts)
+        print("B %5d D %5d C %4d: %7.2f us (events), %6.1f GB/s; CTA-0 phases [us]: %s" % (
+            B, D, C, t, nb / t / 1e3, "  ".join("%s %.2f" % (n.split(" ")[0], m) for n, m in zip(NAMES, med))))
+        print("      " + " | ".join("%s: %.2f" % (n, m) for n, m in zip(NAMES, med)))
+
+
+if __name__ == "__main__":
+    main()
