@@ -1043,6 +1043,244 @@ __global__ void __launch_bounds__(kThreads) conv16_persistent_kernel(const __gri
   if (warp == 5) tc::tmem_dealloc(tmem_base, 2 * BN);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same persistent scheme on CTA PAIRS (tcgen05 cta_group::2): a pair walks 256 x BN output tiles (BN up to 256). Each CTA
+// gathers its own 128 im2col rows and stages HALF of the weight tile; the leader issues one 256 x BN x 16 MMA per k-step.
+// Why: these convolutions are bound by the L2 -> SM operand stream (~10.5 TB/s measured: 450 TF/s at 44 FLOP/B on the 64-channel
+// layers, 683 TF/s at 64 FLOP/B on the 256-channel ones, profiles/r1_conv_variants.md), and a 256 x 256 pair tile moves half the
+// operand bytes per FLOP of two 128 x 128 tiles (256 x 128: 3/4; 256 x 64: 5/6).
+// Co-residency: a CTA of this kernel takes >= 180 KB of shared memory, i.e. a whole SM (and its cluster the whole TPC), so no other
+// TMEM-allocating CTA can sit next to it and tcgen05.alloc.cta_group::2 can never wait on a partner that waits on it — the
+// dead-lock the 2-CTA-per-SM pair variants of conv_gemm_kernel could run into under concurrent streams.
+template <int BN>
+struct PairCfg {
+  static constexpr uint32_t kB = (BN / 2) * 128;                 // this CTA's half of the weight tile, bytes per stage
+  static constexpr uint32_t kStage = kABytes + kB;
+  static constexpr int kStages = BN == 256 ? 6 : (BN == 128 ? 8 : 9);
+  static constexpr size_t kSmem = (size_t)kStages * kStage + 1024;
+};
+
+template <int BN, int ET>
+__global__ void __launch_bounds__(kThreads, 1) conv16_pair_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                  const __grid_constant__ CUtensorMap tmap_g, ConvGemmParams p,
+                                                                  int tiles_m, int tiles) {
+  using Cfg = PairCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr uint32_t kStageBytes = Cfg::kStage;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_stat[4 * 2 * BN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_tiles = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t rank = tc::cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&acc_full_bar[b]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty_bar[b]), 8);     // 4 epilogue warps of each CTA of the pair
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap);
+    tc::tma_prefetch_desc(&tmap_g);
+  }
+  if (warp == 5) {
+    tc::tmem_alloc2(tc::smem_u32(&tmem_slot), 2 * BN);
+    tc::tmem_relinquish2();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int KB = p.KB;
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = cluster; tile < tiles; tile += nclusters) {
+        const int m0 = (tile % tiles_m) * 256 + (int)rank * 128, n0 = (tile / tiles_m) * BN + (int)rank * (BN / 2);
+        const int ow = m0 % p.OW, t = m0 / p.OW;
+        const int gw = ow * p.mul + p.g_base_w, gh = (t % p.OH) * p.mul + p.g_base_h, gn = t / p.OH;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ((it / STAGES) & 1) ^ 1);
+          const uint32_t stage = smem_tiles + s * kStageBytes;
+          const uint32_t bar = tc::smem_u32(&full_bar[s]);
+          const int tap = kb / p.kcb, cb = kb - tap * p.kcb;
+          const int ti = tap / p.ns, tj = tap - ti * p.ns;
+          if (rank == 0) tc::mbar_arrive_expect_tx(bar, 2u * kStageBytes);          // both CTAs' bytes land on the leader
+          tc::tma_load_im2col_4d_2sm(stage, &tmap_g, bar, cb * 64, gw, gh, gn, (uint16_t)p.off_s[tj], (uint16_t)p.off_r[ti]);
+          tc::tma_load_2d_2sm(stage + kABytes, &tmap, bar, (p.tap_r[ti] * p.S + p.tap_s[tj]) * p.CinW + cb * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_f16(256, BN, ET >= 2 ? 1 : 0, ET == 2 ? 1 : 0, 0, 0);
+      int it = 0, nt = 0;
+      for (int tile = cluster; tile < tiles; tile += nclusters, ++nt) {
+        const int buf = nt & 1;
+        tc::mbar_wait(tc::smem_u32(&acc_empty_bar[buf]), ((nt >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)buf * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(tc::smem_u32(&full_bar[s]), (it / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint32_t stage = smem_tiles + s * kStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = tc::make_smem_desc(stage + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            const uint64_t bd = tc::make_smem_desc(stage + kABytes + k * 32u, 16u, 1024u, tc::kLayoutSw128);
+            tc::umma_f16_2sm(acc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit_2sm(tc::smem_u32(&empty_bar[s]), (uint16_t)3);
+        }
+        tc::umma_commit_2sm(tc::smem_u32(&acc_full_bar[buf]), (uint16_t)3);
+      }
+    }
+  } else {
+    const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;
+    int nt = 0;
+    for (int tile = cluster; tile < tiles; tile += nclusters, ++nt) {
+      const int buf = nt & 1;
+      const int bx = (tile % tiles_m) * 2 + (int)rank;             // 128-row tile index (BatchNorm partials are per 128 rows)
+      const int m0 = bx * 128, n0 = (tile / tiles_m) * BN;
+      tc::mbar_wait(tc::smem_u32(&acc_full_bar[buf]), (nt >> 1) & 1);
+      tc::tc_fence_after();
+      const int m = m0 + warp * 32 + lane;
+      float* orow = nullptr;
+      if (m < p.M) {
+        long long orow_idx = m;
+        if (p.o_mul > 1) {
+          const int j = m % p.OW;
+          const int t = m / p.OW;
+          orow_idx = ((long long)(t / p.OH) * p.o_H + (t % p.OH) * p.o_mul + p.o_ph) * p.o_W + j * p.o_mul + p.o_pw;
+        }
+        orow = p.out + orow_idx * p.ldo + n0;
+      }
+      const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(acc + c, v);
+        tc::tmem_ld_wait();
+        if (orow != nullptr) {
+          float4* dst = reinterpret_cast<float4*>(orow + c);
+          float4 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+          if (p.out_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x *= oscale; o[j].y *= oscale; o[j].z *= oscale; o[j].w *= oscale; }
+          }
+          if (p.accumulate) {
+            float4 old[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) old[j] = dst[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x += old[j].x; o[j].y += old[j].y; o[j].z += old[j].z; o[j].w += old[j].w; }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = o[j];
+        }
+        if (p.stat_part != nullptr) {      // BatchNorm partial sums of this warp's 32 rows (see conv_gemm_kernel)
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(v[j]); b[j] = a[j] * a[j]; }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float sa = up ? a[i] : a[i + off], ka = up ? a[i + off] : a[i];
+              const float sb = up ? b[i] : b[i + off], kb2 = up ? b[i + off] : b[i];
+              a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+              b[i] = kb2 + __shfl_xor_sync(0xffffffffu, sb, off);
+            }
+          }
+          s_stat[(warp * 2 + 0) * BN + c + lane] = a[0];
+          s_stat[(warp * 2 + 1) * BN + c + lane] = b[0];
+        }
+      }
+      // the accumulator buffer has been read completely: hand it back to the leader's MMA warp
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_leader(tc::smem_u32(&acc_empty_bar[buf]));
+      if (p.stat_part != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+        if (m0 < p.M) {                                   // a 128-row tile entirely past M (odd tile count) has no partial row
+          for (int t = threadIdx.x; t < BN; t += 128) {
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { sa += s_stat[(w * 2 + 0) * BN + t]; sb += s_stat[(w * 2 + 1) * BN + t]; }
+            float* dstp = p.stat_part + (size_t)bx * 2 * p.Cout + n0 + t;
+            dstp[0] = sa;
+            dstp[p.Cout] = sb;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_stat is rewritten by the next tile
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();                       // no CTA exits while its peer can still signal its barriers / read its smem
+  if (warp == 5) tc::tmem_dealloc2(tmem_base, 2 * BN);
+}
+
+// MLA_CONV_PAIR16=0 keeps fprop16 / dgrad16 on the single-CTA persistent kernel.
+bool conv_pair16() {
+  static const bool v = [] {
+    const char* e = getenv("MLA_CONV_PAIR16");
+    return e != nullptr ? e[0] == '1' : true;
+  }();
+  return v && !force_gather();
+}
+
+template <int BN, int ET>
+int launch_conv16_pair(const void* w16, bool bf16, long long wrows, long long wcols, const CUtensorMap& gmap,
+                       const ConvGemmParams& p, int n_tiles_n, cudaStream_t st) {
+  using Cfg = PairCfg<BN>;
+  CUtensorMap map;
+  int rc = make_map_2d16(&map, w16, bf16, wrows, wcols, BN / 2);          // box {64 k, BN / 2 rows}: one CTA's half
+  if (rc) return rc;
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_acquire)) {
+    MLA_CUDA_TRY(cudaFuncSetAttribute(conv16_pair_kernel<BN, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+    configured.store(1, std::memory_order_release);
+  }
+  const int tiles_m = (p.M + 255) / 256, tiles = tiles_m * n_tiles_n;
+  const int nclusters = std::max(1, std::min(tiles, mla::device_info().sm_count / 2));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MLA_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv16_pair_kernel<BN, ET>, map, gmap, p, tiles_m, tiles));
+  mla::count_launch();
+  return 0;
+}
+
+// tile width of the pair kernel for `nch` output channels (0 = not applicable)
+int pair16_bn(int nch, int M, int KB) {
+  if (!conv_pair16() || KB <= 0 || M < 512) return 0;
+  return nch % 256 == 0 ? 256 : (nch % 128 == 0 ? 128 : 64);
+}
+
 // MLA_CONV_PERSIST=0 goes back to one tile per CTA for fprop16 / dgrad16. Default on: fprop16 301 -> 381 TF/s, dgrad16
 // 316 -> 378 TF/s, ResNet step 9.6 -> 8.8 ms (profiles/runs/f8_bench_*.json).
 bool conv_persist() {
@@ -1101,6 +1339,12 @@ extern "C" int mla_conv2d_fprop16(const void* x16, const void* w16, float* y, in
   if (rc) return rc;
   dim3 grid((p.M + 127) / 128, Cout / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (const int bnp = pair16_bn(Cout, p.M, p.KB)) {
+    const long long wc = (long long)R * S * Cin;
+    return bnp == 256 ? launch_conv16_pair<256, 1>(w16, false, Cout, wc, gmap, p, Cout / 256, st)
+         : bnp == 128 ? launch_conv16_pair<128, 1>(w16, false, Cout, wc, gmap, p, Cout / 128, st)
+                      : launch_conv16_pair<64, 1>(w16, false, Cout, wc, gmap, p, Cout / 64, st);
+  }
   if (conv_persist() && p.KB > 0)
     return BN == 64 ? launch_conv16_persistent<64, 4, 1>(map, gmap, p, Cout / BN, st)
                     : launch_conv16_persistent<128, 3, 1>(map, gmap, p, Cout / BN, st);
@@ -1593,6 +1837,12 @@ static int dgrad16_impl(const void* dy16, const void* wt16, float* dx, int N, in
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto go = [&](const ConvGemmParams& q, dim3 g) {
+    if (const int bnp = bf16 ? 0 : pair16_bn(Cin, q.M, q.KB)) {
+      const long long wc = (long long)R * S * Cout;
+      return bnp == 256 ? launch_conv16_pair<256, 1>(wt16, false, Cin, wc, gmap, q, Cin / 256, st)
+           : bnp == 128 ? launch_conv16_pair<128, 1>(wt16, false, Cin, wc, gmap, q, Cin / 128, st)
+                        : launch_conv16_pair<64, 1>(wt16, false, Cin, wc, gmap, q, Cin / 64, st);
+    }
     if (conv_persist() && q.KB > 0) {
       if (bf16)
         return BN == 64 ? launch_conv16_persistent<64, 4, 2>(map, gmap, q, (int)g.y, st)
@@ -1678,7 +1928,11 @@ int wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
   pl->NT = (Cin == 64 && S == 3 && !force_gather()) ? 3 : 1;
   const int tiles = (R * S / pl->NT) * ((Cin + pl->BN - 1) / pl->BN) * ((Cout + 127) / 128);
   static const int waves3 = [] { const char* e = getenv("MLA_WGRAD_WAVES"); return e ? atoi(e) : 2; }();
-  static const int waves1 = [] { const char* e = getenv("MLA_WGRAD_TARGET"); return e ? std::max(1, atoi(e)) : 4; }();
+  // split-K target: every extra split writes (and the reduction re-reads) a full fp32 copy of dw, so layers whose tiles alone
+  // nearly fill the GPU get ONE wave of CTAs; only layers with very few tiles split deeper (measured on the ResNet-18 shapes:
+  // 1.22 -> 1.04 ms per visual backward, profiles/r2_wgrad_split_sweep.txt)
+  static const int waves_env = [] { const char* e = getenv("MLA_WGRAD_TARGET"); return e ? std::max(1, atoi(e)) : 0; }();
+  const int waves1 = waves_env ? waves_env : (tiles < 16 ? 2 : 1);
   const int target = (pl->NT == 3 ? waves3 : waves1) * di.sm_count;   // CTAs in total (2 are resident per SM)
   int splits = (target + tiles - 1) / tiles;
   const int min_kb = kp == 32 ? 8 : 4;                                    // >= 256 pixels per split

@@ -333,7 +333,7 @@ int make_plan(int B, int D, int C, GsPlan* pl) {
   int grid = (D + rpc - 1) / rpc;
   if (D > kMaxCB * kCB) return MLA_E_SHAPE;
   size_t smem = ((size_t)2 * D + (size_t)rpc * D + (size_t)kGT * D + (size_t)kWarps * kGT * kRB + 32) * sizeof(float);
-  if (smem > (size_t)di.smem_optin) return MLA_E_SHAPE;
+  if (smem + 256 > (size_t)di.smem_optin) return MLA_E_SHAPE;
   // raw-feature reduction: the batch rows are dealt to the CTAs in contiguous slices (>= 1 row each); inside a CTA the
   // warps split columns (and rows, when D has fewer than kWarps 128-column chunks)
   int rows_per_nb = (B + grid - 1) / grid;
@@ -376,9 +376,10 @@ extern "C" int mla_gs_project(float* P, const float* feat, const float* feat_sum
 
   static std::atomic<size_t> s_smem_set{0};
   if (pl.smem > s_smem_set.load(std::memory_order_relaxed)) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(gs_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)di.smem_optin));
-    s_smem_set.store((size_t)di.smem_optin, std::memory_order_relaxed);
+    // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static barrier word
+    const size_t want = std::min((size_t)di.smem_optin - 256, std::max(pl.smem, (size_t)128 * 1024));
+    MLA_CUDA_TRY(cudaFuncSetAttribute(gs_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+    s_smem_set.store(want, std::memory_order_relaxed);
   }
   char* w = static_cast<char*>(ws);
   GsParams prm;

@@ -42,6 +42,8 @@ CONV_CASES = [  # N, H, W, Cin, Cout, R, stride
     (2, 8, 8, 64, 64, 1, 1), (2, 8, 8, 64, 64, 3, 1), (1, 16, 16, 64, 128, 3, 2), (2, 9, 6, 128, 128, 3, 1),
     (3, 14, 14, 128, 256, 1, 2), (2, 7, 7, 256, 512, 3, 2), (1, 17, 12, 512, 512, 3, 1), (3, 33, 24, 64, 128, 3, 2),
     (5, 13, 11, 64, 64, 3, 1),
+    # large enough for the CTA-pair kernel (256-row tiles): 256-column, 128-column and 64-column pair tiles, ragged last tile
+    (8, 14, 14, 256, 256, 3, 1), (12, 14, 14, 256, 512, 3, 2), (9, 17, 12, 128, 128, 3, 1), (11, 13, 11, 64, 64, 3, 1),
 ]
 
 
