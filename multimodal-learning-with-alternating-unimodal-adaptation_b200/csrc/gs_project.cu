@@ -214,7 +214,9 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     if (tid == 0) p.ws_norm[blockIdx.x] = (double)bs;
   }
   if (stamp) p.ws_ts[5] = tc::globaltimer_ns();
+  if (tid == 0) p.ws_ts[16 + blockIdx.x] = tc::globaltimer_ns();     // every CTA's arrival at the last barrier
   grid.sync();
+  if (stamp) p.ws_ts[8] = tc::globaltimer_ns();
 
   // ---------------- phase C: normalise, write P, project the gradient
   double tot = 0.0;
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     for (; c < G; ++c) tot += __ldcg(p.ws_norm + c);
   }
   const float nrm = (float)sqrt(tot);
+  if (stamp) p.ws_ts[9] = tc::globaltimer_ns();
   {
     const int n4 = nrows * D4;
     for (int i = tid; i < n4; i += kThreads) {
@@ -345,7 +348,7 @@ int make_plan(int B, int D, int C, GsPlan* pl) {
   pl->off_part = off; off += mla::align_up((size_t)nb * D * 4, 256);
   pl->off_norm = off; off += mla::align_up((size_t)grid * 8, 256);
   pl->off_g = off;    off += mla::align_up((size_t)max(C, 1) * D * 4, 256);
-  pl->off_ts = off;   off += 256;
+  pl->off_ts = off;   off += 4096;
   pl->total = off;
   return 0;
 }

@@ -81,6 +81,45 @@ class FlatGrads:
             self.flat.mul_(1.0 / world_size())
 
 
+_aux_groups = {}
+
+
+def aux_group(tag):
+    """A second communicator (own NCCL stream) for collectives that must not queue behind the main group's — the deferred
+    encoder's gradient buckets. Created collectively: every rank must ask for the same tags in the same order."""
+    if not is_dist():
+        return None
+    g = _aux_groups.get(tag)
+    if g is None:
+        g = dist.new_group()
+        _aux_groups[tag] = g
+    return g
+
+
+class BucketedAllReduce:
+    """Sum-all-reduce of one flat gradient buffer as two buckets issued asynchronously while the backward pass is still
+    producing the other one: `tail(off)` = elements [off, n) (the layers nearest the loss: complete first), `head(off)` =
+    [0, off). `wait()` makes the CURRENT stream wait for both. With world_size 1 everything is a no-op."""
+
+    def __init__(self, flat, group=None):
+        self.flat, self.group, self.works = flat, group, []
+
+    def _issue(self, t):
+        if is_dist() and t.numel():
+            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def tail(self, off):
+        self._issue(self.flat[off:])
+
+    def head(self, off):
+        self._issue(self.flat[:off])
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
 def allreduce_sum_(t):
     if is_dist():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -483,7 +483,21 @@ class ResNetPlan:
             torch._foreach_add_(self.nbt, 1)
 
     # ----------------------------------------------------------------------- backward
-    def backward(self, dfeat, serial=None):
+    def tail_bucket_offset(self):
+        """Element offset, inside the encoder's flat parameter / gradient buffer, of the first layer4 parameter: everything
+        from there on (75 % of a ResNet-18's parameters) has its gradient complete after backward segment 0."""
+        first = next(iter(self.net.layer4.parameters()))
+        off = 0
+        for q in self._params:
+            if q is first:
+                return off
+            off += q.numel()
+        raise RuntimeError("layer4 parameters not found in the encoder's parameter list")
+
+    def backward(self, dfeat, serial=None, on_segment=None):
+        """Native backward. `on_segment(k)` (optional) makes the pass run as two replayed launch sequences — k = 0: pooling
+        + layer4 (called when every layer4 gradient is complete on the current stream), k = 1: layer3 .. stem — so that a
+        data-parallel caller can start the all-reduce of the layer4 bucket while the rest of the backward still runs."""
         if not self.trained_forward:
             raise RuntimeError("encoder backward needs a training-mode forward on the same plan")
         if serial is not None and serial != self.serial:
@@ -498,17 +512,32 @@ class ResNetPlan:
             # addresses are stable, so the launch sequence can be replayed as a graph keyed on them
             for p in params:
                 _grad_buffer(p)
-            if len(self._graphs) > 8:
+            if len(self._graphs) > 12:
                 self._graphs.clear(); self._warm.clear()
-            self._run(("bwd", params[0].grad.data_ptr(), params[-1].grad.data_ptr()), self._backward_body)
+            key = (params[0].grad.data_ptr(), params[-1].grad.data_ptr())
+            if on_segment is None:
+                self._run(("bwd",) + key, self._backward_body)
+            else:
+                self._run(("bwd0",) + key, lambda: self._backward_body(0))
+                on_segment(0)
+                self._run(("bwd1",) + key, lambda: self._backward_body(1))
+                on_segment(1)
         else:
             self._backward_body()                        # fresh gradient tensors every call (plain autograd use): eager
+            if on_segment is not None:
+                on_segment(0)
+                on_segment(1)
         self.trained_forward = False
 
-    def _backward_body(self):
+    def _backward_body(self, seg=None):
+        """seg None: the whole pass; 0: transposed filters + pooling + layer4 (its weight gradients joined at the end);
+        1: layer3 .. stem, continuing from the gradient segment 0 left in `self._seg_dout`."""
         L, N, st = self.L, self.N, _lib.stream_ptr()
         net = self.net
         dfeat = self.dfeat_static
+        first, last = seg in (None, 0), seg in (None, 1)
+        nblk = len(self.blocks)
+        split = nblk - len(net.layer4)                   # blocks [split, nblk) belong to layer4
         self._slot_events.clear()                        # only events of THIS pass order its buffer reuse
         # Weight gradients leave the critical path: every wgrad (and its split-K reduction) runs on the plan's own side
         # stream as soon as its dy exists, concurrently with the BN-backward / dgrad chain that continues on `cur`.
@@ -549,13 +578,17 @@ class ResNetPlan:
                 events[(slot, tuple(dy.shape))] = done
 
         f16 = self.f16
-        if f16:      # transposed fp16 filters: the K-major B operand of dgrad16 (weights are those of this step's forward)
-            _chk(L.mla_filter_transpose16_batch(_p(self.flat), _p(self.wt16), _p(self.tr_table), self.tr_nseg, self.tr_tiles,
-                                                0, st), "mla_filter_transpose16_batch")
-        last = self.blocks[-1]
-        dout = self.tmp("dXa", last["out"].shape)
-        _chk(L.mla_avgpool_backward(_p(dfeat), _p(dout), self.B, self.rows, self.C_out, st), "mla_avgpool_backward")
-        for i in range(len(self.blocks) - 1, -1, -1):
+        if first:
+            if f16:  # transposed fp16 filters: the K-major B operand of dgrad16 (weights are those of this step's forward)
+                _chk(L.mla_filter_transpose16_batch(_p(self.flat), _p(self.wt16), _p(self.tr_table), self.tr_nseg,
+                                                    self.tr_tiles, 0, st), "mla_filter_transpose16_batch")
+            dout = self.tmp("dXa", self.blocks[-1]["out"].shape)
+            _chk(L.mla_avgpool_backward(_p(dfeat), _p(dout), self.B, self.rows, self.C_out, st), "mla_avgpool_backward")
+        else:
+            dout = self._seg_dout
+        hi = nblk - 1 if first else split - 1
+        lo = 0 if last else split
+        for i in range(hi, lo - 1, -1):
             b = self.blocks[i]
             blk, s, cin, cout = b["blk"], b["stride"], b["cin"], b["cout"]
             xin = self.blocks[i - 1]["out"] if i > 0 else self.p0
@@ -611,6 +644,10 @@ class ResNetPlan:
                 dx = g                                  # identity shortcut: dX starts as the masked gradient
                 dg(dy1, blk.conv1.weight, dx, N, b["h"], b["w"], cin, cout, 3, s, 1, True, st, gs=b["bn1"].gscale)
             dout = dx
+        if not last:
+            self._seg_dout = dout
+            cur.wait_stream(wsm)                        # every layer4 gradient is complete on `cur`
+            return
         # stem: maxpool+relu backward, BN backward, weight gradient (no dgrad: the input needs none)
         g0 = self.tmp("g0", self.y0.shape)
         _chk(L.mla_maxpool_relu_backward(_p(dout), _p(self.p0), _p(self.idx0), _p(g0), N, self.OH0, self.OW0, 64, st),

@@ -120,6 +120,11 @@ class _TurnState:
         self.flat = [mdist.FlatGrads(g) for g in self.encoders]
         self._dfeat = {}
         self._side = {}
+        # data parallel: every encoder's gradients travel as two asynchronous buckets (layer4 first, while the rest of the
+        # backward runs); encoders whose backward is deferred to a side stream use their own communicator so that their
+        # buckets never queue in front of the next turn's small head all-reduce
+        self.buckets = [mdist.BucketedAllReduce(fg.flat, mdist.aux_group("enc%d" % m) if m < len(self.flat) - 1 else None)
+                        for m, fg in enumerate(self.flat)]
 
     def dfeat_buffer(self, m, feat):
         """d(loss)/d(feature) of modality m: its own buffer, because the encoder backward that reads it may still be
@@ -211,13 +216,20 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                     stream.wait_stream(torch.cuda.current_stream())        # dfeat is ready
                 with torch.cuda.stream(stream):
                     st.flat[m].attach()
-                    plan.backward(o["dfeat"], getattr(feat, "_mla_serial", None))
-                    if world > 1 and not deferred:                         # encoder-gradient all-reduce
-                        mdist.allreduce_sum_(st.flat[m].flat)
+                    if world > 1:
+                        # encoder-gradient all-reduce, bucketed and overlapped — the layer4 bucket (75 % of the
+                        # bytes) leaves while layer3 .. stem are still being differentiated; only the small head bucket of
+                        # the last encoder is exposed
+                        bk, off = st.buckets[m], plan.tail_bucket_offset()
+                        plan.backward(o["dfeat"], getattr(feat, "_mla_serial", None),
+                                      on_segment=lambda k, bk=bk, off=off: bk.tail(off) if k == 0 else bk.head(off))
+                        if not deferred:
+                            bk.wait()
+                    else:
+                        plan.backward(o["dfeat"], getattr(feat, "_mla_serial", None))
                 if deferred:
-                    # its all-reduce is issued with the deferred update below: collectives of one communicator run in
-                    # issue order, so issuing it here would park the NEXT turn's small head all-reduce behind this
-                    # whole backward pass and serialise the two encoders again
+                    # (a deferred encoder's buckets use their own communicator: on the main one they would park the NEXT
+                    # turn's small head all-reduce behind this whole backward pass and serialise the two encoders again)
                     st.flat[m].detach()
                     pending.append((m, stream))
             else:                                  # autograd encoders (m3ae): gradients ACCUMULATE into the views
@@ -235,7 +247,7 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
             for m, stream in pending:
                 torch.cuda.current_stream().wait_stream(stream)
                 if world > 1:
-                    mdist.allreduce_sum_(st.flat[m].flat)
+                    st.buckets[m].wait()                                   # its buckets were issued during the backward
                 st.flat[m].attach()
             optimizer.step()
             optimizer.zero_grad()

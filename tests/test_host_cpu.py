@@ -192,6 +192,12 @@ assert g.shape == (4, 3) and g[0, 0] == 0 and g[3, 0] == 1
 g = mdist.all_gather_rows(torch.full((3 - 2 * rank, 2), float(rank + 5)))
 assert g.shape == (4, 2) and g[:3].eq(5).all() and g[3].eq(6).all()
 assert mdist.gather_sizes(3 - 2 * rank, "cpu") == [3, 1]
+# bucketed asynchronous all-reduce (tail bucket first, own communicator) == one all-reduce of the whole buffer
+flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+bk = mdist.BucketedAllReduce(flat, mdist.aux_group("enc0"))
+bk.tail(6); bk.head(6); bk.wait()
+assert torch.equal(flat, torch.arange(10, dtype=torch.float32) * 3), flat
+assert mdist.aux_group("enc0") is mdist.aux_group("enc0")
 # loss mean over ranks == global mean
 l = torch.tensor([loc["loss"]], dtype=torch.float64); mdist.allreduce_sum_(l)
 assert abs(l.item() / world - full["loss"]) < 1e-12

@@ -36,14 +36,18 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
             ws = ops._ws[("gs", P.device)].buf
-            st = ws[nbytes - 256:nbytes - 256 + 64].view(torch.int64).tolist()
+            st = ws[nbytes - 4096:nbytes].view(torch.int64).tolist()
             phases.append([(st[i + 1] - st[i]) / 1e3 for i in range(7)])
+            arr = [x for x in st[16:16 + 148] if x > 0]
+            extra = "last barrier: CTA arrivals span %.2f us (CTA0 at +%.2f); after barrier +%.2f us, norm +%.2f us, write +%.2f us" % (
+                (max(arr) - min(arr)) / 1e3, (st[5] - min(arr)) / 1e3, (st[8] - max(arr)) / 1e3, (st[9] - st[8]) / 1e3,
+                (st[6] - st[9]) / 1e3)
         med = [statistics.median(p[i] for p in phases) for i in range(7)]
         nb = 4 * (B * D + 2 * D * D + 2 * C * D)
         t = statistics.median(ts)
         print("B %5d D %5d C %4d: %7.2f us (events), %6.1f GB/s; CTA-0 phases [us]: %s" % (
             B, D, C, t, nb / t / 1e3, "  ".join("%s %.2f" % (n.split(" ")[0], m) for n, m in zip(NAMES, med))))
-        print("      " + " | ".join("%s: %.2f" % (n, m) for n, m in zip(NAMES, med)))
+        print("      " + extra)
 
 
 if __name__ == "__main__":

@@ -68,15 +68,20 @@ def layer(N, H, W, Cin, Cout, R, stride):
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "visual"
+    only = set(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else None      # e.g. "0,6": conv indices to run
     N, h, w = (128, 56, 56) if which == "visual" else (64, 65, 47)
     tot = [0.0] * 4
     cin = 64
+    idx = -1
     for li, (planes, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2))):
         ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
         convs = [(N, h, w, cin, planes, 3, stride, 1), (N, ho, wo, planes, planes, 3, 1, 3)]
         if stride != 1:
             convs.append((N, h, w, cin, planes, 1, stride, 1))
         for (n_, hh, ww, ci, co, r, s_, mult) in convs:
+            idx += 1
+            if only is not None and idx not in only:
+                continue
             t = layer(n_, hh, ww, ci, co, r, s_)
             for i in range(4):
                 tot[i] += t[i] * mult
