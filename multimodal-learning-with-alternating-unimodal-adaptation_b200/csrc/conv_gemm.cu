@@ -1241,11 +1241,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv16_pair_kernel(const __grid_c
   if (warp == 5) tc::tmem_dealloc2(tmem_base, 2 * BN);
 }
 
-// MLA_CONV_PAIR16=0 keeps fprop16 / dgrad16 on the single-CTA persistent kernel.
+// MLA_CONV_PAIR16=1 routes fprop16 / dgrad16 through this kernel. OFF by default — measured on the ResNet-18 shapes of the
+// bench batch (profiles/r2_conv_pair.md): 256 x 256 pair tiles tie with the single-CTA kernel on the 256 / 512-channel layers
+// (0.049 vs 0.047 ms: 98 tiles on 74 clusters = two rounds, half of the second one idle) and lose on the 64 / 128-channel
+// ones (0.100 vs 0.081 ms, 0.062 vs 0.055 ms), where one CTA per SM cannot hide the accumulator hand-back across the
+// pair. The single-CTA kernel already runs at 82-88 % of the chip's L2 -> SM throughput cap on these layers (ncu: 693 MB of
+// TMA loads in 66 us on 56x56x64), so the lever the pairs pull (operand bytes) is the right one; what they lack is
+// scheduling granularity. Kept selectable, and covered by tests/test_gpu_encoder_kernels.py::test_conv_pair_kernel.
 bool conv_pair16() {
   static const bool v = [] {
     const char* e = getenv("MLA_CONV_PAIR16");
-    return e != nullptr ? e[0] == '1' : true;
+    return e != nullptr && e[0] == '1';
   }();
   return v && !force_gather();
 }

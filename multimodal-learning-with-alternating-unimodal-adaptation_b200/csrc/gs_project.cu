@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   const int nrows = max(0, min(p.rows_per_cta, D - row0));
   const bool stamp = (blockIdx.x == 0 && tid == 0);
   if (stamp) p.ws_ts[0] = tc::globaltimer_ns();
+  if (tid == 0) p.ws_ts[176 + blockIdx.x] = tc::globaltimer_ns();     // every CTA's start
 
   // ---------------- phase 0: P rows -> smem (async), feat partial sums, grad copy
   if (tid == 0) {
@@ -219,21 +220,22 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   if (stamp) p.ws_ts[8] = tc::globaltimer_ns();
 
   // ---------------- phase C: normalise, write P, project the gradient
-  double tot = 0.0;
+  // ||P'||_F^2 = sum of the per-CTA partials in CTA order (identical in every CTA): the partials are fetched once per CTA
+  // (one L2 load per thread, NOT one per thread and partial: 75k threads polling the same 148 lines cost 30 us) and added
+  // by one thread from shared memory
   {
-    // fixed order, identical in every CTA; 8 loads in flight
-    int c = 0;
+    double* s_nrm = reinterpret_cast<double*>(s_G);               // s_G is free until the projection
     const int G = (int)gridDim.x;
-    for (; c + 8 <= G; c += 8) {
-      double v[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = __ldcg(p.ws_norm + c + q);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) tot += v[q];
+    for (int c = tid; c < G; c += kThreads) s_nrm[c] = __ldcg(p.ws_norm + c);
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int c = 0; c < G; ++c) tot += s_nrm[c];
+      s_red[0] = (float)sqrt(tot);
     }
-    for (; c < G; ++c) tot += __ldcg(p.ws_norm + c);
+    __syncthreads();
   }
-  const float nrm = (float)sqrt(tot);
+  const float nrm = s_red[0];
   if (stamp) p.ws_ts[9] = tc::globaltimer_ns();
   {
     const int n4 = nrows * D4;
@@ -247,7 +249,10 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     }
   }
   if (stamp) p.ws_ts[6] = tc::globaltimer_ns();
-  if (p.grad_w == nullptr) return;
+  if (p.grad_w == nullptr) {
+    if (tid == 0) p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns();
+    return;
+  }
   __syncthreads();
 
   // grad_w[c][i] = sum_j G[c][j] * P[i][j]. Work unit = (group of kRB rows, kCB-column chunk): the unit's P block sits in
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     }
   }
   if (stamp) p.ws_ts[7] = tc::globaltimer_ns();
+  if (tid == 0) p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns();     // every CTA's end
 }
 
 struct GsPlan {

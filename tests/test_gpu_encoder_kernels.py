@@ -331,3 +331,33 @@ def test_conv_argument_errors(L):
     xb, yb = torch.zeros(8, 16, 16, 64, device="cuda"), torch.zeros(8, 16, 16, 64, device="cuda")
     assert L.mla_conv2d_wgrad_workspace_bytes(8, 16, 16, 64, 64, 3, 3, 1, 1) > 256
     assert L.mla_conv2d_wgrad(P(xb), P(yb), P(w), 8, 16, 16, 64, 64, 3, 3, 1, 1, None, 0, st()) < 0    # split-K workspace missing
+
+
+_PAIR_WORKER = r"""
+import sys
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(root)r + "/tests")
+import torch
+import test_gpu_encoder_kernels as T
+from mla_b200 import _lib
+L = _lib.lib()
+torch.backends.cudnn.allow_tf32 = False
+for case in [(8, 14, 14, 256, 256, 3, 1), (12, 14, 14, 256, 512, 3, 2), (9, 17, 12, 128, 128, 3, 1), (11, 13, 11, 64, 64, 3, 1)]:
+    T.test_conv_2byte_operands(L, case)
+    T.test_conv_backward_scaled_fp16_operands(L, case, 1.0)
+print("pair kernel ok")
+"""
+
+
+def test_conv_pair_kernel(L, tmp_path):
+    """The opt-in CTA-pair persistent kernel (MLA_CONV_PAIR16=1: cta_group::2, 256 x {64, 128, 256} tiles) through the
+    same parity checks as the default kernels: forward with BatchNorm partial sums, plain and accumulating dgrad."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "pair_worker.py"
+    script.write_text(_PAIR_WORKER % {"root": root})
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MLA_CONV_PAIR16="1"))
+    assert r.returncode == 0 and "pair kernel ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -38,7 +38,11 @@ def main():
             ws = ops._ws[("gs", P.device)].buf
             st = ws[nbytes - 4096:nbytes].view(torch.int64).tolist()
             phases.append([(st[i + 1] - st[i]) / 1e3 for i in range(7)])
-            arr = [x for x in st[16:16 + 148] if x > 0]
+            g = (D + max(4, -(-D // 148)) - 1) // max(4, -(-D // 148))
+            arr = st[16:16 + g]
+            t_start, t_end = st[176:176 + g], st[336:336 + g]
+            span = "kernel: first CTA start -> last CTA end %.2f us; CTA starts span %.2f us, ends span %.2f us" % (
+                (max(t_end) - min(t_start)) / 1e3, (max(t_start) - min(t_start)) / 1e3, (max(t_end) - min(t_end)) / 1e3)
             extra = "last barrier: CTA arrivals span %.2f us (CTA0 at +%.2f); after barrier +%.2f us, norm +%.2f us, write +%.2f us" % (
                 (max(arr) - min(arr)) / 1e3, (st[5] - min(arr)) / 1e3, (st[8] - max(arr)) / 1e3, (st[9] - st[8]) / 1e3,
                 (st[6] - st[9]) / 1e3)
@@ -48,6 +52,7 @@ def main():
         print("B %5d D %5d C %4d: %7.2f us (events), %6.1f GB/s; CTA-0 phases [us]: %s" % (
             B, D, C, t, nb / t / 1e3, "  ".join("%s %.2f" % (n.split(" ")[0], m) for n, m in zip(NAMES, med))))
         print("      " + extra)
+        print("      " + span)
 
 
 if __name__ == "__main__":
