@@ -140,19 +140,29 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     if (stamp) p.ws_ts[1] = tc::globaltimer_ns();
     grid.sync();
     if (stamp) p.ws_ts[2] = tc::globaltimer_ns();
-    // r[j] = inv_batch * sum_c part[c][j]  (fixed order over c; 8 partials in flight)
-    for (int j = gtid; j < D; j += gthreads) {
-      float s = 0.f;
-      int c = 0;
-      for (; c + 8 <= p.nb; c += 8) {
-        float v[8];
+    // r[j] = inv_batch * sum_c part[c][j]. Eight lanes share a column: lane q adds the partials c = q, q + 8, ... (all of its
+    // loads in flight at once), then the eight sub-sums are added in lane order — a fixed tree, identical on every rank.
+    {
+      const int q = lane & 7;
+      for (int j = (gtid >> 3); j < D; j += (gthreads >> 3)) {
+        float v[24];
+        int n = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = __ldcg(p.ws_part + (size_t)(c + q) * D + j);
+        for (int u = 0; u < 24; ++u) {
+          const int c = q + 8 * u;
+          if (c < p.nb) { v[u] = __ldcg(p.ws_part + (size_t)c * D + j); n = u + 1; }
+        }
+        float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) s += v[q];
+        for (int u = 0; u < 24; ++u)
+          if (u < n) s += v[u];
+        for (int c = q + 8 * 24; c < p.nb; c += 8) s += __ldcg(p.ws_part + (size_t)c * D + j);      // nb > 192: not on 148 SMs
+        // lanes 8k .. 8k+7 hold the sub-sums of one column: add them in lane order
+        float t = __shfl_sync(0xffffffffu, s, (lane & ~7));
+#pragma unroll
+        for (int u = 1; u < 8; ++u) t += __shfl_sync(0xffffffffu, s, (lane & ~7) + u);
+        if (q == 0) p.ws_r[j] = t * p.inv_batch;
       }
-      for (; c < p.nb; ++c) s += __ldcg(p.ws_part + (size_t)c * D + j);
-      p.ws_r[j] = s * p.inv_batch;
     }
     grid.sync();
     for (int j = tid; j < D; j += kThreads) s_r[j] = __ldcg(p.ws_r + j);
@@ -189,12 +199,11 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     scal_den = __fadd_rn(p.alpha, mla::block_sum(part, s_red));
   }
   float sq = 0.f;
-  {
-    const int n4 = nrows * D4;
-    for (int i = tid; i < n4; i += kThreads) {
-      const int lr = i / D4, j4 = i - lr * D4;
-      const float ki = s_k[row0 + lr];
-      float4 pv = ld4(s_P + (size_t)lr * D + 4 * j4);
+  for (int lr = 0; lr < nrows; ++lr) {
+    const float ki = s_k[row0 + lr];
+    float* prow = s_P + (size_t)lr * D;
+    for (int j4 = tid; j4 < D4; j4 += kThreads) {
+      float4 pv = ld4(prow + 4 * j4);
       const float4 kv = ld4(s_k + 4 * j4);
       const float4 rv = ld4(s_r + 4 * j4);
       // Same operation order and roundings as utils.py:36 (no FMA contraction):
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
       }
       MLA_GS_UPD(x) MLA_GS_UPD(y) MLA_GS_UPD(z) MLA_GS_UPD(w)
 #undef MLA_GS_UPD
-      st4(s_P + (size_t)lr * D + 4 * j4, pv);
+      st4(prow + 4 * j4, pv);
     }
   }
   {
@@ -237,15 +246,15 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   }
   const float nrm = s_red[0];
   if (stamp) p.ws_ts[9] = tc::globaltimer_ns();
-  {
-    const int n4 = nrows * D4;
-    for (int i = tid; i < n4; i += kThreads) {
-      const int lr = i / D4, j4 = i - lr * D4;
-      float4 pv = ld4(s_P + (size_t)lr * D + 4 * j4);
+  for (int lr = 0; lr < nrows; ++lr) {
+    float* prow = s_P + (size_t)lr * D;
+    float4* grow = reinterpret_cast<float4*>(p.P + (size_t)(row0 + lr) * D);
+    for (int j4 = tid; j4 < D4; j4 += kThreads) {
+      float4 pv = ld4(prow + 4 * j4);
       pv.x = __fdiv_rn(pv.x, nrm); pv.y = __fdiv_rn(pv.y, nrm);
       pv.z = __fdiv_rn(pv.z, nrm); pv.w = __fdiv_rn(pv.w, nrm);
-      st4(s_P + (size_t)lr * D + 4 * j4, pv);
-      __stcs(reinterpret_cast<float4*>(p.P + (size_t)(row0 + lr) * D) + j4, pv);
+      st4(prow + 4 * j4, pv);
+      __stcs(grow + j4, pv);
     }
   }
   if (stamp) p.ws_ts[6] = tc::globaltimer_ns();
