@@ -123,6 +123,9 @@ MLA_API int    mla_conv2d_fprop(const float* x, const float* w, float* y, int N,
  * [mla_conv2d_fprop_stat_tiles(...)][2][Cout] floats = (sum y, sum y^2) per 128-row output tile; feed them to
  * mla_bn_stats_from_partials (saves the statistics pass over y). */
 MLA_API int    mla_conv2d_fprop_stat_tiles(int N, int H, int W, int R, int S, int stride, int pad);
+/* The same count for mla_conv2d_fprop16, whose 64 -> 64 channel 3x3 / stride-1 layers run on the halo-strip kernel with
+ * resident weights (tiles of whole image rows instead of 128 output pixels). */
+MLA_API int    mla_conv2d_fprop16_stat_tiles(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
 MLA_API int    mla_conv2d_fprop_bnstats(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
                         int Cout, int R, int S, int stride, int pad, float* stat_part, void* stream);
 MLA_API int    mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin,

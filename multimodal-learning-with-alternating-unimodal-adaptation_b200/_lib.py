@@ -35,6 +35,7 @@ _SIGNATURES = {
                                _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "mla_conv2d_fprop": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p]),
     "mla_conv2d_fprop_stat_tiles": (_c_int, [_c_int] * 7),
+    "mla_conv2d_fprop16_stat_tiles": (_c_int, [_c_int] * 9),
     "mla_conv2d_fprop_bnstats": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_void_p]),
     "mla_bn_stats_from_partials": (_c_int, [_c_void_p, _c_int, _c_ll, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                             _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,

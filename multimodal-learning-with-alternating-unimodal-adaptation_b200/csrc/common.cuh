@@ -23,13 +23,14 @@ const DeviceInfo& device_info();
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-// Halo-resident 3x3 / stride-1 convolution path (conv_strip.cu). tiles == 0: not applicable, use the im2col kernel.
+// Halo-resident 3x3 / stride-1 convolution path with resident weights (conv_strip16.cu: 64 -> 64 channels, fp16 operands).
+// tiles == 0: not applicable, use the im2col kernel.
 struct StripPlan {
   int Wp, TR, tiles_per_img, tiles;
 };
-StripPlan strip_plan(int N, int H, int W, int R, int S, int stride, int pad);
-int conv_strip_run(int mode, const float* src, const float* w, float* out, int N, int H, int W, int Cin, int Cout,
-                   int accumulate, float* stat_part, const StripPlan& pl, void* stream);
+StripPlan strip16_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+int conv_strip16_run(int mode, const void* src16, const void* w16, float* out, int N, int H, int W, int accumulate,
+                     float* stat_part, const float* out_scale, const StripPlan& pl, void* stream);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -699,8 +699,16 @@ extern "C" int mla_conv2d_fprop(const float* x, const float* w, float* y, int N,
 extern "C" int mla_conv2d_fprop_stat_tiles(int N, int H, int W, int R, int S, int stride, int pad) {
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (N < 1 || OH < 1 || OW < 1) return 0;
+  return (int)(((long long)N * OH * OW + 127) / 128);
+}
+
+// Rows of the [tile][2][Cout] BatchNorm partial-sum buffer mla_conv2d_fprop16 writes for this geometry (the strip kernel of
+// the 64-channel layers tiles by image rows, everything else by 128 output pixels).
+extern "C" int mla_conv2d_fprop16_stat_tiles(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
+  const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
+  if (N < 1 || OH < 1 || OW < 1) return 0;
   if (!force_gather()) {
-    const mla::StripPlan sp = mla::strip_plan(N, H, W, R, S, stride, pad);
+    const mla::StripPlan sp = mla::strip16_plan(N, H, W, Cin, Cout, R, S, stride, pad);
     if (sp.tiles > 0) return sp.tiles;
   }
   return (int)(((long long)N * OH * OW + 127) / 128);
@@ -720,10 +728,6 @@ static int conv2d_fprop_impl(const float* x, const float* w, float* y, int N, in
   if (di.ok != 1) return di.ok;
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (OH <= 0 || OW <= 0 || (long long)N * OH * OW > 0x7fffffffLL) return MLA_E_SHAPE;
-  if (!force_gather()) {   // 3x3 / stride 1: halo-resident strip kernel (9 taps from one shared-memory copy of the input)
-    const mla::StripPlan sp = mla::strip_plan(N, H, W, R, S, stride, pad);
-    if (sp.tiles > 0) return mla::conv_strip_run(0, x, w, y, N, H, W, Cin, Cout, 0, stat_part, sp, stream);
-  }
   ConvGemmParams p{};
   p.src = x; p.Hs = H; p.Ws = W; p.Cs = Cin; p.OH = OH; p.OW = OW; p.M = N * OH * OW; p.R = R; p.S = S;
   p.mul = stride; p.sgn = 1; p.off = -pad; p.div = 1; p.kcb = Cin / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
@@ -790,10 +794,6 @@ extern "C" int mla_conv2d_dgrad(const float* dy, const float* w, float* dx, int 
   if (di.ok != 1) return di.ok;
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (OH <= 0 || OW <= 0 || (long long)N * H * W > 0x7fffffffLL) return MLA_E_SHAPE;
-  if (!force_gather()) {
-    const mla::StripPlan sp = mla::strip_plan(N, H, W, R, S, stride, pad);
-    if (sp.tiles > 0) return mla::conv_strip_run(1, dy, w, dx, N, H, W, Cin, Cout, accumulate ? 1 : 0, nullptr, sp, stream);
-  }
   ConvGemmParams p{};
   p.src = dy; p.Hs = OH; p.Ws = OW; p.Cs = Cout; p.OH = H; p.OW = W; p.M = N * H * W; p.R = R; p.S = S;
   p.mul = 1; p.sgn = -1; p.off = pad; p.div = stride; p.kcb = Cout / 32; p.KB = R * S * p.kcb; p.CinW = Cin;
@@ -1331,6 +1331,10 @@ extern "C" int mla_conv2d_fprop16(const void* x16, const void* w16, float* y, in
   if (di.ok != 1) return di.ok;
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (OH <= 0 || OW <= 0 || (long long)N * OH * OW > 0x7fffffffLL) return MLA_E_SHAPE;
+  if (!force_gather()) {   // 64 -> 64, 3x3 / stride 1: halo-resident strips, weights resident in shared memory
+    const mla::StripPlan sp = mla::strip16_plan(N, H, W, Cin, Cout, R, S, stride, pad);
+    if (sp.tiles > 0) return mla::conv_strip16_run(0, x16, w16, y, N, H, W, 0, stat_part, nullptr, sp, stream);
+  }
   ConvGemmParams p{};
   p.OH = OH; p.OW = OW; p.M = N * OH * OW; p.R = R; p.S = S; p.mul = stride;
   p.kcb = Cin / 64; p.KB = R * S * p.kcb; p.CinW = Cin;
@@ -1833,6 +1837,11 @@ static int dgrad16_impl(const void* dy16, const void* wt16, float* dx, int N, in
   if (di.ok != 1) return di.ok;
   const int OH = out_size(H, R, stride, pad), OW = out_size(W, S, stride, pad);
   if (OH <= 0 || OW <= 0 || (long long)N * H * W > 0x7fffffffLL) return MLA_E_SHAPE;
+  if (!bf16 && !force_gather()) {
+    const mla::StripPlan sp = mla::strip16_plan(N, H, W, Cin, Cout, R, S, stride, pad);
+    if (sp.tiles > 0)
+      return mla::conv_strip16_run(1, dy16, wt16, dx, N, H, W, accumulate ? 1 : 0, nullptr, out_scale, sp, stream);
+  }
   ConvGemmParams p{};
   p.OH = H; p.OW = W; p.M = N * H * W; p.R = R; p.S = S; p.mul = 1;
   p.kcb = Cout / 64; p.CinW = Cout;      // GEMM K = dy channels; a filter tap spans Cout columns of the transposed filter

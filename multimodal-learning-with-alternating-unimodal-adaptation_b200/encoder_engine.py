@@ -196,9 +196,12 @@ class ResNetPlan:
         nb = max(self.L.mla_bn_workspace_bytes(self.M0, 64),
                  max(self.L.mla_bn_workspace_bytes(N * b["ho"] * b["wo"], b["cout"]) for b in self.blocks))
         tl = self.L.mla_conv2d_fprop_stat_tiles
+        tl16 = self.L.mla_conv2d_fprop16_stat_tiles
         self.stat_part = torch.empty(max([tl(N, self.OH0, self.OW0, 1, 1, 1, 0) * 2 * 64] +
                                          [max(tl(N, b["h"], b["w"], 3, 3, b["stride"], 1), tl(N, b["ho"], b["wo"], 3, 3, 1, 1),
-                                              tl(N, b["h"], b["w"], 1, 1, b["stride"], 0)) * 2 * b["cout"]
+                                              tl(N, b["h"], b["w"], 1, 1, b["stride"], 0),
+                                              tl16(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3, b["stride"], 1),
+                                              tl16(N, b["ho"], b["wo"], b["cout"], b["cout"], 3, 3, 1, 1)) * 2 * b["cout"]
                                           for b in self.blocks]),
                                      dtype=torch.float32, device=dev)          # per-tile BN partial sums (fprop epilogue)
         self.bn_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)      # ticket counters start at 0 (mla_b200.h)
@@ -269,7 +272,8 @@ class ResNetPlan:
         OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
         M = N * OH * OW
         bn = b.bn
-        _chk(self.L.mla_bn_stats_from_partials(_p(self.stat_part), (M + 127) // 128, M, b.C, _p(bn.weight), _p(bn.bias),
+        ntiles = self.L.mla_conv2d_fprop16_stat_tiles(N, H, W, Cin, Cout, R, R, stride, pad)
+        _chk(self.L.mla_bn_stats_from_partials(_p(self.stat_part), ntiles, M, b.C, _p(bn.weight), _p(bn.bias),
                                                _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps),
                                                _p(b.mean), _p(b.invstd), _p(b.scale), _p(b.shift), _p(self.bn_ws),
                                                self.bn_ws.numel(), st), "mla_bn_stats_from_partials")

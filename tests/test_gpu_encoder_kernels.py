@@ -44,6 +44,9 @@ CONV_CASES = [  # N, H, W, Cin, Cout, R, stride
     (5, 13, 11, 64, 64, 3, 1),
     # large enough for the CTA-pair kernel (256-row tiles): 256-column, 128-column and 64-column pair tiles, ragged last tile
     (8, 14, 14, 256, 256, 3, 1), (12, 14, 14, 256, 512, 3, 2), (9, 17, 12, 128, 128, 3, 1), (11, 13, 11, 64, 64, 3, 1),
+    # 64 -> 64 channel 3x3 / 1 geometries that take the halo-strip kernel with resident weights: the two layer1 shapes of the
+    # benchmark (56x56, 65x47: odd height -> a one-row last tile), the widest supported row (W + 2 = 64), several tiles / CTA
+    (2, 56, 56, 64, 64, 3, 1), (2, 65, 47, 64, 64, 3, 1), (1, 9, 62, 64, 64, 3, 1), (160, 20, 30, 64, 64, 3, 1),
 ]
 
 
@@ -107,6 +110,15 @@ def test_conv_2byte_operands(L, case):
                                      stride, pad)
     assert relf(y.permute(0, 3, 1, 2), yr) < 2e-5
     assert relf(dx.permute(0, 3, 1, 2), dxr) < 2e-5
+    # the same forward with BatchNorm partial sums from the epilogue: identical y, partials add up to the sums of y
+    tiles = L.mla_conv2d_fprop16_stat_tiles(N, H, W, Cin, Cout, R, R, stride, pad)
+    part = torch.full((tiles, 2, Cout), float("nan"), device="cuda")
+    y2 = torch.empty_like(y)
+    assert L.mla_conv2d_fprop16(P(x16), P(w16), P(y2), N, H, W, Cin, Cout, R, R, stride, pad, P(part), st()) == 0
+    torch.cuda.synchronize()
+    flat = y2.view(-1, Cout).double()
+    assert torch.equal(y2, y)
+    assert relf(part[:, 0].double().sum(0), flat.sum(0)) < 1e-5 and relf(part[:, 1].double().sum(0), (flat * flat).sum(0)) < 1e-5
     # fp16 operands carry TF32's mantissa: against the unrounded fp32 convolution the error is the TF32 one
     assert relf(y.permute(0, 3, 1, 2), F.conv2d(x, w, None, stride, pad)) < 2e-3
     # wgrad16: bf16 x bf16, both operands MN-major (K = pixels)

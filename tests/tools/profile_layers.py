@@ -48,7 +48,7 @@ def layer(N, H, W, Cin, Cout, R, stride):
     dw = torch.empty(Cout, R, R, Cin, device="cuda")
     nb = L.mla_conv2d_wgrad16_workspace_bytes(N, H, W, Cin, Cout, R, R, stride, pad)
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
-    part = torch.zeros(((N * OH * OW + 127) // 128) * 2 * Cout, device="cuda")
+    part = torch.zeros(L.mla_conv2d_fprop16_stat_tiles(N, H, W, Cin, Cout, R, R, stride, pad) * 2 * Cout, device="cuda")
 
     def chk(rc):
         assert rc == 0, rc
