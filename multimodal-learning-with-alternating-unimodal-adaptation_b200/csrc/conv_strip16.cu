@@ -16,8 +16,12 @@
 // row of m is strip row m + r * Wp + s. Rows with wp >= W (2 per image row) and rows past TR * Wp are garbage: computed,
 // never stored, masked out of the BatchNorm partial sums. dgrad is the same walk over dy with the taps flipped and the
 // transposed filter [Cin][R][S][Cout] (so both directions are the same K-major GEMM).
-// Warp roles: warp 4 = TMA producer (weights once, then one strip per tile into a 3-deep ring), warp 5 = MMA issuer (36
+// Warp roles: warp 4 = TMA producer (weights once, then one strip per tile into a 2-deep ring), warp 5 = MMA issuer (36
 // tcgen05.mma kind::f16 128 x 64 x 16 per tile into one of two TMEM accumulators), warps 0-3 = epilogue of the previous tile.
+// Epilogue: the accumulator rows are compacted (padded columns dropped) into a 128B-swizzled shared-memory staging tile and
+// leave through TWO TMA STORES per tile (32 channels x W pixels x TR rows each; rows past the image are clipped by the TMA) —
+// cp.reduce.async.bulk.tensor .add for the accumulating dgrad, so the `+=` happens in L2 and the SM never reads dx. (Per-
+// thread 16-byte row stores were the bound of this kernel: 2.4 us per tile against 0.6 us of MMAs.)
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -25,7 +29,8 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kC = 64;                       // channels in and out
-constexpr int kStages = 3;                   // strips in flight
+constexpr int kStages = 2;                   // strips in flight
+constexpr uint32_t kStageOut = 2 * 128 * 128;  // staging tile: 2 channel halves x 128 rows x 128 B (fp32)
 constexpr uint32_t kTapBytes = kC * 128;     // one filter tap: 64 rows (output channels) x 64 fp16
 constexpr uint32_t kWBytes = 9 * kTapBytes;  // 72 KB
 
@@ -43,8 +48,24 @@ struct Strip16Params {
   const float* out_scale;
 };
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                                     const __grid_constant__ CUtensorMap tmap_x,
+                                                                    const __grid_constant__ CUtensorMap tmap_o,
                                                                     Strip16Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_bar, full_bar[kStages], empty_bar[kStages], acc_full_bar[2], acc_empty_bar[2];
@@ -54,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
   const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;                       // 9 taps x 8 KB
   const uint32_t a_base = base + kWBytes;             // strip ring
+  const uint32_t o_base = a_base + kStages * p.a_stage;   // two output staging tiles
 
   if (threadIdx.x == 0) {
     tc::mbar_init(tc::smem_u32(&w_bar), 1);
@@ -70,6 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
   if (warp == 4 && lane == 0) {
     tc::tma_prefetch_desc(&tmap_w);
     tc::tma_prefetch_desc(&tmap_x);
+    tc::tma_prefetch_desc(&tmap_o);
   }
   if (warp == 5) {
     tc::tmem_alloc(tc::smem_u32(&tmem_slot), 2 * kC);
@@ -131,12 +154,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
     const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;
     const int m = warp * 32 + lane;
     const int lr = m / p.Wp, wp = m - lr * p.Wp;
+    const bool in_box = lr < p.TR && wp < p.W;           // this thread's row exists in the compacted TR x W staging tile
+    const int crow = lr * p.W + wp;                      // its row there
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int n = tile / p.tiles_per_img, h0 = (tile - n * p.tiles_per_img) * p.TR;
-      const bool valid = lr < p.TR && wp < p.W && h0 + lr < p.H;
-      float* orow = valid ? p.out + (((long long)n * p.H + h0 + lr) * p.W + wp) * kC : nullptr;
+      const bool valid = in_box && h0 + lr < p.H;
+      const uint32_t stg = o_base + (uint32_t)buf * kStageOut;
+      // the staging tile of two tiles ago must have been read by its TMA store
+      if (threadIdx.x == 0) bulk_wait_read<1>();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       tc::mbar_wait(tc::smem_u32(&acc_full_bar[buf]), (it >> 1) & 1);
       tc::tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * kC;
@@ -145,26 +173,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
         uint32_t v[32];
         tc::tmem_ld32(acc + c, v);
         tc::tmem_ld_wait();
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(orow + c);
-          float4 o[8];
+        if (in_box) {
+          // half c / 32 of the staging tile: row `crow` of 128 B, 16-byte chunk j at position j ^ (crow & 7) (SWIZZLE_128B)
+          const uint32_t rowp = stg + (uint32_t)(c >> 5) * (128u * 128u) + (uint32_t)crow * 128u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
-          if (p.out_scale != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { o[j].x *= oscale; o[j].y *= oscale; o[j].z *= oscale; o[j].w *= oscale; }
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (p.out_scale != nullptr) { o.x *= oscale; o.y *= oscale; o.z *= oscale; o.w *= oscale; }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + tc::swz16(j, crow)), "f"(o.x), "f"(o.y),
+                         "f"(o.z), "f"(o.w)
+                         : "memory");
           }
-          if (p.accumulate) {
-            float4 old[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) old[j] = dst[j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { o[j].x += old[j].x; o[j].y += old[j].y; o[j].z += old[j].z; o[j].w += old[j].w; }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = o[j];
         }
         if (p.stat_part != nullptr) {
           float a[32], b[32];
@@ -188,8 +208,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty_bar[buf]));
+      tc::fence_proxy_async();                             // staging writes -> visible to the TMA (async proxy)
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // whole tile staged (and s_stat complete)
+      if (threadIdx.x == 0) {
+        if (p.accumulate) {
+          tma_reduce_add_4d(&tmap_o, stg, 0, 0, h0, n);
+          tma_reduce_add_4d(&tmap_o, stg + 128u * 128u, 32, 0, h0, n);
+        } else {
+          tma_store_4d(&tmap_o, stg, 0, 0, h0, n);
+          tma_store_4d(&tmap_o, stg + 128u * 128u, 32, 0, h0, n);
+        }
+        bulk_commit();
+      }
       if (p.stat_part != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
         for (int t = threadIdx.x; t < kC; t += 128) {
           float sa = 0.f, sb = 0.f;
 #pragma unroll
@@ -198,9 +229,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
           dstp[0] = sa;
           dstp[kC] = sb;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_stat is rewritten by the next tile
+        // (s_stat is rewritten only after the next tile's first bar.sync)
       }
     }
+    if (threadIdx.x == 0) bulk_wait_all();                 // the last stores have left shared memory and are complete
   }
 
   tc::tc_fence_before();
@@ -252,6 +284,19 @@ int make_strip_map16(CUtensorMap* m, const void* ptr, int N, int H, int W, int C
   return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
 }
 
+// NHWC fp32 output {C, W, H, N}: box {32 channels (128 B), W pixels, rows image rows, 1 image}, 128B-swizzled staging
+int make_out_map(CUtensorMap* m, float* ptr, int N, int H, int W, int C, int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return MLA_E_NODEVICE;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32u, (cuuint32_t)W, (cuuint32_t)rows, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MLA_E_BADARG;
+}
+
 }  // namespace
 
 namespace mla {
@@ -285,20 +330,22 @@ int conv_strip16_run(int mode, const void* src16, const void* w16, float* out, i
   p.a_stage = (uint32_t)align_up((size_t)128 * (130 + 2 * pl.Wp), 1024);
   p.strip_tx = (uint32_t)(128 * pl.Wp * (pl.TR + 2));
   p.out = out; p.accumulate = accumulate; p.stat_part = stat_part; p.out_scale = out_scale;
-  CUtensorMap wmap, xmap;
+  CUtensorMap wmap, xmap, omap;
   int rc = make_weight_map16(&wmap, w16, kC, 9LL * kC, kC);
   if (rc) return rc;
   rc = make_strip_map16(&xmap, src16, N, H, W, kC, pl.Wp, pl.TR + 2);
   if (rc) return rc;
-  const size_t smem = 1024 + kWBytes + (size_t)kStages * p.a_stage;
+  rc = make_out_map(&omap, out, N, H, W, kC, pl.TR);
+  if (rc) return rc;
+  const size_t smem = 1024 + kWBytes + (size_t)kStages * p.a_stage + 2 * (size_t)kStageOut;
   static std::atomic<size_t> configured{0};
   if (smem > configured.load(std::memory_order_acquire)) {
-    const size_t want = 1024 + kWBytes + (size_t)kStages * 33 * 1024;          // Wp <= 64: a_stage <= 33 KB
+    const size_t want = 1024 + kWBytes + (size_t)kStages * 33 * 1024 + 2 * (size_t)kStageOut;   // Wp <= 64: a_stage <= 33 KB
     MLA_CUDA_TRY(cudaFuncSetAttribute(conv_strip16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
     configured.store(want, std::memory_order_release);
   }
   const int grid = std::min(pl.tiles, di.sm_count);
-  conv_strip16_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(wmap, xmap, p);
+  conv_strip16_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(wmap, xmap, omap, p);
   MLA_CUDA_TRY(cudaGetLastError());
   count_launch();
   return 0;
