@@ -16,10 +16,11 @@
 // row of m is strip row m + r * Wp + s. Rows with wp >= W (2 per image row) and rows past TR * Wp are garbage: computed,
 // never stored, masked out of the BatchNorm partial sums. dgrad is the same walk over dy with the taps flipped and the
 // transposed filter [Cin][R][S][Cout] (so both directions are the same K-major GEMM).
-// Warp roles: warp 4 = TMA producer (weights once, then one strip per tile into a 2-deep ring), warp 5 = MMA issuer (36
+// Warp roles: warp 4 = TMA producer (weights once, then one strip per tile into a 3-deep ring), warp 5 = MMA issuer (36
 // tcgen05.mma kind::f16 128 x 64 x 16 per tile into one of two TMEM accumulators), warps 0-3 = epilogue of the previous tile.
 // Epilogue: the accumulator rows are compacted (padded columns dropped) into a 128B-swizzled shared-memory staging tile and
-// leave through TWO TMA STORES per tile (32 channels x W pixels x TR rows each; rows past the image are clipped by the TMA) —
+// leave through TWO TMA STORES per tile (32 channels x W pixels x TR rows each, alternating between two 16 KB staging
+// halves; rows past the image are clipped by the TMA) —
 // cp.reduce.async.bulk.tensor .add for the accumulating dgrad, so the `+=` happens in L2 and the SM never reads dx. (Per-
 // thread 16-byte row stores were the bound of this kernel: 2.4 us per tile against 0.6 us of MMAs.)
 #include "common.cuh"
@@ -29,8 +30,8 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kC = 64;                       // channels in and out
-constexpr int kStages = 2;                   // strips in flight
-constexpr uint32_t kStageOut = 2 * 128 * 128;  // staging tile: 2 channel halves x 128 rows x 128 B (fp32)
+constexpr int kStages = 3;                   // strips in flight (one strip = one tile: the TMA round trip of ~2 us needs >= 2 ahead)
+constexpr uint32_t kHalfOut = 128 * 128;     // staging of one 32-channel half of a tile: 128 rows x 128 B (fp32)
 constexpr uint32_t kTapBytes = kC * 128;     // one filter tap: 64 rows (output channels) x 64 fp16
 constexpr uint32_t kWBytes = 9 * kTapBytes;  // 72 KB
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
   const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;                       // 9 taps x 8 KB
   const uint32_t a_base = base + kWBytes;             // strip ring
-  const uint32_t o_base = a_base + kStages * p.a_stage;   // two output staging tiles
+  const uint32_t o_base = a_base + kStages * p.a_stage;   // two 16 KB output staging halves
 
   if (threadIdx.x == 0) {
     tc::mbar_init(tc::smem_u32(&w_bar), 1);
@@ -161,21 +162,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
       const int buf = it & 1;
       const int n = tile / p.tiles_per_img, h0 = (tile - n * p.tiles_per_img) * p.TR;
       const bool valid = in_box && h0 + lr < p.H;
-      const uint32_t stg = o_base + (uint32_t)buf * kStageOut;
-      // the staging tile of two tiles ago must have been read by its TMA store
-      if (threadIdx.x == 0) bulk_wait_read<1>();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       tc::mbar_wait(tc::smem_u32(&acc_full_bar[buf]), (it >> 1) & 1);
       tc::tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * kC;
 #pragma unroll 1
       for (int c = 0; c < kC; c += 32) {
+        const uint32_t stg = o_base + (uint32_t)(c >> 5) * kHalfOut;     // channels [c, c + 32) of every tile use this half
+        // its previous occupant (the same half of the previous tile = the commit group before the latest one) must have
+        // been read by its TMA store
+        if (threadIdx.x == 0) bulk_wait_read<1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         uint32_t v[32];
         tc::tmem_ld32(acc + c, v);
         tc::tmem_ld_wait();
+        if (c + 32 == kC) {                                               // the accumulator has been read completely
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty_bar[buf]));
+        }
         if (in_box) {
-          // half c / 32 of the staging tile: row `crow` of 128 B, 16-byte chunk j at position j ^ (crow & 7) (SWIZZLE_128B)
-          const uint32_t rowp = stg + (uint32_t)(c >> 5) * (128u * 128u) + (uint32_t)crow * 128u;
+          // row `crow` of 128 B, 16-byte chunk j at position j ^ (crow & 7) (SWIZZLE_128B)
+          const uint32_t rowp = stg + (uint32_t)crow * 128u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
@@ -204,21 +211,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_strip16_kernel(const __grid_
           s_stat[(warp * 2 + 0) * kC + c + lane] = a[0];
           s_stat[(warp * 2 + 1) * kC + c + lane] = b[0];
         }
-      }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty_bar[buf]));
-      tc::fence_proxy_async();                             // staging writes -> visible to the TMA (async proxy)
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // whole tile staged (and s_stat complete)
-      if (threadIdx.x == 0) {
-        if (p.accumulate) {
-          tma_reduce_add_4d(&tmap_o, stg, 0, 0, h0, n);
-          tma_reduce_add_4d(&tmap_o, stg + 128u * 128u, 32, 0, h0, n);
-        } else {
-          tma_store_4d(&tmap_o, stg, 0, 0, h0, n);
-          tma_store_4d(&tmap_o, stg + 128u * 128u, 32, 0, h0, n);
+        tc::fence_proxy_async();                             // staging writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // this half is staged (second half: s_stat complete too)
+        if (threadIdx.x == 0) {
+          if (p.accumulate) tma_reduce_add_4d(&tmap_o, stg, c, 0, h0, n);
+          else tma_store_4d(&tmap_o, stg, c, 0, h0, n);
+          bulk_commit();
         }
-        bulk_commit();
       }
       if (p.stat_part != nullptr) {
         for (int t = threadIdx.x; t < kC; t += 128) {
@@ -337,10 +336,10 @@ int conv_strip16_run(int mode, const void* src16, const void* w16, float* out, i
   if (rc) return rc;
   rc = make_out_map(&omap, out, N, H, W, kC, pl.TR);
   if (rc) return rc;
-  const size_t smem = 1024 + kWBytes + (size_t)kStages * p.a_stage + 2 * (size_t)kStageOut;
+  const size_t smem = 1024 + kWBytes + (size_t)kStages * p.a_stage + 2 * (size_t)kHalfOut;
   static std::atomic<size_t> configured{0};
   if (smem > configured.load(std::memory_order_acquire)) {
-    const size_t want = 1024 + kWBytes + (size_t)kStages * 33 * 1024 + 2 * (size_t)kStageOut;   // Wp <= 64: a_stage <= 33 KB
+    const size_t want = 1024 + kWBytes + (size_t)kStages * 33 * 1024 + 2 * (size_t)kHalfOut;   // Wp <= 64: a_stage <= 33 KB
     MLA_CUDA_TRY(cudaFuncSetAttribute(conv_strip16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
     configured.store(want, std::memory_order_release);
   }
