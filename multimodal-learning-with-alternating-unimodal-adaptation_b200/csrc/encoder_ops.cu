@@ -219,7 +219,7 @@ struct BnFinal {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kRedThreads, 4) channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+__global__ void __launch_bounds__(kRedThreads, MODE == 1 ? 3 : 4) channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                                      const float* __restrict__ z,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, long long M, int C,
@@ -339,14 +339,14 @@ __global__ void __launch_bounds__(kRedThreads, 4) channel_reduce_kernel(const fl
     const double* pp = part + (size_t)chunk * nrb * 128 + col;
     double sum = 0;
     // this serial tail sits on the critical path of every BatchNorm launch (up to 592 partial rows on the 64-channel
-    // layers): 16 independent L2 loads in flight per thread, added in row order
+    // layers): 12 independent L2 loads in flight per thread, added in row order
     int blk = half;
-    for (; blk + 30 < nrb; blk += 32) {
-      double v[16];
+    for (; blk + 22 < nrb; blk += 24) {
+      double v[12];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = __ldcg(pp + (size_t)(blk + 2 * u) * 128);
+      for (int u = 0; u < 12; ++u) v[u] = __ldcg(pp + (size_t)(blk + 2 * u) * 128);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) sum += v[u];
+      for (int u = 0; u < 12; ++u) sum += v[u];
     }
     for (; blk < nrb; blk += 2) sum += __ldcg(pp + (size_t)blk * 128);
     if (half == 1) s_half[col] = sum;

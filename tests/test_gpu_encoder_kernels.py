@@ -47,6 +47,7 @@ CONV_CASES = [  # N, H, W, Cin, Cout, R, stride
     # 64 -> 64 channel 3x3 / 1 geometries that take the halo-strip kernel with resident weights: the two layer1 shapes of the
     # benchmark (56x56, 65x47: odd height -> a one-row last tile), the widest supported row (W + 2 = 64), several tiles / CTA
     (2, 56, 56, 64, 64, 3, 1), (2, 65, 47, 64, 64, 3, 1), (1, 9, 62, 64, 64, 3, 1), (160, 20, 30, 64, 64, 3, 1),
+    (4, 17, 12, 64, 64, 3, 1), (8, 16, 16, 64, 64, 3, 1), (3, 33, 24, 64, 64, 3, 1),      # 9-, 7- and 4-row strip tiles
 ]
 
 
