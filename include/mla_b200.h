@@ -318,6 +318,37 @@ MLA_API int    mla_filter_transpose16_batch(const float* flat, void* flat_t16, c
                         int bf16, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * The 7x7 / stride 2 / pad 3 stem convolution without an im2col matrix (stem_s2d.cu) — models/backbone.py:78-83,149,
+ * 150-152 (conv1 -> bn1 -> relu -> maxpool) and their autograd. Cin <= 4, 64 output channels, fp16 operands.
+ *   mla_stem_s2d_pack      raw NCHW / NCTHW fp32 input (strides as in mla_stem_im2col) -> the zero-padded space-to-depth
+ *                          tensor xs16 [N][OH+3][OW+3][16] fp16 (mla_stem_s2d_input_elems elements): cell (r, q) channel
+ *                          (pr*2+pc)*Cin + c = x[n][c][2r+pr-3][2q+pc-3]
+ *   mla_stem_s2d_weights   w [64][7][7][Cin] fp32 (channels_last OIHW) -> w2_16 [64][4][4][16] fp16, regrouped the same way
+ *   mla_stem_s2d_fprop     y16 [N][OH][OW][64] fp16 = conv(xs16, w2_16); stat_part (may be NULL) receives the BatchNorm
+ *                          partial sums of the fp32 accumulators, [mla_stem_s2d_tiles][2][64] (-> mla_bn_stats_from_partials)
+ *   mla_stem_s2d_wgrad     dw [64][7][7][Cin] = *out_scale * sum over pixels dy16^T patch(xs16); deterministic
+ *   mla_bn_relu_maxpool16  mla_bn_relu_maxpool_ex over the fp16 y16; idx bit 4 marks pooled values that are not positive
+ *   mla_pool_bn_backward_f16  BatchNorm backward of the stem with the ReLU + MaxPool backward folded in: dp = gradient of the
+ *                          POOLED activation [N][PH][PW][C] fp32, idx from mla_bn_relu_maxpool16, (H, W) = pre-pool extent;
+ *                          dy16 = fp16(dy * F), gscale = {F, 1 / F} as in mla_bn_backward_f16. ws: mla_bn_workspace_bytes.
+ */
+MLA_API long long mla_stem_s2d_input_elems(int N, int H, int W);
+MLA_API int    mla_stem_s2d_tiles(int N, int H, int W);
+MLA_API int    mla_stem_s2d_pack(const float* in, void* xs16, int N, int T, long long sB, long long sT, long long sC, int Cin,
+                        int H, int W, void* stream);
+MLA_API int    mla_stem_s2d_weights(const float* w, void* w2_16, int Cin, void* stream);
+MLA_API int    mla_stem_s2d_fprop(const void* xs16, const void* w2_16, void* y16, int N, int H, int W, float* stat_part,
+                        void* stream);
+MLA_API size_t mla_stem_s2d_wgrad_workspace_bytes(void);
+MLA_API int    mla_stem_s2d_wgrad(const void* xs16, const void* dy16, const float* out_scale, float* dw, int N, int H, int W,
+                        int Cin, void* ws, size_t ws_bytes, void* stream);
+MLA_API int    mla_bn_relu_maxpool16(const void* y16, const float* scale, const float* shift, float* out, void* out16,
+                        unsigned char* idx, int N, int H, int W, int C, void* stream);
+MLA_API int    mla_pool_bn_backward_f16(const float* dp, const unsigned char* idx, const void* y16, const float* mean,
+                        const float* invstd, const float* gamma, int N, int H, int W, int C, float* dgamma, float* dbeta,
+                        void* dy16, float* gscale, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * OGM / OGM-GE gradient modulation of the joint-training step — main.py:312-410.
  *   mla_ogm_scores   score[m] = sum_b softmax(logits[m])[b][label[b]], b added in index order   main.py:315-317, 373-374
  *                    `logits` is a HOST array of M (2 or 3) device pointers to B x C matrices; ws >= M * B floats.

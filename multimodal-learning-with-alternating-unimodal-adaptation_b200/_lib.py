@@ -88,6 +88,15 @@ _SIGNATURES = {
     "mla_conv2d_dgrad16_f16": (_c_int, [_c_void_p] * 4 + [_c_int] * 10 + [_c_void_p]),
     "mla_conv2d_wgrad16_f16": (_c_int, [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),
     "mla_filter_transpose16_batch": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "mla_stem_s2d_input_elems": (_c_ll, [_c_int] * 3),
+    "mla_stem_s2d_tiles": (_c_int, [_c_int] * 3),
+    "mla_stem_s2d_pack": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_void_p]),
+    "mla_stem_s2d_weights": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "mla_stem_s2d_fprop": (_c_int, [_c_void_p] * 3 + [_c_int] * 3 + [_c_void_p, _c_void_p]),
+    "mla_stem_s2d_wgrad_workspace_bytes": (_c_size_t, []),
+    "mla_stem_s2d_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p, _c_size_t, _c_void_p]),
+    "mla_bn_relu_maxpool16": (_c_int, [_c_void_p] * 6 + [_c_int] * 4 + [_c_void_p]),
+    "mla_pool_bn_backward_f16": (_c_int, [_c_void_p] * 6 + [_c_int] * 4 + [_c_void_p] * 5 + [_c_size_t, _c_void_p]),
     "mla_ogm_scores_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "mla_ogm_scores": (_c_int, [ctypes.POINTER(_c_void_p), _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p,
                                 _c_size_t, _c_void_p]),

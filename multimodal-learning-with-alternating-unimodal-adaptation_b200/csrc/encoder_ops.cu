@@ -201,8 +201,77 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict
 // finalisation (statistics / running stats, or dgamma / dbeta) for its 64 channels. No second launch.
 // MODE 0: a = x, b = x*x (BN statistics).
 // MODE 1: g = dz * (z > 0 or no mask); a = g, b = g * (y - mean) * invstd (BN backward sums).
+// MODE 3: MODE 1 for the stem, walking the POOLED pixels (M = their number): g = the pooled gradient where the ReLU is alive,
+//         x = the fp16 convolution output at the window's argmax (pool_window); the |g| bound is multiplied by 4 (a pre-pool
+//         pixel can be the argmax of four windows).
 // MODE 2: x = per-tile partial sums [rows = tiles][2][C] written by the fprop epilogue: a = x[r][0][c],
 //         b = x[r][1][c]; finalised like MODE 0 (f.M = the real number of pixels).
+__device__ __forceinline__ float4 ldh4(const __half* p) {     // four fp16 -> float4 (8-byte aligned)
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// The stem's fused ReLU + MaxPool(3, 2, 1) in the backward pass (C = 64). idx = argmax window position 0..8 of a pooled
+// element, with bit 4 set when the pooled value was not positive (dead ReLU: matches no position).
+struct PoolGather {
+  const float* dp;              // [N][PH][PW][C] gradient of the pooled activation
+  const unsigned char* idx;     // [N][PH][PW][C]
+  const __half* y16;            // [N][H][W][C] convolution output (MODE 3 of the reduction reads it at the argmax)
+  int H, W, PH, PW;             // pre-pool / pooled extent
+};
+// Gradient at pre-pool pixel (n, h, w), channels [c, c + 4): the sum over the (at most four) pooling windows that contain the
+// pixel of dp where the window's recorded argmax is this pixel.
+__device__ __forceinline__ float4 pool_gather(const PoolGather& pg, int n, int h, int w, int c, int C) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int oh0 = h >> 1, oh1 = (h + 1) >> 1, ow0 = w >> 1, ow1 = (w + 1) >> 1;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int oh = a ? oh1 : oh0;
+    if ((a && oh1 == oh0) || oh >= pg.PH) continue;
+    const int r = h - (2 * oh - 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ow = b ? ow1 : ow0;
+      if ((b && ow1 == ow0) || ow >= pg.PW) continue;
+      const int pos = r * 3 + (w - (2 * ow - 1));
+      const long long o = (((long long)n * pg.PH + oh) * pg.PW + ow) * C + c;
+      const uchar4 id = *reinterpret_cast<const uchar4*>(pg.idx + o);
+      const float4 d = ld4(pg.dp + o);
+      if (id.x == pos) acc.x += d.x;
+      if (id.y == pos) acc.y += d.y;
+      if (id.z == pos) acc.z += d.z;
+      if (id.w == pos) acc.w += d.w;
+    }
+  }
+  return acc;
+}
+// MODE 3 of the reduction walks the POOLED pixels (4x fewer than the pre-pool ones): sum g = sum over windows of dp, sum g * xhat =
+// sum over windows of dp * xhat(argmax). Returns dp masked by the dead flag in `g` and the convolution output at each channel's
+// argmax in `x`.
+__device__ __forceinline__ void pool_window(const PoolGather& pg, unsigned prow, int c, int C, float4* x, float4* g) {
+  const unsigned pw = prow % (unsigned)pg.PW, t = prow / (unsigned)pg.PW;
+  const unsigned ph = t % (unsigned)pg.PH, n = t / (unsigned)pg.PH;
+  const long long o = (long long)prow * C + c;
+  const uchar4 id = *reinterpret_cast<const uchar4*>(pg.idx + o);
+  const float4 d = ld4(pg.dp + o);
+  const unsigned char ids[4] = {id.x, id.y, id.z, id.w};
+  const float ds[4] = {d.x, d.y, d.z, d.w};
+  float xs[4], gs[4];
+  const __half* ybase = pg.y16 + (((long long)n * pg.H + (2 * (int)ph - 1)) * pg.W + (2 * (int)pw - 1)) * C + c;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int pos = ids[q];
+    const bool alive = pos < 9;
+    const int r = (pos * 11) >> 5, s2 = pos - 3 * r;          // pos / 3, pos % 3 for 0..8
+    xs[q] = alive ? __half2float(ybase[((long long)r * pg.W + s2) * C + q]) : 0.f;
+    gs[q] = alive ? ds[q] : 0.f;
+  }
+  *x = make_float4(xs[0], xs[1], xs[2], xs[3]);
+  *g = make_float4(gs[0], gs[1], gs[2], gs[3]);
+}
+
 struct BnFinal {
   long long M;
   // MODE 0
@@ -216,10 +285,11 @@ struct BnFinal {
   // order-independent, hence deterministic) max over the chunk of |g| * |gamma| * invstd; the last block of the chunk
   // publishes it to cbound[chunk] and clears the accumulator. NULL = off.
   unsigned int* bound_bits; float* cbound;
+  PoolGather pool;     // MODE 3
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kRedThreads, MODE == 1 ? 3 : 4) channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+__global__ void __launch_bounds__(kRedThreads, (MODE == 1 || MODE == 3) ? 3 : 4) channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                                      const float* __restrict__ z,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, long long M, int C,
@@ -237,7 +307,7 @@ __global__ void __launch_bounds__(kRedThreads, MODE == 1 ? 3 : 4) channel_reduce
   double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
   {
     float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
-    if (MODE == 1) { mu = ld4(mean + c0); is = ld4(invstd + c0); }
+    if (MODE == 1 || MODE == 3) { mu = ld4(mean + c0); is = ld4(invstd + c0); }
     // this thread's rows: r0 + ty + 16 * i, i < n. Four rows per step with all their loads issued first (memory-level
     // parallelism); fp32 accumulation over at most 32 rows, then flushed to double.
     const long long n = (r1 - r0 - ty + 15) / 16;
@@ -288,8 +358,12 @@ __global__ void __launch_bounds__(kRedThreads, MODE == 1 ? 3 : 4) channel_reduce
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long o = (i + u) * 16 * rs;
-        v[u] = ld4(xp + o);
-        w[u] = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
+        if (MODE == 3) {
+          pool_window(f.pool, (unsigned)(r0 + ty + (i + u) * 16), c0, C, &v[u], &w[u]);
+        } else {
+          v[u] = ld4(xp + o);
+          w[u] = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
+        }
         nb[u] = bits(o, r0 + ty + (i + u) * 16);
       }
 #pragma unroll
@@ -298,8 +372,13 @@ __global__ void __launch_bounds__(kRedThreads, MODE == 1 ? 3 : 4) channel_reduce
     }
     for (; i < n; ++i) {
       const long long o = i * 16 * rs;
-      const float4 v = ld4(xp + o);
-      const float4 w = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
+      float4 v, w;
+      if (MODE == 3) {
+        pool_window(f.pool, (unsigned)(r0 + ty + i * 16), c0, C, &v, &w);
+      } else {
+        v = ld4(xp + o);
+        w = (MODE == 2) ? ld4(xp + o + C) : (MODE == 1 ? ld4(dzp + o) : one);
+      }
       row(v, w, bits(o, r0 + ty + i * 16));
     }
     flush();
@@ -308,11 +387,12 @@ __global__ void __launch_bounds__(kRedThreads, MODE == 1 ? 3 : 4) channel_reduce
       s_acc[ty][0][4 * tx + q] = a[q];
       s_acc[ty][1][4 * tx + q] = b[q];
     }
-    if (MODE == 1 && f.bound_bits != nullptr) {
+    if ((MODE == 1 || MODE == 3) && f.bound_bits != nullptr) {
       const float4 ga = ld4(f.gamma + c0);
       float m = fmaxf(fmaxf(gmx[0] * fabsf(ga.x) * is.x, gmx[1] * fabsf(ga.y) * is.y),
                       fmaxf(gmx[2] * fabsf(ga.z) * is.z, gmx[3] * fabsf(ga.w) * is.w));
       m = mla::warp_max(m);
+      if (MODE == 3) m *= 4.f;
       if (!(m == m)) m = __int_as_float(0x7f800000);                   // NaN gradients: the bound becomes +inf
       if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&f.bound_bits[chunk], __float_as_uint(m));
     }
@@ -356,7 +436,7 @@ __global__ void __launch_bounds__(kRedThreads, MODE == 1 ? 3 : 4) channel_reduce
   __syncthreads();
   if (threadIdx.x == 0) {
     counters[chunk] = 0;   // leave the workspace reusable
-    if (MODE == 1 && f.bound_bits != nullptr) {
+    if ((MODE == 1 || MODE == 3) && f.bound_bits != nullptr) {
       f.cbound[chunk] = __uint_as_float(atomicExch(&f.bound_bits[chunk], 0u));
     }
   }
@@ -406,6 +486,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        unsigned int* __restrict__ mask_out, uint2* __restrict__ out16,
                                                        uint2* __restrict__ out16b) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool pow2 = (C4 & (C4 - 1)) == 0;
   // the loop bound is warp-uniform (i0 - lane), so all 32 lanes stay together for the mask shuffles
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 - (threadIdx.x & 31) < n4; i0 += 4 * stride) {
     float4 v[4], r[4];
@@ -424,7 +505,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
       const bool live = i < n4;                    // tail lanes of the last warp only take part in the shuffles
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) {
-        const int c = (int)(i % C4) * 4;
+        const int c = (pow2 ? (int)(i & (C4 - 1)) : (int)(i % C4)) * 4;     // (a 64-bit modulo costs ~100 instructions)
         const float4 sc = ld4(scale + c), sh = ld4(shift + c);
         o = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z),
                         fmaf(v[u].w, sc.w, sh.w));
@@ -437,7 +518,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
           o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
         }
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (out != nullptr) st4(out + 4 * i, tf32r4(o));   // fp32 copy: residual add / pooling / TF32 convolutions
+        // fp32 copy: residual add / pooling, and the operand of the TF32 convolutions — rounded to TF32 only when it is
+        // one (no 2-byte copy requested): on the 2-byte path the residual stream stays in full fp32, as under cuDNN
+        if (out != nullptr) st4(out + 4 * i, (out16 == nullptr && out16b == nullptr) ? tf32r4(o) : o);
         if (out16 != nullptr) out16[i] = pack_h4(o);       // fp16 copy: the operand of the kind::f16 forward convolutions
         if (out16b != nullptr) out16b[i] = pack_b4(o);     // bf16 copy: the x operand of the kind::f16 wgrad
       }
@@ -476,8 +559,9 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { gscale[0] = F; gscale[1] = 1.f / F; }
   }
+  const bool pow2 = (C4 & (C4 - 1)) == 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
+    const int c = (pow2 ? (int)(i & (C4 - 1)) : (int)(i % C4)) * 4;
     float4 g = ld4(dz + 4 * i);
     if (z != nullptr) {
       const float4 zz = ld4(z + 4 * i);
@@ -576,6 +660,118 @@ __global__ void maxpool_relu_bwd_kernel(const float* __restrict__ dp, const floa
       }
     }
     st4(g + 4 * i, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  }
+}
+
+__device__ __forceinline__ void unpack_h8(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __half22float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+
+// The same fused BN + ReLU + MaxPool over the stem convolution's fp16 output (stem_s2d.cu), C = 64: one block per pooled row
+// (n, ph), one thread per (pooled pixel, 8 channels) — no integer division, 16-byte loads. idx bit 4 marks a pooled value
+// that is not positive (dead ReLU), so the backward gather needs neither the pooled activation nor a separate mask.
+__global__ void __launch_bounds__(256) bn_relu_maxpool16_kernel(const __half* __restrict__ y, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, float* __restrict__ out,
+                                                                uint4* __restrict__ out16, unsigned char* __restrict__ idx,
+                                                                int H, int W, int OH, int OW) {
+  constexpr int C = 64;
+  const int n = blockIdx.x / OH, oh = blockIdx.x - n * OH;
+  for (int j = threadIdx.x; j < OW * 8; j += blockDim.x) {
+    const int ow = j >> 3, c = (j & 7) * 8;
+    float sc[8], sh[8];
+    *reinterpret_cast<float4*>(sc) = ld4(scale + c); *reinterpret_cast<float4*>(sc + 4) = ld4(scale + c + 4);
+    *reinterpret_cast<float4*>(sh) = ld4(shift + c); *reinterpret_cast<float4*>(sh + 4) = ld4(shift + c + 4);
+    uint4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * oh - 1 + r;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * ow - 1 + s;
+        ok[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
+        if (ok[r * 3 + s]) v[r * 3 + s] = *reinterpret_cast<const uint4*>(y + (((long long)n * H + h) * W + w) * C + c);
+      }
+    }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bi[q] = 0; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (!ok[t]) continue;
+      float x[8];
+      unpack_h8(v[t], x);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float a = fmaxf(fmaf(x[q], sc[q], sh[q]), 0.f);
+        if (a > best[q]) { best[q] = a; bi[q] = t; }
+      }
+    }
+    const long long o = (((long long)n * OH + oh) * OW + ow) * C + c;
+    if (out != nullptr) {
+      st4(out + o, make_float4(best[0], best[1], best[2], best[3]));
+      st4(out + o + 4, make_float4(best[4], best[5], best[6], best[7]));
+    }
+    if (out16 != nullptr) {
+      const uint2 lo = pack_h4(make_float4(best[0], best[1], best[2], best[3]));
+      const uint2 hi = pack_h4(make_float4(best[4], best[5], best[6], best[7]));
+      out16[o >> 3] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+    unsigned b[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) b[q] = (unsigned)bi[q] | (best[q] > 0.f ? 0u : 16u);
+    *reinterpret_cast<uint2*>(idx + o) = make_uint2(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24),
+                                                    b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+  }
+}
+
+// BatchNorm backward of the stem with the MaxPool + ReLU backward folded in: g is gathered from the pooled gradient, xhat
+// comes from the fp16 convolution output, dy leaves as fp16 * F (see bn_bwd_apply_kernel). The dense fp32 gradient of the
+// pre-pool activation (411 MB per visual batch: written once, read twice) never exists. One block per pre-pool row (n, h), one
+// thread per (pixel, 8 channels); C = 64.
+__global__ void __launch_bounds__(256) pool_bn_bwd_apply_kernel(PoolGather pg, const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ sums,
+                                                                float inv_m, uint4* __restrict__ dy16,
+                                                                const float* __restrict__ cbound, int chunks,
+                                                                float* __restrict__ gscale) {
+  constexpr int C = 64;
+  float F = 1.f;
+  {
+    float bound = 0.f;
+    for (int k = 0; k < chunks; ++k) bound = fmaxf(bound, cbound[k]);
+    if (bound > 0.f && bound < __int_as_float(0x7f800000)) {
+      int e;
+      frexpf(bound, &e);
+      e = max(-100, min(100, 9 - e));
+      F = ldexpf(1.f, e);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { gscale[0] = F; gscale[1] = 1.f / F; }
+  }
+  const int n = blockIdx.x / pg.H, h = blockIdx.x - n * pg.H;
+  for (int j = threadIdx.x; j < pg.W * 8; j += blockDim.x) {
+    const int w = j >> 3, c = (j & 7) * 8;
+    const long long o = (((long long)n * pg.H + h) * pg.W + w) * C + c;
+    const uint4 yv = *reinterpret_cast<const uint4*>(pg.y16 + o);
+    const float4 g0 = pool_gather(pg, n, h, w, c, C), g1 = pool_gather(pg, n, h, w, c + 4, C);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float v[8], r[8];
+    unpack_h8(yv, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float mu = __ldg(mean + c + q), is = __ldg(invstd + c + q), ga = __ldg(gamma + c + q);
+      const float db = __ldg(sums + c + q), dg = __ldg(sums + C + c + q);
+      r[q] = ga * is * (g[q] - db * inv_m - (v[q] - mu) * is * dg * inv_m) * F;
+    }
+    const uint2 lo = pack_h4_sat(make_float4(r[0], r[1], r[2], r[3])), hi = pack_h4_sat(make_float4(r[4], r[5], r[6], r[7]));
+    dy16[o >> 3] = make_uint4(lo.x, lo.y, hi.x, hi.y);
   }
 }
 
@@ -888,6 +1084,54 @@ extern "C" int mla_maxpool_relu_backward(const float* dp, const float* p, const 
   const long long total = (long long)N * H * W * (C / 4);
   maxpool_relu_bwd_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dp, p, idx, g, N, H, W, C / 4,
                                                                                              OH, OW);
+  MLA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mla_bn_relu_maxpool16(const void* y16, const float* scale, const float* shift, float* out, void* out16,
+                                     unsigned char* idx, int N, int H, int W, int C, void* stream) {
+  if (!y16 || !scale || !shift || (!out && !out16) || !idx || N < 1 || H < 1 || W < 1) return MLA_E_BADARG;
+  if (C != 64) return MLA_E_SHAPE;
+  if (!mla::aligned16(y16) || !mla::aligned16(out) || !mla::aligned16(out16) || (reinterpret_cast<uintptr_t>(idx) & 7u))
+    return MLA_E_BADARG;
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  bn_relu_maxpool16_kernel<<<N * OH, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(y16), scale, shift, out, static_cast<uint4*>(out16), idx, H, W, OH, OW);
+  MLA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mla_pool_bn_backward_f16(const float* dp, const unsigned char* idx, const void* y16, const float* mean,
+                                        const float* invstd, const float* gamma, int N, int H, int W, int C, float* dgamma,
+                                        float* dbeta, void* dy16, float* gscale, void* ws, size_t ws_bytes, void* stream) {
+  if (!dp || !idx || !y16 || !mean || !invstd || !gamma || !dy16 || !gscale || N < 1 || H < 1 || W < 1) return MLA_E_BADARG;
+  if (C != 64) return MLA_E_SHAPE;
+  if (!mla::aligned16(dp) || !mla::aligned16(y16) || !mla::aligned16(dy16) || (reinterpret_cast<uintptr_t>(idx) & 7u))
+    return MLA_E_BADARG;
+  const long long M = (long long)N * H * W;
+  const int PH = (H + 2 - 3) / 2 + 1, PW = (W + 2 - 3) / 2 + 1;
+  const long long MP = (long long)N * PH * PW;           // the reduction walks the pooled pixels
+  if (MP >= (1LL << 31)) return MLA_E_SHAPE;
+  RedPlan pl;
+  int rc = red_plan(MP, C, &pl);
+  if (rc) return rc;
+  if (!ws || ws_bytes < pl.bytes) return MLA_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* sums = reinterpret_cast<float*>(base + pl.off_sums);
+  BnFinal f{};
+  f.M = M; f.dgamma = dgamma; f.dbeta = dbeta; f.sums = sums; f.gamma = gamma;
+  f.bound_bits = reinterpret_cast<unsigned int*>(base + pl.off_bound);
+  float* cbound = reinterpret_cast<float*>(base + pl.off_bound) + 64;
+  f.cbound = cbound;
+  f.pool.dp = dp; f.pool.idx = idx; f.pool.y16 = static_cast<const __half*>(y16);
+  f.pool.H = H; f.pool.W = W; f.pool.PH = PH; f.pool.PW = PW;
+  channel_reduce_kernel<3><<<dim3(pl.nrb, pl.chunks), kRedThreads, 0, st>>>(
+      nullptr, nullptr, nullptr, mean, invstd, MP, C, pl.rows_per_block, reinterpret_cast<double*>(base + pl.off_part),
+      reinterpret_cast<unsigned int*>(base), f, nullptr);
+  MLA_LAUNCH_CHECK();
+  pool_bn_bwd_apply_kernel<<<N * H, 256, 0, st>>>(f.pool, mean, invstd, gamma, sums, 1.f / (float)M,
+                                                 static_cast<uint4*>(dy16), cbound, pl.chunks, gscale);
   MLA_LAUNCH_CHECK();
   return 0;
 }

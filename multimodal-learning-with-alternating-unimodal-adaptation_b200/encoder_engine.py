@@ -32,6 +32,9 @@ _STEM_KP16 = {1: 64, 3: 192}   # ... to a multiple of 64 (k-blocks of 64 2-byte 
 # 2-byte stem: the im2col matrix leaves as ONE fp16 copy (operand of fprop16 and of wgrad16) instead of TF32 fp32, the stem
 # GEMMs run at the kind::f16 rate, and BN backward writes dy as scaled fp16 only. Needs USE_F16.
 STEM_F16 = True
+# im2col-free stem (csrc/stem_s2d.cu): space-to-depth input, sliding-window TMA, fp16 conv output, BN backward with the
+# MaxPool / ReLU backward folded in. Needs USE_F16 and STEM_F16; MLA_STEM_S2D=0 goes back to the im2col GEMM.
+STEM_S2D = os.environ.get("MLA_STEM_S2D", "1") != "0"
 
 
 def _p(t):
@@ -154,15 +157,24 @@ class ResNetPlan:
         self.M0 = N * self.OH0 * self.OW0
         e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)   # noqa: E731
         half = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)          # noqa: E731
-        if self.stem16:
+        self.s2d = bool(self.stem16 and STEM_S2D and Cin <= 4)
+        if self.s2d:
+            self.col = self.col16 = None
+            self.xs16 = torch.empty(self.L.mla_stem_s2d_input_elems(N, H, W), dtype=torch.float16, device=dev)
+            self.w2_16 = half(64, 256)
+            self.y0_16 = half(N, self.OH0, self.OW0, 64)
+            self.stem_tiles = self.L.mla_stem_s2d_tiles(N, H, W)
+            self.stem_ws = torch.empty(self.L.mla_stem_s2d_wgrad_workspace_bytes(), dtype=torch.uint8, device=dev)
+        elif self.stem16:
             self.col = None
             self.col16 = half(self.M0, self.Kp)
             self.wpad16 = half(64, self.Kp)
         else:
             self.col = e(self.M0, self.Kp)
-        self.wpad = e(64, self.Kp)
-        self.dwpad = e(64, self.Kp)
-        self.y0 = e(N, self.OH0, self.OW0, 64)
+        if not self.s2d:
+            self.wpad = e(64, self.Kp)
+            self.dwpad = e(64, self.Kp)
+            self.y0 = e(N, self.OH0, self.OW0, 64)
         self.p0 = e(N, self.PH, self.PW, 64)
         self.p0_16 = half(N, self.PH, self.PW, 64) if self.f16 else None
         self.w16 = torch.empty(self.flat.numel(), dtype=torch.float16, device=dev) if self.f16 else None     # fp16 weights
@@ -197,7 +209,8 @@ class ResNetPlan:
                  max(self.L.mla_bn_workspace_bytes(N * b["ho"] * b["wo"], b["cout"]) for b in self.blocks))
         tl = self.L.mla_conv2d_fprop_stat_tiles
         tl16 = self.L.mla_conv2d_fprop16_stat_tiles
-        self.stat_part = torch.empty(max([tl(N, self.OH0, self.OW0, 1, 1, 1, 0) * 2 * 64] +
+        self.stat_part = torch.empty(max([tl(N, self.OH0, self.OW0, 1, 1, 1, 0) * 2 * 64,
+                                          (self.stem_tiles if self.s2d else 0) * 2 * 64] +
                                          [max(tl(N, b["h"], b["w"], 3, 3, b["stride"], 1), tl(N, b["ho"], b["wo"], 3, 3, 1, 1),
                                               tl(N, b["h"], b["w"], 1, 1, b["stride"], 0),
                                               tl16(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3, b["stride"], 1),
@@ -205,8 +218,8 @@ class ResNetPlan:
                                           for b in self.blocks]),
                                      dtype=torch.float32, device=dev)          # per-tile BN partial sums (fprop epilogue)
         self.bn_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)      # ticket counters start at 0 (mla_b200.h)
-        nw = (self.L.mla_conv2d_wgrad16_workspace_bytes if self.stem16 else self.L.mla_conv2d_wgrad_workspace_bytes)(
-            N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
+        nw = 0 if self.s2d else (self.L.mla_conv2d_wgrad16_workspace_bytes if self.stem16
+                                 else self.L.mla_conv2d_wgrad_workspace_bytes)(N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 1, 0)
         for b in self.blocks:
             nw = max(nw, self.L.mla_conv2d_wgrad_workspace_bytes(N, b["h"], b["w"], b["cin"], b["cout"], 3, 3,
                                                                   b["stride"], 1),
@@ -404,7 +417,10 @@ class ResNetPlan:
         else:                              # [B,1,H,W]
             sB, sT, sC = self.Cin * HW, 0, HW
         # the only launch that reads the caller's buffer (its address changes from batch to batch): outside the graph
-        if self.stem16:
+        if self.s2d:
+            _chk(L.mla_stem_s2d_pack(_p(x), _p(self.xs16), N, self.T, sB, sT, sC, self.Cin, self.H, self.W, st),
+                 "mla_stem_s2d_pack")
+        elif self.stem16:
             _chk(L.mla_stem_im2col16(_p(x), _p(self.col16), None, N, self.T, sB, sT, sC,
                                      self.Cin, self.H, self.W, 7, 7, 2, 3, self.Kp, st), "mla_stem_im2col16")
         else:
@@ -420,8 +436,25 @@ class ResNetPlan:
         L, N, st = self.L, self.N, _lib.stream_ptr()
         net = self.net
         K = 49 * self.Cin
-        _chk(L.mla_round_tf32(_p(self.flat), _p(self.wr), self.flat.numel(), st), "mla_round_tf32")
-        if self.stem16:
+        if not (self.f16 and self.s2d):       # the TF32-rounded weights are read by the kind::tf32 kernels only
+            _chk(L.mla_round_tf32(_p(self.flat), _p(self.wr), self.flat.numel(), st), "mla_round_tf32")
+        if self.s2d:
+            # the stem as a 4x4 / stride 1 convolution over 2x2 space-to-depth cells, straight from the packed input
+            _chk(L.mla_stem_s2d_weights(_p(net.conv1.weight), _p(self.w2_16), self.Cin, st), "mla_stem_s2d_weights")
+            t = _conv_timer_begin()
+            _chk(L.mla_stem_s2d_fprop(_p(self.xs16), _p(self.w2_16), _p(self.y0_16), N, self.H, self.W,
+                                      _p(self.stat_part) if training else None, st), "mla_stem_s2d_fprop")
+            _conv_timer_end(t, "fprop16", N, self.OH0, self.OW0, K, 64, 1, 1, 0)
+            if training:
+                bn = self.bn0.bn
+                _chk(L.mla_bn_stats_from_partials(_p(self.stat_part), self.stem_tiles, self.M0, 64, _p(bn.weight),
+                                                  _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.momentum),
+                                                  float(bn.eps), _p(self.bn0.mean), _p(self.bn0.invstd), _p(self.bn0.scale),
+                                                  _p(self.bn0.shift), _p(self.bn_ws), self.bn_ws.numel(), st),
+                     "mla_bn_stats_from_partials")
+            else:
+                self._bn_coeffs(None, 0, self.bn0, False, st)
+        elif self.stem16:
             # the stem as an fp16 GEMM over the fp16 im2col matrix (same 10-bit operand mantissa as the TF32 path)
             _chk(L.mla_pad_rows(_p(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
             _chk(L.mla_cast16(_p(self.wpad), _p(self.wpad16), self.wpad.numel(), 0, st), "mla_cast16")
@@ -442,9 +475,13 @@ class ResNetPlan:
             _chk(L.mla_pad_rows(self._wptr(net.conv1.weight), _p(self.wpad), 64, K, self.Kp, 0, st), "mla_pad_rows")
             self._conv_bn(self.col, self.wpad, self.y0, N, self.OH0, self.OW0, self.Kp, 64, 1, 1, 0, self.bn0, training, st,
                           k_alg=K)
-        _chk(L.mla_bn_relu_maxpool_ex(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.p0_16),
-                                      None, _p(self.idx0), N, self.OH0, self.OW0, 64, st),
-             "mla_bn_relu_maxpool")
+        if self.s2d:
+            _chk(L.mla_bn_relu_maxpool16(_p(self.y0_16), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.p0_16),
+                                         _p(self.idx0), N, self.OH0, self.OW0, 64, st), "mla_bn_relu_maxpool16")
+        else:
+            _chk(L.mla_bn_relu_maxpool_ex(_p(self.y0), _p(self.bn0.scale), _p(self.bn0.shift), _p(self.p0), _p(self.p0_16),
+                                          None, _p(self.idx0), N, self.OH0, self.OW0, 64, st),
+                 "mla_bn_relu_maxpool")
         f16 = self.f16
         if f16:      # fp16 copy of every parameter (same offsets as the flat buffer): the B operand of fprop16
             _chk(L.mla_cast16(_p(self.flat), _p(self.w16), self.flat.numel(), 0, st), "mla_cast16")
@@ -651,6 +688,27 @@ class ResNetPlan:
         if not last:
             self._seg_dout = dout
             cur.wait_stream(wsm)                        # every layer4 gradient is complete on `cur`
+            return
+        if self.s2d:
+            # stem: BN backward with the MaxPool / ReLU backward gathered inside its two passes (the dense gradient of the
+            # pre-pool activation never exists), then the weight gradient straight from the packed input
+            bn = self.bn0.bn
+            dy0 = buf16("dy0", self.y0_16.shape)
+            _chk(L.mla_pool_bn_backward_f16(_p(dout), _p(self.idx0), _p(self.y0_16), _p(self.bn0.mean), _p(self.bn0.invstd),
+                                            _p(bn.weight), N, self.OH0, self.OW0, 64, _p(_grad_buffer(bn.weight)),
+                                            _p(_grad_buffer(bn.bias)), _p(dy0), _p(self.bn0.gscale), _p(self.bn_ws),
+                                            self.bn_ws.numel(), st), "mla_pool_bn_backward_f16")
+            dw0 = _grad_buffer(net.conv1.weight)
+            if wsm is not cur:
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                wsm.wait_event(ready)
+            with torch.cuda.stream(wsm):
+                t = _conv_timer_begin()
+                _chk(L.mla_stem_s2d_wgrad(_p(self.xs16), _p(dy0), self.bn0.gscale.data_ptr() + 4, _p(dw0), N, self.H, self.W,
+                                          self.Cin, _p(self.stem_ws), self.stem_ws.numel(), wst), "mla_stem_s2d_wgrad")
+                _conv_timer_end(t, "wgrad16", N, self.OH0, self.OW0, 49 * self.Cin, 64, 1, 1, 0)
+            cur.wait_stream(wsm)
             return
         # stem: maxpool+relu backward, BN backward, weight gradient (no dgrad: the input needs none)
         g0 = self.tmp("g0", self.y0.shape)
