@@ -544,6 +544,12 @@ int run_fwd(const AttnParams& p, const float* qkv, cudaStream_t st) {
   const long long n4 = (long long)p.B * p.S * p.H * DH * 3 / 4;
   cast_scale16_kernel<<<cast_grid(n4), 256, 0, st>>>(qkv, reinterpret_cast<uint2*>(const_cast<__half*>(p.qkv)), n4, nullptr);
   MLA_CUDA_TRY(cudaGetLastError());
+  if (mla::attn_tc_applicable(p.S, DH)) {        // head width 64, S <= 527: the tcgen05 / TMEM kernel (attention_tc.cu)
+    const int rc = mla::attn_fwd_tc(p.qkv, p.mask, p.out, p.lse, p.B, p.S, p.H, p.scale, st);
+    if (rc != 0) return rc;
+    mla::count_launch(2);
+    return 0;
+  }
   dim3 grid((p.S + kTile - 1) / kTile, p.H, p.B);
   attn_fwd_kernel<DH><<<grid, kThreads, fwd_smem<DH>(), st>>>(p);
   MLA_CUDA_TRY(cudaGetLastError());

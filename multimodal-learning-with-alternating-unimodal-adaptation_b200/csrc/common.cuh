@@ -32,6 +32,10 @@ StripPlan strip16_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int
 int conv_strip16_run(int mode, const void* src16, const void* w16, float* out, int N, int H, int W, int accumulate,
                      float* stat_part, const float* out_scale, const StripPlan& pl, void* stream);
 
+// tcgen05 attention forward for head width 64 (attention_tc.cu); `applicable` also honours MLA_ATTN_TC=0
+bool attn_tc_applicable(int S, int Dh);
+int attn_fwd_tc(const void* qkv16, const float* mask, float* out, float* stats, int B, int S, int H, float scale, void* stream);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

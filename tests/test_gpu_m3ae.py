@@ -222,9 +222,12 @@ def _attention_ref(qkv, mask, H, scale):
 
 @pytest.mark.parametrize("B,S,H,Dh,masked", [(2, 513, 12, 64, True), (3, 257, 12, 64, False), (4, 13, 2, 32, True),
                                              (1, 64, 1, 64, True), (2, 65, 3, 32, False), (1, 1, 2, 64, False),
-                                             (2, 130, 4, 64, "all")])
+                                             (2, 130, 4, 64, "all"), (2, 71, 2, 64, True), (1, 527, 3, 64, True),
+                                             (3, 16, 2, 64, False), (2, 300, 5, 64, True), (2, 15, 1, 64, "all"),
+                                             (1, 384, 2, 64, False)])
 def test_fused_attention_forward_backward(built_lib, B, S, H, Dh, masked):
-    """csrc/attention.cu against the reference formulation in fp64: ragged sequence lengths (tiles of 64), padded keys
+    """csrc/attention.cu / attention_tc.cu (tcgen05 forward for head width 64: keys in multiples of 16 on the tensor cores, the
+    remainder on the CUDA cores, 1 or 2 UMMA column blocks) against the reference formulation in fp64: ragged sequence lengths, padded keys
     (filled with -1e7, no gradient to their scores), a batch row whose keys are ALL padded (uniform weights, like the
     reference), both head widths."""
     from mla_b200 import m3ae
