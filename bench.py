@@ -178,79 +178,97 @@ def cpu_baseline():
 SWEEP_D, SWEEP_B, SWEEP_C = (512, 768, 1024, 2048), (64, 256, 1024, 4096), (6, 101)     # BASELINE.json configs[4]
 
 
-def _time_launch(torch, fn, flush, reps=10, warm=3):
-    """Median CUDA-event time of fn() on the current stream, the L2 flushed (256 MB written) before every timed launch."""
-    for _ in range(warm):
-        fn()
-    ts = []
-    for _ in range(reps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e-3)
-    return statistics.median(ts)
+def _time_launch(torch, make_set, run, nbytes, launches=24, warm=3):
+    """Median CUDA-event time of one launch of run(set). Cold inputs without evicting the kernel's code: the launches walk
+    over `nsets` independent argument sets whose total footprint exceeds twice the 126 MB L2 (whenever nsets <= 128 allows
+    it: the remaining points are latency-bound and labelled so), so every launch reads its inputs from HBM. Every timed
+    launch is preceded by a ~60 us spin kernel, which lets the host run ahead: event, launch and event are queued before
+    the GPU reaches them, and the events bracket the launch only (no host enqueue time, no flush traffic)."""
+    nsets = max(2, min(128, -(-(300 << 20) // max(nbytes, 1)) + 1))
+    sets = [make_set() for _ in range(nsets)]
+    for i in range(min(warm, nsets)):
+        run(sets[i])
+    torch.cuda.synchronize()
+    n = max(launches, nsets)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for i in range(n):
+        torch.cuda._sleep(120000)
+        ev[i][0].record()
+        run(sets[i % nsets])
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    return statistics.median(a.elapsed_time(b) for a, b in ev) * 1e-3, nsets
 
 
 def _point(pk, t, nbytes, **kw):
     # a launch whose algorithmic bytes would take < 3 us at the HBM peak cannot be HBM-bound: launch latency, grid-wide
     # synchronisation and L2 residency decide its time (SURVEY F12); such points are labelled, not hidden
-    d = dict(kw, us=t * 1e6, bytes=nbytes, gbs=nbytes / t / 1e9, frac=nbytes / t / 1e9 / pk["hbm"])
+    t, nsets = t
+    d = dict(kw, us=t * 1e6, bytes=nbytes, gbs=nbytes / t / 1e9, frac=nbytes / t / 1e9 / pk["hbm"], sets=nsets)
     d["regime"] = "latency" if nbytes / (pk["hbm"] * 1e9) < 3e-6 else "bandwidth"
     return d
 
 
 def gs_sweep(torch, ops, pk):
     """GSPlugin HBM GB/s (second half of BASELINE.json's metric) over the full configs[4] grid: algorithmic bytes
-    4*(B*D + 2*D*D + 2*C*D) / CUDA-event time, L2 flushed between launches."""
+    4*(B*D + 2*D*D + 2*C*D) / CUDA-event time of one launch, inputs cold (rotating argument sets, see _time_launch)."""
     from mla_b200.gs_plugin import GSPlugin
     dev = torch.device("cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     alpha = GSPlugin.alpha(1, 10)
     pts = []
     for D in SWEEP_D:
         for B in SWEEP_B:
             for C in SWEEP_C:
-                feat = torch.randn(B, D, device=dev).relu()
-                grad = torch.randn(C, D, device=dev)
-                P = torch.eye(D, device=dev)
-                t = _time_launch(torch, lambda: ops.gs_project(P, grad, alpha, feat=feat), flush)
-                pts.append(_point(pk, t, 4 * (B * D + 2 * D * D + 2 * C * D), B=B, D=D, C=C))
+                nbytes = 4 * (B * D + 2 * D * D + 2 * C * D)
+                mk = lambda: (torch.eye(D, device=dev), torch.randn(C, D, device=dev), torch.randn(B, D, device=dev).relu())
+                t = _time_launch(torch, mk, lambda s: ops.gs_project(s[0], s[1], alpha, feat=s[2]), nbytes)
+                pts.append(_point(pk, t, nbytes, B=B, D=D, C=C))
+    return pts
+
+
+def gs_beyond_sweep(torch, ops, pk):
+    """Informational, outside configs[4]: the same kernel at batch sizes where the feature stream dominates the fixed costs
+    (cooperative launch, three grid barriers, the dependent P phases) that bound the sweep's 67 MB top point."""
+    from mla_b200.gs_plugin import GSPlugin
+    dev = torch.device("cuda")
+    alpha = GSPlugin.alpha(1, 10)
+    pts = []
+    for B in (16384, 65536):
+        D, C = 2048, 6
+        nbytes = 4 * (B * D + 2 * D * D + 2 * C * D)
+        mk = lambda: (torch.eye(D, device=dev), torch.randn(C, D, device=dev), torch.randn(B, D, device=dev).relu())
+        t = _time_launch(torch, mk, lambda s: ops.gs_project(s[0], s[1], alpha, feat=s[2]), nbytes, launches=12)
+        pts.append(_point(pk, t, nbytes, B=B, D=D, C=C))
     return pts
 
 
 def head_sweep(torch, ops, pk):
     """Shared head forward + backward (main.py:432-435): algorithmic bytes 4*(2*B*D + 3*C*D + 2*B*C)."""
     dev = torch.device("cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     pts = []
     for D in SWEEP_D:
         for B in SWEEP_B:
             for C in SWEEP_C:
-                feat = torch.randn(B, D, device=dev).relu()
-                W = torch.randn(C, D, device=dev) * 0.05
-                b = torch.zeros(C, device=dev)
-                label = torch.randint(0, C, (B,), device=dev)
-                out = {}
-                t = _time_launch(torch, lambda: ops.head_ce(feat, W, b, label, out=out), flush)
-                pts.append(_point(pk, t, 4 * (2 * B * D + 3 * C * D + 2 * B * C), B=B, D=D, C=C))
+                nbytes = 4 * (2 * B * D + 3 * C * D + 2 * B * C)
+                mk = lambda: (torch.randn(B, D, device=dev).relu(), torch.randn(C, D, device=dev) * 0.05,
+                              torch.zeros(C, device=dev), torch.randint(0, C, (B,), device=dev), {})
+                t = _time_launch(torch, mk, lambda s: ops.head_ce(s[0], s[1], s[2], s[3], out=s[4]), nbytes)
+                pts.append(_point(pk, t, nbytes, B=B, D=D, C=C))
     return pts
 
 
 def fusion_sweep(torch, ops, pk):
     """Test-time entropy fusion + argmax + counters (main.py:65-106, 640-676): bytes 4*(M+1)*B*C + 8*B."""
     dev = torch.device("cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     pts = []
     for M in (2, 3):
         for B in SWEEP_B:
             for C in SWEEP_C:
-                outs = [torch.randn(B, C, device=dev) for _ in range(M)]
-                label = torch.randint(0, C, (B,), device=dev)
-                hits = torch.zeros(M + 1, C, dtype=torch.int64, device=dev)
-                num = torch.zeros(C, dtype=torch.int64, device=dev)
-                t = _time_launch(torch, lambda: ops.fuse_eval(outs, label, hits=hits, num=num), flush)
-                pts.append(_point(pk, t, 4 * (M + 1) * B * C + 8 * B, M=M, B=B, C=C))
+                nbytes = 4 * (M + 1) * B * C + 8 * B
+                mk = lambda: ([torch.randn(B, C, device=dev) for _ in range(M)], torch.randint(0, C, (B,), device=dev),
+                              torch.zeros(M + 1, C, dtype=torch.int64, device=dev), torch.zeros(C, dtype=torch.int64, device=dev))
+                t = _time_launch(torch, mk, lambda s: ops.fuse_eval(s[0], s[1], hits=s[2], num=s[3]), nbytes)
+                pts.append(_point(pk, t, nbytes, M=M, B=B, C=C))
     return pts
 
 
@@ -542,7 +560,7 @@ def run_native(a, rank, world):
     if not a.no_sweep and world == 1:
         # BASELINE.json configs[4]: D {512..2048} x B {64..4096} x C {6, 101} (x M {2, 3} for the fusion kernel). The headline
         # point of each kernel is its best bandwidth-regime point; every point (latency-bound ones labelled) is listed
-        for key, fn, kern in (("gs", gs_sweep, "gs_project_kernel"), ("head", head_sweep, "head_fwd_kernel + head_bwd_kernel"),
+        for key, fn, kern in (("gs", gs_sweep, "gs_project_kernel"), ("head", head_sweep, "head_rows_kernel + head_cols_kernel + head_reduce_kernel (C <= 16) / head_fwd_kernel + head_bwd_kernel"),
                               ("fusion", fusion_sweep, "fuse_eval_kernel")):
             pts = fn(torch, ops, pk)
             top = max(pts, key=lambda p: p["gbs"])
@@ -551,8 +569,13 @@ def run_native(a, rank, world):
                                       "traffic": prof.get("gs_traffic") if key == "gs" else None, "peak_source": pk["source"],
                                       "point": {k: v for k, v in top.items() if k not in ("gbs", "frac")},
                                       "latency_bound_points": sum(1 for p in pts if p["regime"] == "latency"),
-                                      "points": len(pts)}
+                                      "points": len(pts),
+                                      "timing": "CUDA events around ONE launch, median of >= 24 launches; inputs cold: the launches "
+                                                "rotate over `sets` independent argument sets (> 2x the 126 MB L2 in total when "
+                                                "sets < 128), no L2 flush"}
             out[key + "_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()} for p in pts]
+        out["gs_beyond_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()}
+                                  for p in gs_beyond_sweep(torch, ops, pk)]
     if not a.no_tf32_leg and world == 1 and encoder_engine.USE_F16:
         out["value_tf32"] = tf32_leg(a)
     if not a.no_eager and world == 1:

@@ -3,13 +3,17 @@
 //
 //   phase 0  one thread issues bulk async copies (cp.async.bulk, completing on an mbarrier) of the CTA's row slice of P
 //            into shared memory: P leaves HBM ONCE, with zero register cost, while every warp of the CTA streams
-//            its share of feat (raw-feature path: CTA-blocked rows, up to 16 independent 512-byte loads in flight per
-//            warp, fixed-order partial sums) and grad_w is copied to the workspace (the in-place projection can't race)
-//   phase 1  r = inv_batch * sum of the per-CTA partials (fixed order), one column slice per thread of the grid
+//            its share of feat (raw-feature path: CTA = (batch slice, 256-column chunk), up to 16 independent 512-byte
+//            loads in flight per warp, fixed-order partial sums) and grad_w is copied to the workspace (the in-place
+//            projection can't race)
+//   phase 1  r = inv_batch * sum of the <= 20 partial rows (slice order), formed by every CTA for itself: one grid barrier
 //   phase A  k = P r^T          from the shared-memory rows
 //   phase B  P' = P - (k k^T) ./ (alpha + k r)   in shared memory, + sum(P'^2) partials
-//   phase C  P = P' / ||P'||_F  written to HBM once; grad_w = grad_w @ P^T from the smem-resident rows: every warp owns a
-//            (4-row group, 512-column chunk) block held in registers, staged gradient rows are read once per 16 FMAs
+//   phase C  P = P' / ||P'||_F  written to HBM once; grad_w = grad_w @ P^T from the smem-resident rows: a warp owns a
+//            (4-row group, column chunk) block of P in registers and walks the gradient rows four at a time; the gradient is
+//            streamed through two cp.async-fed staging buffers (tile t+1 lands while tile t is multiplied, one barrier per
+//            tile), the 16 lane-partial sums of a (4 classes x 4 rows) block are reduced with one butterfly transpose
+//            (16 shuffles instead of 80), column-chunk partials are combined in chunk order
 //
 // HBM traffic is the algorithmic minimum 4*(B*D + 2*D*D + 2*C*D) bytes: feat is read once, P is read once and
 // written once. All reductions have a fixed order, so every rank of a data-parallel job
@@ -23,10 +27,12 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kGT = 8;        // grad rows staged per tile in phase C
 constexpr int kRB = 4;        // P rows per register block in phase C
-constexpr int kCB = 512;      // columns per register block in phase C (4 float4 per lane and row)
-constexpr int kMaxCB = 4;     // D <= kMaxCB * kCB
+constexpr int kCT = 4;        // gradient rows (classes) per register block in phase C
+constexpr int kMaxD = 2048;   // widest P (14 rows per CTA on 148 SMs = 112 KB of shared memory)
+constexpr int kStageFloats = 8192;   // one gradient staging buffer (32 KB); there are two
+constexpr int kMaxStageRows = 16;
+constexpr int kMaxUnits = 64;        // (row group, column chunk, class block) units of one staged tile
 
 struct GsParams {
   float* P;
@@ -39,6 +45,8 @@ struct GsParams {
   int rows_per_cta;
   int nb;           // CTAs that hold a batch slice in the raw-feature reduction
   int rows_per_nb;  // batch rows per such CTA
+  int stage_rows;   // gradient rows per staging buffer (multiple of kCT)
+  int nq;           // float4 per lane of a projection column chunk (chunk = nq * 128 columns): 1, 2 or 4
   float* ws_r;      // [D]
   float* ws_k;      // [D]
   float* ws_part;   // [nb][D]
@@ -57,16 +65,63 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// One (4-row group, nq * 128-column chunk, 4-class block) unit of the projection. `a` = the unit's block of P (registers,
+// loaded by the caller); G = staged gradient rows [ct][D]. The 16 lane-partial sums acc[class][row] are reduced over the
+// warp with a butterfly transpose: after the four exchange steps lane l holds the sum (over one half-warp) of value l & 15,
+// the last step adds the two half-warps. Fixed order -> deterministic. Lanes 0..15 store value `lane` to out[lane].
+template <int NQ>
+__device__ __forceinline__ void project_unit(const float4 (&a)[kRB][4], const float* __restrict__ G, int D, int jb, int c_lo,
+                                             int ct, int lane, float* __restrict__ out) {
+  float acc[kCT * kRB];
+#pragma unroll
+  for (int i = 0; i < kCT * kRB; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int j = jb + (q * 32 + lane) * 4;
+    if (j < D) {
+      float4 gv[kCT];
+#pragma unroll
+      for (int cc = 0; cc < kCT; ++cc) {
+        const int c = min(c_lo + cc, ct - 1);                      // rows past the tile repeat the last one (never stored)
+        gv[cc] = ld4(G + (size_t)c * D + j);
+      }
+#pragma unroll
+      for (int cc = 0; cc < kCT; ++cc) {
+#pragma unroll
+        for (int rr = 0; rr < kRB; ++rr) {
+          float t = acc[cc * kRB + rr];
+          t = fmaf(gv[cc].x, a[rr][q].x, t); t = fmaf(gv[cc].y, a[rr][q].y, t);
+          t = fmaf(gv[cc].z, a[rr][q].z, t); t = fmaf(gv[cc].w, a[rr][q].w, t);
+          acc[cc * kRB + rr] = t;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? acc[i] : acc[i + o];
+      const float keep = up ? acc[i + o] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  const float tot = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 16);
+  if (lane < 16) out[lane] = tot;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ float s_nrmf;
   const int D = p.D, D4 = p.D >> 2;
   float* s_r = smem;                      // [D]
   float* s_k = s_r + D;                   // [D]
   float* s_P = s_k + D;                   // [rows_per_cta][D]
-  float* s_G = s_P + (size_t)p.rows_per_cta * D;  // [kGT][D]   (phase 0: scratch of the feature reduction)
-  float* s_red = s_G + (size_t)kGT * D;   // [kWarps * kGT * kRB]
+  float* s_G = s_P + (size_t)p.rows_per_cta * D;  // [2][kStageFloats] gradient staging (phase 0: feature-reduction scratch)
+  float* s_red = s_G + 2 * kStageFloats;  // [2][kMaxUnits][16] projection partials; block_sum scratch; norm partials
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gtid = blockIdx.x * kThreads + tid;
@@ -92,80 +147,74 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     for (int i = gtid; i < n4; i += gthreads) st4(p.ws_g + 4 * (size_t)i, ld4(p.grad_w + 4 * (size_t)i));
   }
   if (p.feat != nullptr) {
-    // CTA c < nb sums batch rows [c * rows_per_nb, ...). Inside the CTA a unit = (128-column chunk, row split): with few
-    // column chunks (small D) the rows are split over the warps as well; the row-split partials are combined through
-    // shared memory in split order (fixed -> deterministic).
-    if ((int)blockIdx.x < p.nb) {
-      const int cchunks = (D + 127) / 128;
-      const int rsplit = min(kGT, max(1, kWarps / cchunks));     // the scratch holds kGT rows of D
-      const int b0 = blockIdx.x * p.rows_per_nb, b1 = min(p.B, b0 + p.rows_per_nb);
-      float* scratch = s_G;                                     // [rsplit][D]  (rsplit * D <= kGT * D)
-      for (int u = warp; u < cchunks * rsplit; u += kWarps) {
-        const int cc = u % cchunks, rs = u / cchunks;
-        const int col = cc * 128 + lane * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col < D) {
-          const float* src = p.feat + col;
-          int b = b0 + rs;
-          for (; b + 15 * rsplit < b1; b += 16 * rsplit) {      // 16 independent row segments in flight
-            float4 v[16];
+    // Feature reduction. CTA (s, ch) = (batch slice, 256-column chunk) sums rows [s * rows_per_nb, ...) of its columns: warp
+    // = (128-column half, one of 8 row splits), up to 16 independent 512-byte row segments in flight per warp; the row-split
+    // partials are combined through shared memory in split order. Slicing by columns as well keeps the number of partial
+    // rows small (nb <= 20 at D = 2048), so that after ONE grid barrier every CTA can form the whole of r by itself.
+    const int cch = (D + 255) / 256;
+    if ((int)blockIdx.x < p.nb * cch) {
+      const int sl = blockIdx.x / cch, ch = blockIdx.x - sl * cch;
+      const int b0 = sl * p.rows_per_nb, b1 = min(p.B, b0 + p.rows_per_nb);
+      const int h = warp & 1, rs = warp >> 1;
+      constexpr int kRS = kWarps / 2;
+      float* scratch = s_G;                                     // [kRS][256]
+      const int col = ch * 256 + h * 128 + lane * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < D) {
+        const float* src = p.feat + col;
+        int b = b0 + rs;
+        for (; b + 15 * kRS < b1; b += 16 * kRS) {              // 16 independent row segments in flight
+          float4 v[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = ldcs4(src + (size_t)(b + q * rsplit) * D);
+          for (int q = 0; q < 16; ++q) v[q] = ldcs4(src + (size_t)(b + q * kRS) * D);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
-          }
-          {                                                     // tail: the remaining (< 16) rows, all loads first
-            float4 v[16];
-            int n = 0;
+          for (int q = 0; q < 16; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+        }
+        {                                                       // tail: the remaining (< 16) rows, all loads first
+          float4 v[16];
+          int n = 0;
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (b + q * rsplit < b1) { v[q] = ldcs4(src + (size_t)(b + q * rsplit) * D); n = q + 1; }
+          for (int q = 0; q < 16; ++q)
+            if (b + q * kRS < b1) { v[q] = ldcs4(src + (size_t)(b + q * kRS) * D); n = q + 1; }
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (q < n) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
-          }
-          st4(scratch + (size_t)rs * D + col, acc);
+          for (int q = 0; q < 16; ++q)
+            if (q < n) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
         }
       }
+      st4(scratch + rs * 256 + h * 128 + lane * 4, acc);
       __syncthreads();
-      for (int j4 = tid; j4 < D4; j4 += kThreads) {
-        float4 s = ld4(scratch + 4 * j4);
-        for (int rs = 1; rs < rsplit; ++rs) {
-          const float4 v = ld4(scratch + (size_t)rs * D + 4 * j4);
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      if (tid < 64 && ch * 256 + 4 * tid < D) {
+        float4 t = ld4(scratch + 4 * tid);
+#pragma unroll
+        for (int q = 1; q < kRS; ++q) {
+          const float4 v = ld4(scratch + q * 256 + 4 * tid);
+          t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
-        st4(p.ws_part + (size_t)blockIdx.x * D + 4 * j4, s);
+        st4(p.ws_part + (size_t)sl * D + ch * 256 + 4 * tid, t);
       }
     }
     if (stamp) p.ws_ts[1] = tc::globaltimer_ns();
     grid.sync();
     if (stamp) p.ws_ts[2] = tc::globaltimer_ns();
-    // r[j] = inv_batch * sum_c part[c][j]. Eight lanes share a column: lane q adds the partials c = q, q + 8, ... (all of its
-    // loads in flight at once), then the eight sub-sums are added in lane order — a fixed tree, identical on every rank.
-    {
-      const int q = lane & 7;
-      for (int j = (gtid >> 3); j < D; j += (gthreads >> 3)) {
-        float v[24];
-        int n = 0;
+    // r = inv_batch * (sum of the nb partial rows, in slice order): formed by every CTA for itself, eight loads in flight
+    for (int j4 = tid; j4 < D4; j4 += kThreads) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* src = reinterpret_cast<const float4*>(p.ws_part) + j4;
+      int c = 0;
+      for (; c + 8 <= p.nb; c += 8) {
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 24; ++u) {
-          const int c = q + 8 * u;
-          if (c < p.nb) { v[u] = __ldcg(p.ws_part + (size_t)c * D + j); n = u + 1; }
-        }
-        float s = 0.f;
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(c + q) * D4);
 #pragma unroll
-        for (int u = 0; u < 24; ++u)
-          if (u < n) s += v[u];
-        for (int c = q + 8 * 24; c < p.nb; c += 8) s += __ldcg(p.ws_part + (size_t)c * D + j);      // nb > 192: not on 148 SMs
-        // lanes 8k .. 8k+7 hold the sub-sums of one column: add them in lane order
-        float t = __shfl_sync(0xffffffffu, s, (lane & ~7));
-#pragma unroll
-        for (int u = 1; u < 8; ++u) t += __shfl_sync(0xffffffffu, s, (lane & ~7) + u);
-        if (q == 0) p.ws_r[j] = t * p.inv_batch;
+        for (int q = 0; q < 8; ++q) { t.x += v[q].x; t.y += v[q].y; t.z += v[q].z; t.w += v[q].w; }
       }
+      for (; c < p.nb; ++c) {
+        const float4 v = __ldcg(src + (size_t)c * D4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      t.x *= p.inv_batch; t.y *= p.inv_batch; t.z *= p.inv_batch; t.w *= p.inv_batch;
+      st4(s_r + 4 * j4, t);
     }
-    grid.sync();
-    for (int j = tid; j < D; j += kThreads) s_r[j] = __ldcg(p.ws_r + j);
   } else {
     for (int j = tid; j < D; j += kThreads) s_r[j] = p.feat_sum[j] * p.inv_batch;
   }
@@ -189,6 +238,19 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   if (stamp) p.ws_ts[4] = tc::globaltimer_ns();
   grid.sync();
 
+  // the workspace copy of the gradient is complete (grid barrier above): start streaming its first tile now, it lands while
+  // the update below runs. Staging buffer b holds gradient rows [t * stage_rows, ...) of tile t, t & 1 == b.
+  const int ntiles = (p.grad_w != nullptr && nrows > 0) ? (p.C + p.stage_rows - 1) / p.stage_rows : 0;
+  auto issue_tile = [&](int t) {
+    const int c0 = t * p.stage_rows, ct = min(p.stage_rows, p.C - c0);
+    const float* src = p.ws_g + (size_t)c0 * D;
+    const uint32_t dst = tc::smem_u32(s_G + (size_t)(t & 1) * kStageFloats);
+    for (int i = tid; i < ct * D4; i += kThreads) tc::cp_async16(dst + 16u * (uint32_t)i, src + 4 * (size_t)i, 16u);
+    tc::cp_async_commit();
+  };
+  if (ntiles > 0) issue_tile(0);
+  if (ntiles > 1) issue_tile(1);                                // both staging buffers are free
+
   // ---------------- phase B: elementwise update in smem + sum of squares
   for (int j = tid; j < D; j += kThreads) s_k[j] = __ldcg(p.ws_k + j);
   __syncthreads();
@@ -199,24 +261,38 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     scal_den = __fadd_rn(p.alpha, mla::block_sum(part, s_red));
   }
   float sq = 0.f;
-  for (int lr = 0; lr < nrows; ++lr) {
-    const float ki = s_k[row0 + lr];
-    float* prow = s_P + (size_t)lr * D;
-    for (int j4 = tid; j4 < D4; j4 += kThreads) {
-      float4 pv = ld4(prow + 4 * j4);
-      const float4 kv = ld4(s_k + 4 * j4);
-      const float4 rv = ld4(s_r + 4 * j4);
+  // a thread owns float4 column j4 of every row: k_j / r_j are read once, four rows are updated together (16 independent
+  // divisions in flight)
+  for (int j4 = tid; j4 < D4; j4 += kThreads) {
+    const float4 kv = ld4(s_k + 4 * j4);
+    const float4 rv = ld4(s_r + 4 * j4);
+    for (int lr0 = 0; lr0 < nrows; lr0 += 4) {
+      float4 pv[4];
+      float ki[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int lr = min(lr0 + u, nrows - 1);
+        pv[u] = ld4(s_P + (size_t)lr * D + 4 * j4);
+        ki[u] = s_k[row0 + lr];
+      }
       // Same operation order and roundings as utils.py:36 (no FMA contraction):
       //   P - (k_i*k_j) / (alpha + k_i*r_j)
-#define MLA_GS_UPD(c)                                                                       \
-      {                                                                                     \
-        const float den = (p.mode == 0) ? __fadd_rn(p.alpha, __fmul_rn(ki, rv.c)) : scal_den; \
-        pv.c = __fsub_rn(pv.c, __fdiv_rn(__fmul_rn(ki, kv.c), den));                        \
-        sq = fmaf(pv.c, pv.c, sq);                                                          \
+#define MLA_GS_UPD(u, c)                                                                       \
+      {                                                                                        \
+        const float den = (p.mode == 0) ? __fadd_rn(p.alpha, __fmul_rn(ki[u], rv.c)) : scal_den; \
+        pv[u].c = __fsub_rn(pv[u].c, __fdiv_rn(__fmul_rn(ki[u], kv.c), den));                  \
       }
-      MLA_GS_UPD(x) MLA_GS_UPD(y) MLA_GS_UPD(z) MLA_GS_UPD(w)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { MLA_GS_UPD(u, x) MLA_GS_UPD(u, y) MLA_GS_UPD(u, z) MLA_GS_UPD(u, w) }
 #undef MLA_GS_UPD
-      st4(prow + 4 * j4, pv);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (lr0 + u < nrows) {
+          st4(s_P + (size_t)(lr0 + u) * D + 4 * j4, pv[u]);
+          sq = fmaf(pv[u].x, pv[u].x, sq); sq = fmaf(pv[u].y, pv[u].y, sq);
+          sq = fmaf(pv[u].z, pv[u].z, sq); sq = fmaf(pv[u].w, pv[u].w, sq);
+        }
+      }
     }
   }
   {
@@ -229,106 +305,111 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   if (stamp) p.ws_ts[8] = tc::globaltimer_ns();
 
   // ---------------- phase C: normalise, write P, project the gradient
-  // ||P'||_F^2 = sum of the per-CTA partials in CTA order (identical in every CTA): the partials are fetched once per CTA
-  // (one L2 load per thread, NOT one per thread and partial: 75k threads polling the same 148 lines cost 30 us) and added
-  // by one thread from shared memory
+  // ||P'||_F^2 = sum of the per-CTA partials, identical in every CTA: the partials are fetched once per CTA (one L2 load per
+  // thread), lane l of warp 0 adds partials l, l + 32, ... in order, then a fixed shuffle tree (fp64)
   {
-    double* s_nrm = reinterpret_cast<double*>(s_G);               // s_G is free until the projection
+    double* s_nrm = reinterpret_cast<double*>(s_red);
     const int G = (int)gridDim.x;
     for (int c = tid; c < G; c += kThreads) s_nrm[c] = __ldcg(p.ws_norm + c);
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       double tot = 0.0;
-      for (int c = 0; c < G; ++c) tot += s_nrm[c];
-      s_red[0] = (float)sqrt(tot);
+      for (int c = lane; c < G; c += 32) tot += s_nrm[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == 0) s_nrmf = (float)sqrt(tot);
     }
     __syncthreads();
   }
-  const float nrm = s_red[0];
+  const float nrm = s_nrmf;
   if (stamp) p.ws_ts[9] = tc::globaltimer_ns();
-  for (int lr = 0; lr < nrows; ++lr) {
-    float* prow = s_P + (size_t)lr * D;
-    float4* grow = reinterpret_cast<float4*>(p.P + (size_t)(row0 + lr) * D);
-    for (int j4 = tid; j4 < D4; j4 += kThreads) {
-      float4 pv = ld4(prow + 4 * j4);
-      pv.x = __fdiv_rn(pv.x, nrm); pv.y = __fdiv_rn(pv.y, nrm);
-      pv.z = __fdiv_rn(pv.z, nrm); pv.w = __fdiv_rn(pv.w, nrm);
-      st4(prow + 4 * j4, pv);
-      __stcs(grow + j4, pv);
+  for (int j4 = tid; j4 < D4; j4 += kThreads) {
+    for (int lr0 = 0; lr0 < nrows; lr0 += 4) {
+      float4 pv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pv[u] = ld4(s_P + (size_t)min(lr0 + u, nrows - 1) * D + 4 * j4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pv[u].x = __fdiv_rn(pv[u].x, nrm); pv[u].y = __fdiv_rn(pv[u].y, nrm);
+        pv[u].z = __fdiv_rn(pv[u].z, nrm); pv[u].w = __fdiv_rn(pv[u].w, nrm);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (lr0 + u < nrows) {
+          st4(s_P + (size_t)(lr0 + u) * D + 4 * j4, pv[u]);
+          __stcs(reinterpret_cast<float4*>(p.P + (size_t)(row0 + lr0 + u) * D) + j4, pv[u]);
+        }
+      }
     }
   }
   if (stamp) p.ws_ts[6] = tc::globaltimer_ns();
-  if (p.grad_w == nullptr) {
+  if (ntiles == 0) {
     if (tid == 0) p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns();
     return;
   }
-  __syncthreads();
 
-  // grad_w[c][i] = sum_j G[c][j] * P[i][j]. Work unit = (group of kRB rows, kCB-column chunk): the unit's P block sits in
-  // registers (kRB x 4 float4 per lane) and every staged G value is loaded once per kRB * 4 FMAs. A pass covers whole row
-  // groups (all their column chunks); when a pass has fewer units than warps, several warps share a unit and split the
-  // staged gradient rows. The column-chunk partials of one (c, row) are combined through shared memory in chunk order.
+  // grad_w[c][i] = sum_j G[c][j] * P[i][j] for the CTA's rows i. Unit = (group g of kRB rows, column chunk ch, class block
+  // cb of kCT staged rows); index ((cb * ngroups) + g) * nchunks + ch. A warp keeps one (g, ch) block of P in registers for as
+  // long as it can (always, when there are at most kWarps such blocks) and walks the class blocks of every tile.
   const int ngroups = (nrows + kRB - 1) / kRB;
-  const int nchunks = (D + kCB - 1) / kCB;
-  const int gpp = max(1, kWarps / nchunks);                     // row groups per pass
-  for (int c0 = 0; c0 < p.C; c0 += kGT) {
-    const int ct = min(kGT, p.C - c0);
-    __syncthreads();
-    for (int i = tid; i < ct * D4; i += kThreads)
-      st4(s_G + 4 * (size_t)i, __ldcg(reinterpret_cast<const float4*>(p.ws_g + (size_t)c0 * D) + i));
-    __syncthreads();
-    for (int g0 = 0; g0 < ngroups; g0 += gpp) {
-      const int gn = min(gpp, ngroups - g0);                    // groups in this pass
-      const int units = gn * nchunks;                           // <= kWarps
-      const int csplit = max(1, kWarps / units);
-      const int ul = warp % units, csub = warp / units;
-      if (csub < csplit) {
-        const int g = g0 + ul / nchunks, ch = ul % nchunks;
-        const int jb = ch * kCB;
-        float4 a[kRB][4];
+  const int chunk = p.nq * 128;
+  const int nchunks = (D + chunk - 1) / chunk;
+  const int GC = ngroups * nchunks;
+  const int wpg = max(1, kWarps / GC);                          // warps sharing a (g, ch) block (they split the class blocks)
+  float4 a[kRB][4];
+  int have_gc = -1;
+  auto load_block = [&](int gc) {
+    if (gc == have_gc) return;
+    have_gc = gc;
+    const int g = gc / nchunks, jb = (gc - g * nchunks) * chunk;
 #pragma unroll
-        for (int rr = 0; rr < kRB; ++rr) {
-          const int lr = min(g * kRB + rr, nrows - 1);
+    for (int rr = 0; rr < kRB; ++rr) {
+      const int lr = min(g * kRB + rr, nrows - 1);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = jb + (q * 32 + lane) * 4;
-            a[rr][q] = (j < D) ? ld4(s_P + (size_t)lr * D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        for (int c = csub; c < ct; c += csplit) {
-          float sacc[kRB];
-#pragma unroll
-          for (int rr = 0; rr < kRB; ++rr) sacc[rr] = 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = jb + (q * 32 + lane) * 4;
-            if (j < D) {
-              const float4 gv = ld4(s_G + (size_t)c * D + j);
-#pragma unroll
-              for (int rr = 0; rr < kRB; ++rr) {
-                sacc[rr] = fmaf(gv.x, a[rr][q].x, sacc[rr]); sacc[rr] = fmaf(gv.y, a[rr][q].y, sacc[rr]);
-                sacc[rr] = fmaf(gv.z, a[rr][q].z, sacc[rr]); sacc[rr] = fmaf(gv.w, a[rr][q].w, sacc[rr]);
-              }
-            }
-          }
-#pragma unroll
-          for (int rr = 0; rr < kRB; ++rr) {
-            const float t = mla::warp_sum(sacc[rr]);
-            if (lane == 0) s_red[(ul * kGT + c) * kRB + rr] = t;
-          }
-        }
+      for (int q = 0; q < 4; ++q) {
+        const int j = jb + (q * 32 + lane) * 4;
+        a[rr][q] = (q < p.nq && j < D) ? ld4(s_P + (size_t)lr * D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      __syncthreads();
-      for (int t = tid; t < gn * ct * kRB; t += kThreads) {      // (group, c, row): chunks added in chunk order
-        const int rr = t % kRB, c = (t / kRB) % ct, gl = t / (kRB * ct);
-        const int lr = (g0 + gl) * kRB + rr;
+    }
+  };
+  for (int t = 0; t <= ntiles; ++t) {
+    if (t == 0 && ntiles > 1) tc::cp_async_wait<1>(); else tc::cp_async_wait<0>();   // tile t has landed (this thread's part) ...
+    __syncthreads();                // ... and everybody's; every warp has finished tile t - 1 (its partials are complete)
+    if (t >= 1 && t + 1 < ntiles) issue_tile(t + 1);             // into the buffer tile t - 1 has just released
+    if (t >= 1) {                   // combine tile t - 1: column-chunk partials in chunk order
+      const int tp = t - 1, c0 = tp * p.stage_rows, ct = min(p.stage_rows, p.C - c0);
+      const float* red = s_red + (size_t)(tp & 1) * kMaxUnits * 16;
+      for (int o = tid; o < ct * ngroups * kRB; o += kThreads) {
+        const int rr = o % kRB, g = (o / kRB) % ngroups, c = o / (kRB * ngroups);
+        const int lr = g * kRB + rr;
         if (lr < nrows) {
+          const int cb = c / kCT, cc = c - cb * kCT;
+          const float* src = red + ((size_t)(cb * ngroups + g) * nchunks) * 16 + cc * kRB + rr;
           float acc = 0.f;
-          for (int ch = 0; ch < nchunks; ++ch) acc += s_red[((gl * nchunks + ch) * kGT + c) * kRB + rr];
+          for (int ch = 0; ch < nchunks; ++ch) acc += src[ch * 16];
           p.grad_w[(size_t)(c0 + c) * D + row0 + lr] = acc;
         }
       }
-      __syncthreads();
+    }
+    if (t < ntiles) {
+      const int c0 = t * p.stage_rows, ct = min(p.stage_rows, p.C - c0);
+      const int ncb = (ct + kCT - 1) / kCT;
+      const float* G = s_G + (size_t)(t & 1) * kStageFloats;
+      float* red = s_red + (size_t)(t & 1) * kMaxUnits * 16;
+      auto run = [&](int gc, int cb) {
+        load_block(gc);
+        const int g = gc / nchunks, ch = gc - g * nchunks;
+        float* out = red + ((size_t)(cb * ngroups + g) * nchunks + ch) * 16;
+        if (p.nq == 4) project_unit<4>(a, G, D, ch * chunk, cb * kCT, ct, lane, out);
+        else if (p.nq == 2) project_unit<2>(a, G, D, ch * chunk, cb * kCT, ct, lane, out);
+        else project_unit<1>(a, G, D, ch * chunk, cb * kCT, ct, lane, out);
+      };
+      if (GC >= kWarps) {
+        for (int gc = warp; gc < GC; gc += kWarps)
+          for (int cb = 0; cb < ncb; ++cb) run(gc, cb);
+      } else if (warp / GC < wpg) {
+        for (int cb = warp / GC; cb < ncb; cb += wpg) run(warp % GC, cb);
+      }
     }
   }
   if (stamp) p.ws_ts[7] = tc::globaltimer_ns();
@@ -336,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
 }
 
 struct GsPlan {
-  int grid, rows_per_cta, nb, rows_per_nb;
+  int grid, rows_per_cta, nb, rows_per_nb, stage_rows, nq;
   size_t smem;
   size_t off_r, off_k, off_part, off_norm, off_g, off_ts, total;
 };
@@ -349,14 +430,26 @@ int make_plan(int B, int D, int C, GsPlan* pl) {
   int rpc = (D + sms - 1) / sms;
   if (rpc < 4) rpc = min(4, D);          // tiny D: fewer, fuller CTAs
   int grid = (D + rpc - 1) / rpc;
-  if (D > kMaxCB * kCB) return MLA_E_SHAPE;
-  size_t smem = ((size_t)2 * D + (size_t)rpc * D + (size_t)kGT * D + (size_t)kWarps * kGT * kRB + 32) * sizeof(float);
+  if (D > kMaxD) return MLA_E_SHAPE;
+  size_t smem = ((size_t)2 * D + (size_t)rpc * D + (size_t)2 * kStageFloats + (size_t)2 * kMaxUnits * 16 + 32) * sizeof(float);
   if (smem + 256 > (size_t)di.smem_optin) return MLA_E_SHAPE;
-  // raw-feature reduction: the batch rows are dealt to the CTAs in contiguous slices (>= 1 row each); inside a CTA the
-  // warps split columns (and rows, when D has fewer than kWarps 128-column chunks)
-  int rows_per_nb = (B + grid - 1) / grid;
+  // projection geometry: column chunks of nq * 128, gradient rows staged per tile (a multiple of kCT that fits one staging
+  // buffer and keeps a tile's (row group, chunk, class block) units within the partial-sum scratch)
+  const int nq = D > 1024 ? 4 : (D > 512 ? 2 : 1);
+  const int ngroups = (rpc + kRB - 1) / kRB, nchunks = (D + nq * 128 - 1) / (nq * 128);
+  int stage_rows = std::min(kMaxStageRows, kStageFloats / D) / kCT * kCT;
+  while (stage_rows > kCT && ngroups * nchunks * (stage_rows / kCT) > kMaxUnits) stage_rows -= kCT;
+  if (stage_rows < kCT || ngroups * nchunks * (stage_rows / kCT) > kMaxUnits) return MLA_E_SHAPE;
+  // raw-feature reduction: CTA = (batch slice, 256-column chunk). The number of slices nb (= partial rows every CTA sums
+  // after the first barrier) is bounded by the CTAs available per chunk, by >= 8 rows per slice and by 160 KB of partials
+  const int cch = (D + 255) / 256;
+  int nb_cap = std::min(std::max(1, grid / cch), std::max(1, B / 8));
+  nb_cap = std::max(1, std::min(nb_cap, (160 * 1024) / (D * 4)));
+  if (cch > grid) return MLA_E_SHAPE;
+  int rows_per_nb = (B + nb_cap - 1) / nb_cap;
   int nb = (B + rows_per_nb - 1) / rows_per_nb;
   pl->grid = grid; pl->rows_per_cta = rpc; pl->nb = nb; pl->rows_per_nb = rows_per_nb; pl->smem = smem;
+  pl->stage_rows = stage_rows; pl->nq = nq;
   size_t off = 0;
   pl->off_r = off;    off += mla::align_up((size_t)D * 4, 256);
   pl->off_k = off;    off += mla::align_up((size_t)D * 4, 256);
@@ -404,6 +497,7 @@ extern "C" int mla_gs_project(float* P, const float* feat, const float* feat_sum
   prm.P = P; prm.feat = feat; prm.feat_sum = feat_sum; prm.inv_batch = inv_batch; prm.alpha = alpha;
   prm.grad_w = grad_w; prm.B = B; prm.D = D; prm.C = C; prm.mode = mode;
   prm.rows_per_cta = pl.rows_per_cta; prm.nb = pl.nb; prm.rows_per_nb = pl.rows_per_nb;
+  prm.stage_rows = pl.stage_rows; prm.nq = pl.nq;
   prm.ws_r = reinterpret_cast<float*>(w + pl.off_r);
   prm.ws_k = reinterpret_cast<float*>(w + pl.off_k);
   prm.ws_part = reinterpret_cast<float*>(w + pl.off_part);
