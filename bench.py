@@ -242,6 +242,30 @@ def gs_beyond_sweep(torch, ops, pk):
     return pts
 
 
+def producer_leg(torch, pk):
+    """Informational: the visual dataset tuple producer — 64 samples x 2 decoded 360 x 480 RGB frames
+    (uint8, already resident in HBM) -> [64, 3, 2, 224, 224] fp32, the reference's evaluation transform
+    (dataset/dataset.py:133-138). Algorithmic bytes: frames read once + output written once."""
+    import numpy as np
+    from mla_b200 import ops
+    dev = torch.device("cuda")
+    B, T, H, W, S = 64, 2, 360, 480, 224
+    nbytes = B * T * H * W * 3 + B * 3 * T * S * S * 4
+    desc = np.zeros((B * T, 10), np.int32)
+    for n in range(B * T):
+        desc[n] = (n * H * W * 3, 0, H, W, 0, 0, H, W, 0, n)
+
+    def mk():
+        return (torch.randint(0, 256, (B * T * H * W * 3,), dtype=torch.uint8, device=dev), torch.from_numpy(desc).to(dev),
+                torch.empty(B, 3, T, S, S, device=dev))
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    t, nsets = _time_launch(torch, mk, lambda s: ops.frames_to_batch(s[0], s[1], B, T, S, H, mean, std, out=s[2]), nbytes,
+                            launches=12)
+    return {"kernels": "frame_coeffs_kernel + frame_hpass_kernel + frame_vpass_kernel", "us": t * 1e6, "bytes": nbytes,
+            "gbs": nbytes / t / 1e9, "frac_of_hbm_peak": nbytes / t / 1e9 / pk["hbm"], "samples_per_s": B / t, "sets": nsets,
+            "workload": "64 x 2 frames 360x480x3 uint8 -> [64,3,2,224,224] fp32, bit-identical to torchvision on PIL"}
+
+
 def head_sweep(torch, ops, pk):
     """Shared head forward + backward (main.py:432-435): algorithmic bytes 4*(2*B*D + 3*C*D + 2*B*C)."""
     dev = torch.device("cuda")
@@ -576,6 +600,7 @@ def run_native(a, rank, world):
             out[key + "_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()} for p in pts]
         out["gs_beyond_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()}
                                   for p in gs_beyond_sweep(torch, ops, pk)]
+        out["frame_producer"] = producer_leg(torch, pk)
     if not a.no_tf32_leg and world == 1 and encoder_engine.USE_F16:
         out["value_tf32"] = tf32_leg(a)
     if not a.no_eager and world == 1:

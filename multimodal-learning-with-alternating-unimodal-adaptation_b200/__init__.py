@@ -8,6 +8,7 @@ repo root (`import mla_b200`). Names mirror the reference's modules:
     AVClassifier, M3AEClassifier, Modal3Classifier (models/basic_model.py, models/m3ae.py, models/cav_mae.py)
     ConcatFusion, ConcatFusion3                  (models/fusion_modules.py)
     resnet18                                     (models/backbone.py)
+    FrameBatchProducer                           (dataset/dataset.py: the visual transform pipeline, per batch on the GPU)
 """
 from . import _lib, ops  # noqa: F401
 from .gs_plugin import GSPlugin  # noqa: F401
@@ -20,3 +21,4 @@ from .cav_mae import Modal3Classifier  # noqa: F401
 from .utils import setup_seed, weight_init  # noqa: F401
 from .engine import ModuleHolder, train_epoch, valid  # noqa: F401
 from .main import get_arguments  # noqa: F401
+from .dataset import FrameBatchProducer  # noqa: F401

@@ -811,13 +811,15 @@ struct RedPlan {
   // whatever (M, C) the call has: one workspace serves every BatchNorm layer of an encoder.
   size_t off_sums, off_part, off_bound, bytes;
 };
-int red_plan(long long M, int C, RedPlan* pl) {
+// per_sm = resident CTAs per SM of the reduction kernel that will run (its __launch_bounds__ minimum): the grid is ONE full
+// wave. (A cap of 4 per SM under a residency of 3 — the backward modes — ran as 1 1/3 waves: 2.9 TB/s on the 56x56x64 layer.)
+int red_plan(long long M, int C, RedPlan* pl, int per_sm = 4) {
   if (M < 1 || C < 64 || (C & 63) || C > 4096) return MLA_E_SHAPE;
   const mla::DeviceInfo& di = mla::device_info();
   if (di.ok != 1) return di.ok;
   pl->chunks = C / 64;
   long long nrb = (M + 127) / 128;                                   // >= 8 rows per thread
-  const long long cap = max(1, 4 * di.sm_count / pl->chunks);
+  const long long cap = max(1, per_sm * di.sm_count / pl->chunks);
   if (nrb > cap) nrb = cap;
   pl->rows_per_block = (M + nrb - 1) / nrb;
   pl->nrb = (int)((M + pl->rows_per_block - 1) / pl->rows_per_block);
@@ -1003,7 +1005,7 @@ static int bn_backward_impl(const float* dz, const float* z, const unsigned int*
   if (!dz || !y || !mean || !invstd || !gamma || (!dy && !dy16)) return MLA_E_BADARG;
   if (gscale != nullptr && !dy16) return MLA_E_BADARG;
   RedPlan pl;
-  int rc = red_plan(M, C, &pl);
+  int rc = red_plan(M, C, &pl, 3);
   if (rc) return rc;
   if (!ws || ws_bytes < pl.bytes) return MLA_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1113,7 +1115,7 @@ extern "C" int mla_pool_bn_backward_f16(const float* dp, const unsigned char* id
   const long long MP = (long long)N * PH * PW;           // the reduction walks the pooled pixels
   if (MP >= (1LL << 31)) return MLA_E_SHAPE;
   RedPlan pl;
-  int rc = red_plan(MP, C, &pl);
+  int rc = red_plan(MP, C, &pl, 3);
   if (rc) return rc;
   if (!ws || ws_bytes < pl.bytes) return MLA_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

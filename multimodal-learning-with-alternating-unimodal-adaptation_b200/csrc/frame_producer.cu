@@ -1,0 +1,213 @@
+// Dataset tuple producer for the visual modality — replaces, per batch, what the reference does per
+// sample on the CPU in dataset/dataset.py:123-161 (AVDataset.__getitem__; the same Compose in :448-480 / :753-803):
+//     PIL image -> RandomResizedCrop(224) [+ RandomHorizontalFlip]  |  Resize((224, 224))      (torchvision on PIL)
+//               -> ToTensor() -> Normalize(mean, std) -> frames stacked on a new dim 1: [3, T, 224, 224]
+// Input: the decoded uint8 HWC RGB frames of a batch packed into one device buffer + one descriptor per frame (geometry,
+// crop box, flip, destination slot). Output: the model's input tensor [B, 3, T, OH, OW] fp32, BIT-IDENTICAL to the
+// torchvision / Pillow path:
+//   * Pillow's Image.resize(BILINEAR) (what torchvision's Resize / resized_crop call on PIL images) is a two-pass separable
+//     convolution with an antialiasing support that grows with the down-scaling factor (libImaging/Resample.c): per output
+//     coordinate, a window [xmin, xmin + n) of normalised triangle weights computed in double precision, converted to 22-bit
+//     fixed point ((int)(0.5 + k * 2^22)), accumulated in int32 from 2^21, shifted and clipped to 8 bits — horizontally into
+//     an 8-bit intermediate image first, then vertically. frame_coeffs_kernel restates precompute_coeffs() +
+//     normalize_coeffs_8bpc() operation by operation in IEEE double (explicit _rn intrinsics: no FMA contraction);
+//     frame_hpass_kernel / frame_vpass_kernel restate ImagingResampleHorizontal_8bpc / Vertical_8bpc.
+//   * ToTensor = float(u8) / 255 (IEEE division), Normalize = (x - mean) / std in fp32, in that order.
+// The crop is a window of the source frame (PIL crop copies pixels, resize then works on the copy: same values).
+#include <math.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxK = 32;          // taps per output coordinate: ceil(scale) * 2 + 1 <= 32  ->  crop / out < 15.5
+constexpr int kPrec = 32 - 8 - 2;  // PRECISION_BITS of Resample.c
+constexpr int kDescInts = 10;      // {src offset lo, hi, H, W, top, left, crop_h, crop_w, flip, out slot}
+
+struct Desc {
+  long long off;
+  int H, W, top, left, ch, cw, flip, slot;
+};
+__device__ __forceinline__ Desc load_desc(const int* __restrict__ d, int f) {
+  const int* p = d + (size_t)f * kDescInts;
+  Desc r;
+  r.off = (long long)(unsigned int)p[0] | ((long long)p[1] << 32);
+  r.H = p[2]; r.W = p[3]; r.top = p[4]; r.left = p[5]; r.ch = p[6]; r.cw = p[7]; r.flip = p[8]; r.slot = p[9];
+  return r;
+}
+
+struct Lim {
+  int OH, OW, max_crop_h, nslots;
+  long long src_bytes;
+};
+// A descriptor every kernel may act on: the crop window inside the frame, the frame inside the source buffer, the taps
+// within kMaxK (ceil(scale) * 2 + 1), the destination slot inside the batch. Invalid frames are skipped by every kernel and
+// reported through `status`.
+__device__ __forceinline__ bool desc_ok(const Desc& d, const Lim& l) {
+  return d.H > 0 && d.W > 0 && d.ch > 0 && d.cw > 0 && d.top >= 0 && d.left >= 0 && d.top + d.ch <= d.H &&
+         d.left + d.cw <= d.W && d.ch <= l.max_crop_h && d.slot >= 0 && d.slot < l.nslots && d.off >= 0 &&
+         d.off + (long long)d.H * d.W * 3 <= l.src_bytes && ((d.cw + l.OW - 1) / l.OW) * 2 + 1 <= kMaxK &&
+         ((d.ch + l.OH - 1) / l.OH) * 2 + 1 <= kMaxK;
+}
+
+// tables per frame: [axis 0 = horizontal: OW entries | axis 1 = vertical: OH entries], each entry {xmin, n, k[kMaxK]}
+constexpr int kEntry = 2 + kMaxK;
+
+__global__ void __launch_bounds__(128) frame_coeffs_kernel(const int* __restrict__ desc, Lim lim, int* __restrict__ tab) {
+  const int OH = lim.OH, OW = lim.OW;
+  const int f = blockIdx.y, axis = blockIdx.z;
+  const int out_size = axis == 0 ? OW : OH;
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xx >= out_size) return;
+  const Desc d = load_desc(desc, f);
+  if (!desc_ok(d, lim)) return;
+  const int in_size = axis == 0 ? d.cw : d.ch;
+  int* e = tab + ((size_t)f * (OW + OH) + (axis == 0 ? 0 : OW) + xx) * kEntry;
+  // precompute_coeffs(inSize, in0 = 0, in1 = inSize, outSize, BILINEAR: support 1.0)
+  const double scale = __ddiv_rn((double)in_size, (double)out_size);
+  const double fscale = scale < 1.0 ? 1.0 : scale;
+  const double support = fscale;                                  // 1.0 * filterscale
+  const double ss = __ddiv_rn(1.0, fscale);
+  const double center = __dmul_rn((double)xx + 0.5, scale);       // in0 + (xx + 0.5) * scale, in0 = 0
+  int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  double k[kMaxK];
+  double ww = 0.0;
+#pragma unroll 1
+  for (int x = 0; x < xmax; ++x) {
+    double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+    if (a < 0.0) a = -a;
+    const double w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+    k[x] = w;
+    ww = __dadd_rn(ww, w);
+  }
+  e[0] = xmin;
+  e[1] = xmax;
+#pragma unroll 1
+  for (int x = 0; x < kMaxK; ++x) {
+    int v = 0;
+    if (x < xmax) {
+      double c = k[x];
+      if (ww != 0.0) c = __ddiv_rn(c, ww);
+      // normalize_coeffs_8bpc: (int)(+-0.5 + k * (1 << PRECISION_BITS)), truncation toward zero
+      const double s = __dmul_rn(c, (double)(1 << kPrec));
+      v = c < 0.0 ? (int)__dadd_rn(-0.5, s) : (int)__dadd_rn(0.5, s);
+    }
+    e[2 + x] = v;
+  }
+}
+
+__device__ __forceinline__ int clip8(int v) {
+  v >>= kPrec;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// tmp[f][row][xo][c] = horizontal pass over row (top + row) of the crop window
+__global__ void __launch_bounds__(256) frame_hpass_kernel(const unsigned char* __restrict__ src, const int* __restrict__ desc,
+                                                          const int* __restrict__ tab, Lim lim, long long tmp_stride,
+                                                          unsigned char* __restrict__ tmp) {
+  const int OH = lim.OH, OW = lim.OW;
+  const int f = blockIdx.y;
+  const Desc d = load_desc(desc, f);
+  if (!desc_ok(d, lim)) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)d.ch * OW) return;
+  const int row = (int)(i / OW), xo = (int)(i - (long long)row * OW);
+  const int* e = tab + ((size_t)f * (OW + OH) + xo) * kEntry;
+  const int xmin = e[0], n = e[1];
+  const unsigned char* p = src + d.off + ((long long)(d.top + row) * d.W + d.left + xmin) * 3;
+  int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0;
+  for (int t = 0; t < n; ++t) {
+    const int k = e[2 + t];
+    s0 += (int)p[3 * t] * k; s1 += (int)p[3 * t + 1] * k; s2 += (int)p[3 * t + 2] * k;
+  }
+  unsigned char* o = tmp + (long long)f * tmp_stride + ((long long)row * OW + xo) * 3;
+  o[0] = (unsigned char)clip8(s0); o[1] = (unsigned char)clip8(s1); o[2] = (unsigned char)clip8(s2);
+}
+
+// vertical pass + ToTensor + Normalize + flip + scatter into [B, 3, T, OH, OW]
+__global__ void __launch_bounds__(256) frame_vpass_kernel(const unsigned char* __restrict__ tmp, const int* __restrict__ desc,
+                                                          const int* __restrict__ tab, Lim lim, int T,
+                                                          long long tmp_stride, float3 mean, float3 std,
+                                                          float* __restrict__ out) {
+  const int OH = lim.OH, OW = lim.OW;
+  const int f = blockIdx.y;
+  const Desc d = load_desc(desc, f);
+  if (!desc_ok(d, lim)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OH * OW) return;
+  const int yo = i / OW, xo = i - yo * OW;
+  const int* e = tab + ((size_t)f * (OW + OH) + OW + yo) * kEntry;
+  const int ymin = e[0], n = e[1];
+  const unsigned char* p = tmp + (long long)f * tmp_stride + ((long long)ymin * OW + xo) * 3;
+  int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0;
+  for (int t = 0; t < n; ++t) {
+    const int k = e[2 + t];
+    const unsigned char* q = p + (long long)t * OW * 3;
+    s0 += (int)q[0] * k; s1 += (int)q[1] * k; s2 += (int)q[2] * k;
+  }
+  const int b = d.slot / T, tt = d.slot - b * T;
+  const int xf = d.flip ? OW - 1 - xo : xo;
+  const size_t plane = (size_t)OH * OW;
+  float* o = out + (((size_t)b * 3) * T + tt) * plane + (size_t)yo * OW + xf;
+  // ToTensor: u8 -> float / 255; Normalize: (x - mean) / std — IEEE fp32, no contraction
+  o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)clip8(s0), 255.f), mean.x), std.x);
+  o[(size_t)T * plane] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)clip8(s1), 255.f), mean.y), std.y);
+  o[2 * (size_t)T * plane] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)clip8(s2), 255.f), mean.z), std.z);
+}
+
+// the descriptors live in device memory: the first invalid one is reported as status = index + 1 (0 = all valid)
+__global__ void frame_check_kernel(const int* __restrict__ desc, int nframes, Lim lim, int* __restrict__ bad) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  if (!desc_ok(load_desc(desc, f), lim)) atomicMax(bad, f + 1);
+}
+
+size_t tab_bytes(int nframes, int OH, int OW) { return mla::align_up((size_t)nframes * (OW + OH) * kEntry * sizeof(int), 256); }
+
+}  // namespace
+
+extern "C" size_t mla_frames_to_batch_workspace_bytes(int nframes, int OH, int OW, int max_crop_h) {
+  if (nframes < 1 || OH < 1 || OW < 1 || max_crop_h < 1) return 0;
+  return 256 + tab_bytes(nframes, OH, OW) + mla::align_up((size_t)nframes * max_crop_h * OW * 3, 256);
+}
+
+extern "C" int mla_frames_to_batch(const unsigned char* src, long long src_bytes, const int* desc, int nframes, int B, int T,
+                                   int OH, int OW, int max_crop_h, const float* mean3, const float* std3, float* out,
+                                   int* status, void* ws, size_t ws_bytes, void* stream) {
+  if (!src || !desc || !mean3 || !std3 || !out || nframes < 1 || B < 1 || T < 1 || OH < 1 || OW < 1 || max_crop_h < 1 ||
+      src_bytes < 1)
+    return MLA_E_BADARG;
+  if ((long long)OH * OW >= (1LL << 30)) return MLA_E_SHAPE;
+  const size_t need = mla_frames_to_batch_workspace_bytes(nframes, OH, OW, max_crop_h);
+  if (!ws || ws_bytes < need) return MLA_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  int* tab = reinterpret_cast<int*>(base + 256);
+  unsigned char* tmp = reinterpret_cast<unsigned char*>(base + 256 + tab_bytes(nframes, OH, OW));
+  const long long tmp_stride = (long long)max_crop_h * OW * 3;
+  Lim lim;
+  lim.OH = OH; lim.OW = OW; lim.max_crop_h = max_crop_h; lim.nslots = B * T; lim.src_bytes = src_bytes;
+  if (status != nullptr) {
+    MLA_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
+    frame_check_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(desc, nframes, lim, status);
+    MLA_CUDA_TRY(cudaGetLastError());
+    mla::count_launch();
+  }
+  const int omax = OH > OW ? OH : OW;
+  frame_coeffs_kernel<<<dim3((omax + 127) / 128, nframes, 2), 128, 0, st>>>(desc, lim, tab);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  const long long hmax = (long long)max_crop_h * OW;
+  frame_hpass_kernel<<<dim3((unsigned)((hmax + 255) / 256), nframes), 256, 0, st>>>(src, desc, tab, lim, tmp_stride, tmp);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  frame_vpass_kernel<<<dim3((OH * OW + 255) / 256, nframes), 256, 0, st>>>(tmp, desc, tab, lim, T, tmp_stride,
+                                                                           make_float3(mean3[0], mean3[1], mean3[2]),
+                                                                           make_float3(std3[0], std3[1], std3[2]), out);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  return 0;
+}

@@ -205,6 +205,33 @@ def ogm_modulate(flat_grad, seg_off, seg_len, max_len, coeff, noise=None, seg_st
 # ----------------------------------------------------------------------------------------------
 # Encoder convolutions (NHWC activations, [Cout][R][S][Cin] weights)
 # ----------------------------------------------------------------------------------------------
+def frames_to_batch(src, desc, B, T, size, max_crop_h, mean, std, out=None, status=None):
+    """uint8 HWC RGB frames -> the visual input tensor [B, 3, T, OH, OW] (dataset/dataset.py:123-161). `src` = packed frames
+    (uint8, CUDA), `desc` = int32 CUDA tensor [nframes, 10] (see mla_frames_to_batch), `status` = optional int32 CUDA scalar."""
+    L = _lib.lib()
+    _need_cuda(src, desc, out, status)
+    if src.dtype != torch.uint8 or desc.dtype != torch.int32 or desc.dim() != 2 or desc.shape[1] != 10:
+        raise RuntimeError("frames_to_batch: src must be uint8 and desc int32 [nframes, 10]")
+    OH, OW = (size, size) if isinstance(size, int) else size
+    nframes = desc.shape[0]
+    if out is None:
+        out = torch.empty(B, 3, T, OH, OW, dtype=torch.float32, device=src.device)
+    elif tuple(out.shape) != (B, 3, T, OH, OW) or out.dtype != torch.float32:
+        raise RuntimeError("frames_to_batch: out must be float32 [B, 3, T, OH, OW]")
+    if status is not None and (status.dtype != torch.int32 or status.numel() != 1):
+        raise RuntimeError("frames_to_batch: status must be one int32")
+    nbytes = L.mla_frames_to_batch_workspace_bytes(nframes, OH, OW, int(max_crop_h))
+    if nbytes == 0:
+        raise RuntimeError("frames_to_batch: unsupported shape")
+    ws = _workspace("frames", nbytes, src.device)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    rc = L.mla_frames_to_batch(_lib.ptr(src), src.numel(), _lib.ptr(desc), nframes, B, T, OH, OW, int(max_crop_h), m3, s3,
+                               _lib.ptr(out), _lib.ptr(status), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "mla_frames_to_batch")
+    return out
+
+
 def _conv_out(x, k, stride, pad):
     return (x + 2 * pad - k) // stride + 1
 

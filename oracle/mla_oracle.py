@@ -16,6 +16,11 @@ It restates, on the CPU, what the reference computes on the path named by BASELI
   * m3ae encoders / M3AEClassifier    models/m3ae.py:65-224,337-370, basic_model.py:184-200 (torch CPU fp32)
   * CAV-MAE audio / Modal3Classifier  models/cav_mae.py:69-151,337-351, basic_model.py:252-275 (torch CPU fp32; the
                                       block's Attention / Mlp come from un-vendored timm==0.4.5: those two UNPINNED)
+  * visual dataset transform           dataset/dataset.py:123-161 (numpy integer arithmetic). Its arithmetic lives in
+                                      third-party libraries the reference calls — torchvision.transforms (Resize /
+                                      RandomResizedCrop / ToTensor / Normalize) over Pillow's Image.resize(BILINEAR)
+                                      (libImaging/Resample.c) — which ARE installed here (torchvision 0.26, Pillow 12.2):
+                                      pinned by running them live in tests/test_oracle_frames.py plus a committed fixture.
 
 Pinning: the reference ships no tests or golden vectors, so this oracle is
 pinned against OUTPUTS OF THE REFERENCE ITSELF, executed in the build container under torch
@@ -689,3 +694,93 @@ def synthetic_av_batch(batch, seed, spec_hw=(257, 188), frames=2, image_hw=(224,
 
 def math_isclose(a, b, rel):
     return math.isclose(a, b, rel_tol=rel, abs_tol=rel)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Visual dataset transform (dataset/dataset.py:123-161): torchvision Resize / resized_crop on PIL images -> ToTensor ->
+# Normalize. Pillow's bilinear resampling (libImaging/Resample.c: precompute_coeffs, normalize_coeffs_8bpc,
+# ImagingResampleHorizontal_8bpc / Vertical_8bpc) restated in numpy integer arithmetic.
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """(bounds [out, 2] = (xmin, n), fixed-point coefficients [out, ksize] int32) of Pillow's BILINEAR filter for a full-box
+    resize in_size -> out_size: support = max(scale, 1), triangle weights normalised per output coordinate in double,
+    then (int)(+-0.5 + k * 2^22)."""
+    scale = float(in_size) / out_size
+    fscale = max(scale, 1.0)
+    support = 1.0 * fscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / fscale
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.float64)
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            a = -a if a < 0.0 else a
+            w = 1.0 - a if a < 1.0 else 0.0
+            kk[xx, x] = w
+            ww += w
+        if ww != 0.0:
+            for x in range(xmax):
+                kk[xx, x] /= ww
+        bounds[xx] = (xmin, xmax)
+    ki = np.where(kk < 0, (-0.5 + kk * (1 << PIL_PRECISION_BITS)).astype(np.int64),
+                  (0.5 + kk * (1 << PIL_PRECISION_BITS)).astype(np.int64)).astype(np.int32)
+    return bounds, ki
+
+
+def _pil_pass(img, out_size, axis):
+    """One resampling pass along `axis` (1 = horizontal, 0 = vertical) of a uint8 [H, W, C] image."""
+    bounds, k = pil_bilinear_coeffs(img.shape[axis], out_size)
+    shape = list(img.shape)
+    shape[axis] = out_size
+    out = np.zeros(shape, np.uint8)
+    src = img.astype(np.int64)
+    for o in range(out_size):
+        lo, n = bounds[o]
+        win = src[:, lo:lo + n, :] if axis == 1 else src[lo:lo + n, :, :]
+        kw = k[o, :n].astype(np.int64)
+        acc = (win * (kw[None, :, None] if axis == 1 else kw[:, None, None])).sum(axis=axis) + (1 << (PIL_PRECISION_BITS - 1))
+        val = np.clip(acc >> PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+        if axis == 1:
+            out[:, o, :] = val
+        else:
+            out[o, :, :] = val
+    return out
+
+
+def pil_resize_u8(img, out_h, out_w):
+    """Image.resize((out_w, out_h), BILINEAR) of a uint8 [H, W, C] array: horizontal pass into an 8-bit intermediate, then
+    the vertical pass (Resample.c:ImagingResampleInner; a pass whose size does not change is skipped, as Pillow does)."""
+    img = np.ascontiguousarray(img)
+    if img.shape[1] != out_w:
+        img = _pil_pass(img, out_w, 1)
+    if img.shape[0] != out_h:
+        img = _pil_pass(img, out_h, 0)
+    return img
+
+
+def frames_to_tensor(batch_of_frames, params, size, mean, std):
+    """dataset/dataset.py:123-161 for a whole batch: per frame crop (top, left, h, w) -> resize to size x size -> hflip if
+    flagged -> ToTensor (u8 / 255, fp32) -> Normalize ((x - mean) / std, fp32); frames stacked on dim 1.
+    Returns float32 [B, 3, T, size, size]."""
+    B, T = len(batch_of_frames), len(batch_of_frames[0])
+    out = np.zeros((B, 3, T, size, size), np.float32)
+    m = np.asarray(mean, np.float32)[:, None, None]
+    s = np.asarray(std, np.float32)[:, None, None]
+    n = 0
+    for b in range(B):
+        for t in range(T):
+            top, left, h, w, flip = params[n]
+            n += 1
+            img = pil_resize_u8(batch_of_frames[b][t][top:top + h, left:left + w], size, size)
+            if flip:
+                img = img[:, ::-1]
+            x = img.transpose(2, 0, 1).astype(np.float32) / np.float32(255)
+            out[b, :, t] = (x - m) / s
+    return out

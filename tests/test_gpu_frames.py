@@ -1,0 +1,91 @@
+"""GPU: the visual dataset tuple producer — csrc/frame_producer.cu through the C ABI
+(`FrameBatchProducer` -> ops.frames_to_batch -> mla_frames_to_batch) against torchvision / Pillow run live on the host,
+against the committed fixture of the reference's train-mode Compose (dataset/dataset.py:126-132), and against the numpy
+oracle. Integer resampling + IEEE fp32 normalisation: the bar is BIT-EXACT."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mla_oracle as orc
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+
+
+def _frame(rng, H, W):
+    y, x = np.mgrid[0:H, 0:W]
+    img = np.stack([127 + 120 * np.sin(x / 7.0 + c) * np.cos(y / 11.0 - c) for c in range(3)], -1)
+    img += rng.normal(0, 12, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+@pytest.fixture(scope="module")
+def producer_cls(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from mla_b200.dataset import FrameBatchProducer
+    return FrameBatchProducer
+
+
+@pytest.mark.parametrize("shapes", [[(360, 480)] * 4, [(224, 224), (100, 130), (513, 300), (37, 41)],
+                                    [(720, 1280), (225, 223), (1080, 1920), (64, 3000)]])
+def test_eval_transform_equals_torchvision_bit_for_bit(producer_cls, shapes):
+    """dataset.py:133-138: Resize((224, 224)) -> ToTensor -> Normalize, two frames per sample."""
+    from PIL import Image
+    from torchvision import transforms
+    rng = np.random.default_rng(len(shapes) + shapes[0][0])
+    frames = [[_frame(rng, *shapes[0]), _frame(rng, *shapes[1])], [_frame(rng, *shapes[2]), _frame(rng, *shapes[3])]]
+    tf = transforms.Compose([transforms.Resize(size=(224, 224)), transforms.ToTensor(), transforms.Normalize(MEAN, STD)])
+    ref = torch.stack([torch.cat([tf(Image.fromarray(f)).unsqueeze(1).float() for f in s], 1) for s in frames])   # :147-156
+    out = producer_cls(224, "test")(frames)
+    assert out.shape == (2, 3, 2, 224, 224) and out.is_cuda
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_train_transform_reproduces_the_seeded_reference_compose(producer_cls):
+    """Fixture: RandomResizedCrop -> RandomHorizontalFlip -> ToTensor -> Normalize under torch.manual_seed(7), executed by
+    torchvision (tests/golden/make_golden_frames.py). Same seed here: same crops, same flips, same bits."""
+    g = np.load(os.path.join(HERE, "golden", "frames.npz"))
+    frames = [[g["f00"], g["f01"]], [g["f10"], g["f11"]]]
+    prod = producer_cls(int(g["size"]), "train", g["mean"], g["std"])
+    torch.manual_seed(int(g["seed"]))
+    drawn = prod._params([f for s in frames for f in s])
+    assert [list(p[:4]) + [int(p[4])] for p in drawn] == g["params"].tolist()
+    torch.manual_seed(int(g["seed"]))
+    out = prod(frames)
+    assert np.array_equal(out.cpu().numpy(), g["expected"])
+
+
+def test_explicit_crops_flips_and_batch_layout_vs_oracle(producer_cls):
+    rng = np.random.default_rng(11)
+    B, T = 5, 3
+    frames = [[_frame(rng, int(rng.integers(40, 400)), int(rng.integers(40, 400))) for _ in range(T)] for _ in range(B)]
+    params = []
+    for s in frames:
+        for f in s:
+            H, W = f.shape[:2]
+            h, w = int(rng.integers(8, H + 1)), int(rng.integers(8, W + 1))
+            params.append((int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1)), h, w, bool(rng.integers(0, 2))))
+    for size in (224, 96):
+        out = producer_cls(size, "train")(frames, params=params)
+        assert np.array_equal(out.cpu().numpy(), orc.frames_to_tensor(frames, params, size, MEAN, STD))
+    again = producer_cls(96, "train")(frames, params=params)
+    assert torch.equal(out, again)                                              # deterministic
+
+
+def test_identity_resize_and_errors(producer_cls):
+    rng = np.random.default_rng(5)
+    f = _frame(rng, 224, 224)
+    out = producer_cls(224, "test")([[f]])
+    x = torch.from_numpy(f).permute(2, 0, 1).float().div(255)
+    ref = (x - torch.tensor(MEAN)[:, None, None]) / torch.tensor(STD)[:, None, None]
+    assert torch.equal(out.cpu()[0, :, 0], ref)                                 # scale 1: weights (1, 0) -> the input pixels
+    prod = producer_cls(32, "train")
+    with pytest.raises(RuntimeError):
+        prod([[f]], params=[(200, 0, 100, 100, False)])                         # crop leaves the frame
+    with pytest.raises(RuntimeError):
+        producer_cls(8, "test")([[f]])                                          # 224 / 8 = 28 > 15.5: outside the tap budget
+    with pytest.raises(ValueError):
+        prod([[f.astype(np.float32)]])
