@@ -77,7 +77,7 @@ MLA_API int    mla_gs_project(float* P, const float* feat, const float* feat_sum
  *   dW = dlogits^T feat ; db = sum_b dlogits ; dfeat = dlogits W ; feat_sum = sum_b feat
  * loss is the LOCAL mean (sum_b / B). Any of dW, db, dfeat, feat_sum, logits may be NULL
  * to skip that output (forward-only: pass dW = db = dfeat = NULL).
- * Supported: D % 4 == 0, 1 <= C <= 1024, label in [0, C). Two launches, deterministic.
+ * Supported: D % 4 == 0, 1 <= C <= 1024, label in [0, C). Three (C <= 16) to six launches, deterministic.
  */
 MLA_API size_t mla_head_ce_workspace_bytes(int B, int D, int C);
 MLA_API int    mla_head_ce(const float* feat, const float* W, const float* bias, const int64_t* label,

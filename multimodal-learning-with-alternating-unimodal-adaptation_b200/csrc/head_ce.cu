@@ -2,9 +2,9 @@
 // backward restricted to the head — reference main.py:432-435 with
 // models/fusion_modules.py:19 and nn.CrossEntropyLoss (main.py:130).
 //
-//   kernel 1 (warp per sample): logits, log-softmax loss per row, dlogits
-//   kernel 2 (thread per feature column): dW / db / feat_sum (reduction over the batch in a
-//            fixed order) and dfeat (independent per sample), all in one launch
+//   C <= 16 (CREMA-D 6, IEMOCAP 4): memory-bound; head_rows / head_cols / head_reduce kernels (below)
+//   C  > 16 (Food-101 101):         FMA-bound; three register-tiled fp32 GEMM launches + softmax / reductions (below)
+// Every reduction has a fixed order (deterministic, identical on every data-parallel rank).
 //
 // feat_sum (sum_b feat) is emitted here because this kernel already streams feat; the GS
 // projection consumes it (after the data-parallel all-reduce) instead of re-reading feat.
@@ -15,153 +15,8 @@
 
 namespace {
 
-constexpr int kFwdThreads = 256;
-constexpr int kFwdWarps = kFwdThreads / 32;
-constexpr int kBwdThreads = 128;
-constexpr int kTile = 32;  // c-chunk (dW part) and b-chunk (dfeat part)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-
-// smem: [kFwdWarps][D] feature rows, [kFwdWarps][Cpad] logits
-__global__ void __launch_bounds__(kFwdThreads) head_fwd_kernel(
-    const float* __restrict__ feat, const float* __restrict__ W, const float* __restrict__ bias,
-    const int64_t* __restrict__ label, int B, int D, int C, float grad_scale,
-    float* __restrict__ logits, float* __restrict__ dlogits, float* __restrict__ rowloss) {
-  extern __shared__ __align__(16) float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Cpad = (C + 31) & ~31;
-  float* s_f = smem + (size_t)warp * D;
-  float* s_l = smem + (size_t)kFwdWarps * D + (size_t)warp * Cpad;
-  const int D4 = D >> 2;
-  for (int b = blockIdx.x * kFwdWarps + warp; b < B; b += gridDim.x * kFwdWarps) {
-    const float* fr = feat + (size_t)b * D;
-    for (int j4 = lane; j4 < D4; j4 += 32) *reinterpret_cast<float4*>(s_f + 4 * j4) = ld4(fr + 4 * j4);
-    __syncwarp();
-    for (int c = 0; c < C; ++c) {
-      const float* wr = W + (size_t)c * D;
-      float acc = 0.f;
-      for (int j4 = lane; j4 < D4; j4 += 32) {
-        const float4 w = ld4(wr + 4 * j4);
-        const float4 f = *reinterpret_cast<const float4*>(s_f + 4 * j4);
-        acc = fmaf(w.x, f.x, acc); acc = fmaf(w.y, f.y, acc);
-        acc = fmaf(w.z, f.z, acc); acc = fmaf(w.w, f.w, acc);
-      }
-      acc = mla::warp_sum(acc);
-      if (lane == (c & 31)) s_l[c] = acc + (bias ? bias[c] : 0.f);
-    }
-    __syncwarp();
-    // log-softmax over C
-    float m = -INFINITY;
-    for (int c = lane; c < C; c += 32) m = fmaxf(m, s_l[c]);
-    m = mla::warp_max(m);
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += expf(s_l[c] - m);
-    s = mla::warp_sum(s);
-    const float lse = logf(s);
-    // an out-of-range label (nn.CrossEntropyLoss raises a device assert for it) poisons this row's loss and gradient
-    // with NaN instead of reading shared memory out of bounds: the error surfaces in the step's loss
-    const long long lab64 = label[b];
-    const bool lab_ok = lab64 >= 0 && lab64 < (long long)C;
-    const int lab = lab_ok ? (int)lab64 : 0;
-    for (int c = lane; c < C; c += 32) {
-      const float l = s_l[c];
-      if (logits) logits[(size_t)b * C + c] = l;
-      if (dlogits) {
-        const float pr = expf(l - m - lse);
-        dlogits[(size_t)b * C + c] = lab_ok ? (pr - (c == lab ? 1.f : 0.f)) * grad_scale : __int_as_float(0x7fc00000);
-      }
-    }
-    if (lane == 0) rowloss[b] = lab_ok ? -(s_l[lab] - m - lse) : __int_as_float(0x7fc00000);
-    __syncwarp();
-  }
-}
-
-// blockIdx.y <  ncc : dW rows [c0, c0+32), db, (c0 == 0: feat_sum, loss)
-// blockIdx.y >= ncc : dfeat rows [b0, b0+32)
-__global__ void __launch_bounds__(kBwdThreads) head_bwd_kernel(
-    const float* __restrict__ feat, const float* __restrict__ W, const float* __restrict__ dl,
-    const float* __restrict__ rowloss, int B, int D, int C, int ncc, float* __restrict__ dW,
-    float* __restrict__ db, float* __restrict__ dfeat, float* __restrict__ feat_sum,
-    float* __restrict__ loss) {
-  __shared__ float s_t[kTile][kTile + 1];
-  __shared__ float s_red[32];
-  const int j = blockIdx.x * kBwdThreads + threadIdx.x;
-  const bool jok = j < D;
-  if ((int)blockIdx.y < ncc) {
-    const int c0 = blockIdx.y * kTile;
-    const int ct = min(kTile, C - c0);
-    float acc[kTile];
-#pragma unroll
-    for (int c = 0; c < kTile; ++c) acc[c] = 0.f;
-    float fsum = 0.f;
-    for (int b0 = 0; b0 < B; b0 += kTile) {
-      const int bt = min(kTile, B - b0);
-      __syncthreads();
-      for (int i = threadIdx.x; i < kTile * kTile; i += kBwdThreads) {
-        const int bb = i / kTile, cc = i % kTile;
-        s_t[bb][cc] = (dl != nullptr && bb < bt && cc < ct) ? dl[(size_t)(b0 + bb) * C + c0 + cc] : 0.f;
-      }
-      __syncthreads();
-      if (jok) {
-        for (int bb = 0; bb < bt; ++bb) {
-          const float f = feat[(size_t)(b0 + bb) * D + j];
-          fsum += f;
-#pragma unroll
-          for (int c = 0; c < kTile; ++c) acc[c] = fmaf(s_t[bb][c], f, acc[c]);
-        }
-      }
-    }
-    if (jok) {
-      if (dW) {
-#pragma unroll
-        for (int c = 0; c < kTile; ++c)
-          if (c < ct) dW[(size_t)(c0 + c) * D + j] = acc[c];
-      }
-      if (c0 == 0 && feat_sum) feat_sum[j] = fsum;
-    }
-    if (blockIdx.x == 0) {
-      if (db && dl && (int)threadIdx.x < ct) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += dl[(size_t)b * C + c0 + threadIdx.x];
-        db[c0 + threadIdx.x] = s;
-      }
-      if (c0 == 0 && loss) {
-        float s = 0.f;
-        for (int b = threadIdx.x; b < B; b += kBwdThreads) s += rowloss[b];
-        s = mla::block_sum(s, s_red);
-        if (threadIdx.x == 0) *loss = s / (float)B;
-      }
-    }
-  } else {
-    const int b0 = ((int)blockIdx.y - ncc) * kTile;
-    const int bt = min(kTile, B - b0);
-    float acc[kTile];
-#pragma unroll
-    for (int b = 0; b < kTile; ++b) acc[b] = 0.f;
-    for (int c0 = 0; c0 < C; c0 += kTile) {
-      const int ct = min(kTile, C - c0);
-      __syncthreads();
-      for (int i = threadIdx.x; i < kTile * kTile; i += kBwdThreads) {
-        const int bb = i / kTile, cc = i % kTile;
-        s_t[cc][bb] = (bb < bt && cc < ct) ? dl[(size_t)(b0 + bb) * C + c0 + cc] : 0.f;
-      }
-      __syncthreads();
-      if (jok) {
-        for (int cc = 0; cc < ct; ++cc) {
-          const float w = W[(size_t)(c0 + cc) * D + j];
-#pragma unroll
-          for (int b = 0; b < kTile; ++b) acc[b] = fmaf(s_t[cc][b], w, acc[b]);
-        }
-      }
-    }
-    if (jok) {
-#pragma unroll
-      for (int b = 0; b < kTile; ++b)
-        if (b < bt) dfeat[(size_t)(b0 + b) * D + j] = acc[b];
-    }
-  }
-}
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // Small-C path (C <= 16: CREMA-D 6, IEMOCAP 4, MVSA 3): the head is memory-bound — feat is read once from HBM (logits) and
@@ -381,6 +236,214 @@ __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Large-C path (C > 16: Food-101's 101 classes): the head is three small fp32 GEMMs, bound by the FMA rate rather than HBM
+// (6 B D C FLOP against 4 (2 B D + 3 C D + 2 B C) bytes: 150 FLOP / byte at C = 101). fp32 accuracy is part of the contract
+// (rel 1e-5 against the fp64 oracle), so they run on the CUDA cores: one register-tiled kernel (64 x 64 tile, 4 x 4 per
+// thread, 16-deep k-steps, operands staged transposed in shared memory so that every thread reads two float4 per 16 FMAs)
+// instantiated for the three operand layouts:
+//   logits = feat W^T (+ b)          A = feat [B][D] (k contiguous), B = W [C][D] (k contiguous)
+//   dfeat  = dlogits W               A = dlogits [B][C] (k contiguous), B = W [C][D] (n contiguous)
+//   [dW; feat_sum] = [dlogits | 1]^T feat   A = dlogits^T (m contiguous) with a virtual all-ones row C, B = feat (n contiguous);
+//                                    split over the batch, partials added in split order (deterministic)
+// plus head_softmax_kernel (a warp per sample: loss, dlogits) and head_db_loss_kernel (a warp per class, fixed tree).
+constexpr int kGT = 64, kGK = 16, kGPad = 4;
+
+template <bool A_KC, bool B_NC>
+__global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm,
+                                                        int ldb, float* __restrict__ Cm, int ldc, int M, int N, int K,
+                                                        int k_per_split, const float* __restrict__ bias_n, int ones_row) {
+  __shared__ __align__(16) float As[kGK][kGT + kGPad];
+  __shared__ __align__(16) float Bs[kGK][kGT + kGPad];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.y * kGT, n0 = blockIdx.x * kGT;
+  const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kb; k0 < ke; k0 += kGK) {
+    float ra[4], rb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {               // 64 x 16 elements of each operand, four per thread
+      int m, k;
+      if (A_KC) { k = t & 15; m = (t >> 4) + 16 * i; } else { m = t & 63; k = (t >> 6) + 4 * i; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < ke) v = (gm == ones_row) ? 1.f : (A_KC ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm]);
+      ra[i] = v;
+      int n, k2;
+      if (B_NC) { n = t & 63; k2 = (t >> 6) + 4 * i; } else { k2 = t & 15; n = (t >> 4) + 16 * i; }
+      const int gn = n0 + n, gk2 = k0 + k2;
+      rb[i] = (gn < N && gk2 < ke) ? (B_NC ? Bm[(size_t)gk2 * ldb + gn] : Bm[(size_t)gn * ldb + gk2]) : 0.f;
+    }
+    __syncthreads();                            // the previous k-step has been consumed
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (A_KC) As[t & 15][(t >> 4) + 16 * i] = ra[i]; else As[(t >> 6) + 4 * i][t & 63] = ra[i];
+      if (B_NC) Bs[(t >> 6) + 4 * i][t & 63] = rb[i]; else Bs[t & 15][(t >> 4) + 16 * i] = rb[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kGK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  float* out = Cm + (size_t)blockIdx.z * M * ldc;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) out[(size_t)gm * ldc + gn] = acc[i][j] + (bias_n != nullptr ? bias_n[gn] : 0.f);
+    }
+  }
+}
+
+// a warp per sample: (the split-K partial logits added in split order, + bias ->) logits row, log-softmax, loss, dlogits
+__global__ void __launch_bounds__(256) head_softmax_kernel(float* __restrict__ logits, const float* __restrict__ lpart, int S,
+                                                           const float* __restrict__ bias, const int64_t* __restrict__ label,
+                                                           int B, int C, float grad_scale, float* __restrict__ dlogits,
+                                                           float* __restrict__ rowloss) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float* row = logits + (size_t)b * C;
+  if (lpart != nullptr) {
+    const size_t n = (size_t)B * C;
+    for (int c = lane; c < C; c += 32) {
+      float t = 0.f;
+      for (int sp = 0; sp < S; ++sp) t += __ldcg(lpart + (size_t)sp * n + (size_t)b * C + c);
+      row[c] = t + (bias != nullptr ? bias[c] : 0.f);
+    }
+    __syncwarp();
+  }
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+  m = mla::warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+  s = mla::warp_sum(s);
+  const float lse = logf(s);
+  const long long lab64 = label[b];
+  const bool ok = lab64 >= 0 && lab64 < (long long)C;
+  const int lab = ok ? (int)lab64 : 0;
+  const float nan = __int_as_float(0x7fc00000);
+  if (dlogits != nullptr)
+    for (int c = lane; c < C; c += 32)
+      dlogits[(size_t)b * C + c] = ok ? (expf(row[c] - m - lse) - (c == lab ? 1.f : 0.f)) * grad_scale : nan;
+  if (lane == 0) rowloss[b] = ok ? -(row[lab] - m - lse) : nan;
+}
+
+// block c < C: db[c] = sum_b dl[b][c] (lanes over b, fixed tree over the 8 warps); block C: loss = mean of the row losses
+__global__ void __launch_bounds__(256) head_db_loss_kernel(const float* __restrict__ dl, const float* __restrict__ rowloss, int B,
+                                                           int C, float* __restrict__ db, float* __restrict__ loss) {
+  __shared__ float s_red[32];
+  const int c = blockIdx.x;
+  float t = 0.f;
+  if (c < C) {
+    if (db == nullptr || dl == nullptr) return;
+    for (int b = threadIdx.x; b < B; b += 256) t += dl[(size_t)b * C + c];
+    t = mla::block_sum(t, s_red);
+    if (threadIdx.x == 0) db[c] = t;
+  } else {
+    if (loss == nullptr) return;
+    for (int b = threadIdx.x; b < B; b += 256) t += rowloss[b];
+    t = mla::block_sum(t, s_red);
+    if (threadIdx.x == 0) *loss = t / (float)B;
+  }
+}
+
+// partial[s][rows][D] -> dW rows [0, C) and feat_sum (row C), splits added in order
+__global__ void __launch_bounds__(256) head_split_reduce_kernel(const float* __restrict__ part, int S, int C, int D,
+                                                                float* __restrict__ dW, float* __restrict__ feat_sum) {
+  const long long n = (long long)(C + 1) * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += __ldcg(part + (size_t)s * n + i);
+    if (i < (long long)C * D) { if (dW) dW[i] = t; }
+    else if (feat_sum) feat_sum[i - (long long)C * D] = t;
+  }
+}
+
+struct LargePlan { int S, k_per_split, S1, k1_per_split; size_t off_logits, off_rowloss, off_part, off_lpart, bytes; };
+LargePlan large_plan(int B, int D, int C) {
+  LargePlan pl;
+  const mla::DeviceInfo& di = mla::device_info();
+  const int sms = di.ok == 1 ? di.sm_count : 148;
+  const int tiles = ((C + 1 + kGT - 1) / kGT) * ((D + kGT - 1) / kGT);
+  int S = std::max(1, std::min((2 * sms + tiles - 1) / tiles, B / 128));      // >= 128 batch rows per split, ~2 CTAs per SM
+  S = std::min(S, 32);
+  pl.k_per_split = ((B + S - 1) / S + kGK - 1) / kGK * kGK;
+  pl.S = (B + pl.k_per_split - 1) / pl.k_per_split;
+  pl.off_logits = mla::align_up((size_t)B * C * 4, 256);                       // [0, off_logits): dlogits
+  pl.off_rowloss = pl.off_logits + mla::align_up((size_t)B * C * 4, 256);
+  pl.off_part = pl.off_rowloss + mla::align_up((size_t)B * 4, 256);
+  // the logits GEMM is split over D when its (batch tile, class tile) grid alone would leave most SMs idle (small batches):
+  // >= 64 columns per split; the partials are added in split order by the softmax kernel
+  const int tiles1 = ((B + kGT - 1) / kGT) * ((C + kGT - 1) / kGT);
+  int S1 = std::max(1, std::min(std::min((sms + tiles1 - 1) / tiles1, D / 64), 32));
+  pl.k1_per_split = ((D + S1 - 1) / S1 + kGK - 1) / kGK * kGK;
+  pl.S1 = (D + pl.k1_per_split - 1) / pl.k1_per_split;
+  pl.off_lpart = pl.off_part + mla::align_up((size_t)pl.S * (C + 1) * D * 4, 256);
+  pl.bytes = pl.off_lpart + (pl.S1 > 1 ? mla::align_up((size_t)pl.S1 * B * C * 4, 256) : 0);
+  return pl;
+}
+
+int run_large(const float* feat, const float* W, const float* bias, const int64_t* label, int B, int D, int C, float* logits,
+              float* loss, float* dW, float* db, float* dfeat, float* feat_sum, float grad_scale, void* ws, cudaStream_t st) {
+  const LargePlan pl = large_plan(B, D, C);
+  char* base = static_cast<char*>(ws);
+  float* dl = reinterpret_cast<float*>(base);
+  float* lg = logits != nullptr ? logits : reinterpret_cast<float*>(base + pl.off_logits);
+  float* rowloss = reinterpret_cast<float*>(base + pl.off_rowloss);
+  float* part = reinterpret_cast<float*>(base + pl.off_part);
+  const bool need_bwd = dW || db || dfeat;
+  const dim3 blk(256);
+  float* lpart = pl.S1 > 1 ? reinterpret_cast<float*>(base + pl.off_lpart) : nullptr;
+  head_gemm_kernel<true, false><<<dim3((C + kGT - 1) / kGT, (B + kGT - 1) / kGT, pl.S1), blk, 0, st>>>(
+      feat, D, W, D, lpart != nullptr ? lpart : lg, C, B, C, D, pl.k1_per_split, lpart != nullptr ? nullptr : bias, -1);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  head_softmax_kernel<<<(B + 7) / 8, 256, 0, st>>>(lg, lpart, pl.S1, bias, label, B, C, grad_scale, need_bwd ? dl : nullptr,
+                                                   rowloss);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  if (dfeat != nullptr) {
+    head_gemm_kernel<true, true><<<dim3((D + kGT - 1) / kGT, (B + kGT - 1) / kGT, 1), blk, 0, st>>>(
+        dl, C, W, D, dfeat, D, B, D, C, C, nullptr, -1);
+    MLA_CUDA_TRY(cudaGetLastError());
+    mla::count_launch();
+  }
+  if (dW != nullptr || feat_sum != nullptr) {
+    // rows [0, C) = dlogits^T feat (only when gradients are wanted), last row = the virtual all-ones row = sum_b feat.
+    // Always through the partial buffer: the reduction also splits the rows into dW and feat_sum.
+    const int rows = dW != nullptr ? C + 1 : 1, ones = dW != nullptr ? C : 0;
+    head_gemm_kernel<false, true><<<dim3((D + kGT - 1) / kGT, (rows + kGT - 1) / kGT, pl.S), blk, 0, st>>>(
+        dl, C, feat, D, part, D, rows, D, B, pl.k_per_split, nullptr, ones);
+    MLA_CUDA_TRY(cudaGetLastError());
+    mla::count_launch();
+    const long long n = (long long)rows * D;
+    head_split_reduce_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 4LL * mla::device_info().sm_count), 256, 0, st>>>(
+        part, pl.S, rows - 1, D, dW, feat_sum);
+    MLA_CUDA_TRY(cudaGetLastError());
+    mla::count_launch();
+  }
+  head_db_loss_kernel<<<C + 1, 256, 0, st>>>(need_bwd ? dl : nullptr, rowloss, B, C, db, loss);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  return 0;
+}
+
 struct SmallPlan { int S, rows_per_split; size_t off_rowloss, off_part, bytes; };
 SmallPlan small_plan(int B, int D, int C) {
   SmallPlan pl;
@@ -439,8 +502,9 @@ int run_small(const float* feat, const float* W, const float* bias, const int64_
 
 extern "C" size_t mla_head_ce_workspace_bytes(int B, int D, int C) {
   if (B < 1 || D < 4 || C < 1) return 0;
-  if (C <= kSC) return small_plan(B, D, C).bytes;
-  return mla::align_up((size_t)B * C * 4, 256) + mla::align_up((size_t)B * 4, 256);
+  // the larger of the two plans: MLA_HEAD_SMALL=0 may route a small C through the tiled path
+  const size_t large = large_plan(B, D, C).bytes;
+  return C <= kSC ? std::max(small_plan(B, D, C).bytes, large) : large;
 }
 
 extern "C" int mla_head_ce(const float* feat, const float* W, const float* bias, const int64_t* label, int B, int D,
@@ -460,33 +524,5 @@ extern "C" int mla_head_ce(const float* feat, const float* W, const float* bias,
     if (C <= 8) return run_small<8>(feat, W, bias, label, B, D, C, logits, loss, dW, db, dfeat, feat_sum, grad_scale, ws, st);
     return run_small<16>(feat, W, bias, label, B, D, C, logits, loss, dW, db, dfeat, feat_sum, grad_scale, ws, st);
   }
-  float* dl = reinterpret_cast<float*>(ws);
-  float* rowloss = reinterpret_cast<float*>(static_cast<char*>(ws) + mla::align_up((size_t)B * C * 4, 256));
-  const bool need_bwd = dW || db || dfeat;
-
-  const int Cpad = (C + 31) & ~31;
-  const size_t smem1 = ((size_t)kFwdWarps * D + (size_t)kFwdWarps * Cpad) * sizeof(float);
-  if (smem1 > (size_t)di.smem_optin) return MLA_E_SHAPE;
-  static std::atomic<size_t> s_smem_set{48 * 1024};
-  if (smem1 > s_smem_set.load(std::memory_order_relaxed)) {
-    MLA_CUDA_TRY(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
-    s_smem_set.store((size_t)di.smem_optin, std::memory_order_relaxed);
-  }
-  int grid1 = (B + kFwdWarps - 1) / kFwdWarps;
-  grid1 = grid1 > 4 * di.sm_count ? 4 * di.sm_count : grid1;
-  head_fwd_kernel<<<grid1, kFwdThreads, smem1, st>>>(feat, W, bias, label, B, D, C, grad_scale, logits,
-                                                    need_bwd ? dl : nullptr, rowloss);
-  MLA_CUDA_TRY(cudaGetLastError());
-  mla::count_launch();
-
-  const int ncc = (C + kTile - 1) / kTile;
-  const int nbc = dfeat ? (B + kTile - 1) / kTile : 0;
-  // without backward outputs a single c-chunk still produces feat_sum / loss
-  const int ny = (need_bwd ? ncc : 1) + nbc;
-  dim3 grid2((D + kBwdThreads - 1) / kBwdThreads, ny);
-  head_bwd_kernel<<<grid2, kBwdThreads, 0, st>>>(feat, W, need_bwd ? dl : nullptr, rowloss, B, D, C,
-                                                need_bwd ? ncc : 1, dW, db, dfeat, feat_sum, loss);
-  MLA_CUDA_TRY(cudaGetLastError());
-  mla::count_launch();
-  return 0;
+  return run_large(feat, W, bias, label, B, D, C, logits, loss, dW, db, dfeat, feat_sum, grad_scale, ws, st);
 }
