@@ -150,7 +150,11 @@ def test_head_vs_reference_fixture(ops, golden, name):
     assert relf(o["feat_sum"].cpu().numpy(), g[k + "feat"].astype(np.float64).sum(0)) < 1e-6
 
 
-@pytest.mark.parametrize("B,D,C", [(64, 512, 6), (64, 768, 101), (64, 768, 4), (3, 2048, 33), (517, 512, 6), (1, 64, 1)])
+@pytest.mark.parametrize("B,D,C", [(64, 512, 6), (64, 768, 101), (64, 768, 4), (3, 2048, 33), (517, 512, 6), (1, 64, 1),
+                                   # the tiled large-C path: tile edges (C = 17, 64, 65, 129), the logits GEMM split over D (small
+                                   # batches), the weight-gradient GEMM split over the batch (B >= 256), narrow / ragged D
+                                   (64, 768, 17), (130, 132, 65), (1, 2048, 64), (4096, 64, 129), (1000, 516, 101), (2, 4, 20),
+                                   (333, 1024, 1000)])
 def test_head_vs_oracle_seeded(ops, B, D, C):
     rng = np.random.default_rng(B + D + C)
     feat = np.maximum(rng.standard_normal((B, D)), 0).astype(np.float32)
@@ -164,6 +168,9 @@ def test_head_vs_oracle_seeded(ops, B, D, C):
     assert abs(float(o["loss"]) - ref["loss"]) < 1e-5 * max(1, abs(ref["loss"]))
     fwd = ops.head_ce(dev(feat), dev(W), dev(b), dev(lab, torch.int64), need_grad=False)
     assert torch.equal(fwd["logits"], o["logits"]) and fwd["dW"] is None
+    assert relf(fwd["feat_sum"].cpu().numpy(), ref["feat_sum"]) < 1e-5      # the forward-only call still emits sum_b feat
+    again = ops.head_ce(dev(feat), dev(W), dev(b), dev(lab, torch.int64), grad_scale=1.0 / (2 * B))
+    assert all(torch.equal(again[k], o[k]) for k in ("logits", "dW", "db", "dfeat", "feat_sum", "loss"))      # deterministic
 
 
 def test_head_out_of_range_label_poisons_the_loss(ops):
