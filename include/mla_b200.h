@@ -371,18 +371,22 @@ MLA_API int    mla_ogm_modulate(float* grad, const long long* seg_off, const lon
  * dataset/dataset.py:123-161 (same Compose at :448-480, :753-803): PIL RandomResizedCrop(+ RandomHorizontalFlip) or
  * Resize((OH, OW)) -> ToTensor -> Normalize -> T frames stacked on dim 1.
  *   src        packed uint8 HWC RGB frames (device), src_bytes long
- *   desc       DEVICE array [nframes][10] int32: {src offset lo, hi (bytes), H, W, crop top, left, crop_h, crop_w, flip,
- *              destination slot b * T + t}; the crop box is (0, 0, H, W) for the evaluation transform
+ *   desc       DEVICE array [nframes][14] int32: {src offset lo, hi (bytes), H, W, crop top, left, crop_h, crop_w, flip,
+ *              destination slot b * T + t, RH, RW, oy, ox}: the crop box is resampled to RH x RW and the [OH, OW] output is
+ *              the window of that image at (oy, ox). Resize((OH, OW)) / RandomResizedCrop: crop box (0, 0, H, W) or the
+ *              drawn one, RH = OH, RW = OW, oy = ox = 0. Resize(s) + CenterCrop(s) (dataset.py:251-256, 414-421): shorter
+ *              side -> s, (oy, ox) = the centre-crop origin.
+ *   filter     0 = BILINEAR (AVDataset), 1 = BICUBIC (CAVDataset, M3AEDataset)
  *   mean3/std3 HOST arrays of 3 floats (read at launch)
  *   out        [B, 3, T, OH, OW] fp32 — bit-identical to torchvision's PIL path (Pillow's two-pass antialiased bilinear
  *              resampling with 8-bit intermediate and 22-bit fixed-point coefficients, float(u8) / 255, (x - mean) / std)
  *   status     optional DEVICE int: 0, or 1 + the index of an invalid descriptor (such frames are skipped)
- * crop / output ratios up to 15.5 per axis (MLA_E_SHAPE is NOT raised for larger ones: they are reported through status).
+ * crop / output ratios up to 15.5 (bilinear) or 7.5 (bicubic) per axis; larger ones are reported through status.
  */
 MLA_API size_t mla_frames_to_batch_workspace_bytes(int nframes, int OH, int OW, int max_crop_h);
 MLA_API int    mla_frames_to_batch(const unsigned char* src, long long src_bytes, const int* desc, int nframes, int B, int T,
-                        int OH, int OW, int max_crop_h, const float* mean3, const float* std3, float* out, int* status,
-                        void* ws, size_t ws_bytes, void* stream);
+                        int OH, int OW, int max_crop_h, int filter, const float* mean3, const float* std3, float* out,
+                        int* status, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -2,12 +2,15 @@
 // sample on the CPU in dataset/dataset.py:123-161 (AVDataset.__getitem__; the same Compose in :448-480 / :753-803):
 //     PIL image -> RandomResizedCrop(224) [+ RandomHorizontalFlip]  |  Resize((224, 224))      (torchvision on PIL)
 //               -> ToTensor() -> Normalize(mean, std) -> frames stacked on a new dim 1: [3, T, 224, 224]
+// and the deterministic transform of the other datasets (CAVDataset :251-256, M3AEDataset test mode :414-421):
+//     Resize(s, BICUBIC) [shorter side -> s] -> CenterCrop(s) -> ToTensor() -> Normalize(mean, std)
 // Input: the decoded uint8 HWC RGB frames of a batch packed into one device buffer + one descriptor per frame (geometry,
 // crop box, flip, destination slot). Output: the model's input tensor [B, 3, T, OH, OW] fp32, BIT-IDENTICAL to the
 // torchvision / Pillow path:
 //   * Pillow's Image.resize(BILINEAR) (what torchvision's Resize / resized_crop call on PIL images) is a two-pass separable
 //     convolution with an antialiasing support that grows with the down-scaling factor (libImaging/Resample.c): per output
-//     coordinate, a window [xmin, xmin + n) of normalised triangle weights computed in double precision, converted to 22-bit
+//     coordinate, a window [xmin, xmin + n) of normalised filter weights (BILINEAR: triangle, support 1; BICUBIC: Keys
+//     a = -0.5, support 2) computed in double precision, converted to 22-bit
 //     fixed point ((int)(0.5 + k * 2^22)), accumulated in int32 from 2^21, shifted and clipped to 8 bits — horizontally into
 //     an 8-bit intermediate image first, then vertically. frame_coeffs_kernel restates precompute_coeffs() +
 //     normalize_coeffs_8bpc() operation by operation in IEEE double (explicit _rn intrinsics: no FMA contraction);
@@ -21,32 +24,42 @@ namespace {
 
 constexpr int kMaxK = 32;          // taps per output coordinate: ceil(scale) * 2 + 1 <= 32  ->  crop / out < 15.5
 constexpr int kPrec = 32 - 8 - 2;  // PRECISION_BITS of Resample.c
-constexpr int kDescInts = 10;      // {src offset lo, hi, H, W, top, left, crop_h, crop_w, flip, out slot}
+constexpr int kDescInts = 14;      // {src offset lo, hi, H, W, top, left, crop_h, crop_w, flip, out slot, RH, RW, oy, ox}
 
+// (RH, RW) = size the crop window is RESAMPLED to; the [OH, OW] output is the window of that image starting at (oy, ox):
+// Resize((OH, OW)) / RandomResizedCrop: RH = OH, RW = OW, oy = ox = 0;  Resize(s) + CenterCrop(s): the shorter side -> s,
+// (oy, ox) = the centre-crop origin (only the output window is ever computed; its pixels do not depend on the rest).
 struct Desc {
   long long off;
-  int H, W, top, left, ch, cw, flip, slot;
+  int H, W, top, left, ch, cw, flip, slot, RH, RW, oy, ox;
 };
 __device__ __forceinline__ Desc load_desc(const int* __restrict__ d, int f) {
   const int* p = d + (size_t)f * kDescInts;
   Desc r;
   r.off = (long long)(unsigned int)p[0] | ((long long)p[1] << 32);
   r.H = p[2]; r.W = p[3]; r.top = p[4]; r.left = p[5]; r.ch = p[6]; r.cw = p[7]; r.flip = p[8]; r.slot = p[9];
+  r.RH = p[10]; r.RW = p[11]; r.oy = p[12]; r.ox = p[13];
   return r;
 }
 
 struct Lim {
-  int OH, OW, max_crop_h, nslots;
+  int OH, OW, max_crop_h, nslots, bicubic;
   long long src_bytes;
 };
+// taps per output coordinate: (int)ceil(support) * 2 + 1, support = filter support (1 bilinear, 2 bicubic) * max(in / out, 1)
+__host__ __device__ __forceinline__ int taps(int in_size, int out_size, int bicubic) {
+  const int fs = bicubic ? 2 : 1;
+  const int up = in_size > out_size ? (fs * in_size + out_size - 1) / out_size : fs;       // ceil(fs * in / out)
+  return up * 2 + 1;
+}
 // A descriptor every kernel may act on: the crop window inside the frame, the frame inside the source buffer, the taps
 // within kMaxK (ceil(scale) * 2 + 1), the destination slot inside the batch. Invalid frames are skipped by every kernel and
 // reported through `status`.
 __device__ __forceinline__ bool desc_ok(const Desc& d, const Lim& l) {
   return d.H > 0 && d.W > 0 && d.ch > 0 && d.cw > 0 && d.top >= 0 && d.left >= 0 && d.top + d.ch <= d.H &&
          d.left + d.cw <= d.W && d.ch <= l.max_crop_h && d.slot >= 0 && d.slot < l.nslots && d.off >= 0 &&
-         d.off + (long long)d.H * d.W * 3 <= l.src_bytes && ((d.cw + l.OW - 1) / l.OW) * 2 + 1 <= kMaxK &&
-         ((d.ch + l.OH - 1) / l.OH) * 2 + 1 <= kMaxK;
+         d.off + (long long)d.H * d.W * 3 <= l.src_bytes && d.oy >= 0 && d.ox >= 0 && d.oy + l.OH <= d.RH &&
+         d.ox + l.OW <= d.RW && taps(d.cw, d.RW, l.bicubic) <= kMaxK && taps(d.ch, d.RH, l.bicubic) <= kMaxK;
 }
 
 // tables per frame: [axis 0 = horizontal: OW entries | axis 1 = vertical: OH entries], each entry {xmin, n, k[kMaxK]}
@@ -61,13 +74,15 @@ __global__ void __launch_bounds__(128) frame_coeffs_kernel(const int* __restrict
   const Desc d = load_desc(desc, f);
   if (!desc_ok(d, lim)) return;
   const int in_size = axis == 0 ? d.cw : d.ch;
+  const int full = axis == 0 ? d.RW : d.RH;                       // size of the resampled image along this axis
+  const int xf = xx + (axis == 0 ? d.ox : d.oy);                  // this output coordinate inside it
   int* e = tab + ((size_t)f * (OW + OH) + (axis == 0 ? 0 : OW) + xx) * kEntry;
-  // precompute_coeffs(inSize, in0 = 0, in1 = inSize, outSize, BILINEAR: support 1.0)
-  const double scale = __ddiv_rn((double)in_size, (double)out_size);
+  // precompute_coeffs(inSize, in0 = 0, in1 = inSize, outSize, filter): BILINEAR support 1.0, BICUBIC support 2.0 (a = -0.5)
+  const double scale = __ddiv_rn((double)in_size, (double)full);
   const double fscale = scale < 1.0 ? 1.0 : scale;
-  const double support = fscale;                                  // 1.0 * filterscale
+  const double support = __dmul_rn(lim.bicubic ? 2.0 : 1.0, fscale);
   const double ss = __ddiv_rn(1.0, fscale);
-  const double center = __dmul_rn((double)xx + 0.5, scale);       // in0 + (xx + 0.5) * scale, in0 = 0
+  const double center = __dmul_rn((double)xf + 0.5, scale);       // in0 + (xx + 0.5) * scale, in0 = 0
   int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
   if (xmin < 0) xmin = 0;
   int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
@@ -79,7 +94,15 @@ __global__ void __launch_bounds__(128) frame_coeffs_kernel(const int* __restrict
   for (int x = 0; x < xmax; ++x) {
     double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
     if (a < 0.0) a = -a;
-    const double w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+    double w;
+    if (lim.bicubic) {
+      // bicubic_filter, a = -0.5:  |x| < 1: ((a + 2) x - (a + 3)) x x + 1;  |x| < 2: (((x - 5) x + 8) x - 4) a
+      if (a < 1.0) w = __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.5, a), 2.5), a), a), 1.0);
+      else if (a < 2.0) w = __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(a, 5.0), a), 8.0), a), 4.0), -0.5);
+      else w = 0.0;
+    } else {
+      w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+    }
     k[x] = w;
     ww = __dadd_rn(ww, w);
   }
@@ -175,10 +198,10 @@ extern "C" size_t mla_frames_to_batch_workspace_bytes(int nframes, int OH, int O
 }
 
 extern "C" int mla_frames_to_batch(const unsigned char* src, long long src_bytes, const int* desc, int nframes, int B, int T,
-                                   int OH, int OW, int max_crop_h, const float* mean3, const float* std3, float* out,
-                                   int* status, void* ws, size_t ws_bytes, void* stream) {
+                                   int OH, int OW, int max_crop_h, int filter, const float* mean3, const float* std3,
+                                   float* out, int* status, void* ws, size_t ws_bytes, void* stream) {
   if (!src || !desc || !mean3 || !std3 || !out || nframes < 1 || B < 1 || T < 1 || OH < 1 || OW < 1 || max_crop_h < 1 ||
-      src_bytes < 1)
+      src_bytes < 1 || (filter != 0 && filter != 1))
     return MLA_E_BADARG;
   if ((long long)OH * OW >= (1LL << 30)) return MLA_E_SHAPE;
   const size_t need = mla_frames_to_batch_workspace_bytes(nframes, OH, OW, max_crop_h);
@@ -189,7 +212,7 @@ extern "C" int mla_frames_to_batch(const unsigned char* src, long long src_bytes
   unsigned char* tmp = reinterpret_cast<unsigned char*>(base + 256 + tab_bytes(nframes, OH, OW));
   const long long tmp_stride = (long long)max_crop_h * OW * 3;
   Lim lim;
-  lim.OH = OH; lim.OW = OW; lim.max_crop_h = max_crop_h; lim.nslots = B * T; lim.src_bytes = src_bytes;
+  lim.OH = OH; lim.OW = OW; lim.max_crop_h = max_crop_h; lim.nslots = B * T; lim.bicubic = filter; lim.src_bytes = src_bytes;
   if (status != nullptr) {
     MLA_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     frame_check_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(desc, nframes, lim, status);

@@ -4,6 +4,10 @@ sample on CPU workers (dataset/dataset.py:123-161 `AVDataset.__getitem__`; the s
     train:  RandomResizedCrop(224) -> RandomHorizontalFlip() -> ToTensor() -> Normalize(IMAGENET_MEAN, IMAGENET_STD)
     test:   Resize(size=(224, 224))                          -> ToTensor() -> Normalize(...)
     frames of a sample stacked on a new dim 1 -> [3, T, 224, 224]
+and the deterministic transform of the other datasets (CAVDataset dataset.py:251-256, M3AEDataset test mode :414-421):
+    center: Resize(s, BICUBIC) [shorter side -> s] -> CenterCrop(s) -> ToTensor() -> Normalize(...)
+(M3AEDataset's TRAINING transform is timm's create_transform — RandomResizedCropAndInterpolation + colour jitter from the
+un-vendored timm==0.4.5 — and is not reproduced.)
 
 `FrameBatchProducer` takes the DECODED frames (uint8 HWC RGB arrays: decoding stays on the host, PIL / the loader's
 workers), draws the crop / flip parameters on the host exactly as torchvision does — same functions, same order of torch
@@ -50,17 +54,32 @@ def random_resized_crop_params(height, width, scale=(0.08, 1.0), ratio=(3.0 / 4.
     return (height - h) // 2, (width - w) // 2, h, w
 
 
+def resize_center_crop_params(height, width, size):
+    """Resize(size) + CenterCrop(size) on a PIL image (torchvision.transforms.functional): the shorter side becomes `size`,
+    the longer int(size * long / short); the crop origin is int(round((extent - size) / 2.0)) (Python's round).
+    Returns (RH, RW, oy, ox)."""
+    if width <= height:
+        rw, rh = size, int(size * height / width)
+    else:
+        rh, rw = size, int(size * width / height)
+    return rh, rw, int(round((rh - size) / 2.0)), int(round((rw - size) / 2.0))
+
+
 class FrameBatchProducer:
     """producer(batch_of_frames) -> CUDA tensor [B, 3, T, size, size], the `image` member of the reference's batch tuple
     (main.py:159). `batch_of_frames`: B samples x T frames, each a uint8 numpy array [H, W, 3] (any sizes).
 
     mode 'train' draws RandomResizedCrop + RandomHorizontalFlip parameters per frame in the reference's order (crop, then
-    flip: one Compose call per frame, dataset.py:147-150); mode 'test' resizes whole frames. Explicit `params` (a list of
-    (top, left, h, w, flip) per frame, sample-major) override the random draws."""
+    flip: one Compose call per frame, dataset.py:147-150); mode 'test' resizes whole frames; mode 'center' = Resize(size) +
+    CenterCrop(size). `interpolation` 'bilinear' (AVDataset) or 'bicubic' (CAVDataset / M3AEDataset). Explicit `params` (a
+    list of (top, left, h, w, flip) per frame, sample-major) override the random draws."""
 
-    def __init__(self, size=224, mode="train", mean=IMAGENET_MEAN, std=IMAGENET_STD, device="cuda"):
-        if mode not in ("train", "test"):
-            raise ValueError("mode must be 'train' or 'test'")
+    def __init__(self, size=224, mode="train", mean=IMAGENET_MEAN, std=IMAGENET_STD, device="cuda", interpolation="bilinear"):
+        if mode not in ("train", "test", "center"):
+            raise ValueError("mode must be 'train', 'test' or 'center'")
+        if interpolation not in ("bilinear", "bicubic"):
+            raise ValueError("interpolation must be 'bilinear' or 'bicubic'")
+        self.bicubic = interpolation == "bicubic"
         self.size, self.mode, self.mean, self.std = int(size), mode, tuple(mean), tuple(std)
         self.device = torch.device(device)
         self._pinned = None
@@ -95,23 +114,27 @@ class FrameBatchProducer:
         if self._pinned is None or self._pinned.numel() < total:
             self._pinned = torch.empty(total, dtype=torch.uint8).pin_memory() if self.device.type == "cuda" else torch.empty(total, dtype=torch.uint8)
         host = self._pinned[:total].numpy()
-        desc = np.zeros((len(frames), 10), np.int32)
+        desc = np.zeros((len(frames), 14), np.int32)
         off = 0
         for n, (f, (i, j, h, w, flip)) in enumerate(zip(frames, params)):
             host[off:off + f.size] = f.reshape(-1)
             lo = off & 0xFFFFFFFF
+            if self.mode == "center":                              # the (whole-frame) box is resized, then centre-cropped
+                rh, rw, oy, ox = resize_center_crop_params(h, w, self.size)
+            else:
+                rh, rw, oy, ox = self.size, self.size, 0, 0
             desc[n] = (lo - (1 << 32) if lo >= (1 << 31) else lo, off >> 32, f.shape[0], f.shape[1], i, j, h, w,
-                       1 if flip else 0, n)
+                       1 if flip else 0, n, rh, rw, oy, ox)
             off += f.size
         src = self._pinned[:total].to(self.device, non_blocking=True)
         ddesc = torch.from_numpy(desc).to(self.device, non_blocking=True)
         if self._status is None:
             self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         res = ops.frames_to_batch(src, ddesc, B, T, self.size, max(p[2] for p in params), self.mean, self.std, out=out,
-                                  status=self._status if check else None)
+                                  status=self._status if check else None, bicubic=self.bicubic)
         if check:
             bad = int(self._status.item())
             if bad:
                 raise RuntimeError("frame %d has an invalid descriptor (crop outside the frame, or a crop / output ratio above "
-                                   "15.5)" % (bad - 1))
+                                   "15.5 bilinear / 7.5 bicubic)" % (bad - 1))
         return res

@@ -29,6 +29,34 @@ def rank():
     return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
 
 
+def bind_host_to_gpu(device_index=None):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs `local_cpulist` of the GPU's PCI function), so
+    that the pinned host batches it allocates afterwards live in that node's memory: with one process per GPU on a
+    two-socket box, unpinned processes put most input buffers on the wrong socket and the per-step H2D copies of all ranks
+    (8 x 89 MB for configs[1]) funnel through the inter-socket link. Returns the CPU set, or None when the topology is not
+    exposed (containers without sysfs NUMA data, single-node hosts): then nothing changes. MLA_NUMA_BIND=0 disables it."""
+    if os.environ.get("MLA_NUMA_BIND", "1") == "0" or not torch.cuda.is_available() or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        idx = torch.cuda.current_device() if device_index is None else device_index
+        pr = torch.cuda.get_device_properties(idx)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)                  # never widen what the launcher / cgroup allows
+        if not cpus or cpus == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from torchrun's environment (RANK/WORLD_SIZE/LOCAL_RANK/MASTER_*)."""
     ws = int(os.environ.get("WORLD_SIZE", "1"))
@@ -38,6 +66,7 @@ def init_from_env(backend=None):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        bind_host_to_gpu()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group(backend=backend)
     return rank(), world_size()

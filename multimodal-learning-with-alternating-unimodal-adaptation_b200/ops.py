@@ -205,13 +205,14 @@ def ogm_modulate(flat_grad, seg_off, seg_len, max_len, coeff, noise=None, seg_st
 # ----------------------------------------------------------------------------------------------
 # Encoder convolutions (NHWC activations, [Cout][R][S][Cin] weights)
 # ----------------------------------------------------------------------------------------------
-def frames_to_batch(src, desc, B, T, size, max_crop_h, mean, std, out=None, status=None):
-    """uint8 HWC RGB frames -> the visual input tensor [B, 3, T, OH, OW] (dataset/dataset.py:123-161). `src` = packed frames
-    (uint8, CUDA), `desc` = int32 CUDA tensor [nframes, 10] (see mla_frames_to_batch), `status` = optional int32 CUDA scalar."""
+def frames_to_batch(src, desc, B, T, size, max_crop_h, mean, std, out=None, status=None, bicubic=False):
+    """uint8 HWC RGB frames -> the visual input tensor [B, 3, T, OH, OW] (dataset/dataset.py:123-161, 251-256, 414-421).
+    `src` = packed frames (uint8, CUDA), `desc` = int32 CUDA tensor [nframes, 14] (see mla_frames_to_batch), `status` =
+    optional int32 CUDA scalar."""
     L = _lib.lib()
     _need_cuda(src, desc, out, status)
-    if src.dtype != torch.uint8 or desc.dtype != torch.int32 or desc.dim() != 2 or desc.shape[1] != 10:
-        raise RuntimeError("frames_to_batch: src must be uint8 and desc int32 [nframes, 10]")
+    if src.dtype != torch.uint8 or desc.dtype != torch.int32 or desc.dim() != 2 or desc.shape[1] != 14:
+        raise RuntimeError("frames_to_batch: src must be uint8 and desc int32 [nframes, 14]")
     OH, OW = (size, size) if isinstance(size, int) else size
     nframes = desc.shape[0]
     if out is None:
@@ -226,7 +227,8 @@ def frames_to_batch(src, desc, B, T, size, max_crop_h, mean, std, out=None, stat
     ws = _workspace("frames", nbytes, src.device)
     m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
-    rc = L.mla_frames_to_batch(_lib.ptr(src), src.numel(), _lib.ptr(desc), nframes, B, T, OH, OW, int(max_crop_h), m3, s3,
+    rc = L.mla_frames_to_batch(_lib.ptr(src), src.numel(), _lib.ptr(desc), nframes, B, T, OH, OW, int(max_crop_h),
+                               1 if bicubic else 0, m3, s3,
                                _lib.ptr(out), _lib.ptr(status), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "mla_frames_to_batch")
     return out

@@ -703,13 +703,26 @@ def math_isclose(a, b, rel):
 PIL_PRECISION_BITS = 32 - 8 - 2
 
 
-def pil_bilinear_coeffs(in_size, out_size):
-    """(bounds [out, 2] = (xmin, n), fixed-point coefficients [out, ksize] int32) of Pillow's BILINEAR filter for a full-box
-    resize in_size -> out_size: support = max(scale, 1), triangle weights normalised per output coordinate in double,
-    then (int)(+-0.5 + k * 2^22)."""
+def _pil_filter(x, bicubic):
+    """Resample.c: bilinear_filter (support 1) / bicubic_filter (support 2, a = -0.5)."""
+    x = -x if x < 0.0 else x
+    if not bicubic:
+        return 1.0 - x if x < 1.0 else 0.0
+    a = -0.5
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_bilinear_coeffs(in_size, out_size, bicubic=False):
+    """(bounds [out, 2] = (xmin, n), fixed-point coefficients [out, ksize] int32) of Pillow's BILINEAR (or BICUBIC) filter
+    for a full-box resize in_size -> out_size: support = filter support * max(scale, 1), weights normalised per output
+    coordinate in double, then (int)(+-0.5 + k * 2^22)."""
     scale = float(in_size) / out_size
     fscale = max(scale, 1.0)
-    support = 1.0 * fscale
+    support = (2.0 if bicubic else 1.0) * fscale
     ksize = int(math.ceil(support)) * 2 + 1
     ss = 1.0 / fscale
     bounds = np.zeros((out_size, 2), np.int32)
@@ -720,9 +733,7 @@ def pil_bilinear_coeffs(in_size, out_size):
         xmax = min(int(center + support + 0.5), in_size) - xmin
         ww = 0.0
         for x in range(xmax):
-            a = (x + xmin - center + 0.5) * ss
-            a = -a if a < 0.0 else a
-            w = 1.0 - a if a < 1.0 else 0.0
+            w = _pil_filter((x + xmin - center + 0.5) * ss, bicubic)
             kk[xx, x] = w
             ww += w
         if ww != 0.0:
@@ -734,9 +745,9 @@ def pil_bilinear_coeffs(in_size, out_size):
     return bounds, ki
 
 
-def _pil_pass(img, out_size, axis):
+def _pil_pass(img, out_size, axis, bicubic=False):
     """One resampling pass along `axis` (1 = horizontal, 0 = vertical) of a uint8 [H, W, C] image."""
-    bounds, k = pil_bilinear_coeffs(img.shape[axis], out_size)
+    bounds, k = pil_bilinear_coeffs(img.shape[axis], out_size, bicubic)
     shape = list(img.shape)
     shape[axis] = out_size
     out = np.zeros(shape, np.uint8)
@@ -754,15 +765,29 @@ def _pil_pass(img, out_size, axis):
     return out
 
 
-def pil_resize_u8(img, out_h, out_w):
-    """Image.resize((out_w, out_h), BILINEAR) of a uint8 [H, W, C] array: horizontal pass into an 8-bit intermediate, then
-    the vertical pass (Resample.c:ImagingResampleInner; a pass whose size does not change is skipped, as Pillow does)."""
+def pil_resize_u8(img, out_h, out_w, bicubic=False):
+    """Image.resize((out_w, out_h), BILINEAR | BICUBIC) of a uint8 [H, W, C] array: horizontal pass into an 8-bit
+    intermediate, then the vertical pass (Resample.c:ImagingResampleInner; a pass whose size does not change is skipped, as
+    Pillow does)."""
     img = np.ascontiguousarray(img)
     if img.shape[1] != out_w:
-        img = _pil_pass(img, out_w, 1)
+        img = _pil_pass(img, out_w, 1, bicubic)
     if img.shape[0] != out_h:
-        img = _pil_pass(img, out_h, 0)
+        img = _pil_pass(img, out_h, 0, bicubic)
     return img
+
+
+def resize_center_crop_u8(img, size, bicubic=True):
+    """transforms.Resize(size, BICUBIC) + transforms.CenterCrop(size) on a PIL image (dataset/dataset.py:251-253, 415-416):
+    shorter side -> size, longer side int(size * long / short), crop origin int(round((extent - size) / 2.0))."""
+    H, W = img.shape[:2]
+    if W <= H:
+        rw, rh = size, int(size * H / W)
+    else:
+        rh, rw = size, int(size * W / H)
+    r = pil_resize_u8(img, rh, rw, bicubic)
+    oy, ox = int(round((rh - size) / 2.0)), int(round((rw - size) / 2.0))
+    return r[oy:oy + size, ox:ox + size]
 
 
 def frames_to_tensor(batch_of_frames, params, size, mean, std):

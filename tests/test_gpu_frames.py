@@ -87,5 +87,25 @@ def test_identity_resize_and_errors(producer_cls):
         prod([[f]], params=[(200, 0, 100, 100, False)])                         # crop leaves the frame
     with pytest.raises(RuntimeError):
         producer_cls(8, "test")([[f]])                                          # 224 / 8 = 28 > 15.5: outside the tap budget
+    with pytest.raises(RuntimeError):
+        producer_cls(24, "test", interpolation="bicubic")([[f]])                # 224 / 24 = 9.3 > 7.5 for the bicubic filter
     with pytest.raises(ValueError):
         prod([[f.astype(np.float32)]])
+
+
+@pytest.mark.parametrize("shapes,size", [([(360, 480), (480, 360), (224, 224), (301, 500)], 224),
+                                         ([(256, 341), (1000, 700), (230, 229), (260, 256)], 256)])
+def test_bicubic_resize_center_crop_equals_torchvision_bit_for_bit(producer_cls, shapes, size):
+    """dataset.py:251-256 (CAVDataset.preprocess, size 224) and :414-421 (M3AEDataset.preprocess_test, size 256):
+    Resize(s, BICUBIC) -> CenterCrop(s) -> ToTensor -> Normalize. Only the crop window is computed on the GPU."""
+    from PIL import Image
+    from torchvision import transforms
+    rng = np.random.default_rng(size + shapes[1][0])
+    frames = [[_frame(rng, *hw)] for hw in shapes]
+    mean, std = [0.4850, 0.4560, 0.4060], [0.2290, 0.2240, 0.2250]
+    tf = transforms.Compose([transforms.Resize(size, interpolation=transforms.InterpolationMode.BICUBIC),
+                             transforms.CenterCrop(size), transforms.ToTensor(), transforms.Normalize(mean=mean, std=std)])
+    ref = torch.stack([tf(Image.fromarray(s[0])) for s in frames])
+    out = producer_cls(size, "center", mean, std, interpolation="bicubic")(frames)
+    assert out.shape == (4, 3, 1, size, size)
+    assert torch.equal(out.cpu()[:, :, 0], ref)

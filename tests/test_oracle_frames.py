@@ -77,3 +77,21 @@ def test_committed_fixture():
     params = [tuple(int(v) for v in p[:4]) + (bool(p[4]),) for p in g["params"]]
     out = orc.frames_to_tensor(frames, params, int(g["size"]), g["mean"], g["std"])
     assert np.array_equal(out, g["expected"])
+
+
+@pytest.mark.parametrize("H,W,size", [(360, 480, 224), (480, 360, 224), (224, 224, 224), (301, 500, 224), (256, 341, 256),
+                                      (1000, 700, 256), (230, 229, 224)])
+def test_bicubic_resize_center_crop_restatement_matches_the_reference_compose(H, W, size):
+    """dataset.py:251-256 (CAVDataset.preprocess) / :414-421 (M3AEDataset.preprocess_test) through torchvision itself."""
+    import PIL
+    from PIL import Image
+    from torchvision import transforms
+    from mla_b200.dataset import resize_center_crop_params
+    img = _frame(np.random.default_rng(H * 3 + W), H, W)
+    tf = transforms.Compose([transforms.Resize(size, interpolation=transforms.InterpolationMode.BICUBIC),
+                             transforms.CenterCrop(size)])
+    ref = np.asarray(tf(Image.fromarray(img)))
+    assert np.array_equal(orc.resize_center_crop_u8(img, size), ref)
+    rh, rw, oy, ox = resize_center_crop_params(H, W, size)
+    full = np.asarray(Image.fromarray(img).resize((rw, rh), PIL.Image.BICUBIC))
+    assert np.array_equal(full[oy:oy + size, ox:ox + size], ref)               # the host mirror's window arithmetic
