@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------------------------
 // Large-C path (C > 16: Food-101's 101 classes): the head is three small fp32 GEMMs, bound by the FMA rate rather than HBM
 // (6 B D C FLOP against 4 (2 B D + 3 C D + 2 B C) bytes: 150 FLOP / byte at C = 101). fp32 accuracy is part of the contract
-// (rel 1e-5 against the fp64 oracle), so they run on the CUDA cores: one register-tiled kernel (64 x 64 tile, 4 x 4 per
+// (rel 1e-5 against an fp64 evaluation), so they run on the CUDA cores: one register-tiled kernel (64 x 64 tile, 4 x 4 per
 // thread, 16-deep k-steps, operands staged transposed in shared memory so that every thread reads two float4 per 16 FMAs)
 // instantiated for the three operand layouts:
 //   logits = feat W^T (+ b)          A = feat [B][D] (k contiguous), B = W [C][D] (k contiguous)

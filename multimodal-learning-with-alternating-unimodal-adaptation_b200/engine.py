@@ -195,6 +195,7 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
         losses = []
         pending = []
         for m, feat in enumerate(feats):                                   # a -> v -> (t)
+            deferred_m = None
             if feat_streams is not None:           # this turn starts as soon as ITS encoder's forward has finished
                 torch.cuda.current_stream().wait_stream(feat_streams[m])
                 feat.record_stream(torch.cuda.current_stream())
@@ -232,6 +233,7 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                     # turn's small head all-reduce behind this whole backward pass and serialise the two encoders again)
                     st.flat[m].detach()
                     pending.append((m, stream))
+                    deferred_m = m
             else:                                  # autograd encoders (m3ae): gradients ACCUMULATE into the views
                 st.flat[m].attach(zero=True)
                 feat.backward(o["dfeat"])
@@ -241,16 +243,22 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                                     feat_sum=o["feat_sum"], inv_batch=inv_global)     # main.py:437-438
             optimizer.step()                                               # main.py:439
             optimizer.zero_grad()                                          # main.py:440
+            if deferred_m is not None:
+                # the deferred encoder's own SGD update (its share of main.py:439), queued on ITS side stream behind its
+                # backward pass and gradient buckets: it runs while the next turn is busy instead of at the end of the step.
+                # Only this encoder's gradients are attached at this point (the head's were just cleared), so the caller's
+                # optimizer touches nothing else; parameters and momentum buffers of different encoders are disjoint.
+                with torch.cuda.stream(pending[-1][1]):
+                    if world > 1:
+                        st.buckets[deferred_m].wait()                      # its buckets were issued during the backward
+                    st.flat[deferred_m].attach()
+                    optimizer.step()
+                    optimizer.zero_grad()
+                deferred_m = None
             gs_plugin.exp_count += 1                                       # main.py:442
             losses.append(o["loss"].clone())
-        if pending:                                                        # deferred encoder updates (main.py:439)
-            for m, stream in pending:
-                torch.cuda.current_stream().wait_stream(stream)
-                if world > 1:
-                    st.buckets[m].wait()                                   # its buckets were issued during the backward
-                st.flat[m].attach()
-            optimizer.step()
-            optimizer.zero_grad()
+        for m, stream in pending:                                          # the next forward reads the updated encoders
+            torch.cuda.current_stream().wait_stream(stream)
         # main.py:472 (fp32, like the reference; with three modalities the mixed loss still ignores the third)
         mix = losses[0] * av_alpha + losses[1] * (1 - av_alpha)
         step_vec = torch.cat([mix] + losses).double()                      # (_loss, _loss_a, _loss_v[, _loss_t]) of this step
