@@ -261,7 +261,7 @@ def producer_leg(torch, pk):
     mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
     t, nsets = _time_launch(torch, mk, lambda s: ops.frames_to_batch(s[0], s[1], B, T, S, H, mean, std, out=s[2]), nbytes,
                             launches=12)
-    return {"kernels": "frame_coeffs_kernel + frame_hpass_kernel + frame_vpass_kernel", "us": t * 1e6, "bytes": nbytes,
+    return {"kernels": "frame_coeffs_kernel + frame_resample_kernel", "us": t * 1e6, "bytes": nbytes,
             "gbs": nbytes / t / 1e9, "frac_of_hbm_peak": nbytes / t / 1e9 / pk["hbm"], "samples_per_s": B / t, "sets": nsets,
             "workload": "64 x 2 frames 360x480x3 uint8 -> [64,3,2,224,224] fp32, bit-identical to torchvision on PIL"}
 
@@ -576,10 +576,10 @@ def run_native(a, rank, world):
                       for k, v in conv["by_kind"].items())
         peak = conv["flops"] / t_ideal / 1e12
         ach = conv["flops"] / conv["seconds"] / 1e12
-        out["roofline"] = {"kernel": "conv16_persistent_kernel (fprop16 / dgrad16) + conv_gemm_kernel (wgrad16): tcgen05 implicit GEMM, im2col-TMA fed, kind::f16 (fp16 operands, scaled fp16 gradients, stem included)",
+        out["roofline"] = {"kernel": "conv16_persistent_kernel + conv_strip16_kernel (fprop16 / dgrad16) + conv_gemm_kernel (wgrad16) + stem_s2d kernels: tcgen05 implicit GEMM, TMA fed, kind::f16 (fp16 operands, scaled fp16 gradients)",
                            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                            "traffic": prof.get("conv_traffic"),
-                           "traffic_source": "ncu --set full capture of one 56x56x64 fprop16 launch (profiles/), not this run",
+                           "traffic_source": prof.get("conv_traffic_source", "ncu --set full capture (profiles/), not this run"),
                            "peak_source": "FLOP-weighted blend of bf16_tflops_sustained (f16 launches) and 0.5x (tf32 launches), "
                                           + pk["source"],
                            "launches_per_step": conv["launches"] / a.steps,
