@@ -9,8 +9,7 @@
 //   phase 1  r = inv_batch * sum of the <= 20 partial rows (slice order), formed by every CTA for itself: one grid barrier
 //   phase A  k = P r^T          from the shared-memory rows
 //   phase B  P' = P - (k k^T) ./ (alpha + k r)   in shared memory, + sum(P'^2) partials
-//   phase C  P = P' / ||P'||_F  normalised in shared memory and written to HBM once by bulk shared -> global copies
-//            (cp.async.bulk: the TMA engine drains the rows while the SM projects); grad_w = grad_w @ P^T from the smem-resident rows: a warp owns a
+//   phase C  P = P' / ||P'||_F  written to HBM once; grad_w = grad_w @ P^T from the smem-resident rows: a warp owns a
 //            (4-row group, column chunk) block of P in registers and walks the gradient rows four at a time; the gradient is
 //            streamed through two cp.async-fed staging buffers (tile t+1 lands while tile t is multiplied, one barrier per
 //            tile), the 16 lane-partial sums of a (4 classes x 4 rows) block are reduced with one butterfly transpose
@@ -59,13 +58,6 @@ struct GsParams {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
-
-// shared -> global bulk copy (TMA engine, no LSU traffic); completion tracked by the thread's bulk async-group
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -340,23 +332,23 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
         pv[u].z = __fdiv_rn(pv[u].z, nrm); pv[u].w = __fdiv_rn(pv[u].w, nrm);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (lr0 + u < nrows) st4(s_P + (size_t)(lr0 + u) * D + 4 * j4, pv[u]);
+      for (int u = 0; u < 4; ++u) {
+        if (lr0 + u < nrows) {
+          st4(s_P + (size_t)(lr0 + u) * D + 4 * j4, pv[u]);
+          __stcs(reinterpret_cast<float4*>(p.P + (size_t)(row0 + lr0 + u) * D) + j4, pv[u]);
+        }
+      }
     }
   }
-  // P leaves through the TMA engine: one bulk shared -> global copy per row, issued by one thread. The stores never enter
-  // the LSU queue, so the projection's shared-memory loads do not wait behind 112 KB of write-back per SM.
+  // (Measured alternatives that did NOT help this phase and the projection after it at D = 2048: writing P back with bulk
+  // shared -> global copies issued by one thread instead of these streaming stores (+2 us); a rolled, shared-memory-fed
+  // projection loop with a third of the code size (equal at C = 6, +3 us at C = 101). The normalisation loop itself — 28 k
+  // IEEE divisions per SM at 16 warps — is what bounds the phase.)
   if (stamp) p.ws_ts[15] = tc::globaltimer_ns();
-  tc::fence_proxy_async();                  // the normalised rows (generic-proxy stores) -> visible to the async proxy
   __syncthreads();
-  if (tid == 0 && nrows > 0) {
-    for (int lr = 0; lr < nrows; ++lr)
-      bulk_s2g(p.P + (size_t)(row0 + lr) * D, tc::smem_u32(s_P + (size_t)lr * D), (uint32_t)D * 4u);
-    bulk_commit();
-  }
   if (stamp) p.ws_ts[6] = tc::globaltimer_ns();
   if (ntiles == 0) {
-    if (tid == 0) { bulk_wait_read(); p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns(); }
+    if (tid == 0) p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns();
     return;
   }
 
@@ -427,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
     if (stamp && t < 2) p.ws_ts[11 + 2 * t] = tc::globaltimer_ns();
   }
   if (stamp) p.ws_ts[7] = tc::globaltimer_ns();
-  if (tid == 0) { bulk_wait_read(); p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns(); }     // every CTA's end: rows read out
+  if (tid == 0) p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns();     // every CTA's end
 }
 
 struct GsPlan {

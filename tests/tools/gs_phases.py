@@ -44,7 +44,7 @@ def main():
             t_start, t_end = st[176:176 + g], st[336:336 + g]
             span = "kernel: first CTA start -> last CTA end %.2f us; CTA starts span %.2f us, ends span %.2f us" % (
                 (max(t_end) - min(t_start)) / 1e3, (max(t_start) - min(t_start)) / 1e3, (max(t_end) - min(t_end)) / 1e3)
-            proj = "projection detail (CTA 0): normalise loop %.2f us, fence + barrier + bulk issue %.2f; tile 0 ready +%.2f, multiplied +%.2f, tile 1 ready +%.2f, multiplied +%.2f, last barrier +%.2f, tail +%.2f" % (
+            proj = "projection detail (CTA 0): normalise + store loop %.2f us, barrier %.2f; tile 0 ready +%.2f, multiplied +%.2f, tile 1 ready +%.2f, multiplied +%.2f, last barrier +%.2f, tail +%.2f" % (
                 (st[15] - st[9]) / 1e3, (st[6] - st[15]) / 1e3, (st[10] - st[6]) / 1e3, (st[11] - st[10]) / 1e3,
                 (st[12] - st[11]) / 1e3, (st[13] - st[12]) / 1e3, (st[14] - st[13]) / 1e3, (st[7] - st[14]) / 1e3)
             extra = "last barrier: CTA arrivals span %.2f us (CTA0 at +%.2f); after barrier +%.2f us, norm +%.2f us, write +%.2f us" % (
