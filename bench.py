@@ -179,7 +179,7 @@ SWEEP_D, SWEEP_B, SWEEP_C = (512, 768, 1024, 2048), (64, 256, 1024, 4096), (6, 1
 
 
 def _time_launch(torch, make_set, run, nbytes, launches=24, warm=3):
-    """Median CUDA-event time of one launch of run(set). Cold inputs without evicting the kernel's code: the launches walk
+    """CUDA-event time of one launch of run(set) (trimmed mean over >= 24 launches). Cold inputs without evicting the kernel's code: the launches walk
     over `nsets` independent argument sets whose total footprint exceeds twice the 126 MB L2 (whenever nsets <= 128 allows
     it: the remaining points are latency-bound and labelled so), so every launch reads its inputs from HBM. Every timed
     launch is preceded by a ~60 us spin kernel, which lets the host run ahead: event, launch and event are queued before
@@ -197,7 +197,11 @@ def _time_launch(torch, make_set, run, nbytes, launches=24, warm=3):
         run(sets[i % nsets])
         ev[i][1].record()
     torch.cuda.synchronize()
-    return statistics.median(a.elapsed_time(b) for a, b in ev) * 1e-3, nsets
+    # CUDA-event timestamps tick every ~2 us on this GPU: the median of single-launch times snaps to that grid (36.9 / 38.9 us
+    # for the same kernel from run to run), so the estimate is the mean of the central half of the samples instead
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    mid = ts[len(ts) // 4: len(ts) - len(ts) // 4]
+    return sum(mid) / len(mid) * 1e-3, nsets
 
 
 def _point(pk, t, nbytes, **kw):
@@ -602,7 +606,7 @@ def run_native(a, rank, world):
                                       "point": {k: v for k, v in top.items() if k not in ("gbs", "frac")},
                                       "latency_bound_points": sum(1 for p in pts if p["regime"] == "latency"),
                                       "points": len(pts),
-                                      "timing": "CUDA events around ONE launch, median of >= 24 launches; inputs cold: the launches "
+                                      "timing": "CUDA events around ONE launch, mean of the central half of >= 24 launches (event timestamps tick every ~2 us); inputs cold: the launches "
                                                 "rotate over `sets` independent argument sets (> 2x the 126 MB L2 in total when "
                                                 "sets < 128), no L2 flush"}
             out[key + "_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()} for p in pts]

@@ -85,14 +85,16 @@ __device__ __forceinline__ void project_unit(const float4 (&a)[kRB][4], const fl
         const int c = min(c_lo + cc, ct - 1);                      // rows past the tile repeat the last one (never stored)
         gv[cc] = ld4(G + (size_t)c * D + j);
       }
-      // component-outermost order: 16 independent FMAs between two updates of the same accumulator (the 4-deep dependent
-      // chain per accumulator of the obvious order left the FMA pipe half idle with four warps per scheduler)
-#define MLA_GS_FMA(comp)                                                                                   \
-      _Pragma("unroll") for (int cc = 0; cc < kCT; ++cc)                                                   \
-        _Pragma("unroll") for (int rr = 0; rr < kRB; ++rr)                                                 \
-          acc[cc * kRB + rr] = fmaf(gv[cc].comp, a[rr][q].comp, acc[cc * kRB + rr]);
-      MLA_GS_FMA(x) MLA_GS_FMA(y) MLA_GS_FMA(z) MLA_GS_FMA(w)
-#undef MLA_GS_FMA
+#pragma unroll
+      for (int cc = 0; cc < kCT; ++cc) {
+#pragma unroll
+        for (int rr = 0; rr < kRB; ++rr) {
+          float t = acc[cc * kRB + rr];
+          t = fmaf(gv[cc].x, a[rr][q].x, t); t = fmaf(gv[cc].y, a[rr][q].y, t);
+          t = fmaf(gv[cc].z, a[rr][q].z, t); t = fmaf(gv[cc].w, a[rr][q].w, t);
+          acc[cc * kRB + rr] = t;
+        }
+      }
     }
   }
 #pragma unroll
@@ -342,10 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1) gs_project_kernel(GsParams p) {
   }
   // (Measured alternatives that did NOT help this phase and the projection after it at D = 2048: writing P back with bulk
   // shared -> global copies issued by one thread instead of these streaming stores (+2 us); a rolled, shared-memory-fed
-  // projection loop with a third of the code size (equal at C = 6, +3 us at C = 101). The normalisation loop itself — 28 k
-  // IEEE divisions per SM at 16 warps — is what bounds the phase.)
+  // projection loop with a third of the code size (equal at C = 6, +3 us at C = 101); component-outermost FMA order in the
+  // projection (+2 us). The normalisation loop itself — 28 k IEEE divisions per SM at 16 warps — is what bounds the phase.)
   if (stamp) p.ws_ts[15] = tc::globaltimer_ns();
-  __syncthreads();
   if (stamp) p.ws_ts[6] = tc::globaltimer_ns();
   if (ntiles == 0) {
     if (tid == 0) p.ws_ts[336 + blockIdx.x] = tc::globaltimer_ns();
