@@ -126,9 +126,10 @@ def aux_group(tag):
 
 
 class BucketedAllReduce:
-    """Sum-all-reduce of one flat gradient buffer as two buckets issued asynchronously while the backward pass is still
-    producing the other one: `tail(off)` = elements [off, n) (the layers nearest the loss: complete first), `head(off)` =
-    [0, off). `wait()` makes the CURRENT stream wait for both. With world_size 1 everything is a no-op."""
+    """Sum-all-reduce of one flat gradient buffer as buckets issued asynchronously while the backward pass is still producing
+    the others: `span(lo, hi)` = elements [lo, hi); `tail(off)` = [off, n) (the layers nearest the loss: complete first),
+    `head(off)` = [0, off). `wait()` makes the CURRENT stream wait for every bucket issued so far. With world_size 1
+    everything is a no-op."""
 
     def __init__(self, flat, group=None):
         self.flat, self.group, self.works = flat, group, []
@@ -136,6 +137,9 @@ class BucketedAllReduce:
     def _issue(self, t):
         if is_dist() and t.numel():
             self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def span(self, lo, hi):
+        self._issue(self.flat[lo:hi])
 
     def tail(self, off):
         self._issue(self.flat[off:])
@@ -153,6 +157,14 @@ def allreduce_sum_(t):
     if is_dist():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def allreduce_sum_async(t):
+    """Issue the sum-all-reduce of `t` (it starts once the work queued on the current stream so far is done) and return the
+    handle; `.wait()` makes the then-current stream wait for the result. None when not distributed."""
+    if is_dist():
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+    return None
 
 
 def all_gather_rows(t, sizes=None):

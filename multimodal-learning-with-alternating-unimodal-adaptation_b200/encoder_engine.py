@@ -527,18 +527,27 @@ class ResNetPlan:
     def tail_bucket_offset(self):
         """Element offset, inside the encoder's flat parameter / gradient buffer, of the first layer4 parameter: everything
         from there on (75 % of a ResNet-18's parameters) has its gradient complete after backward segment 0."""
-        first = next(iter(self.net.layer4.parameters()))
-        off = 0
+        return self.bucket_offsets()[-1]
+
+    def bucket_offsets(self):
+        """(first layer2 parameter, first layer4 parameter) as element offsets into the flat buffer: the gradient ranges
+        [off4, n), [off2, off4), [0, off2) are complete after backward segments 0, 1, 2."""
+        firsts = [next(iter(self.net.layer2.parameters())), next(iter(self.net.layer4.parameters()))]
+        offs, off = [None, None], 0
         for q in self._params:
-            if q is first:
-                return off
+            for i, f in enumerate(firsts):
+                if q is f:
+                    offs[i] = off
             off += q.numel()
-        raise RuntimeError("layer4 parameters not found in the encoder's parameter list")
+        if None in offs:
+            raise RuntimeError("layer2 / layer4 parameters not found in the encoder's parameter list")
+        return tuple(offs)
 
     def backward(self, dfeat, serial=None, on_segment=None):
-        """Native backward. `on_segment(k)` (optional) makes the pass run as two replayed launch sequences — k = 0: pooling
-        + layer4 (called when every layer4 gradient is complete on the current stream), k = 1: layer3 .. stem — so that a
-        data-parallel caller can start the all-reduce of the layer4 bucket while the rest of the backward still runs."""
+        """Native backward. `on_segment(k)` (optional) makes the pass run as three replayed launch sequences — k = 0: pooling
+        + layer4 (called when every layer4 gradient is complete on the current stream), k = 1: layer3 + layer2, k = 2: layer1
+        + stem — so that a data-parallel caller can start the all-reduce of each bucket while the rest of the backward still
+        runs; only the small layer1 + stem bucket (0.16 M of 11.2 M parameters) is exposed at the end."""
         if not self.trained_forward:
             raise RuntimeError("encoder backward needs a training-mode forward on the same plan")
         if serial is not None and serial != self.serial:
@@ -559,24 +568,24 @@ class ResNetPlan:
             if on_segment is None:
                 self._run(("bwd",) + key, self._backward_body)
             else:
-                self._run(("bwd0",) + key, lambda: self._backward_body(0))
-                on_segment(0)
-                self._run(("bwd1",) + key, lambda: self._backward_body(1))
-                on_segment(1)
+                for k in range(3):
+                    self._run(("bwd%d" % k,) + key, lambda k=k: self._backward_body(k))
+                    on_segment(k)
         else:
             self._backward_body()                        # fresh gradient tensors every call (plain autograd use): eager
             if on_segment is not None:
-                on_segment(0)
-                on_segment(1)
+                for k in range(3):
+                    on_segment(k)
         self.trained_forward = False
 
     def _backward_body(self, seg=None):
         """seg None: the whole pass; 0: transposed filters + pooling + layer4 (its weight gradients joined at the end);
-        1: layer3 .. stem, continuing from the gradient segment 0 left in `self._seg_dout`."""
+        1: layer3 + layer2, 2: layer1 + stem, each continuing from the gradient the previous segment left in
+        `self._seg_dout`."""
         L, N, st = self.L, self.N, _lib.stream_ptr()
         net = self.net
         dfeat = self.dfeat_static
-        first, last = seg in (None, 0), seg in (None, 1)
+        first, last = seg in (None, 0), seg in (None, 2)
         nblk = len(self.blocks)
         split = nblk - len(net.layer4)                   # blocks [split, nblk) belong to layer4
         self._slot_events.clear()                        # only events of THIS pass order its buffer reuse
@@ -627,8 +636,8 @@ class ResNetPlan:
             _chk(L.mla_avgpool_backward(_p(dfeat), _p(dout), self.B, self.rows, self.C_out, st), "mla_avgpool_backward")
         else:
             dout = self._seg_dout
-        hi = nblk - 1 if first else split - 1
-        lo = 0 if last else split
+        split2 = len(net.layer1)                         # blocks [0, split2) belong to layer1
+        hi, lo = {None: (nblk - 1, 0), 0: (nblk - 1, split), 1: (split - 1, split2), 2: (split2 - 1, 0)}[seg]
         for i in range(hi, lo - 1, -1):
             b = self.blocks[i]
             blk, s, cin, cout = b["blk"], b["stride"], b["cin"], b["cout"]

@@ -202,8 +202,10 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
             fdet = feat.detach()
             st.head_out["dfeat"] = st.dfeat_buffer(m, fdet)                # one dfeat buffer per modality (see below)
             o = head_turn(fc, fdet, label, grad_scale=inv_global, out=st.head_out)   # main.py:432-435 (head part)
-            if world > 1:                                                  # the small head all-reduce
-                mdist.allreduce_sum_(st.packed)
+            # the small head all-reduce ([dW | db | sum_b feat], 14 KB). Only the GS projection and the head's SGD
+            # read its result — the encoder backward differentiates the LOCAL loss through dfeat — so it is issued here and
+            # awaited after the backward has been queued: its latency hides behind the first backward kernels
+            head_ar = mdist.allreduce_sum_async(st.packed) if world > 1 else None
             plan = getattr(feat, "_mla_plan", None)
             if plan is not None:
                 # main.py:435 (encoder part), native backward launched directly. Every encoder but the last runs its
@@ -219,11 +221,12 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                     st.flat[m].attach()
                     if world > 1:
                         # encoder-gradient all-reduce, bucketed and overlapped — the layer4 bucket (75 % of the
-                        # bytes) leaves while layer3 .. stem are still being differentiated; only the small head bucket of
-                        # the last encoder is exposed
-                        bk, off = st.buckets[m], plan.tail_bucket_offset()
+                        # bytes) leaves while layer3 .. stem are still being differentiated, layer3 + layer2 (24 %) during
+                        # layer1 + stem; only the 0.6 MB layer1 + stem bucket of the last encoder is exposed
+                        bk, (off2, off4) = st.buckets[m], plan.bucket_offsets()
+                        spans = ((off4, st.flat[m].flat.numel()), (off2, off4), (0, off2))
                         plan.backward(o["dfeat"], getattr(feat, "_mla_serial", None),
-                                      on_segment=lambda k, bk=bk, off=off: bk.tail(off) if k == 0 else bk.head(off))
+                                      on_segment=lambda k, bk=bk, spans=spans: bk.span(*spans[k]))
                         if not deferred:
                             bk.wait()
                     else:
@@ -239,6 +242,8 @@ def train_epoch(args, epoch, model, device, dataloader, optimizer, scheduler,
                 feat.backward(o["dfeat"])
                 if world > 1:
                     mdist.allreduce_sum_(st.flat[m].flat)
+            if head_ar is not None:
+                head_ar.wait()
             gs_plugin.before_update(fc, fdet, batch_step, len_dataloader, gs_plugin.exp_count,
                                     feat_sum=o["feat_sum"], inv_batch=inv_global)     # main.py:437-438
             optimizer.step()                                               # main.py:439
