@@ -404,6 +404,29 @@ def eager_baseline(torch, steps=5, warm=2):
     return res
 
 
+def measure_tf32_peak(torch):
+    """Measured dense TF32 rate of this GPU the way MEASURED_PEAKS.json measures bf16: torch.matmul (cuBLAS) on 8192^3 fp32
+    operands with allow_tf32, best of 8, CUDA events. (BASELINE.md section 3 left the TF32 peak 'to do'; the roofline of the
+    TF32 step is stated against this number instead of an assumed half of the bf16 peak.)"""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        x = torch.randn(n, n, device="cuda")
+        y = torch.randn(n, n, device="cuda")
+        best = float("inf")
+        for _ in range(2):
+            torch.matmul(x, y)
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(x, y); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        return 2.0 * n ** 3 / best / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def tf32_leg(a):
     """The same K timed steps with TF32 operands (kind::tf32 tensor-core instructions, MLA_F16=0) in a child process:
     the operand format is fixed when the package is imported. Returns {value, ms_per_step} or {error}."""
@@ -466,7 +489,8 @@ def run_native(a, rank, world):
     launches = _lib.launch_count() + encoder_engine.GRAPH_LAUNCHES - l0     # eager launches + graph-replayed kernel nodes
     if a.tf32_leg:                          # child process of tf32_leg(): the device-resident timed region only
         print(json.dumps({"value": BATCH * world * a.steps / t_dev, "ms_per_step": 1e3 * t_dev / a.steps, "unit": "samples/s",
-                          "dtype": "tf32" if not encoder_engine.USE_F16 else "f16"}), flush=True)
+                          "dtype": "tf32" if not encoder_engine.USE_F16 else "f16",
+                          "encoder_tflops": FLOP_PER_SAMPLE_STEP * BATCH * world * a.steps / t_dev / 1e12}), flush=True)
         return
     # data-parallel invariant: P, the head and both encoders are bit-identical on every rank
     dp_identical = None
@@ -615,6 +639,13 @@ def run_native(a, rank, world):
         out["frame_producer"] = producer_leg(torch, pk)
     if not a.no_tf32_leg and world == 1 and encoder_engine.USE_F16:
         out["value_tf32"] = tf32_leg(a)
+        try:
+            tf32_peak = measure_tf32_peak(torch)
+            out["value_tf32"]["cublas_tf32_tflops_measured"] = tf32_peak
+            if "encoder_tflops" in out["value_tf32"]:
+                out["value_tf32"]["frac_of_measured_tf32_peak"] = out["value_tf32"]["encoder_tflops"] / tf32_peak
+        except Exception as exc:                                             # informational only
+            out["value_tf32"]["cublas_tf32_tflops_measured"] = "error: %s" % exc
     if not a.no_eager and world == 1:
         out["eager_baseline"] = eager_baseline(torch)
     if not a.no_cpu_baseline and world == 1:
