@@ -198,6 +198,16 @@ bk = mdist.BucketedAllReduce(flat, mdist.aux_group("enc0"))
 bk.tail(6); bk.head(6); bk.wait()
 assert torch.equal(flat, torch.arange(10, dtype=torch.float32) * 3), flat
 assert mdist.aux_group("enc0") is mdist.aux_group("enc0")
+# three buckets in the order the backward segments complete them (layer4 | layer3 + 2 | layer1 + stem) next to an
+# asynchronous small all-reduce that is awaited later (the head's [dW | db | sum_b feat] packet)
+flat = torch.arange(12, dtype=torch.float32) * (rank + 1)
+small = torch.full((3,), float(rank + 1))
+work = mdist.allreduce_sum_async(small)
+bk = mdist.BucketedAllReduce(flat)
+bk.span(8, 12); bk.span(3, 8); bk.span(0, 3); bk.wait()
+work.wait()
+assert torch.equal(flat, torch.arange(12, dtype=torch.float32) * 3) and torch.all(small == 3)
+assert mdist.bind_host_to_gpu() is None                     # no CUDA device here: the NUMA binding is a no-op
 # loss mean over ranks == global mean
 l = torch.tensor([loc["loss"]], dtype=torch.float64); mdist.allreduce_sum_(l)
 assert abs(l.item() / world - full["loss"]) < 1e-12
