@@ -388,6 +388,14 @@ MLA_API int    mla_frames_to_batch(const unsigned char* src, long long src_bytes
                         int OH, int OW, int max_crop_h, int filter, const float* mean3, const float* std3, float* out,
                         int* status, void* ws, size_t ws_bytes, void* stream);
 
+/* Audio member of the CAV-MAE-style tuples — dataset/dataset.py:281-294 (fbank_aug: torchaudio FrequencyMasking /
+ * TimeMasking), :312-321 (normalisation, noise, roll) for a whole batch of pre-computed filterbank arrays [B][T][F]:
+ *   out[b][(t + shift) mod T][f] = norm(masked(x[b][t][f])) + noise[b][t][f] * amp[b] / 10
+ * params (DEVICE) [B][6] int32 = {f0, f1, t0, t1, shift, add_noise}: rows f0 <= f < f1 and frames t0 <= t < t1 are zeroed
+ * BEFORE the normalisation (x - mean) / std (skipped when skip_norm); noise may be NULL. fp32, same roundings as torch. */
+MLA_API int    mla_spec_to_batch(const float* fbank, const int* params, const float* amp, const float* noise, float mean,
+                        float std, int skip_norm, int B, int T, int F, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,4 +21,4 @@ from .cav_mae import Modal3Classifier  # noqa: F401
 from .utils import setup_seed, weight_init  # noqa: F401
 from .engine import ModuleHolder, train_epoch, valid  # noqa: F401
 from .main import get_arguments  # noqa: F401
-from .dataset import FrameBatchProducer  # noqa: F401
+from .dataset import FrameBatchProducer, SpecBatchProducer  # noqa: F401

@@ -103,6 +103,7 @@ _SIGNATURES = {
     "mla_ogm_coeff": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p]),
     "mla_ogm_modulate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_ll, _c_void_p, _c_void_p, _c_void_p,
                                   _c_void_p]),
+    "mla_spec_to_batch": (_c_int, [_c_void_p] * 4 + [_c_float, _c_float] + [_c_int] * 4 + [_c_void_p, _c_void_p]),
     "mla_frames_to_batch_workspace_bytes": (_c_size_t, [_c_int] * 4),
     "mla_frames_to_batch": (_c_int, [_c_void_p, _c_ll, _c_void_p] + [_c_int] * 7 + [ctypes.POINTER(_c_float)] * 2 +
                             [_c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),

@@ -18,6 +18,7 @@
 //   * ToTensor = float(u8) / 255 (IEEE division), Normalize = (x - mean) / std in fp32, in that order.
 // The crop is a window of the source frame (PIL crop copies pixels, resize then works on the copy: same values).
 #include <math.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
@@ -232,6 +233,46 @@ extern "C" int mla_frames_to_batch(const unsigned char* src, long long src_bytes
   frame_resample_kernel<<<dim3((OH * OW + 255) / 256, nframes), 256, 0, st>>>(src, desc, tab, lim, T,
                                                                               make_float3(mean3[0], mean3[1], mean3[2]),
                                                                               make_float3(std3[0], std3[1], std3[2]), out);
+  MLA_CUDA_TRY(cudaGetLastError());
+  mla::count_launch();
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Audio member of the CAV-MAE-style tuples (dataset/dataset.py:281-294 fbank_aug, :301-321): the pre-computed filterbank
+// array [T, F] of every sample goes through SpecAugment masks (rows f0..f1 and frames t0..t1 set to 0 BEFORE the
+// normalisation, as the reference does), (x - norm_mean) / norm_std, optional additive noise noise * amp / 10 and a roll
+// along time — one pass, the parameters drawn on the host in the reference's order (mla_b200/dataset.py).
+//   params [B][6] int32 = {f0, f1, t0, t1, roll shift, add noise}; amp [B]; noise [B][T][F] or NULL.
+__global__ void __launch_bounds__(256) spec_augment_kernel(const float* __restrict__ x, const int* __restrict__ params,
+                                                           const float* __restrict__ amp, const float* __restrict__ noise,
+                                                           float mean, float std, int skip_norm, int T, int F,
+                                                           float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int* pr = params + (size_t)b * 6;
+  const int f0 = pr[0], f1 = pr[1], t0 = pr[2], t1 = pr[3], shift = pr[4], has_noise = pr[5];
+  const long long n = (long long)T * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / F), f = (int)(i - (long long)t * F);
+    float v = x[(size_t)b * n + i];
+    if ((f >= f0 && f < f1) || (t >= t0 && t < t1)) v = 0.f;                       // masked_fill(mask, 0.)
+    if (!skip_norm) v = __fdiv_rn(__fsub_rn(v, mean), std);
+    if (has_noise && noise != nullptr)                                            // fbank + rand * amp / 10
+      v = __fadd_rn(v, __fdiv_rn(__fmul_rn(noise[(size_t)b * n + i], amp[b]), 10.f));
+    int tt = (t + shift) % T;                                                     // torch.roll(fbank, shift, 0)
+    if (tt < 0) tt += T;
+    out[(size_t)b * n + (size_t)tt * F + f] = v;
+  }
+}
+
+extern "C" int mla_spec_to_batch(const float* fbank, const int* params, const float* amp, const float* noise, float mean,
+                                 float std, int skip_norm, int B, int T, int F, float* out, void* stream) {
+  if (!fbank || !params || !amp || !out || B < 1 || T < 1 || F < 1 || fbank == out) return MLA_E_BADARG;
+  const long long n = (long long)T * F;
+  const unsigned gx = (unsigned)std::min<long long>((n + 255) / 256, 1024);
+  spec_augment_kernel<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(fbank, params, amp, noise, mean, std, skip_norm,
+                                                                                   T, F, out);
   MLA_CUDA_TRY(cudaGetLastError());
   mla::count_launch();
   return 0;

@@ -138,3 +138,52 @@ class FrameBatchProducer:
                 raise RuntimeError("frame %d has an invalid descriptor (crop outside the frame, or a crop / output ratio above "
                                    "15.5 bilinear / 7.5 bicubic)" % (bad - 1))
         return res
+
+
+def mask_interval(mask_param, size):
+    """torchaudio.functional.mask_along_axis's draws (p = 1.0): value = rand * mask_param, min_value = rand * (size - value);
+    the masked interval is [long(min_value), long(min_value) + long(value)). Two draws from torch's global CPU generator."""
+    if mask_param < 1:
+        return 0, 0
+    value = torch.rand(1) * mask_param
+    min_value = torch.rand(1) * (size - value)
+    start = int(min_value.long())
+    return start, start + int(value.long())
+
+
+class SpecBatchProducer:
+    """The audio member of the CAV-MAE-style tuples for a whole batch (dataset/dataset.py:296-321, `CAVDataset.__getitem__`):
+    pre-computed filterbank arrays [T, F] -> SpecAugment (train + augnois: FrequencyMasking(48), TimeMasking(192), :281-294)
+    -> (x - norm_mean) / norm_std -> (train + augnois + noise) x + rand(T, F) * np.random.rand() / 10, rolled by
+    np.random.randint(-1024, 1024) frames. Parameters and the noise field are drawn on the host, per sample, in the
+    reference's order and from the same generators (torch's CPU generator, numpy's global one); the arithmetic runs in one
+    kernel pass (`mla_spec_to_batch`) with torch's roundings."""
+
+    def __init__(self, mode="train", augnois=True, noise=True, skip_norm=False, norm_mean=-5.081, norm_std=4.4849,
+                 freqm=48, timem=192, device="cuda"):
+        self.train = mode == "train"
+        self.augnois, self.noise, self.skip_norm = bool(augnois), bool(noise), bool(skip_norm)
+        self.mean, self.std, self.freqm, self.timem = float(norm_mean), float(norm_std), int(freqm), int(timem)
+        self.device = torch.device(device)
+
+    def __call__(self, fbanks, out=None):
+        x = torch.stack([torch.as_tensor(np.asarray(f), dtype=torch.float32) for f in fbanks])          # [B, T, F]
+        B, T, F = x.shape
+        params = np.zeros((B, 6), np.int32)
+        amp = np.zeros(B, np.float32)
+        noise = None
+        for b in range(B):
+            if self.train and self.augnois:
+                f0, f1 = mask_interval(self.freqm, F)              # FrequencyMasking on the transposed [F, T] view
+                t0, t1 = mask_interval(self.timem, T)              # TimeMasking
+                params[b, :4] = (f0, f1, t0, t1)
+            if self.noise and self.train and self.augnois:
+                if noise is None:
+                    noise = torch.zeros(B, T, F)
+                noise[b] = torch.rand(T, F)
+                amp[b] = np.float32(np.random.rand())
+                params[b, 4] = np.random.randint(-1024, 1024)
+                params[b, 5] = 1
+        dev = self.device
+        return ops.spec_to_batch(x.to(dev), torch.from_numpy(params).to(dev), torch.from_numpy(amp).to(dev),
+                                 None if noise is None else noise.to(dev), self.mean, self.std, self.skip_norm, out=out)

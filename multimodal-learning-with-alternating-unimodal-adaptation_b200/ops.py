@@ -234,6 +234,25 @@ def frames_to_batch(src, desc, B, T, size, max_crop_h, mean, std, out=None, stat
     return out
 
 
+def spec_to_batch(fbank, params, amp, noise, mean, std, skip_norm=False, out=None):
+    """Filterbank batch [B, T, F] -> masked / normalised / noised / rolled batch (dataset/dataset.py:281-294, 312-321).
+    `params` int32 CUDA [B, 6] = (f0, f1, t0, t1, shift, add_noise), `amp` float32 CUDA [B], `noise` float32 [B, T, F] or None."""
+    L = _lib.lib()
+    _need_cuda(fbank, params, amp, noise, out)
+    if fbank.dim() != 3 or params.dtype != torch.int32 or tuple(params.shape) != (fbank.shape[0], 6) or amp.numel() != fbank.shape[0]:
+        raise RuntimeError("spec_to_batch: fbank [B, T, F], params int32 [B, 6], amp [B]")
+    if noise is not None and noise.shape != fbank.shape:
+        raise RuntimeError("spec_to_batch: noise must have the shape of fbank")
+    B, T, F = fbank.shape
+    if out is None:
+        out = torch.empty_like(fbank)
+    rc = L.mla_spec_to_batch(_lib.ptr(_f32(fbank, "fbank")), _lib.ptr(params), _lib.ptr(_f32(amp, "amp")),
+                             _lib.ptr(_f32(noise, "noise")), float(mean), float(std), 1 if skip_norm else 0, B, T, F,
+                             _lib.ptr(_f32(out, "out")), _lib.stream_ptr())
+    _lib.check(rc, "mla_spec_to_batch")
+    return out
+
+
 def _conv_out(x, k, stride, pad):
     return (x + 2 * pad - k) // stride + 1
 

@@ -109,3 +109,35 @@ def test_bicubic_resize_center_crop_equals_torchvision_bit_for_bit(producer_cls,
     out = producer_cls(size, "center", mean, std, interpolation="bicubic")(frames)
     assert out.shape == (4, 3, 1, size, size)
     assert torch.equal(out.cpu()[:, :, 0], ref)
+
+
+def _reference_cav_audio(fbank, train, augnois, noise, skip_norm, norm_mean=-5.081, norm_std=4.4849):
+    """dataset/dataset.py:281-294 + 301-321 restated line by line on the CPU with torchaudio itself."""
+    import torchaudio
+    fbank = torch.tensor(fbank)
+    if train and augnois:
+        freqm = torchaudio.transforms.FrequencyMasking(48)
+        timem = torchaudio.transforms.TimeMasking(192)
+        fb = torch.transpose(fbank, 0, 1).unsqueeze(0)
+        fb = timem(freqm(fb))
+        fbank = torch.transpose(fb.squeeze(0), 0, 1)
+    if not skip_norm:
+        fbank = (fbank - norm_mean) / (norm_std)
+    if noise and train and augnois:
+        fbank = fbank + torch.rand(fbank.shape[0], fbank.shape[1]) * np.random.rand() / 10
+        fbank = torch.roll(fbank, np.random.randint(-1024, 1024), 0)
+    return fbank
+
+
+@pytest.mark.parametrize("train,augnois,noise,skip_norm", [(True, True, True, False), (True, True, False, False),
+                                                            (False, True, True, False), (True, False, True, True)])
+def test_spec_producer_equals_the_reference_audio_pipeline_bit_for_bit(built_lib, train, augnois, noise, skip_norm):
+    from mla_b200.dataset import SpecBatchProducer
+    rng = np.random.default_rng(3)
+    fbanks = [rng.normal(-5, 4, (1024, 128)).astype(np.float32) for _ in range(3)]
+    torch.manual_seed(11); np.random.seed(11)
+    ref = torch.stack([_reference_cav_audio(f, train, augnois, noise, skip_norm) for f in fbanks])
+    torch.manual_seed(11); np.random.seed(11)
+    out = SpecBatchProducer("train" if train else "test", augnois, noise, skip_norm)(fbanks)
+    assert out.shape == (3, 1024, 128)
+    assert torch.equal(out.cpu(), ref)
