@@ -469,27 +469,45 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   }
 }
 
-// Fixed-order reduction of split-K partials: dw[i] = sum_s part[s][i]. Eight partials are loaded before they are
-// added (memory-level parallelism); the additions keep the order s = 0, 1, 2, ... (deterministic).
-__global__ void __launch_bounds__(64) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                                            long long n4, int splits, long long stride4) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const float4* p4 = reinterpret_cast<const float4*>(part) + i;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+// Fixed-order reduction of split-K partials: dw[i] = sum_s part[s][i]. A thread owns two float4 columns (i and i + n4 / 2
+// rounded up) and loads up to four partials of each before adding them (memory-level parallelism: with 2-4 splits one
+// column per thread left two loads in flight); the additions keep the order s = 0, 1, 2, ... (deterministic).
+__global__ void __launch_bounds__(128) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                             long long n4, int splits, long long stride4) {
+  const long long half = (n4 + 1) / 2;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= half) return;
+  const long long i1 = i0 + half;
+  const bool two = i1 < n4;
+  const float4* p0 = reinterpret_cast<const float4*>(part) + i0;
+  const float4* p1 = reinterpret_cast<const float4*>(part) + (two ? i1 : i0);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
   int s = 0;
-  for (; s + 8 <= splits; s += 8) {
-    float4 v[8];
+  for (; s + 4 <= splits; s += 4) {
+    float4 v[4], w[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcs(p4 + (long long)(s + u) * stride4);
+    for (int u = 0; u < 4; ++u) { v[u] = __ldcs(p0 + (long long)(s + u) * stride4); w[u] = __ldcs(p1 + (long long)(s + u) * stride4); }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    for (int u = 0; u < 4; ++u) {
+      a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w;
+      a1.x += w[u].x; a1.y += w[u].y; a1.z += w[u].z; a1.w += w[u].w;
+    }
   }
-  for (; s < splits; ++s) {
-    const float4 v = __ldcs(p4 + (long long)s * stride4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  {
+    float4 v[3], w[3];
+    const int r = splits - s;                                    // 0 .. 3 remaining partials, all loaded first
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (u < r) { v[u] = __ldcs(p0 + (long long)(s + u) * stride4); w[u] = __ldcs(p1 + (long long)(s + u) * stride4); }
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (u < r) {
+        a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w;
+        a1.x += w[u].x; a1.y += w[u].y; a1.z += w[u].z; a1.w += w[u].w;
+      }
   }
-  reinterpret_cast<float4*>(out)[i] = acc;
+  reinterpret_cast<float4*>(out)[i0] = a0;
+  if (two) reinterpret_cast<float4*>(out)[i1] = a1;
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -2001,7 +2019,7 @@ extern "C" int mla_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   if (rc) return rc;
   if (pl.splits > 1) {
     const long long n4 = p.split_stride / 4;
-    splitk_reduce_kernel<<<(unsigned)((n4 + 63) / 64), 64, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
+    splitk_reduce_kernel<<<(unsigned)(((n4 + 1) / 2 + 127) / 128), 128, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
     MLA_CUDA_TRY(cudaGetLastError());
     mla::count_launch();
   }
@@ -2077,7 +2095,7 @@ static int wgrad16_impl(const void* x16, const void* dy16, float* dw, int N, int
   if (rc) return rc;
   if (pl.splits > 1) {
     const long long n4 = p.split_stride / 4;
-    splitk_reduce_kernel<<<(unsigned)((n4 + 63) / 64), 64, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
+    splitk_reduce_kernel<<<(unsigned)(((n4 + 1) / 2 + 127) / 128), 128, 0, st>>>(static_cast<const float*>(ws), dw, n4, pl.splits, n4);
     MLA_CUDA_TRY(cudaGetLastError());
     mla::count_launch();
   }
