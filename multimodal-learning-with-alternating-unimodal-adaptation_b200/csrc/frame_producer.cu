@@ -252,26 +252,30 @@ __global__ void __launch_bounds__(256) spec_augment_kernel(const float* __restri
   const int b = blockIdx.y;
   const int* pr = params + (size_t)b * 6;
   const int f0 = pr[0], f1 = pr[1], t0 = pr[2], t1 = pr[3], shift = pr[4], has_noise = pr[5];
-  const long long n = (long long)T * F;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i / F), f = (int)(i - (long long)t * F);
-    float v = x[(size_t)b * n + i];
-    if ((f >= f0 && f < f1) || (t >= t0 && t < t1)) v = 0.f;                       // masked_fill(mask, 0.)
-    if (!skip_norm) v = __fdiv_rn(__fsub_rn(v, mean), std);
-    if (has_noise && noise != nullptr)                                            // fbank + rand * amp / 10
-      v = __fadd_rn(v, __fdiv_rn(__fmul_rn(noise[(size_t)b * n + i], amp[b]), 10.f));
-    int tt = (t + shift) % T;                                                     // torch.roll(fbank, shift, 0)
+  const size_t n = (size_t)T * F;
+  // a block walks whole frames t (rows of F bins), threads over the bins: no index division, coalesced rows in and out
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    const bool tmask = t >= t0 && t < t1;
+    int tt = (t + shift) % T;                                                       // torch.roll(fbank, shift, 0)
     if (tt < 0) tt += T;
-    out[(size_t)b * n + (size_t)tt * F + f] = v;
+    const size_t src = (size_t)b * n + (size_t)t * F, dst = (size_t)b * n + (size_t)tt * F;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      float v = x[src + f];
+      if (tmask || (f >= f0 && f < f1)) v = 0.f;                                    // masked_fill(mask, 0.)
+      if (!skip_norm) v = __fdiv_rn(__fsub_rn(v, mean), std);
+      if (has_noise && noise != nullptr)                                            // fbank + rand * amp / 10
+        v = __fadd_rn(v, __fdiv_rn(__fmul_rn(noise[src + f], amp[b]), 10.f));
+      out[dst + f] = v;
+    }
   }
 }
 
 extern "C" int mla_spec_to_batch(const float* fbank, const int* params, const float* amp, const float* noise, float mean,
                                  float std, int skip_norm, int B, int T, int F, float* out, void* stream) {
   if (!fbank || !params || !amp || !out || B < 1 || T < 1 || F < 1 || fbank == out) return MLA_E_BADARG;
-  const long long n = (long long)T * F;
-  const unsigned gx = (unsigned)std::min<long long>((n + 255) / 256, 1024);
-  spec_augment_kernel<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(fbank, params, amp, noise, mean, std, skip_norm,
+  const unsigned gx = (unsigned)std::min(T, 256);
+  const unsigned threads = F >= 256 ? 256 : (F > 64 ? 128 : 64);
+  spec_augment_kernel<<<dim3(gx, B), threads, 0, static_cast<cudaStream_t>(stream)>>>(fbank, params, amp, noise, mean, std, skip_norm,
                                                                                    T, F, out);
   MLA_CUDA_TRY(cudaGetLastError());
   mla::count_launch();

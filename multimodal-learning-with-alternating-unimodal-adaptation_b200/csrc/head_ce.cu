@@ -381,7 +381,7 @@ LargePlan large_plan(int B, int D, int C) {
   const mla::DeviceInfo& di = mla::device_info();
   const int sms = di.ok == 1 ? di.sm_count : 148;
   const int tiles = ((C + 1 + kGT - 1) / kGT) * ((D + kGT - 1) / kGT);
-  int S = std::max(1, std::min((2 * sms + tiles - 1) / tiles, B / 128));      // >= 128 batch rows per split, ~2 CTAs per SM
+  int S = std::max(1, std::min((4 * sms + tiles - 1) / tiles, B / 128));      // >= 128 batch rows per split, ~4 CTAs per SM
   S = std::min(S, 32);
   pl.k_per_split = ((B + S - 1) / S + kGK - 1) / kGK * kGK;
   pl.S = (B + pl.k_per_split - 1) / pl.k_per_split;
@@ -391,7 +391,7 @@ LargePlan large_plan(int B, int D, int C) {
   // the logits GEMM is split over D when its (batch tile, class tile) grid alone would leave most SMs idle (small batches):
   // >= 64 columns per split; the partials are added in split order by the softmax kernel
   const int tiles1 = ((B + kGT - 1) / kGT) * ((C + kGT - 1) / kGT);
-  int S1 = std::max(1, std::min(std::min((sms + tiles1 - 1) / tiles1, D / 64), 32));
+  int S1 = std::max(1, std::min(std::min((4 * sms + tiles1 - 1) / tiles1, D / 64), 32));
   pl.k1_per_split = ((D + S1 - 1) / S1 + kGK - 1) / kGK * kGK;
   pl.S1 = (D + pl.k1_per_split - 1) / pl.k1_per_split;
   pl.off_lpart = pl.off_part + mla::align_up((size_t)pl.S * (C + 1) * D * 4, 256);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # `ncu --set full` captures of the kernels DESIGN.md section 6 discusses, each only after the same command has exited 0
 # without ncu. Run on the GPU box:  bash tests/tools/ncu_capture.sh [tag]   -> gpurun_out/<tag>_*.ncu-rep + CSV summaries
-# (copy the CSVs you want judged into profiles/). Optional second argument: which capture (conv16 | small | m3ae | all).
+# (copy the CSVs you want judged into profiles/). Optional second argument: which capture (conv16 | small | new | m3ae | all).
 tag=${1:-r2}
 which=${2:-all}
 NCU="ncu --set full --clock-control none --import-source on -f"
@@ -18,5 +18,6 @@ EXTRA=()
 want() { [ "$which" = all ] || [ "$which" = "$1" ]; }
 want conv16 && run conv16 "conv16_persistent|conv_gemm_kernel|conv_strip16" 27 python tests/tools/profile_conv16.py
 want small && run small "gs_project|head_rows|head_cols|head_reduce|fuse_eval" 12 python tests/tools/profile_top.py
+want new && run new "head_gemm|head_softmax|head_split|head_db|frame_|spec_augment" 16 python tests/tools/profile_top.py
 want m3ae && run m3ae "linear_gemm_persistent|attn_fwd_tc|attn_bwd|conv_gemm_kernel" 24 python tests/tools/profile_m3ae.py 32 257
 true
