@@ -809,3 +809,18 @@ def frames_to_tensor(batch_of_frames, params, size, mean, std):
             x = img.transpose(2, 0, 1).astype(np.float32) / np.float32(255)
             out[b, :, t] = (x - m) / s
     return out
+
+
+def spec_augment(fbank, params, amp, noise, mean, std, skip_norm=False):
+    """dataset/dataset.py:281-294 (SpecAugment masks, applied to the raw filterbank) + :312-321 (normalisation, additive
+    noise rand * amp / 10, roll along time) for one sample, numpy float32 with torch's roundings.
+    params = (f0, f1, t0, t1, shift, add_noise); fbank / noise [T, F]."""
+    f0, f1, t0, t1, shift, add_noise = [int(v) for v in params]
+    x = np.array(fbank, np.float32, copy=True)
+    x[:, f0:f1] = 0.0
+    x[t0:t1, :] = 0.0
+    if not skip_norm:
+        x = (x - np.float32(mean)) / np.float32(std)
+    if add_noise and noise is not None:
+        x = x + (np.asarray(noise, np.float32) * np.float32(amp)) / np.float32(10)
+    return np.roll(x, shift, axis=0) if add_noise else x

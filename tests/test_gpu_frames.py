@@ -141,3 +141,13 @@ def test_spec_producer_equals_the_reference_audio_pipeline_bit_for_bit(built_lib
     out = SpecBatchProducer("train" if train else "test", augnois, noise, skip_norm)(fbanks)
     assert out.shape == (3, 1024, 128)
     assert torch.equal(out.cpu(), ref)
+    # the kernel against the numpy oracle on explicit parameters (masks at the borders, negative and zero shifts)
+    from mla_b200 import ops
+    params = np.array([[0, 48, 1000, 1024, -1023, 1], [127, 128, 0, 1, 0, 1], [10, 10, 5, 5, 512, 0]], np.int32)
+    amp = np.array([0.73, 0.01, 0.5], np.float32)
+    nz = rng.random((3, 1024, 128)).astype(np.float32)
+    x = np.stack(fbanks)
+    got = ops.spec_to_batch(torch.from_numpy(x).cuda(), torch.from_numpy(params).cuda(), torch.from_numpy(amp).cuda(),
+                            torch.from_numpy(nz).cuda(), -5.081, 4.4849, skip_norm).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(got[b], orc.spec_augment(x[b], params[b], amp[b], nz[b], -5.081, 4.4849, skip_norm))

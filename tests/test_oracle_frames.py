@@ -95,3 +95,28 @@ def test_bicubic_resize_center_crop_restatement_matches_the_reference_compose(H,
     rh, rw, oy, ox = resize_center_crop_params(H, W, size)
     full = np.asarray(Image.fromarray(img).resize((rw, rh), PIL.Image.BICUBIC))
     assert np.array_equal(full[oy:oy + size, ox:ox + size], ref)               # the host mirror's window arithmetic
+
+
+def test_audio_pipeline_restatement_and_host_draws_match_torchaudio():
+    """dataset.py:281-294, 301-321 executed with torchaudio vs the oracle's numpy restatement fed with the parameters the
+    host mirror draws (mla_b200.dataset.mask_interval + numpy's generator) under the same seeds."""
+    import torchaudio
+    from mla_b200.dataset import mask_interval
+    rng = np.random.default_rng(5)
+    fbank = rng.normal(-5, 4, (1024, 128)).astype(np.float32)
+    for seed in range(4):
+        torch.manual_seed(seed); np.random.seed(seed)
+        fb = torch.transpose(torch.tensor(fbank), 0, 1).unsqueeze(0)
+        fb = torchaudio.transforms.TimeMasking(192)(torchaudio.transforms.FrequencyMasking(48)(fb))
+        ref = torch.transpose(fb.squeeze(0), 0, 1)
+        ref = (ref - (-5.081)) / (4.4849)
+        ref = ref + torch.rand(ref.shape[0], ref.shape[1]) * np.random.rand() / 10
+        ref = torch.roll(ref, np.random.randint(-1024, 1024), 0)
+        torch.manual_seed(seed); np.random.seed(seed)
+        f0, f1 = mask_interval(48, 128)
+        t0, t1 = mask_interval(192, 1024)
+        noise = torch.rand(1024, 128).numpy()
+        amp = np.float32(np.random.rand())
+        shift = np.random.randint(-1024, 1024)
+        out = orc.spec_augment(fbank, (f0, f1, t0, t1, shift, 1), amp, noise, -5.081, 4.4849)
+        assert np.array_equal(out, ref.numpy())
