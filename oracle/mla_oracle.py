@@ -823,4 +823,4 @@ def spec_augment(fbank, params, amp, noise, mean, std, skip_norm=False):
         x = (x - np.float32(mean)) / np.float32(std)
     if add_noise and noise is not None:
         x = x + (np.asarray(noise, np.float32) * np.float32(amp)) / np.float32(10)
-    return np.roll(x, shift, axis=0) if add_noise else x
+    return np.roll(x, shift, axis=0)            # the reference only draws a non-zero shift together with the noise
