@@ -8,7 +8,7 @@ set -e
 export MLA_OVERLAP=0 MLA_OVERLAP_WGRAD=0 MLA_GRAPHS=0
 timeout 200 python bench.py --steps 1 --warmup 3 --no-sweep --no-cpu-baseline --no-extra > gpurun_out/step_plain_ss.json 2> gpurun_out/step_plain_ss.err
 echo plain rc=$?
-# 3 warm-up steps + 1 timed step ~ 2100 launches including model set-up: -c 2400 stops right after them
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 2400 --csv --log-file gpurun_out/step_launches.csv \
+# 3 warm-up steps + 1 timed step ~ 2100 launches including model set-up: -c 1800 keeps three complete steps
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv --log-file gpurun_out/step_launches.csv \
   python bench.py --steps 1 --warmup 3 --no-sweep --no-cpu-baseline --no-extra > gpurun_out/step_ncu.log 2>&1 || true
 wc -l gpurun_out/step_launches.csv
