@@ -622,7 +622,11 @@ def run_native(a, rank, world):
         # point of each kernel is its best bandwidth-regime point; every point (latency-bound ones labelled) is listed
         for key, fn, kern in (("gs", gs_sweep, "gs_project_kernel"), ("head", head_sweep, "head_rows_kernel + head_cols_kernel + head_reduce_kernel (C <= 16) / head_fwd_kernel + head_bwd_kernel"),
                               ("fusion", fusion_sweep, "fuse_eval_kernel")):
-            pts = fn(torch, ops, pk)
+            try:
+                pts = fn(torch, ops, pk)
+            except Exception as exc:                                         # a failed sweep never costs the headline line
+                out["roofline_" + key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                continue
             top = max((p for p in pts if p["regime"] != "fp32-compute"), key=lambda p: p["gbs"])
             out["roofline_" + key] = {"kernel": kern, "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"],
                                       "unit": "GB/s", "frac": top["frac"],
@@ -634,9 +638,13 @@ def run_native(a, rank, world):
                                                 "rotate over `sets` independent argument sets (> 2x the 126 MB L2 in total when "
                                                 "sets < 128), no L2 flush"}
             out[key + "_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()} for p in pts]
-        out["gs_beyond_sweep"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()}
-                                  for p in gs_beyond_sweep(torch, ops, pk)]
-        out["frame_producer"] = producer_leg(torch, pk)
+        for key, leg in (("gs_beyond_sweep", lambda: [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()}
+                                                      for p in gs_beyond_sweep(torch, ops, pk)]),
+                         ("frame_producer", lambda: producer_leg(torch, pk))):
+            try:                                                             # informational legs never cost the line
+                out[key] = leg()
+            except Exception as exc:
+                out[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if not a.no_tf32_leg and world == 1 and encoder_engine.USE_F16:
         out["value_tf32"] = tf32_leg(a)
         try:
@@ -649,7 +657,10 @@ def run_native(a, rank, world):
     if not a.no_eager and world == 1:
         out["eager_baseline"] = eager_baseline(torch)
     if not a.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline()
+        try:
+            out["cpu_baseline"] = cpu_baseline()
+        except Exception as exc:
+            out["cpu_baseline"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if not a.no_extra and world == 1:
         out["other_workloads"] = other_workloads(torch)
     print(json.dumps(out), flush=True)
